@@ -1,0 +1,173 @@
+/*
+ * sfno_b200.h -- C ABI of the B200-native SFNO forward path (libsfno_b200.so).
+ *
+ * The reference (Rose-STL-Lab/spherical-dyffusion) is pure Python and has no FFI for this path; the
+ * entry points below are what a binding for its hot path has to call ("What a
+ * C-ABI replacement must export").  Each group cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev is a CUDA device pointer owned by the caller
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *   - functions return 0 (SFNO_OK) or a negative sfno_status; no exceptions cross the ABI
+ *   - forward entry points never allocate: scratch comes from the caller-provided workspace
+ *   - handles are re-entrant per handle (one in-flight call per handle and stream)
+ *   - `precision`: SFNO_PREC_F32 = fp32 storage, fp32 CUDA-core FMA accumulate (parity mode,
+ *                  <= 1e-4 rel-L2 vs the fp32 reference); SFNO_PREC_BF16 = bf16 storage, tcgen05
+ *                  tensor-core MMA with fp32 TMEM accumulators (throughput mode, stated bf16 bound)
+ */
+#ifndef SFNO_B200_H_
+#define SFNO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum sfno_status {
+  SFNO_OK = 0,
+  SFNO_ERR_INVALID_ARGUMENT = -1,
+  SFNO_ERR_CUDA = -2,
+  SFNO_ERR_WORKSPACE_TOO_SMALL = -3,
+  SFNO_ERR_UNSUPPORTED = -4,
+  SFNO_ERR_NO_DEVICE = -5,
+  SFNO_ERR_UNKNOWN_PARAM = -6,
+  SFNO_ERR_SHAPE_MISMATCH = -7
+} sfno_status;
+
+enum { SFNO_GRID_LEGENDRE_GAUSS = 0, SFNO_GRID_EQUIANGULAR = 1 };
+enum { SFNO_PREC_F32 = 0, SFNO_PREC_BF16 = 1 };
+enum { SFNO_OP_DHCONV = 0, SFNO_OP_DIAGONAL = 1 };
+enum { SFNO_ACT_NONE = 0, SFNO_ACT_GELU = 1, SFNO_ACT_RELU = 2, SFNO_ACT_SILU = 3 };
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int sfno_b200_abi_version(void);
+const char* sfno_b200_status_string(int status);
+/* Thread-local text of the last failure (CUDA error string, offending argument ...). */
+const char* sfno_b200_last_error(void);
+/* Number of kernels this library has launched since load (monotonic; used by bench.py). */
+int64_t sfno_b200_launch_count(void);
+
+/* Library-wide switches for tests: "force_simt" = 1 routes bf16 ops to the CUDA-core engine. */
+int sfno_b200_set_option(const char* key, int64_t value);
+
+/* ---- host-side tables (no GPU needed) -----------------------------------------------------------
+ * Replaces torch_harmonics' precompute used at sfnonet.py:551-554 (quadrature.py legendre_gauss_weights /
+ * clenshaw_curtiss_weights, legendre.py legpoly).  Outputs are fp64, row-major:
+ *   nodes[nlat] (cos(colatitude), north -> south), quad_w[nlat],
+ *   weights[mmax][lmax][nlat] = P * quad_w (analysis), pct[mmax][lmax][nlat] (synthesis).
+ * Any output pointer may be NULL. */
+int sfno_sht_tables_host(int nlat, int nlon, int lmax, int mmax, int grid,
+                         double* nodes, double* quad_w, double* weights, double* pct);
+
+/* ---- spherical harmonic transform pair ----------------------------------------------------------
+ * Replaces torch_harmonics.RealSHT / InverseRealSHT objects built at sfnonet.py:551-554 and called at
+ * s2convolutions.py:165,168,186.  The plan owns the device tables (Legendre x quadrature, DFT bases). */
+typedef struct sfno_sht_plan sfno_sht_plan;
+int sfno_sht_plan_create(sfno_sht_plan** plan, int nlat, int nlon, int lmax, int mmax, int grid, int precision);
+int sfno_sht_plan_destroy(sfno_sht_plan* plan);
+/* scratch needed by sfno_sht_forward / sfno_sht_inverse for `fields` = prod(leading dims) 2-D fields */
+size_t sfno_sht_workspace_bytes(const sfno_sht_plan* plan, int64_t fields);
+/* x_dev: fp32 [fields][nlat][nlon]  ->  coeffs_dev: complex64 (interleaved re,im) [fields][lmax][mmax]
+ * == RealSHT.forward: 2*pi*rfft(x, norm="forward")[..., :mmax] contracted with weights[m,l,k]. */
+int sfno_sht_forward(const sfno_sht_plan* plan, const float* x_dev, float* coeffs_dev, int64_t fields,
+                     void* workspace_dev, size_t workspace_bytes, void* stream);
+/* coeffs_dev: complex64 [fields][lmax][mmax] -> x_dev fp32 [fields][nlat][nlon]
+ * == InverseRealSHT.forward: pct contraction then irfft(n=nlon, norm="forward") (Im of m=0/Nyquist dropped). */
+int sfno_sht_inverse(const sfno_sht_plan* plan, const float* coeffs_dev, float* x_dev, int64_t fields,
+                     void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- spectral channel contraction -----------------------------------------------------------------
+ * Replaces _contract_dhconv / _contract_diagonal (contractions.py:147-169) as dispatched by
+ * get_contract_fun (factorizations.py:189-225) and called at s2convolutions.py:172-179.
+ *   x_dev      complex64 [batch][cin][lmax][mmax]
+ *   weight_dev fp32 real view [cin][cout][lmax][2] (dhconv) or [cin][cout][lmax][mmax][2] (diagonal)
+ *   out_dev    complex64 [batch][cout][lmax][mmax]
+ * fp32 CUDA-core arithmetic (the packed tensor-core form lives inside sfno_net_forward). */
+int sfno_spectral_contract(int operator_type, const float* x_dev, const float* weight_dev, float* out_dev,
+                           int batch, int cin, int cout, int lmax, int mmax, void* stream);
+
+/* ---- pointwise pieces (fp32, NCHW) -- exported so each can be parity-tested on its own ------------- */
+/* nn.InstanceNorm2d(C, eps, affine=True, track_running_stats=False) (sfnonet.py:641-647), optionally
+ * fused with time_scale_shift (sfnonet.py:280-287): y = norm(x)*(scale+1)+shift with scale/shift [batch][C]
+ * (either may be NULL).  x_dev,y_dev: [batch][C][hw]. */
+int sfno_instance_norm(const float* x_dev, float* y_dev, const float* gamma_dev, const float* beta_dev,
+                       const float* scale_dev, const float* shift_dev, int batch, int channels, int64_t hw,
+                       float eps, void* workspace_dev, size_t workspace_bytes, void* stream);
+size_t sfno_instance_norm_workspace_bytes(int batch, int channels);
+/* nn.Conv2d(cin, cout, 1) (+bias) (+activation) (+residual add): sfnonet.py:239,308,614-617,739-742, layers.py:73-75.
+ * x_dev [batch][cin][hw], weight_dev [cout][cin], bias_dev [cout] or NULL, residual_dev [batch][cout][hw] or NULL. */
+int sfno_conv1x1(const float* x_dev, const float* weight_dev, const float* bias_dev, const float* residual_dev,
+                 float* y_dev, int batch, int cin, int cout, int64_t hw, int activation, void* stream);
+
+/* ---- whole network -----------------------------------------------------------------------------------
+ * Replaces SphericalFourierNeuralOperatorNet (sfnonet.py:340-841) for inference: ctor arguments of
+ * sfnonet.py:426-466 that reach the hot path, the state_dict layout of SURVEY 8b, and forward()
+ * (sfnonet.py:797-841) including concat_condition_if_needed (_base_model.py:166-192, done by the host
+ * wrapper), time embedding (misc.py:132-148), time_scale_shift (sfnonet.py:280-287), SpectralConvS2.forward
+ * (s2convolutions.py:158-193), MLP (layers.py:73-80), Dropout / DropPath at inference (dyffusion.py:226-235). */
+typedef struct sfno_net_config {
+  int32_t struct_size;         /* = sizeof(sfno_net_config), for ABI evolution */
+  int32_t precision;           /* SFNO_PREC_* */
+  int32_t nlat, nlon;          /* spatial_shape_in (== out; scale_factor must be 1) */
+  int32_t in_chans;            /* num_input_channels + num_conditional_channels */
+  int32_t out_chans;           /* num_output_channels */
+  int32_t embed_dim, num_layers;
+  int32_t mlp_hidden;          /* int(embed_dim * mlp_ratio); 0 = use_mlp False */
+  int32_t operator_type;       /* SFNO_OP_* */
+  int32_t activation;          /* SFNO_ACT_* */
+  int32_t data_grid;           /* SFNO_GRID_* of trans_down / itrans_up; internal grid is Legendre-Gauss */
+  int32_t lmax, mmax;          /* modes_lat, modes_lon (sfnonet.py:526-527) */
+  int32_t pos_embed, big_skip; /* booleans */
+  int32_t instance_norm;       /* 1 = instance_norm, 0 = none */
+  int32_t with_time_emb, time_dim;            /* time_dim = embed_dim * time_dim_mult */
+  int32_t time_scale_shift_before_filter;
+  float   time_scaler, time_shift;            /* time_rescale (sfnonet.py:783-784); 1, 0 when off */
+  float   norm_eps;                           /* 1e-6 */
+  float   dropout_mlp;                        /* p of nn.Dropout inside MLP (layers.py:76-80) */
+  float   drop_path_rate;                     /* linspace(0, rate, num_layers) (sfnonet.py:622) */
+  int32_t max_batch;                          /* workspace / per-sample folded-weight capacity */
+} sfno_net_config;
+
+typedef struct sfno_net sfno_net;
+int sfno_net_create(const sfno_net_config* config, sfno_net** net);
+int sfno_net_destroy(sfno_net* net);
+/* Upload one tensor of the reference state_dict (fp32, contiguous, device memory, reference shape).
+ * `name` is the reference key, e.g. "blocks.3.filter.filter.weight".  The call (re)packs it into the
+ * layout the kernels use; call again after an in-place update (EMA swap, load_state_dict). */
+int sfno_net_set_param(sfno_net* net, const char* name, const float* value_dev, int64_t numel, void* stream);
+/* Names the net expects, '\n'-separated (owned by the net). */
+const char* sfno_net_param_names(const sfno_net* net);
+size_t sfno_net_workspace_bytes(const sfno_net* net, int batch);
+/* x_dev [batch][in_chans][nlat][nlon] fp32, time_dev [batch] fp32 (already range-checked by the caller;
+ * NULL iff !with_time_emb), y_dev [batch][out_chans][nlat][nlon] fp32.
+ * dropout_enabled: nn.Dropout/DropPath in "training" state (inference dropout); seed/offset key the
+ * Philox stream so members differ only by their RNG stream. */
+int sfno_net_forward(sfno_net* net, const float* x_dev, const float* time_dev, float* y_dev, int batch,
+                     int dropout_enabled, uint64_t seed, uint64_t offset,
+                     void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Per-net test switch: "stop_after_block" = -2 run everything (default), -1 stop after encoder + pos-embed,
+ * i stop after block i (the output tensor is then left untouched; read the state with sfno_net_debug_tap). */
+int sfno_net_set_option(sfno_net* net, const char* key, int64_t value);
+/* Debug/test taps: copy an intermediate of the last forward (same workspace) as fp32 into dst_dev.
+ * Known names: "x" (current activation [batch][embed][nlat][nlon]), "t_repr".  Returns the element count or a negative status. */
+int64_t sfno_net_debug_tap(sfno_net* net, const char* name, float* dst_dev, int64_t capacity,
+                           void* workspace_dev, void* stream);
+
+/* ---- ensemble statistics (new; spec = src/evaluation/metrics.py:166-175,199-246) -------------------
+ * members_dev [members][n] fp32 on this rank.  Accumulates sum and sum of squares into sums_dev[2][n]
+ * (fp32, caller zero-initialises, all-reduces across ranks with NCCL, then calls _finalize). */
+int sfno_ensemble_accumulate(const float* members_dev, int members, int64_t n, float* sums_dev, void* stream);
+/* mean_dev[n], var_dev[n] (unbiased over `total_members`, as torch.var) from all-reduced sums. */
+int sfno_ensemble_finalize(const float* sums_dev, int total_members, int64_t n, float* mean_dev, float* var_dev,
+                           void* stream);
+/* Fair CRPS per grid point (metrics.py:199-246): members_dev [members][n] (all members, after all-gather),
+ * truth_dev [n] -> crps_dev [n] = mean_i|x_i - y| - sum_{i<j}|x_i-x_j| / (E*(E-1)) . members <= 64. */
+int sfno_ensemble_crps(const float* members_dev, const float* truth_dev, int members, int64_t n,
+                       float* crps_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFNO_B200_H_ */

@@ -1,0 +1,99 @@
+// Shared helpers for libsfno_b200: status/error plumbing, launch accounting, dtype conversion.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/sfno_b200.h"
+
+namespace sfno {
+
+// ---- error text (thread local) -------------------------------------------------------------------
+std::string& last_error_ref();
+int fail(int status, const char* fmt, ...);
+
+#define SFNO_CHECK_ARG(cond, ...)                                        \
+  do {                                                                   \
+    if (!(cond)) return ::sfno::fail(SFNO_ERR_INVALID_ARGUMENT, __VA_ARGS__); \
+  } while (0)
+
+#define SFNO_CUDA(expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return ::sfno::fail(SFNO_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                          __FILE__, __LINE__);                                                   \
+  } while (0)
+
+#define SFNO_TRY(expr)         \
+  do {                         \
+    int _s = (expr);           \
+    if (_s != SFNO_OK) return _s; \
+  } while (0)
+
+// ---- launch accounting ------------------------------------------------------------------------------
+extern std::atomic<int64_t> g_launch_count;
+inline int post_launch(const char* what) {
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(SFNO_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  }
+  return SFNO_OK;
+}
+
+// ---- small math ---------------------------------------------------------------------------------------
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- storage types --------------------------------------------------------------------------------------
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <class T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float apply_act(int act, float x) {
+  switch (act) {
+    case SFNO_ACT_GELU: return gelu_exact(x);
+    case SFNO_ACT_RELU: return fmaxf(x, 0.0f);
+    case SFNO_ACT_SILU: return x / (1.0f + expf(-x));
+    default: return x;
+  }
+}
+
+// ---- Philox4x32-10 counter RNG (dropout masks; statistical parity only with torch's nn.Dropout) --------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// uniform in [0,1) for element index `idx` of stream (seed, offset)
+__device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t offset, uint64_t idx) {
+  uint4 c = make_uint4((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), (uint32_t)offset, (uint32_t)(offset >> 32));
+  uint4 r = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  uint32_t v = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+  return (v >> 8) * (1.0f / 16777216.0f);
+}
+
+}  // namespace sfno

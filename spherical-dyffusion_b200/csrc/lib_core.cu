@@ -1,0 +1,313 @@
+// Library plumbing, host tables entry point, SHT plan, stand-alone ops of the C ABI.
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "engine.cuh"
+#include "ops.cuh"
+#include "pointwise.cuh"
+#include "sht_plan.cuh"
+#include "tables.h"
+
+namespace sfno {
+
+std::atomic<int64_t> g_launch_count{0};
+
+std::string& last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+
+int fail(int status, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return status;
+}
+
+// ---- table upload -------------------------------------------------------------------------------------
+template <class T>
+static int upload_padded(const std::vector<double>& src, int64_t rows, int cols, int ld, void** dst, size_t* bytes) {
+  std::vector<T> host((size_t)rows * ld);
+  for (int64_t r = 0; r < rows; ++r)
+    for (int c = 0; c < ld; ++c) {
+      float v = c < cols ? (float)src[(size_t)r * cols + c] : 0.0f;
+      if constexpr (std::is_same<T, float>::value) host[(size_t)r * ld + c] = v;
+      else host[(size_t)r * ld + c] = __float2bfloat16_rn(v);
+    }
+  size_t nbytes = host.size() * sizeof(T);
+  SFNO_CUDA(cudaMalloc(dst, nbytes));
+  SFNO_CUDA(cudaMemcpy(*dst, host.data(), nbytes, cudaMemcpyHostToDevice));
+  *bytes += nbytes;
+  return SFNO_OK;
+}
+
+template <class T>
+static int upload_all(const ShtTables& h, ShtDeviceTables& d) {
+  // analysis table keeps [m][l][k]
+  SFNO_TRY(upload_padded<T>(h.weights, (int64_t)d.mmax * d.lmax, d.nlat, d.Kp, &d.wq, &d.bytes));
+  // synthesis table transposed to [m][k][l]
+  std::vector<double> pt((size_t)d.mmax * d.nlat * d.lmax);
+  for (int m = 0; m < d.mmax; ++m)
+    for (int l = 0; l < d.lmax; ++l)
+      for (int k = 0; k < d.nlat; ++k)
+        pt[((size_t)m * d.nlat + k) * d.lmax + l] = h.pct[((size_t)m * d.lmax + l) * d.nlat + k];
+  SFNO_TRY(upload_padded<T>(pt, (int64_t)d.mmax * d.nlat, d.lmax, d.Lq, &d.pt, &d.bytes));
+  std::vector<double> e;
+  build_dft_forward(d.nlon, d.mmax, e);
+  SFNO_TRY(upload_padded<T>(e, 2 * d.mmax, d.nlon, d.Wp, &d.efwd, &d.bytes));
+  build_dft_inverse(d.nlon, d.mmax, e);
+  SFNO_TRY(upload_padded<T>(e, d.nlon, 2 * d.mmax, d.Kq2, &d.einv, &d.bytes));
+  return SFNO_OK;
+}
+
+int sht_tables_upload(int nlat, int nlon, int lmax, int mmax, int grid, int precision, ShtDeviceTables& d) {
+  ShtTables h;
+  if (!build_sht_tables(nlat, nlon, lmax, mmax, grid, h))
+    return fail(SFNO_ERR_INVALID_ARGUMENT, "invalid SHT geometry nlat=%d nlon=%d lmax=%d mmax=%d grid=%d", nlat, nlon, lmax, mmax, grid);
+  if (mmax > nlon / 2 + 1) return fail(SFNO_ERR_INVALID_ARGUMENT, "mmax=%d exceeds nlon/2+1=%d", mmax, nlon / 2 + 1);
+  d = ShtDeviceTables{};
+  d.nlat = nlat; d.nlon = nlon; d.lmax = lmax; d.mmax = mmax; d.grid = grid; d.precision = precision;
+  d.Kp = round_up(nlat, 8); d.Lq = round_up(lmax, 8); d.Wp = round_up(nlon, 8); d.Kq2 = round_up(2 * mmax, 8);
+  int st = precision == SFNO_PREC_BF16 ? upload_all<bf16>(h, d) : upload_all<float>(h, d);
+  if (st != SFNO_OK) sht_tables_free(d);
+  return st;
+}
+
+void sht_tables_free(ShtDeviceTables& t) {
+  cudaFree(t.wq); cudaFree(t.pt); cudaFree(t.efwd); cudaFree(t.einv);
+  t.wq = t.pt = t.efwd = t.einv = nullptr;
+}
+
+// ---- stand-alone SHT through the same ops the network uses (B = 1, C = fields) -----------------------
+struct ShtWs {
+  size_t x_off, f_off, s_off, total;
+};
+static ShtWs sht_ws_layout(const ShtDeviceTables& t, int64_t fields) {
+  const size_t e = t.precision == SFNO_PREC_BF16 ? 2 : 4;
+  ShtWs w{};
+  size_t off = 0;
+  w.x_off = off; off += align_up((size_t)fields * t.nlat * t.nlon * e, 256);
+  w.f_off = off; off += align_up((size_t)t.mmax * 2 * fields * t.Kp * e, 256);
+  w.s_off = off; off += align_up((size_t)t.lmax * t.mmax * 2 * fields * e, 256);
+  w.total = off;
+  return w;
+}
+
+template <class T>
+static int sht_forward_impl(const ShtDeviceTables& t, const float* x, float* coeffs, int64_t fields, char* ws, cudaStream_t st) {
+  const ShtWs L = sht_ws_layout(t, fields);
+  T* xt = (T*)(ws + L.x_off);
+  T* F = (T*)(ws + L.f_off);
+  T* X = (T*)(ws + L.s_off);
+  const int C = (int)fields;
+  const int64_t n = fields * t.nlat * t.nlon;
+  const T* xin;
+  if constexpr (std::is_same<T, float>::value) xin = x;
+  else {
+    convert_planes_kernel<float, T><<<dim3((unsigned)std::min<int64_t>(ceil_div64(n, 256), 4096), 1), 256, 0, st>>>(x, 0, xt, 0, n);
+    SFNO_TRY(post_launch("convert_planes"));
+    xin = xt;
+  }
+  SFNO_CUDA(cudaMemsetAsync(F, 0, (size_t)t.mmax * 2 * fields * t.Kp * sizeof(T), st));
+  OpDft<T> dft{};
+  dft.G = 1; dft.M = C * t.nlat; dft.N = 2 * t.mmax; dft.K = t.nlon;
+  dft.A = xin; dft.Bm = (const T*)t.efwd; dft.a_sk = 1; dft.b_sk = 1;
+  dft.f = F; dft.aff_a = nullptr; dft.aff_d = nullptr;
+  dft.B = 1; dft.C = C; dft.nlat = t.nlat; dft.nlon = t.nlon; dft.Kp = t.Kp; dft.Wp = t.Wp; dft.x_bstride = 0;
+  SFNO_TRY(launch_gemm(dft, st, "dft_fwd"));
+  OpLeg<T> leg{};
+  leg.G = t.mmax; leg.M = 2 * C; leg.N = t.lmax; leg.K = t.nlat;
+  leg.A = F; leg.Bm = (const T*)t.wq; leg.a_sk = 1; leg.b_sk = 1;
+  leg.x = X; leg.Kp = t.Kp; leg.lmax = t.lmax; leg.mmax = t.mmax;
+  SFNO_TRY(launch_gemm(leg, st, "legendre_fwd"));
+  const int64_t total = fields * t.lmax * t.mmax * 2;
+  internal_to_coeffs_kernel<T><<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 8192), 256, 0, st>>>(X, coeffs, C, t.lmax, t.mmax);
+  return post_launch("internal_to_coeffs");
+}
+
+template <class T>
+static int sht_inverse_impl(const ShtDeviceTables& t, const float* coeffs, float* x, int64_t fields, char* ws, cudaStream_t st) {
+  const ShtWs L = sht_ws_layout(t, fields);
+  T* xt = (T*)(ws + L.x_off);
+  T* Gb = (T*)(ws + L.f_off);
+  T* X = (T*)(ws + L.s_off);
+  const int C = (int)fields;
+  const int64_t total = fields * t.lmax * t.mmax * 2;
+  coeffs_to_internal_kernel<T><<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 8192), 256, 0, st>>>(coeffs, X, C, t.lmax, t.mmax);
+  SFNO_TRY(post_launch("coeffs_to_internal"));
+  SFNO_CUDA(cudaMemsetAsync(Gb, 0, (size_t)t.mmax * 2 * fields * t.Kp * sizeof(T), st));
+  OpIleg<T> il{};
+  il.G = t.mmax; il.M = t.nlat; il.N = 2 * C; il.K = t.lmax;
+  il.A = (const T*)t.pt; il.Bm = X; il.a_sk = 1;
+  il.b_goff = il.N; il.b_sk = (int64_t)t.mmax * il.N;  // X layout [l][m][n]
+  il.g_out = Gb; il.B = 1; il.C = C; il.Kp = t.Kp; il.Lq = t.Lq; il.nlat = t.nlat;
+  SFNO_TRY(launch_gemm(il, st, "legendre_inv"));
+  OpIdft<T, float> id{};
+  id.G = 1; id.M = t.nlon; id.N = C * t.Kp; id.K = 2 * t.mmax;
+  id.A = (const T*)t.einv; id.Bm = Gb; id.a_sk = 1; id.b_sk = id.N;
+  id.out = x; id.out_bstride = 0; id.bias = nullptr; id.add = nullptr; id.add_bstride = 0; id.act = SFNO_ACT_NONE;
+  id.C = C; id.nlat = t.nlat; id.nlon = t.nlon; id.Kp = t.Kp; id.Kq2 = t.Kq2;
+  (void)xt;
+  return launch_gemm(id, st, "dft_inv");
+}
+
+// ---- spectral contraction in the reference layout (fp32 CUDA cores) --------------------------------------
+// out[b,o,l,m] = sum_i x[b,i,l,m] * w[i,o,l(,m)]  (complex), one thread per (b,o,l,m)
+__global__ void spectral_contract_kernel(int diagonal, const float2* __restrict__ x, const float2* __restrict__ w,
+                                         float2* __restrict__ out, int B, int Cin, int Cout, int L, int M) {
+  const int64_t total = (int64_t)B * Cout * L * M;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(idx % M);
+    int64_t r = idx / M;
+    const int l = (int)(r % L); r /= L;
+    const int o = (int)(r % Cout);
+    const int b = (int)(r / Cout);
+    float re = 0.0f, im = 0.0f;
+    for (int i = 0; i < Cin; ++i) {
+      const float2 xv = x[(((int64_t)b * Cin + i) * L + l) * M + m];
+      const float2 wv = diagonal ? w[(((int64_t)i * Cout + o) * L + l) * M + m] : w[((int64_t)i * Cout + o) * L + l];
+      re = fmaf(xv.x, wv.x, re); re = fmaf(-xv.y, wv.y, re);
+      im = fmaf(xv.x, wv.y, im); im = fmaf(xv.y, wv.x, im);
+    }
+    out[idx] = make_float2(re, im);
+  }
+}
+
+}  // namespace sfno
+
+using namespace sfno;
+
+extern "C" {
+
+int sfno_b200_abi_version(void) { return 1; }
+
+const char* sfno_b200_status_string(int status) {
+  switch (status) {
+    case SFNO_OK: return "ok";
+    case SFNO_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case SFNO_ERR_CUDA: return "CUDA error";
+    case SFNO_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+    case SFNO_ERR_UNSUPPORTED: return "unsupported configuration";
+    case SFNO_ERR_NO_DEVICE: return "no CUDA device";
+    case SFNO_ERR_UNKNOWN_PARAM: return "unknown parameter name";
+    case SFNO_ERR_SHAPE_MISMATCH: return "shape mismatch";
+    default: return "unknown status";
+  }
+}
+
+const char* sfno_b200_last_error(void) { return last_error_ref().c_str(); }
+int64_t sfno_b200_launch_count(void) { return g_launch_count.load(); }
+
+int sfno_sht_tables_host(int nlat, int nlon, int lmax, int mmax, int grid, double* nodes, double* quad_w,
+                         double* weights, double* pct) {
+  ShtTables t;
+  if (!build_sht_tables(nlat, nlon, lmax, mmax, grid, t)) return fail(SFNO_ERR_INVALID_ARGUMENT, "invalid SHT geometry");
+  if (nodes) memcpy(nodes, t.cost.data(), sizeof(double) * t.cost.size());
+  if (quad_w) memcpy(quad_w, t.quad_w.data(), sizeof(double) * t.quad_w.size());
+  if (weights) memcpy(weights, t.weights.data(), sizeof(double) * t.weights.size());
+  if (pct) memcpy(pct, t.pct.data(), sizeof(double) * t.pct.size());
+  return SFNO_OK;
+}
+
+int sfno_sht_plan_create(sfno_sht_plan** plan, int nlat, int nlon, int lmax, int mmax, int grid, int precision) {
+  SFNO_CHECK_ARG(plan != nullptr, "plan is NULL");
+  SFNO_CHECK_ARG(precision == SFNO_PREC_F32 || precision == SFNO_PREC_BF16, "bad precision %d", precision);
+  auto* p = new sfno_sht_plan();
+  int st = sht_tables_upload(nlat, nlon, lmax, mmax, grid, precision, p->t);
+  if (st != SFNO_OK) { delete p; return st; }
+  *plan = p;
+  return SFNO_OK;
+}
+
+int sfno_sht_plan_destroy(sfno_sht_plan* plan) {
+  if (!plan) return SFNO_OK;
+  sht_tables_free(plan->t);
+  delete plan;
+  return SFNO_OK;
+}
+
+size_t sfno_sht_workspace_bytes(const sfno_sht_plan* plan, int64_t fields) {
+  if (!plan || fields <= 0) return 0;
+  return sht_ws_layout(plan->t, fields).total;
+}
+
+int sfno_sht_forward(const sfno_sht_plan* plan, const float* x_dev, float* coeffs_dev, int64_t fields,
+                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+  SFNO_CHECK_ARG(plan && x_dev && coeffs_dev && workspace_dev, "NULL argument");
+  SFNO_CHECK_ARG(fields > 0 && fields < (1 << 24), "bad field count %lld", (long long)fields);
+  if (workspace_bytes < sht_ws_layout(plan->t, fields).total) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  return plan->t.precision == SFNO_PREC_BF16 ? sht_forward_impl<bf16>(plan->t, x_dev, coeffs_dev, fields, (char*)workspace_dev, st)
+                                             : sht_forward_impl<float>(plan->t, x_dev, coeffs_dev, fields, (char*)workspace_dev, st);
+}
+
+int sfno_sht_inverse(const sfno_sht_plan* plan, const float* coeffs_dev, float* x_dev, int64_t fields,
+                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+  SFNO_CHECK_ARG(plan && x_dev && coeffs_dev && workspace_dev, "NULL argument");
+  SFNO_CHECK_ARG(fields > 0 && fields < (1 << 24), "bad field count %lld", (long long)fields);
+  if (workspace_bytes < sht_ws_layout(plan->t, fields).total) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  return plan->t.precision == SFNO_PREC_BF16 ? sht_inverse_impl<bf16>(plan->t, coeffs_dev, x_dev, fields, (char*)workspace_dev, st)
+                                             : sht_inverse_impl<float>(plan->t, coeffs_dev, x_dev, fields, (char*)workspace_dev, st);
+}
+
+int sfno_spectral_contract(int operator_type, const float* x_dev, const float* weight_dev, float* out_dev, int batch,
+                           int cin, int cout, int lmax, int mmax, void* stream) {
+  SFNO_CHECK_ARG(x_dev && weight_dev && out_dev, "NULL argument");
+  SFNO_CHECK_ARG(operator_type == SFNO_OP_DHCONV || operator_type == SFNO_OP_DIAGONAL, "bad operator_type %d", operator_type);
+  SFNO_CHECK_ARG(batch > 0 && cin > 0 && cout > 0 && lmax > 0 && mmax > 0, "bad sizes");
+  const int64_t total = (int64_t)batch * cout * lmax * mmax;
+  spectral_contract_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 1 << 20), 256, 0, (cudaStream_t)stream>>>(
+      operator_type == SFNO_OP_DIAGONAL, (const float2*)x_dev, (const float2*)weight_dev, (float2*)out_dev, batch, cin, cout, lmax, mmax);
+  return post_launch("spectral_contract");
+}
+
+size_t sfno_instance_norm_workspace_bytes(int batch, int channels) { return (size_t)4 * batch * channels * sizeof(float); }
+
+int sfno_instance_norm(const float* x_dev, float* y_dev, const float* gamma_dev, const float* beta_dev,
+                       const float* scale_dev, const float* shift_dev, int batch, int channels, int64_t hw, float eps,
+                       void* workspace_dev, size_t workspace_bytes, void* stream) {
+  SFNO_CHECK_ARG(x_dev && y_dev && workspace_dev, "NULL argument");
+  SFNO_CHECK_ARG(batch > 0 && channels > 0 && hw > 0, "bad sizes");
+  SFNO_CHECK_ARG((scale_dev == nullptr) == (shift_dev == nullptr), "scale and shift must be given together");
+  if (workspace_bytes < sfno_instance_norm_workspace_bytes(batch, channels)) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int BC = batch * channels;
+  float* mean = (float*)workspace_dev;
+  float* rstd = mean + BC;
+  float* a = rstd + BC;
+  float* d = a + BC;
+  instance_stats_kernel<float><<<BC, 512, 0, st>>>(x_dev, (int64_t)channels * hw, channels, hw, eps, mean, rstd);
+  SFNO_TRY(post_launch("instance_stats"));
+  // scale/shift are given as separate [batch][C] arrays here: stage them as ts = [scale | shift] is not possible
+  // without a copy, so the affine kernel is called with ts == nullptr and scale/shift are applied below.
+  norm_affine_kernel<<<ceil_div(BC, 256), 256, 0, st>>>(mean, rstd, gamma_dev, beta_dev, nullptr, 0, batch, channels, a, d);
+  SFNO_TRY(post_launch("norm_affine"));
+  if (scale_dev) {
+    time_affine_compose_kernel<<<ceil_div(BC, 256), 256, 0, st>>>(a, d, scale_dev, shift_dev, BC);
+    SFNO_TRY(post_launch("time_affine_compose"));
+  }
+  affine_apply_kernel<<<dim3((unsigned)std::min<int64_t>(ceil_div64(hw, 256), 1024), BC), 256, 0, st>>>(x_dev, y_dev, a, d, hw);
+  return post_launch("affine_apply");
+}
+
+int sfno_conv1x1(const float* x_dev, const float* weight_dev, const float* bias_dev, const float* residual_dev,
+                 float* y_dev, int batch, int cin, int cout, int64_t hw, int activation, void* stream) {
+  SFNO_CHECK_ARG(x_dev && weight_dev && y_dev, "NULL argument");
+  SFNO_CHECK_ARG(batch > 0 && cin > 0 && cout > 0 && hw > 0 && hw < (1ll << 31), "bad sizes");
+  OpConv<float, float> op{};
+  op.G = batch; op.M = (int)hw; op.N = cout; op.K = cin;
+  op.A = x_dev; op.Bm = weight_dev; op.a_sk = hw; op.b_sk = 1;
+  op.in_bstride = (int64_t)cin * hw; op.w_bstride = 0; op.ldw = cin;
+  op.bias = bias_dev; op.bias_bstride = 0; op.act = activation;
+  op.drop_p = 0.0f; op.seed = 0; op.offset = 0; op.branch_scale = nullptr;
+  op.res = residual_dev; op.res_bstride = (int64_t)cout * hw; op.res_a = nullptr; op.res_d = nullptr; op.pos = nullptr;
+  op.out = y_dev; op.out_bstride = (int64_t)cout * hw;
+  return launch_gemm(op, (cudaStream_t)stream, "conv1x1");
+}
+
+}  // extern "C"

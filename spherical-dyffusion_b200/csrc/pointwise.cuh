@@ -1,0 +1,230 @@
+// Bandwidth-bound and tiny kernels around the GEMMs: InstanceNorm statistics, norm/time affine
+// coefficients, weight folding, time-embedding MLPs, dtype/layout conversion.
+#pragma once
+#include "common.cuh"
+
+namespace sfno {
+
+// ---- block reductions -----------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// sum over the block; result valid in all threads.  `sh` must hold 33 floats.
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float s = lane < nw ? sh[lane] : 0.0f;
+    s = warp_sum(s);
+    if (lane == 0) sh[32] = s;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+// ---- InstanceNorm statistics: one CTA per (b, c) plane, two passes (second pass hits L2) ----------------
+// nn.InstanceNorm2d semantics (sfnonet.py:641-647): biased variance over H*W.
+template <class T>
+static __global__ void __launch_bounds__(512) instance_stats_kernel(const T* __restrict__ x, int64_t bstride, int C,
+                                                              int64_t hw, float eps, float* __restrict__ mean_out,
+                                                              float* __restrict__ rstd_out) {
+  __shared__ float sh[33];
+  const int bc = blockIdx.x, b = bc / C, c = bc - b * C;
+  const T* p = x + (int64_t)b * bstride + (int64_t)c * hw;
+  float s = 0.0f;
+  for (int64_t i = threadIdx.x; i < hw; i += blockDim.x) s += to_f32(p[i]);
+  const float mean = block_sum(s, sh) / (float)hw;
+  float q = 0.0f;
+  for (int64_t i = threadIdx.x; i < hw; i += blockDim.x) {
+    float d = to_f32(p[i]) - mean;
+    q = fmaf(d, d, q);
+  }
+  const float var = block_sum(q, sh) / (float)hw;
+  if (threadIdx.x == 0) {
+    mean_out[bc] = mean;
+    rstd_out[bc] = rsqrtf(var + eps);
+  }
+}
+
+// ---- per-(b,c) affine of "InstanceNorm -> time_scale_shift" (sfnonet.py:280-287,292-299) -----------------
+//   y = a*x + d,  a = gamma*rstd*(1+scale),  d = (beta - gamma*mean*rstd)*(1+scale) + shift
+// mean/rstd == nullptr -> no normalisation; ts == nullptr -> no time conditioning.
+static __global__ void norm_affine_kernel(const float* __restrict__ mean, const float* __restrict__ rstd,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ ts, int64_t ts_bstride, int B, int C,
+                                   float* __restrict__ a_out, float* __restrict__ d_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  float a = 1.0f, d = 0.0f;
+  if (mean) {
+    const float g = gamma ? gamma[c] : 1.0f, be = beta ? beta[c] : 0.0f;
+    a = g * rstd[i];
+    d = be - g * mean[i] * rstd[i];
+  }
+  if (ts) {
+    const float sc = ts[(int64_t)b * ts_bstride + c] + 1.0f, sf = ts[(int64_t)b * ts_bstride + C + c];
+    a *= sc;
+    d = d * sc + sf;
+  }
+  a_out[i] = a;
+  d_out[i] = d;
+}
+
+// compose a time scale/shift given as separate [B*C] arrays onto an existing affine
+static __global__ void time_affine_compose_kernel(float* __restrict__ a, float* __restrict__ d, const float* __restrict__ scale,
+                                           const float* __restrict__ shift, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float sc = scale[i] + 1.0f;
+  a[i] *= sc;
+  d[i] = d[i] * sc + shift[i];
+}
+
+// ---- fold a per-(b,c) input affine into a 1x1-conv weight: conv(a*x+d) = (W diag(a)) x + (bias + W d) -----
+// one CTA per (b, o); w [cout][cin] fp32 master -> wb [B][cout][ldw] (T), bb [B][cout] fp32
+template <class T>
+static __global__ void __launch_bounds__(128) fold_affine_weight_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                                                 const float* __restrict__ a, const float* __restrict__ d,
+                                                                 int cout, int cin, int ldw, T* __restrict__ wb,
+                                                                 float* __restrict__ bb) {
+  __shared__ float sh[33];
+  const int b = blockIdx.x / cout, o = blockIdx.x - b * cout;
+  const float* wr = w + (int64_t)o * cin;
+  T* dst = wb + ((int64_t)b * cout + o) * ldw;
+  float s = 0.0f;
+  for (int c = threadIdx.x; c < ldw; c += blockDim.x) {
+    float v = 0.0f;
+    if (c < cin) {
+      v = wr[c] * a[b * cin + c];
+      s = fmaf(wr[c], d[b * cin + c], s);
+    }
+    dst[c] = from_f32<T>(v);
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) bb[b * cout + o] = s + (bias ? bias[o] : 0.0f);
+}
+
+// ---- y[b][n] = act_out( sum_k W[n][k] * act_in(x[b][k]) + bias[n] ), one warp per output -------------------
+// time_emb_mlp (misc.py:145-147) and the per-block time_mlp (sfnonet.py:210-213).  fp32 throughout.
+static __global__ void small_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ y, int B, int N, int K,
+                                    int act_in, int act_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * N) return;
+  const int b = warp / N, n = warp - b * N;
+  const float* xr = x + (int64_t)b * K;
+  const float* wr = w + (int64_t)n * K;
+  float s = 0.0f;
+  for (int k = lane; k < K; k += 32) s = fmaf(wr[k], apply_act(act_in, xr[k]), s);
+  s = warp_sum(s);
+  if (lane == 0) y[warp] = apply_act(act_out, s + (bias ? bias[n] : 0.0f));
+}
+
+// SinusoidalPosEmb (misc.py:21-33): emb[b] = [sin(t*f_j), cos(t*f_j)], f_j = exp(-j*ln(1e4)/(half-1))
+static __global__ void sinusoidal_kernel(const float* __restrict__ time, float scaler, float shift, int B, int dim,
+                                  float* __restrict__ emb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (i >= B * half) return;
+  const int b = i / half, j = i - b * half;
+  const float t = time[b] * scaler + shift;
+  const float step = (float)(-9.210340371976184 / (double)(half - 1));
+  const float f = expf((float)j * step);
+  const float e = t * f;
+  emb[(int64_t)b * dim + j] = sinf(e);
+  emb[(int64_t)b * dim + half + j] = cosf(e);
+}
+
+// DropPath factor per sample (drop_path.py:5-22): floor(keep + U) / keep
+static __global__ void drop_path_scale_kernel(float* __restrict__ out, int B, float drop_prob, uint64_t seed, uint64_t offset) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float keep = 1.0f - drop_prob;
+  const float u = philox_uniform(seed, offset, (uint64_t)b);
+  out[b] = floorf(keep + u) / keep;
+}
+
+// ---- conversions -----------------------------------------------------------------------------------------
+// strided copy/convert of [B][C][hw] planes: dst[b*dst_bstride + c*hw + i] = src[b*src_bstride + c*hw + i]
+template <class TS, class TD>
+static __global__ void convert_planes_kernel(const TS* __restrict__ src, int64_t src_bstride, TD* __restrict__ dst,
+                                      int64_t dst_bstride, int64_t per_sample) {
+  const int b = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += (int64_t)gridDim.x * blockDim.x)
+    dst[(int64_t)b * dst_bstride + i] = from_f32<TD>(to_f32(src[(int64_t)b * src_bstride + i]));
+}
+
+// fp32 row-major [rows][cols] -> T [rows][ld] with zero padding (conv / linear weights)
+template <class T>
+static __global__ void pack_rows_kernel(const float* __restrict__ src, int rows, int cols, int ld, T* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * ld) return;
+  const int r = (int)(i / ld), c = (int)(i - (int64_t)r * ld);
+  dst[i] = from_f32<T>(c < cols ? src[(int64_t)r * cols + c] : 0.0f);
+}
+
+// dhconv weight [cin][cout][L][2] fp32 (s2convolutions.py:146) -> packed real form [L][2*cout][2*cin] (T):
+//   rows (ri', o), cols (ri, c):  [[wr, -wi], [wi, wr]]
+template <class T>
+static __global__ void pack_dhconv_weight_kernel(const float* __restrict__ w, int cin, int cout, int L, T* __restrict__ dst) {
+  const int64_t total = (int64_t)L * 2 * cout * 2 * cin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int kk = (int)(i % (2 * cin));
+    int64_t r = i / (2 * cin);
+    int mm = (int)(r % (2 * cout));
+    int l = (int)(r / (2 * cout));
+    int ri_in = kk / cin, c = kk - ri_in * cin;
+    int ri_out = mm / cout, o = mm - ri_out * cout;
+    const float* src = w + (((int64_t)c * cout + o) * L + l) * 2;
+    float wr = src[0], wi = src[1];
+    float v = (ri_out == ri_in) ? wr : (ri_out == 1 ? wi : -wi);
+    dst[i] = from_f32<T>(v);
+  }
+}
+
+// y = a[bc]*x + d[bc] (stand-alone InstanceNorm entry point)
+static __global__ void affine_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ a,
+                                    const float* __restrict__ d, int64_t hw) {
+  const int bc = blockIdx.y;
+  const float aa = a[bc], dd = d[bc];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x)
+    y[(int64_t)bc * hw + i] = fmaf(aa, x[(int64_t)bc * hw + i], dd);
+}
+
+// reference coefficient layout <-> internal spectral layout (B = 1, C = fields):
+//   coeffs [fields][lmax][mmax][2]  <->  X [lmax][mmax][2][fields]
+template <class T>
+static __global__ void coeffs_to_internal_kernel(const float* __restrict__ coeffs, T* __restrict__ x, int fields, int lmax, int mmax) {
+  const int64_t total = (int64_t)fields * lmax * mmax * 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int f = (int)(i % fields);
+    int64_t r = i / fields;
+    int ri = (int)(r & 1);
+    int64_t lm = r >> 1;  // l*mmax + m
+    x[i] = from_f32<T>(coeffs[((int64_t)f * lmax * mmax + lm) * 2 + ri]);
+  }
+}
+template <class T>
+static __global__ void internal_to_coeffs_kernel(const T* __restrict__ x, float* __restrict__ coeffs, int fields, int lmax, int mmax) {
+  const int64_t total = (int64_t)fields * lmax * mmax * 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int ri = (int)(i & 1);
+    int64_t r = i >> 1;
+    int64_t lm = r % ((int64_t)lmax * mmax);
+    int f = (int)(r / ((int64_t)lmax * mmax));
+    coeffs[i] = to_f32(x[(lm * 2 + ri) * fields + f]);
+  }
+}
+
+}  // namespace sfno

@@ -1,0 +1,30 @@
+// Device-side SHT plan: Legendre and DFT tables in the layouts the GEMM ops consume.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "tables.h"
+
+namespace sfno {
+
+struct ShtDeviceTables {
+  int nlat = 0, nlon = 0, lmax = 0, mmax = 0, grid = 0, precision = 0;
+  int Kp = 0;   // nlat rounded up to 8  (row length of F/G rows and of wq rows)
+  int Lq = 0;   // lmax rounded up to 8  (row length of pt rows)
+  int Wp = 0;   // nlon rounded up to 8  (row length of efwd rows)
+  int Kq2 = 0;  // 2*mmax rounded up to 8 (row length of einv rows)
+  void* wq = nullptr;    // [mmax][lmax][Kp]   analysis  (Legendre x quadrature weight), B operand of OpLeg
+  void* pt = nullptr;    // [mmax][nlat][Lq]   synthesis, transposed: A operand of OpIleg
+  void* efwd = nullptr;  // [2*mmax][Wp]       forward DFT basis, B operand of OpDft
+  void* einv = nullptr;  // [nlon][Kq2]        inverse DFT basis, A operand of OpIdft
+  size_t bytes = 0;
+};
+
+int sht_tables_upload(int nlat, int nlon, int lmax, int mmax, int grid, int precision, ShtDeviceTables& out);
+void sht_tables_free(ShtDeviceTables& t);
+
+}  // namespace sfno
+
+struct sfno_sht_plan {
+  sfno::ShtDeviceTables t;
+};

@@ -1,0 +1,483 @@
+"""Drop-in ``SphericalFourierNeuralOperatorNet`` (reference: ``src/models/sfno/sfnonet.py:340-841``).
+
+Same constructor keywords (``sfnonet.py:426-466`` + ``BaseModel`` kwargs ``_base_model.py:46-60``), same
+``forward(inputs, time=None, condition=None, static_condition=None, return_time_emb=False)`` contract and
+the same ``state_dict`` keys/shapes, so released checkpoints load and the Hydra ``_target_`` in
+``src/configs/model/sfno.yaml:5`` can simply point here.  The sub-modules below only *hold parameters*
+under the reference's names; the arithmetic of ``forward`` runs in ``sfno_net_forward`` (C ABI ->
+hand-written sm_100a kernels).  There is no PyTorch fallback.
+
+Extra keywords (not in the reference): ``precision`` ("fp32" parity mode | "bf16" tcgen05 mode),
+``check_time_range`` (keep the reference's host-synchronising time assert, default True).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Any, Literal, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._base_model import ALL_DROPOUT_LAYERS, BaseModel, DropPath
+from ._util import require_cuda_f32, stream_ptr, workspace
+from .harmonics import InverseRealSHT, RealSHT
+
+
+def trunc_normal_(tensor, mean=0.0, std=1.0, a=-2.0, b=2.0):
+    """Truncated normal via the inverse-CDF method with absolute cut-offs, as ``initialization.py:21-73``."""
+    def cdf(x):
+        return (1.0 + math.erf(x / math.sqrt(2.0))) / 2.0
+    with torch.no_grad():
+        lo, hi = cdf((a - mean) / std), cdf((b - mean) / std)
+        tensor.uniform_(2 * lo - 1, 2 * hi - 1)
+        tensor.erfinv_()
+        tensor.mul_(std * math.sqrt(2.0))
+        tensor.add_(mean)
+        tensor.clamp_(min=a, max=b)
+    return tensor
+
+
+class SinusoidalPosEmb(nn.Module):
+    """Parameter-free; kept so that ``time_emb_mlp`` has the reference's module indices (``misc.py:145-147``)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+
+
+class SpectralConvS2(nn.Module):
+    """Parameter holder + stand-alone op for ``s2convolutions.py:45-193`` (dense complex weights only)."""
+
+    def __init__(self, forward_transform, inverse_transform, in_channels, out_channels, scale="auto",
+                 operator_type="diagonal", bias=False):
+        super().__init__()
+        if scale == "auto":
+            scale = 1 / (in_channels * out_channels)
+        self.forward_transform = forward_transform
+        self.inverse_transform = inverse_transform
+        self.modes_lat = inverse_transform.lmax
+        self.modes_lon = inverse_transform.mmax
+        self.scale_residual = ((forward_transform.nlat != inverse_transform.nlat)
+                               or (forward_transform.nlon != inverse_transform.nlon)
+                               or (forward_transform.grid != inverse_transform.grid))
+        self.operator_type = operator_type
+        shape = [in_channels, out_channels]
+        if operator_type == "diagonal":
+            shape += [self.modes_lat, self.modes_lon]
+        elif operator_type == "dhconv":
+            shape += [self.modes_lat]
+        else:
+            raise ValueError(f"Unsupported operator type f{operator_type}")
+        self.weight = nn.Parameter(scale * torch.randn(*shape, 2))
+        if bias:
+            self.bias = nn.Parameter(scale * torch.zeros(1, out_channels, 1, 1))
+
+    def forward(self, x):
+        """Stand-alone execution through the op-level C ABI: returns ``(y, residual)`` like the reference."""
+        dtype = x.dtype
+        residual = x
+        xf = require_cuda_f32(x, "x")
+        X = self.forward_transform(xf)
+        if self.scale_residual:
+            residual = self.inverse_transform(X).to(dtype)
+        B, Cin = X.shape[0], X.shape[1]
+        Cout = self.weight.shape[1]
+        Xr = torch.view_as_real(X.contiguous())
+        Y = torch.empty(B, Cout, self.modes_lat, self.modes_lon, 2, dtype=torch.float32, device=xf.device)
+        w = require_cuda_f32(self.weight.detach(), "weight")
+        with torch.cuda.device(xf.device):
+            _lib.check(_lib.lib().sfno_spectral_contract(_lib.SFNO_OP[self.operator_type], Xr.data_ptr(), w.data_ptr(),
+                                                         Y.data_ptr(), B, Cin, Cout, self.modes_lat, self.modes_lon,
+                                                         stream_ptr(xf.device)), "sfno_spectral_contract")
+        y = self.inverse_transform(torch.view_as_complex(Y))
+        if hasattr(self, "bias"):
+            y = y + self.bias
+        return y.type(dtype), residual
+
+
+class SpectralFilterLayer(nn.Module):
+    """``sfnonet.py:78-155`` restricted to the configured path (linear filter on an SHT)."""
+
+    def __init__(self, forward_transform, inverse_transform, embed_dim, filter_type="linear", operator_type="diagonal"):
+        super().__init__()
+        if filter_type != "linear" or not isinstance(forward_transform, RealSHT):
+            raise NotImplementedError
+        self.filter = SpectralConvS2(forward_transform, inverse_transform, embed_dim, embed_dim,
+                                     operator_type=operator_type, bias=True)
+
+    def forward(self, x):
+        return self.filter(x)
+
+
+class MLP(nn.Module):
+    """Parameter holder for ``layers.py:53-93`` (module indices identical, incl. the dropout entries)."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, output_bias=True, drop_rate=0.0):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        fc1 = nn.Conv2d(in_features, hidden_features, 1, bias=True)
+        act = act_layer()
+        fc2 = nn.Conv2d(hidden_features, out_features, 1, bias=output_bias)
+        if drop_rate > 0.0:
+            drop = nn.Dropout(drop_rate)
+            self.fwd = nn.Sequential(fc1, act, drop, fc2, drop)
+        else:
+            self.fwd = nn.Sequential(fc1, act, fc2)
+
+
+class FourierNeuralOperatorBlock(nn.Module):
+    """Parameter holder for ``sfnonet.py:158-337`` (inner_skip='linear', outer_skip='identity', use_mlp)."""
+
+    def __init__(self, forward_transform, inverse_transform, embed_dim, operator_type, mlp_ratio, drop_rate_mlp, drop_path,
+                 act_layer, norm_layer, time_emb_dim, time_scale_shift_before_filter):
+        super().__init__()
+        self.norm0 = norm_layer()
+        if time_emb_dim is not None:
+            self.time_mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_emb_dim, embed_dim * 2))
+            self.time_scale_shift_before_filter = time_scale_shift_before_filter
+        else:
+            self.time_mlp = None
+            self.time_scale_shift_before_filter = False
+        self.filter = SpectralFilterLayer(forward_transform, inverse_transform, embed_dim, "linear", operator_type)
+        self.inner_skip = nn.Conv2d(embed_dim, embed_dim, 1, 1)
+        self.act_layer = act_layer()
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm1 = norm_layer()
+        self.mlp = MLP(in_features=embed_dim, hidden_features=int(embed_dim * mlp_ratio), act_layer=act_layer, drop_rate=drop_rate_mlp)
+        self.outer_skip = nn.Identity()
+
+
+_ACTS = {"relu": nn.ReLU, "gelu": nn.GELU, "silu": nn.SiLU}
+
+
+class SphericalFourierNeuralOperatorNet(BaseModel):
+    def __init__(
+        self,
+        params: dict = None,
+        spectral_transform: str = "sht",
+        filter_type: str = "linear",
+        operator_type: str = "diagonal",
+        scale_factor: int = 16,
+        embed_dim: int = 256,
+        num_layers: int = 12,
+        use_mlp: int = True,
+        mlp_ratio: int = 2.0,
+        activation_function: str = "gelu",
+        encoder_layers: int = 1,
+        pos_embed: bool = True,
+        dropout_filter: float = 0.0,
+        dropout_mlp: float = 0.0,
+        pos_emb_dropout: float = 0.0,
+        drop_path_rate: float = 0.0,
+        num_blocks: int = 16,
+        sparsity_threshold: float = 0.0,
+        normalization_layer: str = "instance_norm",
+        hard_thresholding_fraction: float = 1.0,
+        use_complex_kernels: bool = True,
+        big_skip: bool = True,
+        rank: float = 1.0,
+        factorization: Any = None,
+        separable: bool = False,
+        complex_network: bool = True,
+        complex_activation: str = "real",
+        spectral_layers: int = 3,
+        checkpointing: int = 0,
+        with_time_emb: bool = False,
+        time_dim_mult: int = 2,
+        time_rescale: bool = False,
+        time_scale_shift_before_filter: bool = True,
+        data_grid: Literal["legendre-gauss", "equiangular"] = "equiangular",
+        precision: str = "fp32",
+        check_time_range: bool = True,
+        **kwargs,
+    ):
+        super().__init__(**kwargs)
+        if self.hparams.debug_mode:
+            embed_dim, num_layers = 16, 2  # sfnonet.py:468-471
+        self.hparams.update(dict(
+            spectral_transform=spectral_transform, filter_type=filter_type, operator_type=operator_type,
+            scale_factor=scale_factor, embed_dim=embed_dim, num_layers=num_layers, use_mlp=use_mlp, mlp_ratio=mlp_ratio,
+            activation_function=activation_function, encoder_layers=encoder_layers, pos_embed=pos_embed,
+            dropout_mlp=dropout_mlp, drop_path_rate=drop_path_rate, normalization_layer=normalization_layer,
+            hard_thresholding_fraction=hard_thresholding_fraction, big_skip=big_skip, with_time_emb=with_time_emb,
+            time_dim_mult=time_dim_mult, time_rescale=time_rescale,
+            time_scale_shift_before_filter=time_scale_shift_before_filter, data_grid=data_grid, precision=precision))
+        # ---- options outside the configured hot path are refused loudly, with the reference's error classes
+        if spectral_transform != "sht":
+            if spectral_transform == "fft":
+                raise NotImplementedError("spectral_transform='fft' is outside the B200 hot path (sfno.yaml:7 uses 'sht')")
+            raise ValueError("Unknown spectral transform")
+        if filter_type != "linear":
+            raise NotImplementedError("only filter_type='linear' is built (sfno.yaml:8)")
+        if operator_type not in ("dhconv", "diagonal"):
+            raise ValueError(f"Unsupported operator type f{operator_type}")
+        if factorization is not None or separable:
+            raise NotImplementedError("factorized / separable spectral weights are outside the hot path")
+        if activation_function not in _ACTS:
+            raise ValueError(f"Unknown activation function {activation_function}")
+        if normalization_layer not in ("instance_norm", "none"):
+            raise NotImplementedError(f"Error, normalization {normalization_layer} not implemented.")
+        if scale_factor != 1:
+            raise NotImplementedError("scale_factor != 1 is not built (sfno.yaml:9 uses 1)")
+        if encoder_layers != 1 or not use_mlp or dropout_filter > 0 or pos_emb_dropout > 0 or checkpointing:
+            raise NotImplementedError("encoder_layers!=1 / use_mlp=False / filter or pos-emb dropout / checkpointing are not built")
+        if precision not in _lib.SFNO_PREC:
+            raise ValueError(f"Unknown precision {precision}")
+
+        self.params = params or {}
+        self.spectral_transform, self.filter_type, self.operator_type = spectral_transform, filter_type, operator_type
+        self.img_shape = tuple(self.spatial_shape_in)
+        self.scale_factor = scale_factor
+        self.in_chans = self.num_input_channels + self.num_conditional_channels
+        self.out_chans = self.num_output_channels
+        self.embed_dim = self.num_features = embed_dim
+        self.num_layers = num_layers
+        self.num_blocks = num_blocks
+        self.hard_thresholding_fraction = hard_thresholding_fraction
+        self.normalization_layer = normalization_layer
+        self.use_mlp = use_mlp
+        self.encoder_layers = encoder_layers
+        self.big_skip = big_skip
+        self.precision = precision
+        self.check_time_range = check_time_range
+        self.mlp_ratio = mlp_ratio
+        self.dropout_mlp = dropout_mlp
+        self.drop_path_rate = drop_path_rate
+        self.activation_name = activation_function
+        self.data_grid = data_grid
+
+        self.h = int(self.img_shape[0] // scale_factor)
+        self.w = int(self.img_shape[1] // scale_factor)
+        modes_lat = int(self.h * hard_thresholding_fraction)
+        modes_lon = int((self.w // 2 + 1) * hard_thresholding_fraction)
+        self.modes_lat, self.modes_lon = modes_lat, modes_lon
+        self.padding = (0, 0)
+
+        # sfnonet.py:551-554
+        self.trans_down = RealSHT(*self.img_shape, lmax=modes_lat, mmax=modes_lon, grid=data_grid, precision=precision).float()
+        self.itrans_up = InverseRealSHT(*self.img_shape, lmax=modes_lat, mmax=modes_lon, grid=data_grid, precision=precision).float()
+        self.trans = RealSHT(self.h, self.w, lmax=modes_lat, mmax=modes_lon, grid="legendre-gauss", precision=precision).float()
+        self.itrans = InverseRealSHT(self.h, self.w, lmax=modes_lat, mmax=modes_lon, grid="legendre-gauss", precision=precision).float()
+        self.img_shape_loc = (self.trans_down.nlat, self.trans_down.nlon)
+        self.img_shape_eff = (self.trans_down.nlat, self.trans_down.nlon)
+        self.h_loc, self.w_loc = self.itrans.nlat, self.itrans.nlon
+
+        act = _ACTS[activation_function]
+        self.activation_function = act
+        # encoder (sfnonet.py:610-618)
+        self.encoder = nn.Sequential(nn.Conv2d(self.in_chans, embed_dim, 1, bias=True), act(),
+                                     nn.Conv2d(embed_dim, embed_dim, 1, bias=False))
+        self.pos_drop = nn.Identity()
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, num_layers)]
+
+        if normalization_layer == "instance_norm":
+            def norm_layer():
+                return nn.InstanceNorm2d(num_features=embed_dim, eps=1e-6, affine=True, track_running_stats=False)
+        else:
+            norm_layer = nn.Identity
+
+        # time embedding (sfnonet.py:654-668)
+        self.time_dim = None
+        self.with_time_emb = with_time_emb
+        if with_time_emb:
+            self.time_dim = embed_dim * time_dim_mult
+            self.time_rescale = time_rescale
+            self.min_time, self.max_time = None, None
+            self.time_scaler, self.time_shift = 1.0, 0.0
+            self.time_emb_mlp = nn.Sequential(SinusoidalPosEmb(embed_dim), nn.Linear(embed_dim, self.time_dim), nn.GELU(),
+                                              nn.Linear(self.time_dim, self.time_dim))
+        else:
+            self.time_rescale = False
+
+        self.blocks = nn.ModuleList([])
+        for i in range(num_layers):
+            fwd = self.trans_down if i == 0 else self.trans
+            inv = self.itrans_up if i == num_layers - 1 else self.itrans
+            self.blocks.append(FourierNeuralOperatorBlock(
+                fwd, inv, embed_dim, operator_type=operator_type, mlp_ratio=mlp_ratio, drop_rate_mlp=dropout_mlp,
+                drop_path=dpr[i], act_layer=act, norm_layer=norm_layer, time_emb_dim=self.time_dim,
+                time_scale_shift_before_filter=time_scale_shift_before_filter))
+
+        # decoder (sfnonet.py:734-744)
+        self.decoder = nn.Sequential(nn.Conv2d(embed_dim + big_skip * self.in_chans, embed_dim, 1, bias=True), act(),
+                                     nn.Conv2d(embed_dim, self.out_chans, 1, bias=False))
+        if pos_embed:
+            self.pos_embed = nn.Parameter(torch.zeros(1, embed_dim, self.img_shape_loc[0], self.img_shape_loc[1]))
+            trunc_normal_(self.pos_embed, std=0.02)
+        self.apply(self._init_weights)
+
+        self._net = None          # sfno_net handle (created on first CUDA forward)
+        self._net_device = None
+        self._param_versions: dict = {}
+        self._calls = 0           # forward counter -> Philox offset, so successive calls draw fresh masks
+        self.dropout_seed = 0
+
+    # ---- reference helpers -------------------------------------------------------------------------------------
+    def _init_weights(self, m):
+        """``sfnonet.py:746-754``."""
+        if isinstance(m, (nn.Linear, nn.Conv2d)):
+            trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {"pos_embed", "cls_token"}
+
+    def set_min_max_time(self, min_time: float, max_time: float):
+        """``sfnonet.py:761-773``."""
+        self.min_time, self.max_time = min_time, max_time
+        if self.time_rescale:
+            self.time_scaler = 1000.0 / (max_time - min_time)
+            self.time_shift = -min_time
+            self._destroy_net()  # scaler/shift are baked into the net config
+
+    # ---- native net management -----------------------------------------------------------------------------------
+    def _destroy_net(self):
+        if self.__dict__.get("_net") is not None:
+            try:
+                _lib.lib().sfno_net_destroy(self._net)
+            except Exception:
+                pass
+        self._net, self._net_device = None, None
+        self._param_versions = {}
+
+    def __del__(self):
+        self._destroy_net()
+
+    def net_config(self, max_batch: int = 1 << 20) -> "_lib.NetConfig":
+        c = _lib.NetConfig()
+        c.struct_size = ctypes.sizeof(_lib.NetConfig)
+        c.precision = _lib.SFNO_PREC[self.precision]
+        c.nlat, c.nlon = self.img_shape
+        c.in_chans, c.out_chans = self.in_chans, self.out_chans
+        c.embed_dim, c.num_layers = self.embed_dim, self.num_layers
+        c.mlp_hidden = int(self.embed_dim * self.mlp_ratio) if self.use_mlp else 0
+        c.operator_type = _lib.SFNO_OP[self.operator_type]
+        c.activation = _lib.SFNO_ACT[self.activation_name]
+        c.data_grid = _lib.SFNO_GRID[self.data_grid]
+        c.lmax, c.mmax = self.modes_lat, self.modes_lon
+        c.pos_embed = int(hasattr(self, "pos_embed") and isinstance(self.pos_embed, nn.Parameter))
+        c.big_skip = int(bool(self.big_skip))
+        c.instance_norm = int(self.normalization_layer == "instance_norm")
+        c.with_time_emb = int(bool(self.with_time_emb))
+        c.time_dim = int(self.time_dim or 0)
+        c.time_scale_shift_before_filter = int(bool(self.hparams.time_scale_shift_before_filter))
+        c.time_scaler = float(self.time_scaler) if self.with_time_emb else 1.0
+        c.time_shift = float(self.time_shift) if self.with_time_emb else 0.0
+        c.norm_eps = 1e-6
+        c.dropout_mlp = float(self.dropout_mlp)
+        c.drop_path_rate = float(self.drop_path_rate)
+        c.max_batch = max_batch
+        return c
+
+    def _ensure_net(self, device):
+        if self._net is not None and self._net_device == device:
+            return
+        self._destroy_net()
+        handle = ctypes.c_void_p()
+        cfg = self.net_config()
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().sfno_net_create(ctypes.byref(cfg), ctypes.byref(handle)), "sfno_net_create")
+        self._net, self._net_device = handle, device
+        self._expected = _lib.lib().sfno_net_param_names(handle).decode().split("\n")
+
+    def sync_parameters(self, device, force: bool = False):
+        """(Re)pack every parameter whose storage or version changed since the last upload.  EMA swaps and
+        ``load_state_dict`` mutate parameters in place (``ema.py:54-91``), which bumps ``_version``."""
+        L = _lib.lib()
+        sd = dict(self.named_parameters())
+        st = stream_ptr(device)
+        for name in self._expected:
+            p = sd.get(name)
+            if p is None:
+                raise KeyError(f"the native net expects parameter {name!r} which this module does not hold")
+            if p.device != device:
+                raise RuntimeError(f"parameter {name} lives on {p.device}, inputs on {device}: move the model with .to()/.cuda()")
+            key = (p.data_ptr(), p._version)
+            if not force and self._param_versions.get(name) == key:
+                continue
+            v = p.detach()
+            if v.dtype != torch.float32 or not v.is_contiguous():
+                v = v.float().contiguous()
+            _lib.check(L.sfno_net_set_param(self._net, name.encode(), v.data_ptr(), v.numel(), st), f"sfno_net_set_param({name})")
+            self._param_versions[name] = key
+
+    def dropout_active(self) -> bool:
+        """True when any dropout layer is in training state (``dyffusion.py:226-235`` inference dropout)."""
+        if self.dropout_mlp <= 0.0 and self.drop_path_rate <= 0.0:
+            return False
+        return any(m.training for m in self.modules() if isinstance(m, ALL_DROPOUT_LAYERS))
+
+    # ---- forward ------------------------------------------------------------------------------------------------------
+    def forward(self, inputs, time=None, condition=None, static_condition=None, return_time_emb: bool = False, **kwargs):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("the B200 path is inference-only; call under torch.no_grad()/inference_mode() and .eval()")
+        x = self.concat_condition_if_needed(inputs, condition, static_condition)
+        in_dtype = x.dtype
+        x = require_cuda_f32(x, "inputs")
+        if x.dim() != 4 or x.shape[1] != self.in_chans or tuple(x.shape[2:]) != tuple(self.img_shape):
+            raise RuntimeError(f"expected input [B,{self.in_chans},{self.img_shape[0]},{self.img_shape[1]}], got {tuple(x.shape)}")
+        B = x.shape[0]
+        device = x.device
+        t_ptr = None
+        if self.with_time_emb:
+            assert self.min_time is not None and self.max_time is not None, \
+                "min_time and max_time must be set before using time embedding"
+            if time is None:
+                raise ValueError("time is None but with_time_emb is True")
+            if not torch.is_tensor(time):
+                time = torch.full((B,), float(time), dtype=torch.float32, device=device)
+            time = time.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+            if time.numel() != B:
+                raise RuntimeError(f"time has {time.numel()} entries for a batch of {B}")
+            if self.check_time_range:  # sfnonet.py:780-782 (host sync, as in the reference)
+                assert bool(((self.min_time <= time) & (time <= self.max_time)).all()), \
+                    f"time must be in [{self.min_time}, {self.max_time}], but time is {time}"
+            t_ptr = time.data_ptr()
+        out = torch.empty(B, self.out_chans, *self.img_shape, dtype=torch.float32, device=device)
+        if B == 0:
+            return (out, None) if return_time_emb else out
+        L = _lib.lib()
+        with torch.cuda.device(device):
+            self._ensure_net(device)
+            self.sync_parameters(device)
+            ws = workspace(device, L.sfno_net_workspace_bytes(self._net, B), "net")
+            drop = self.dropout_active()
+            self._calls += 1
+            _lib.check(L.sfno_net_forward(self._net, x.data_ptr(), t_ptr, out.data_ptr(), B, int(drop),
+                                          int(self.dropout_seed), int(self._calls) * 4096, ws.data_ptr(), ws.numel(),
+                                          stream_ptr(device)), "sfno_net_forward")
+            t_repr = None
+            if return_time_emb and self.with_time_emb:
+                t_repr = torch.empty(B, self.time_dim, dtype=torch.float32, device=device)
+                _lib.check(L.sfno_net_debug_tap(self._net, b"t_repr", t_repr.data_ptr(), t_repr.numel(), ws.data_ptr(),
+                                                stream_ptr(device)), "sfno_net_debug_tap")
+        out = out.to(in_dtype) if in_dtype != torch.float32 else out
+        if return_time_emb:
+            return out, t_repr
+        return out
+
+    # ---- test hook: activation after the encoder (-1) or after block i ----------------------------------------------------
+    def debug_activation(self, stop_after_block: int, inputs, time=None, condition=None, static_condition=None):
+        L = _lib.lib()
+        x = require_cuda_f32(self.concat_condition_if_needed(inputs, condition, static_condition), "inputs")
+        device = x.device
+        with torch.cuda.device(device):
+            self._ensure_net(device)
+            _lib.check(L.sfno_net_set_option(self._net, b"stop_after_block", stop_after_block))
+            try:
+                self.forward(inputs, time=time, condition=condition, static_condition=static_condition)
+                B = x.shape[0]
+                ws = workspace(device, L.sfno_net_workspace_bytes(self._net, B), "net")
+                act = torch.empty(B, self.embed_dim, *self.img_shape, dtype=torch.float32, device=device)
+                _lib.check(L.sfno_net_debug_tap(self._net, b"x", act.data_ptr(), act.numel(), ws.data_ptr(), stream_ptr(device)))
+            finally:
+                _lib.check(L.sfno_net_set_option(self._net, b"stop_after_block", -2))
+        return act

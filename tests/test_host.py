@@ -1,0 +1,160 @@
+"""CPU tests: the C-ABI library loads and exports everything the header declares, host-side tables match
+the oracle, the drop-in module keeps the reference's state_dict layout and error behaviour, and the op
+decomposition used by the CUDA path is algebraically equal to the oracle (tests/emulator.py)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden_cases
+from oracle import harmonics as oh
+from oracle.sfno_oracle import SFNOConfig, SFNOOracle, rel_l2
+
+import spherical_dyffusion_b200 as sb
+from spherical_dyffusion_b200 import _lib
+from emulator import NetEmulator
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "sfno_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(sfno_[a-z0-9_]+)\s*\(", header))
+    declared -= {"sfno_status"}
+    assert len(declared) >= 25
+    cdll = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(cdll, name), f"{name} declared in include/sfno_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    L = sb.lib()
+    assert L.sfno_b200_abi_version() == 1
+    assert L.sfno_b200_status_string(-3) == b"workspace too small"
+
+
+def test_net_config_struct_matches_header():
+    header = open(os.path.join(ROOT, "include", "sfno_b200.h")).read()
+    body = header[header.index("typedef struct sfno_net_config {"):header.index("} sfno_net_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in re.findall(r"(?:int32_t|float)\s+([^;]+);", body):
+        fields += [f.strip() for f in decl.split(",")]
+    assert fields == [f[0] for f in _lib.NetConfig._fields_]
+
+
+@pytest.mark.parametrize("grid", ["legendre-gauss", "equiangular"])
+@pytest.mark.parametrize("nlat,nlon", [(12, 24), (33, 64), (180, 360)])
+def test_host_tables_match_oracle(grid, nlat, nlon):
+    lmax, mmax = nlat, nlon // 2 + 1
+    sht = sb.RealSHT(nlat, nlon, lmax=lmax, mmax=mmax, grid=grid)
+    nodes, qw, wts, pct = sht.tables()
+    o_w, o_pct, _, _ = oh.sht_tables(nlat, nlon, lmax, mmax, grid)
+    o_nodes, o_qw = oh.quadrature(grid, nlat)
+    assert np.abs(qw.numpy() - o_qw).max() < 1e-14
+    assert np.abs(nodes.numpy() - np.cos(np.flip(np.arccos(o_nodes)))).max() < 1e-14
+    scale = np.abs(o_pct).max()
+    assert np.abs(pct.numpy() - o_pct).max() < 1e-11 * scale
+    assert np.abs(wts.numpy() - o_w).max() < 1e-11 * np.abs(o_w).max()
+
+
+def test_host_tables_reject_bad_geometry():
+    with pytest.raises(_lib.SfnoLibraryError):
+        _lib.check(sb.lib().sfno_sht_tables_host(1, 4, 1, 1, 0, None, None, None, None))
+    with pytest.raises(ValueError):
+        sb.RealSHT(8, 16, grid="lobatto")
+
+
+def _module_from_cfg(cfg: SFNOConfig, precision="fp32"):
+    kw = cfg.model_kwargs()
+    m = sb.SphericalFourierNeuralOperatorNet(
+        num_input_channels=cfg.num_input_channels, num_output_channels=cfg.num_output_channels,
+        num_output_channels_raw=cfg.num_output_channels, num_conditional_channels=cfg.num_conditional_channels,
+        spatial_shape_in=cfg.spatial_shape, spatial_shape_out=cfg.spatial_shape, precision=precision, **kw)
+    if cfg.with_time_emb:
+        m.set_min_max_time(cfg.min_time, cfg.max_time)
+    return m.eval()
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_module_state_dict_layout_equals_reference(case, load_golden):
+    fx = load_golden(case)
+    cfg = SFNOConfig(**fx["cfg"])
+    m = _module_from_cfg(cfg)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(fx["state_dict"].keys())
+    for k, v in fx["state_dict"].items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    m.load_state_dict(fx["state_dict"], strict=True)
+    assert m.num_params == sum(v.numel() for v in fx["state_dict"].values())
+
+
+def test_module_init_distributions():
+    cfg = SFNOConfig(num_input_channels=3, num_output_channels=3, num_conditional_channels=1, spatial_shape=(12, 24),
+                     embed_dim=32, num_layers=2, dropout_mlp=0.1, drop_path_rate=0.1)
+    torch.manual_seed(0)
+    m = _module_from_cfg(cfg)
+    sd = m.state_dict()
+    assert "blocks.0.mlp.fwd.3.weight" in sd and "blocks.0.mlp.fwd.2.weight" not in sd  # layers.py:76-80
+    w = sd["blocks.1.mlp.fwd.0.weight"]
+    assert abs(w.std().item() - 0.02) < 0.004 and w.abs().max() <= 2.0
+    assert sd["blocks.0.inner_skip.bias"].abs().max() == 0
+    sw = sd["blocks.0.filter.filter.weight"]
+    assert abs(sw.std().item() - 1 / 32**2) < 0.2 / 32**2
+    assert torch.equal(sd["blocks.0.norm0.weight"], torch.ones(32))
+    assert isinstance(m.blocks[0].drop_path, torch.nn.Identity)       # rate 0 for block 0 (sfnonet.py:622)
+    assert m.blocks[1].drop_path.drop_prob == pytest.approx(0.1)
+    assert m.no_weight_decay() == {"pos_embed", "cls_token"}
+
+
+def test_module_error_behaviour_mirrors_reference():
+    cfg = SFNOConfig(num_input_channels=3, num_output_channels=3, num_conditional_channels=2, spatial_shape=(12, 24),
+                     embed_dim=16, num_layers=2)
+    m = _module_from_cfg(cfg)
+    x = torch.randn(1, 3, 12, 24)
+    with pytest.raises(ValueError):      # _base_model.py:169-172
+        m(x, time=torch.tensor([1.0]))
+    with pytest.raises(RuntimeError):    # no CPU fallback
+        with torch.inference_mode():
+            m(x, time=torch.tensor([1.0]), condition=torch.randn(1, 2, 12, 24))
+    with pytest.raises(ValueError):
+        sb.SphericalFourierNeuralOperatorNet(num_input_channels=1, num_output_channels=1, spatial_shape_in=(8, 16),
+                                             spatial_shape_out=(8, 16), spectral_transform="bogus", scale_factor=1)
+    with pytest.raises(ValueError):
+        sb.SphericalFourierNeuralOperatorNet(num_input_channels=1, num_output_channels=1, spatial_shape_in=(8, 16),
+                                             spatial_shape_out=(8, 16), activation_function="tanh", scale_factor=1)
+    with pytest.raises(NotImplementedError):
+        sb.SphericalFourierNeuralOperatorNet(num_input_channels=1, num_output_channels=1, spatial_shape_in=(8, 16),
+                                             spatial_shape_out=(8, 16), normalization_layer="layer_norm", scale_factor=1)
+    with pytest.raises(NotImplementedError):
+        m.get_loss(x, x)
+
+
+def test_inference_dropout_scope_toggles_dropout_modules():
+    cfg = SFNOConfig(num_input_channels=2, num_output_channels=2, spatial_shape=(12, 24), embed_dim=16, num_layers=2,
+                     dropout_mlp=0.1, drop_path_rate=0.1)
+    m = _module_from_cfg(cfg)
+    assert not m.dropout_active()
+    with m.inference_dropout_scope(condition=True):
+        assert m.dropout_active()
+        assert not m.encoder.training
+    assert not m.dropout_active()
+
+
+def _tables_fn(nlat, nlon, lmax, mmax):
+    def fn(grid):
+        _, _, w, p = sb.RealSHT(nlat, nlon, lmax=lmax, mmax=mmax, grid=grid).tables()
+        return w, p
+    return fn
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_op_decomposition_equals_reference_golden(case, load_golden):
+    """The algebra of csrc/net.cu (emulated on CPU in fp64 with the library's own tables) reproduces the
+    reference output stored in the fixture."""
+    fx = load_golden(case)
+    cfg = SFNOConfig(**fx["cfg"])
+    H, W = cfg.spatial_shape
+    emu = NetEmulator(cfg, fx["state_dict"], _tables_fn(H, W, H, W // 2 + 1))
+    out = emu.forward(fx["inputs"], time=fx["time"], condition=fx["condition"])
+    assert rel_l2(out, fx["output"]) < 5e-6
