@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- SFNO forward throughput on B200 (metric of BASELINE.json: "SFNO fwd samples/s").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU implementation (oracle port)
+
+A "step" is one ACE-sized SFNO forward (forecaster: 34+2 -> 34 channels, embed 256, 8 blocks, dhconv, 180x360)
+on a batch of `--batch` synthetic samples per GPU with random-init weights.  `value` is whole-job samples/s with
+inputs resident in HBM; `e2e` is the same through the public module call with pinned host inputs and a host read
+of the output inside the timed region.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "SFNO fwd samples/s"
+UNIT = "samples/s"
+FORWARDS_PER_STEP = 16.0 / 6.0   # DYffusion window: 6 forecaster + 10 interpolator forwards per 6 output steps
+STEPS_PER_YEAR = 1460.0
+FLOP_PER_SAMPLE = 605.0e9        # dense algorithmic flops of one forecaster forward
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], bf16_tflops_sustained=p.get("bf16_tflops_sustained"),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def workload_config(args):
+    return {"workload": f"ACE SFNO forecaster forward 36->34ch embed256 x8 blocks dhconv 180x360, batch {args.batch}/GPU",
+            "batch_per_gpu": args.batch, "precision": args.precision,
+            "l2": "per-step working set (>= 2.5 GB of activations) exceeds the 126 MB L2; no explicit flush"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        smax = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_case(batch, seed=0):
+    from oracle.sfno_oracle import ACE_FORECASTER, SFNOConfig, random_state_dict
+
+    cfg = SFNOConfig(**ACE_FORECASTER)
+    sd = random_state_dict(cfg, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, 34, 180, 360, generator=g)
+    c = torch.randn(batch, 2, 180, 360, generator=g)
+    t = torch.full((batch,), 3.0)
+    return cfg, sd, x, c, t
+
+
+def cpu_forward_time(cfg, sd, x, c, t, steps, warmup):
+    from oracle.sfno_oracle import SFNOOracle
+
+    orc = SFNOOracle(cfg, sd)
+    for _ in range(warmup):
+        orc(x, time=t, condition=c)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        orc(x, time=t, condition=c)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    """Reference arm: the reference's own PyTorch-CPU algorithm (oracle port; the reference needs packages that
+    are not installable here) on the host cores, one sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg, sd, x, c, t = build_case(1)
+    times = cpu_forward_time(cfg, sd, x, c, t, args.steps, args.warmup)
+    total = sum(times)
+    value = args.steps * 1.0 / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ACE SFNO forecaster forward 36->34ch embed256 x8 blocks dhconv 180x360, batch 1 on host CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{args.steps} forwards of 1 sample (oracle/sfno_oracle.py, fp32, torch CPU)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch.distributed as dist
+
+    import spherical_dyffusion_b200 as sb
+    from spherical_dyffusion_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    cfg, sd, x, c, t = build_case(B, seed=rank)
+    model = sb.SphericalFourierNeuralOperatorNet(
+        num_input_channels=34, num_output_channels=34, num_output_channels_raw=34, num_conditional_channels=2,
+        spatial_shape_in=(180, 360), spatial_shape_out=(180, 360), precision=args.precision, check_time_range=False,
+        **cfg.model_kwargs())
+    model.load_state_dict(sd)
+    model.set_min_max_time(0, 5)
+    model = model.to(dev).eval()
+    xd, cd, td = x.to(dev), c.to(dev), t.to(dev)
+    x_pin, c_pin = x.pin_memory(), c.pin_memory()
+    y_pin = torch.empty(B, 34, 180, 360).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        v = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
+
+    with torch.inference_mode():
+        # ---- device-resident throughput ---------------------------------------------------------------------
+        for _ in range(max(args.warmup, 3)):
+            model(xd, time=td, condition=cd)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            model(xd, time=td, condition=cd)
+        e1.record()
+        barrier()
+        ms_dev = max_over_ranks(e0.elapsed_time(e1))
+        launches = _lib.launch_count() - n0
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ---- end to end through the public call: pinned host -> device -> forward -> host ----------------------
+        def e2e_step():
+            xi = x_pin.to(dev, non_blocking=True)
+            ci = c_pin.to(dev, non_blocking=True)
+            y = model(xi, time=td, condition=ci)
+            y_pin.copy_(y, non_blocking=True)
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+    samples = world * B * args.steps
+    value = samples / (ms_dev * 1e-3)
+    e2e_value = samples / (ms_e2e * 1e-3)
+    pk = peaks()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x.numel() * 4 + c.numel() * 4),
+                "d2h_bytes_per_step": int(y_pin.numel() * 4)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "derived": {
+            "steps_per_s_per_member": value / world / B / FORWARDS_PER_STEP,
+            "member_sypd": value / FORWARDS_PER_STEP * 86400.0 / STEPS_PER_YEAR,
+            "model_tflops": value * FLOP_PER_SAMPLE / 1e12,
+            "model_flops_frac_of_bf16_peak": value / world * FLOP_PER_SAMPLE / 1e12 / pk["bf16_tflops_sustained"],
+        },
+    }
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel, timed live by the library with CUDA events on the launch stream ----
+        try:
+            line["roofline"] = model_roofline(model, xd, td, cd, pk)
+        except Exception as exc:  # keep the bench line even if the profile hook fails
+            line["roofline"] = {"error": str(exc)}
+        # ---- CPU baseline: the oracle port on the host cores, bounded sample ---------------------------------------
+        if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            cfg1, sd1, x1, c1, t1 = build_case(1)
+            times = cpu_forward_time(cfg1, sd1, x1, c1, t1, steps=2, warmup=1)
+            line["cpu_baseline"] = {"value": 1.0 / min(times), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "best of 2 forwards of 1 sample after 1 warm-up (oracle/sfno_oracle.py, fp32 torch CPU)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def model_roofline(model, xd, td, cd, pk):
+    """Per-kernel device times of one forward (CUDA events inside the library) -> roofline of the dominant kernel."""
+    from spherical_dyffusion_b200.profile import profile_forward, roofline_from_profile
+
+    recs = profile_forward(model, xd, td, cd)
+    return roofline_from_profile(recs, pk, model=model, batch=xd.shape[0])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 3
+        args.warmup = args.warmup if args.warmup is not None else 1
+        args.steps = min(args.steps, 8)  # bounded: one step is ~5-10 s of CPU work
+        args.warmup = min(args.warmup, 2)
+        run_reference(args)
+    else:
+        args.steps = args.steps if args.steps is not None else 20
+        args.warmup = args.warmup if args.warmup is not None else 3
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,12 @@ int64_t sfno_b200_launch_count(void);
 /* Library-wide switches for tests: "force_simt" = 1 routes bf16 ops to the CUDA-core engine. */
 int sfno_b200_set_option(const char* key, int64_t value);
 
+/* Per-launch device timing for bench.py: between _begin and _end every kernel launched by this library on
+ * `stream` is followed by a CUDA event; _end synchronises the stream and returns the number of launches, their
+ * names ('\n'-separated) and durations in ms (difference of consecutive events on that stream). */
+int sfno_b200_profile_begin(void* stream);
+int sfno_b200_profile_end(char* names, size_t names_capacity, float* ms, int capacity);
+
 /* ---- host-side tables (no GPU needed) -----------------------------------------------------------
  * Replaces torch_harmonics' precompute used at sfnonet.py:551-554 (quadrature.py legendre_gauss_weights /
  * clenshaw_curtiss_weights, legendre.py legpoly).  Outputs are fp64, row-major:

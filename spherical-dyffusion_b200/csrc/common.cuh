@@ -37,10 +37,13 @@ int fail(int status, const char* fmt, ...);
     if (_s != SFNO_OK) return _s; \
   } while (0)
 
-// ---- launch accounting ------------------------------------------------------------------------------
+// ---- launch accounting + optional per-launch timing (sfno_b200_profile_begin/end) ---------------------
 extern std::atomic<int64_t> g_launch_count;
+extern std::atomic<int> g_profile_on;
+void profile_mark(const char* what);  // records a CUDA event on the profiled stream after a launch
 inline int post_launch(const char* what) {
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  if (g_profile_on.load(std::memory_order_relaxed)) profile_mark(what);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     cudaGetLastError();

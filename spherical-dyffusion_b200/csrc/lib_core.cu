@@ -12,6 +12,24 @@
 namespace sfno {
 
 std::atomic<int64_t> g_launch_count{0};
+std::atomic<int> g_profile_on{0};
+
+// Per-launch timing: one CUDA event after every launch on the profiled stream; durations are differences of
+// consecutive events (the path is a single in-order stream, so launches execute back to back).
+struct Profiler {
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> events;
+  std::vector<std::string> names;
+};
+static Profiler g_prof;
+
+void profile_mark(const char* what) {
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, g_prof.stream);
+  g_prof.events.push_back(e);
+  g_prof.names.emplace_back(what);
+}
 
 std::string& last_error_ref() {
   static thread_local std::string s;
@@ -201,6 +219,41 @@ const char* sfno_b200_status_string(int status) {
 
 const char* sfno_b200_last_error(void) { return last_error_ref().c_str(); }
 int64_t sfno_b200_launch_count(void) { return g_launch_count.load(); }
+
+int sfno_b200_profile_begin(void* stream) {
+  if (g_profile_on.load()) return fail(SFNO_ERR_INVALID_ARGUMENT, "profile already running");
+  for (cudaEvent_t e : g_prof.events) cudaEventDestroy(e);
+  g_prof.events.clear();
+  g_prof.names.clear();
+  g_prof.stream = (cudaStream_t)stream;
+  g_profile_on.store(1);
+  profile_mark("begin");
+  return SFNO_OK;
+}
+
+int sfno_b200_profile_end(char* names, size_t names_capacity, float* ms, int capacity) {
+  if (!g_profile_on.load()) return fail(SFNO_ERR_INVALID_ARGUMENT, "profile not running");
+  g_profile_on.store(0);
+  SFNO_CUDA(cudaStreamSynchronize(g_prof.stream));
+  const int n = (int)g_prof.events.size() - 1;
+  std::string joined;
+  for (int i = 0; i < n && i < capacity; ++i) {
+    float t = 0.0f;
+    cudaEventElapsedTime(&t, g_prof.events[i], g_prof.events[i + 1]);
+    if (ms) ms[i] = t;
+    joined += g_prof.names[i + 1];
+    joined += '\n';
+  }
+  if (names && names_capacity > 0) {
+    size_t len = std::min(names_capacity - 1, joined.size());
+    memcpy(names, joined.data(), len);
+    names[len] = 0;
+  }
+  for (cudaEvent_t e : g_prof.events) cudaEventDestroy(e);
+  g_prof.events.clear();
+  g_prof.names.clear();
+  return std::min(n, capacity);
+}
 
 int sfno_sht_tables_host(int nlat, int nlon, int lmax, int mmax, int grid, double* nodes, double* quad_w,
                          double* weights, double* pct) {

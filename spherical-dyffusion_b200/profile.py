@@ -1,0 +1,94 @@
+"""Per-kernel device timing of one forward (CUDA events recorded by the library after every launch, on the launch
+stream) and the roofline arithmetic used by ``bench.py``.  Algorithmic flops / bytes per launch follow SURVEY.md
+section 8d (dense counts: 1 MAC = 2 flop, 1 complex MAC = 8 flop; minimum HBM traffic = operands read once + result)."""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+
+import torch
+
+from . import _lib
+from ._util import stream_ptr
+
+
+def profile_forward(model, x, time, condition, repeats: int = 3):
+    """Returns an OrderedDict name -> dict(ms_total, launches) averaged over `repeats` forwards."""
+    L = _lib.lib()
+    dev = x.device
+    acc = OrderedDict()
+    with torch.inference_mode(), torch.cuda.device(dev):
+        model(x, time=time, condition=condition)
+        torch.cuda.synchronize(dev)
+        for _ in range(repeats):
+            _lib.check(L.sfno_b200_profile_begin(stream_ptr(dev)), "profile_begin")
+            try:
+                model(x, time=time, condition=condition)
+            finally:
+                cap = 4096
+                names = ctypes.create_string_buffer(1 << 16)
+                ms = (ctypes.c_float * cap)()
+                n = _lib.check(L.sfno_b200_profile_end(names, len(names), ms, cap), "profile_end")
+            for nm, t in zip(names.value.decode().split("\n"), list(ms)[:n]):
+                r = acc.setdefault(nm, dict(ms_total=0.0, launches=0))
+                r["ms_total"] += t / repeats
+                r["launches"] += 1
+    for r in acc.values():
+        r["launches"] //= repeats
+    return acc
+
+
+def algorithmic_work(model, batch: int):
+    """name -> (flops per launch, min bytes per launch, kind) for the GEMM-shaped and streaming kernels."""
+    e = 2 if model.precision == "bf16" else 4
+    B, C, Cin, Cout = batch, model.embed_dim, model.in_chans, model.out_chans
+    H, W = model.img_shape
+    P, Lm, Mm = H * W, model.modes_lat, model.modes_lon
+    hid = int(C * model.mlp_ratio)
+    A = B * C * P * e                 # one activation tensor
+    S = B * C * Lm * Mm * 2 * e       # one spectral tensor
+    Fb = B * C * H * Mm * 2 * e       # longitude-spectral tensor
+    ccat = C + (Cin if model.big_skip else 0)
+    w = {}
+    w["dft_fwd"] = (2.0 * B * C * H * W * 2 * Mm, A + Fb)
+    w["legendre_fwd"] = (4.0 * B * C * Mm * Lm * H, Fb + S + Mm * Lm * H * e)
+    w["legendre_inv"] = (4.0 * B * C * Mm * Lm * H, Fb + S + Mm * Lm * H * e)
+    w["dft_inv"] = (2.0 * B * C * H * W * 2 * Mm, Fb + 2 * A)
+    w["dhconv"] = (8.0 * B * C * C * Lm * Mm, 2 * S + 4 * C * C * Lm * e)
+    w["inner_skip"] = (2.0 * B * P * C * C, 2 * A)
+    w["mlp_fc1"] = (2.0 * B * P * C * hid, A + B * hid * P * e)
+    w["mlp_fc2"] = (2.0 * B * P * C * hid, B * hid * P * e + 2 * A)
+    w["encoder0"] = (2.0 * B * P * Cin * C, B * Cin * P * e + A)
+    w["encoder1"] = (2.0 * B * P * C * C, 3 * A)
+    w["decoder0"] = (2.0 * B * P * ccat * C, B * ccat * P * e + A)
+    w["decoder1"] = (2.0 * B * P * C * Cout, A + B * Cout * P * 4)
+    w["instance_stats0"] = (0.0, A)
+    w["instance_stats1"] = (0.0, A)
+    return w
+
+
+def roofline_from_profile(recs, pk, model=None, batch=None):
+    total = sum(r["ms_total"] for r in recs.values())
+    top_name, top = max(recs.items(), key=lambda kv: kv[1]["ms_total"])
+    out = {"kernel": top_name, "share_of_step": top["ms_total"] / total if total else None,
+           "launches_per_step": top["launches"], "ms_per_launch": top["ms_total"] / max(top["launches"], 1),
+           "step_ms_profiled": total,
+           "per_kernel_ms": {k: round(v["ms_total"], 4) for k, v in sorted(recs.items(), key=lambda kv: -kv[1]["ms_total"])}}
+    if model is not None and batch is not None:
+        work = algorithmic_work(model, batch).get(top_name)
+        if work is not None:
+            flops, nbytes = work
+            sec = out["ms_per_launch"] * 1e-3
+            ridge = pk["bf16_tflops"] * 1e12 / (pk["hbm_gbs"] * 1e9)
+            tensor_bound = model.precision == "bf16" and nbytes > 0 and flops / nbytes > ridge
+            if tensor_bound:
+                out.update(bound="tensor", achieved=flops / sec / 1e12, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s")
+            else:
+                out.update(bound="hbm", achieved=nbytes / sec / 1e9, peak=pk["hbm_gbs"], unit="GB/s")
+            out["frac"] = out["achieved"] / out["peak"]
+            out["peak_source"] = pk["source"]
+            out["algorithmic_flops_per_launch"] = flops
+            out["algorithmic_bytes_per_launch"] = nbytes
+            out["tflops_achieved"] = flops / sec / 1e12
+            out["traffic"] = None
+    return out
