@@ -1,8 +1,38 @@
-// tcgen05 / TMA tensor-core engine for the bf16 ops (placeholder traits; filled in by gemm_tc_impl.cuh).
+// tcgen05 / TMA / TMEM engine for the bf16 batched-GEMM ops (SFNO_PREC_BF16), sm_100a only.
+//
+//   persistent CTAs (one per SM), 128 x BN output tile, K in blocks of 64 bf16 (one 128-byte swizzle span)
+//   warp 0      : TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, 3-D maps {inner, outer, batch})
+//   warp 1      : MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM, 2 stages)
+//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> op.store(): lane = M index = contiguous output index)
+//   smem ring of kStages {A tile, B tile}, mbarrier full/empty; TMEM full/empty barriers decouple the MMA of
+//   tile i+1 from the epilogue of tile i.
+//
+// Operands are consumed directly in the layout they have in HBM: K-contiguous operands as K-major
+// SWIZZLE_128B tiles, M/N-contiguous operands as MN-major SWIZZLE_128B tiles (64-element atoms), so no
+// transposition pass exists anywhere on the path.  Out-of-bounds rows / K are zero-filled by TMA.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace sfno {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+
+struct TmaOperand {
+  const void* base = nullptr;
+  uint64_t dims[3] = {1, 1, 1};      // {inner, outer, batch} in elements
+  uint64_t strides[2] = {0, 0};      // byte strides of dims[1], dims[2]
+  bool batched = false;
+};
+
+struct TcSched {
+  int m_tiles, n_tiles, groups, num_tiles, k_blocks, k16_last;  // k16_last: MMAs (K=16) in the last k block
+  int a_batched, b_batched;
+};
 
 template <class Op>
 struct TcTraits {
@@ -10,9 +40,332 @@ struct TcTraits {
   static bool eligible(const Op&) { return false; }
 };
 
+// ---- PTX wrappers ----------------------------------------------------------------------------------------
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive when all previously issued MMAs of this thread have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+      "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+}  // namespace ptx
+
+// ---- descriptors -----------------------------------------------------------------------------------------
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1, SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> fp32, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn_major, bool b_mn_major, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+template <int BN>
+struct TcSmem {
+  static constexpr int kABytes = TC_BM * TC_BK * 2;
+  static constexpr int kBBytes = BN * TC_BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 6 ? 6 : (200 * 1024) / kStageBytes;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + alignment slack
+};
+
+template <class Op, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Op op, const TcSched sc) {
+  using S = TcSmem<BN>;
+  constexpr int kStages = S::kStages;
+  constexpr uint32_t kTmemCols = 512;  // two accumulator stages of up to 256 fp32 columns
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+  const uint32_t bar_base = smem_base + kStages * S::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  auto a_smem = [&](int s) { return smem_base + s * S::kStageBytes; };
+  auto b_smem = [&](int s) { return smem_base + s * S::kStageBytes + S::kABytes; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tma_a);
+    ptx::prefetch_tmap(&tma_b);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tfull_bar(a), 1);
+      ptx::mbar_init(tempty_bar(a), TC_EPI_WARPS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto decode = [&](int tile, int& g, int& mt, int& nt) {
+    mt = tile % sc.m_tiles;
+    const int r = tile / sc.m_tiles;
+    nt = r % sc.n_tiles;
+    g = r / sc.n_tiles;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x) {
+        int g, mt, nt;
+        decode(tile, g, mt, nt);
+        const int m0 = mt * TC_BM, n0 = nt * BN;
+        const int ga = sc.a_batched ? g : 0, gb = sc.b_batched ? g : 0;
+        for (int kb = 0; kb < sc.k_blocks; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_expect_tx(full_bar(stage), S::kStageBytes);
+          const int k0 = kb * TC_BK;
+          if (Op::A_KCONTIG) {
+            ptx::tma_load_3d(a_smem(stage), &tma_a, full_bar(stage), k0, m0, ga);
+          } else {
+#pragma unroll
+            for (int h = 0; h < TC_BM / 64; ++h)
+              ptx::tma_load_3d(a_smem(stage) + h * (64 * TC_BK * 2), &tma_a, full_bar(stage), m0 + 64 * h, k0, ga);
+          }
+          if (Op::B_KCONTIG) {
+            ptx::tma_load_3d(b_smem(stage), &tma_b, full_bar(stage), k0, n0, gb);
+          } else {
+#pragma unroll
+            for (int h = 0; h < BN / 64; ++h)
+              ptx::tma_load_3d(b_smem(stage) + h * (64 * TC_BK * 2), &tma_b, full_bar(stage), n0 + 64 * h, k0, gb);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(!Op::A_KCONTIG, !Op::B_KCONTIG, BN);
+      // K-major: 8-row atoms of 1024 B (SBO), K advance 32 B per MMA.  MN-major: 64-element atoms, next atom along
+      // M/N after BK rows of 128 B (LBO = 8192), next 8 k-rows after 1024 B (SBO), K advance 2048 B per MMA.
+      constexpr uint32_t a_lbo = Op::A_KCONTIG ? 16u : (uint32_t)(TC_BK * 128), a_kstep = Op::A_KCONTIG ? 32u : 2048u;
+      constexpr uint32_t b_lbo = Op::B_KCONTIG ? 16u : (uint32_t)(TC_BK * 128), b_kstep = Op::B_KCONTIG ? 32u : 2048u;
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < sc.k_blocks; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const int nk = (kb == sc.k_blocks - 1) ? sc.k16_last : TC_BK / 16;
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t ad = make_smem_desc(a_smem(stage) + k * a_kstep, a_lbo, 1024u);
+            const uint64_t bd = make_smem_desc(b_smem(stage) + k * b_kstep, b_lbo, 1024u);
+            ptx::mma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::mma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int ew = warp - 2;              // 0..7
+    const int quad = warp & 3;            // TMEM sub-partition this warp may read: lanes [32*quad, 32*quad+32)
+    const int half = ew >> 2;             // two warps per sub-partition split the columns
+    constexpr int kColsPerWarp = BN / (TC_EPI_WARPS / 4);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x) {
+      int g, mt, nt;
+      decode(tile, g, mt, nt);
+      const int m = mt * TC_BM + quad * 32 + lane;
+      const int n_base = nt * BN + half * kColsPerWarp;
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const bool row_ok = m < op.M;
+      typename Op::Row row{};
+      if (row_ok) row = op.row(g, m);
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * kColsPerWarp);
+#pragma unroll 1
+      for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
+        if (n_base + c0 >= op.N) break;  // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld32(t_row + (uint32_t)c0, r);
+        ptx::tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n_base + c0 + j;
+            if (n < op.N) op.store(row, g, m, n, __uint_as_float(r[j]));
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled();
+int tc_num_sms();
+
+inline int encode_operand(const TmaOperand& o, bool k_contig, int rows_box, CUtensorMap* map, const char* what) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return fail(SFNO_ERR_CUDA, "%s: cuTensorMapEncodeTiled unavailable", what);
+  cuuint64_t dims[3] = {o.dims[0], o.dims[1], o.dims[2]};
+  cuuint64_t strides[2] = {o.strides[0], o.strides[1]};
+  if (dims[2] == 1) strides[1] = strides[0] * dims[1];  // any valid multiple of 16
+  cuuint32_t box[3];
+  if (k_contig) { box[0] = TC_BK; box[1] = (cuuint32_t)rows_box; box[2] = 1; }
+  else { box[0] = 64; box[1] = TC_BK; box[2] = 1; }
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(o.base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SFNO_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d): base=%p dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u,%u)",
+                what, (int)r, o.base, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                (unsigned long long)strides[0], (unsigned long long)strides[1], box[0], box[1], box[2]);
+  return SFNO_OK;
+}
+
+inline bool tma_operand_ok(const TmaOperand& o) {
+  if (((uintptr_t)o.base & 15) != 0) return false;
+  if (o.strides[0] % 16 != 0 || o.strides[0] == 0) return false;
+  if (o.dims[2] > 1 && (o.strides[1] % 16 != 0 || o.strides[1] == 0)) return false;
+  for (int i = 0; i < 3; ++i)
+    if (o.dims[i] == 0 || o.dims[i] > (1ull << 31)) return false;
+  return true;
+}
+
 template <class Op>
-int launch_gemm_tc(const Op&, cudaStream_t, const char* what) {
-  return fail(SFNO_ERR_UNSUPPORTED, "%s: tensor-core engine not built for this op", what);
+int launch_gemm_tc(const Op& op, cudaStream_t stream, const char* what) {
+  using Tr = TcTraits<Op>;
+  constexpr int BN = Tr::BN;
+  using S = TcSmem<BN>;
+  if (op.M <= 0 || op.N <= 0 || op.G <= 0) return SFNO_OK;
+  TmaOperand a, b;
+  Tr::operands(op, a, b);
+  CUtensorMap ma, mb;
+  SFNO_TRY(encode_operand(a, Op::A_KCONTIG, TC_BM, &ma, what));
+  SFNO_TRY(encode_operand(b, Op::B_KCONTIG, BN, &mb, what));
+  TcSched sc;
+  sc.m_tiles = ceil_div(op.M, TC_BM);
+  sc.n_tiles = ceil_div(op.N, BN);
+  sc.groups = op.G;
+  const int64_t tiles = (int64_t)sc.m_tiles * sc.n_tiles * sc.groups;
+  if (tiles > (1ll << 30)) return fail(SFNO_ERR_UNSUPPORTED, "%s: too many tiles", what);
+  sc.num_tiles = (int)tiles;
+  sc.k_blocks = ceil_div(op.K, TC_BK);
+  const int k_rem = op.K - (sc.k_blocks - 1) * TC_BK;
+  sc.k16_last = ceil_div(k_rem, 16);
+  sc.a_batched = a.batched ? 1 : 0;
+  sc.b_batched = b.batched ? 1 : 0;
+  static bool attr_set = false;
+  auto kern = gemm_tc_kernel<Op, BN>;
+  if (!attr_set) {
+    SFNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+  }
+  const int grid = std::min(sc.num_tiles, tc_num_sms());
+  kern<<<grid, TC_THREADS, S::kTotal, stream>>>(ma, mb, op, sc);
+  return post_launch(what);
 }
 
 }  // namespace sfno
