@@ -58,6 +58,11 @@ int sfno_b200_set_option(const char* key, int64_t value);
 int sfno_b200_profile_begin(void* stream);
 int sfno_b200_profile_end(char* names, size_t names_capacity, float* ms, int capacity);
 
+/* Device-vs-device engine cross-check used by the GPU tests: runs op `op_kind` (0 DFT, 1 Legendre, 2 dhconv,
+ * 3 inverse Legendre, 4 inverse DFT, 5 conv1x1) of the given dims on synthetic bf16 operands through the CUDA-core
+ * engine and the tcgen05 engine; result = {max |diff|, max |ref|, tensor-core engine used (0/1), ms per launch, #non-finite}. */
+int sfno_b200_selftest_gemm(int op_kind, const int* dims, int ndims, double* result);
+
 /* ---- host-side tables (no GPU needed) -----------------------------------------------------------
  * Replaces torch_harmonics' precompute used at sfnonet.py:551-554 (quadrature.py legendre_gauss_weights /
  * clenshaw_curtiss_weights, legendre.py legpoly).  Outputs are fp64, row-major:

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "sfno_b200_set_option": (c_int, [c_char_p, c_int64]),
     "sfno_b200_profile_begin": (c_int, [c_void_p]),
     "sfno_b200_profile_end": (c_int, [c_void_p, c_size_t, c_void_p, c_int]),
+    "sfno_b200_selftest_gemm": (c_int, [c_int, POINTER(c_int), c_int, POINTER(c_double)]),
     "sfno_sht_tables_host": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_double), POINTER(c_double),
                                      POINTER(c_double), POINTER(c_double)]),
     "sfno_sht_plan_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int]),

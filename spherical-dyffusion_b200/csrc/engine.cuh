@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc_ops.cuh"
 
 namespace sfno {
 

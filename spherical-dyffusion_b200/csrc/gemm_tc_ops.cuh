@@ -1,0 +1,90 @@
+// TMA operand descriptions of the bf16 ops for the tcgen05 engine (which tensor, which extents, which strides).
+// Extents are the exact logical sizes: TMA zero-fills everything outside, so K / row tails need no padding.
+#pragma once
+#include "gemm_tc.cuh"
+#include "ops.cuh"
+
+namespace sfno {
+
+template <class Op>
+struct TcTraitsBase {
+  static constexpr bool kAvailable = true;
+};
+
+template <class Derived, class Op>
+struct TcEligible {
+  static bool eligible(const Op& op) {
+    TmaOperand a, b;
+    Derived::operands(op, a, b);
+    return tma_operand_ok(a) && tma_operand_ok(b) && op.M > 0 && op.N > 0 && op.K > 0;
+  }
+};
+
+template <>
+struct TcTraits<OpDft<bf16>> : TcTraitsBase<OpDft<bf16>>, TcEligible<TcTraits<OpDft<bf16>>, OpDft<bf16>> {
+  static constexpr int BN = 192;
+  static void operands(const OpDft<bf16>& op, TmaOperand& a, TmaOperand& b) {
+    a.base = op.A; a.dims[0] = op.nlon; a.dims[1] = op.M; a.dims[2] = op.G;
+    a.strides[0] = (uint64_t)op.nlon * 2; a.strides[1] = (uint64_t)op.x_bstride * 2; a.batched = true;
+    b.base = op.Bm; b.dims[0] = op.nlon; b.dims[1] = op.N; b.dims[2] = 1;
+    b.strides[0] = (uint64_t)op.Wp * 2; b.batched = false;
+  }
+};
+
+template <>
+struct TcTraits<OpLeg<bf16>> : TcTraitsBase<OpLeg<bf16>>, TcEligible<TcTraits<OpLeg<bf16>>, OpLeg<bf16>> {
+  static constexpr int BN = 192;
+  static void operands(const OpLeg<bf16>& op, TmaOperand& a, TmaOperand& b) {
+    a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.M; a.dims[2] = op.G;
+    a.strides[0] = (uint64_t)op.Kp * 2; a.strides[1] = (uint64_t)op.M * op.Kp * 2; a.batched = true;
+    b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.lmax; b.dims[2] = op.G;
+    b.strides[0] = (uint64_t)op.Kp * 2; b.strides[1] = (uint64_t)op.lmax * op.Kp * 2; b.batched = true;
+  }
+};
+
+template <>
+struct TcTraits<OpDhconv<bf16>> : TcTraitsBase<OpDhconv<bf16>>, TcEligible<TcTraits<OpDhconv<bf16>>, OpDhconv<bf16>> {
+  static constexpr int BN = 256;
+  static void operands(const OpDhconv<bf16>& op, TmaOperand& a, TmaOperand& b) {
+    a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.M; a.dims[2] = op.G;
+    a.strides[0] = (uint64_t)op.K * 2; a.strides[1] = (uint64_t)op.M * op.K * 2; a.batched = true;
+    b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.N; b.dims[2] = op.G;
+    b.strides[0] = (uint64_t)op.K * 2; b.strides[1] = (uint64_t)op.N * op.K * 2; b.batched = true;
+  }
+};
+
+template <>
+struct TcTraits<OpIleg<bf16>> : TcTraitsBase<OpIleg<bf16>>, TcEligible<TcTraits<OpIleg<bf16>>, OpIleg<bf16>> {
+  static constexpr int BN = 256;
+  static void operands(const OpIleg<bf16>& op, TmaOperand& a, TmaOperand& b) {
+    a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.nlat; a.dims[2] = op.G;
+    a.strides[0] = (uint64_t)op.Lq * 2; a.strides[1] = (uint64_t)op.nlat * op.Lq * 2; a.batched = true;
+    b.base = op.Bm; b.dims[0] = op.N; b.dims[1] = op.K; b.dims[2] = op.G;  // N-contiguous: {n, l, m}
+    b.strides[0] = (uint64_t)op.b_sk * 2; b.strides[1] = (uint64_t)op.b_goff * 2; b.batched = true;
+  }
+};
+
+template <class TOut>
+struct TcTraits<OpIdft<bf16, TOut>> : TcTraitsBase<OpIdft<bf16, TOut>>, TcEligible<TcTraits<OpIdft<bf16, TOut>>, OpIdft<bf16, TOut>> {
+  static constexpr int BN = 256;
+  static void operands(const OpIdft<bf16, TOut>& op, TmaOperand& a, TmaOperand& b) {
+    a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.M; a.dims[2] = 1;
+    a.strides[0] = (uint64_t)op.Kq2 * 2; a.batched = false;
+    b.base = op.Bm; b.dims[0] = op.N; b.dims[1] = op.K; b.dims[2] = 1;  // N-contiguous: {(b,o,kp), (m,ri)}
+    b.strides[0] = (uint64_t)op.b_sk * 2; b.batched = false;
+  }
+};
+
+template <class TOut>
+struct TcTraits<OpConv<bf16, TOut>> : TcTraitsBase<OpConv<bf16, TOut>>, TcEligible<TcTraits<OpConv<bf16, TOut>>, OpConv<bf16, TOut>> {
+  static constexpr int BN = 256;
+  static void operands(const OpConv<bf16, TOut>& op, TmaOperand& a, TmaOperand& b) {
+    a.base = op.A; a.dims[0] = op.M; a.dims[1] = op.K; a.dims[2] = op.G;  // M-contiguous: {pixel, channel, sample}
+    a.strides[0] = (uint64_t)op.M * 2; a.strides[1] = (uint64_t)op.in_bstride * 2; a.batched = true;
+    const bool wb = op.w_bstride != 0;
+    b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.N; b.dims[2] = wb ? op.G : 1;
+    b.strides[0] = (uint64_t)op.ldw * 2; b.strides[1] = (uint64_t)op.w_bstride * 2; b.batched = wb;
+  }
+};
+
+}  // namespace sfno

@@ -214,7 +214,7 @@ static OpConv<T, TOut> make_conv(int B, int P, int cin, int cout, const T* in, i
 template <class T>
 static int run_dft(const sfno_net* n, const ShtDeviceTables& t, int B, const T* x, int64_t x_bs, const float* a, const float* d, T* F, cudaStream_t st) {
   OpDft<T> op{};
-  op.G = 1; op.M = B * n->C * t.nlat; op.N = 2 * t.mmax; op.K = t.nlon;
+  op.G = B; op.M = n->C * t.nlat; op.N = 2 * t.mmax; op.K = t.nlon;
   op.A = x; op.Bm = (const T*)t.efwd; op.a_sk = 1; op.b_sk = 1;
   op.f = F; op.aff_a = a; op.aff_d = d;
   op.B = B; op.C = n->C; op.nlat = t.nlat; op.nlon = t.nlon; op.Kp = t.Kp; op.Wp = t.Wp; op.x_bstride = x_bs;

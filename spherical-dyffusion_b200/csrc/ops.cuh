@@ -21,27 +21,22 @@ namespace sfno {
 template <class T>
 struct OpDft {
   static constexpr bool A_KCONTIG = true, B_KCONTIG = true;
-  int G, M, N, K;
+  int G, M, N, K;  // G = B, M = C*nlat (rows (c,k) of one sample), N = 2*mmax, K = nlon
   const T* A; const T* Bm; int64_t a_sk, b_sk;
   T* f;
   const float* aff_a; const float* aff_d;  // [B*C] or nullptr
   int B, C, nlat, nlon, Kp, Wp;
   int64_t x_bstride;
 
-  __device__ int64_t a_off(int, int m) const {
-    int bc = m / nlat, k = m - bc * nlat;
-    int b = bc / C, c = bc - b * C;
-    return (int64_t)b * x_bstride + ((int64_t)c * nlat + k) * nlon;
-  }
+  __device__ int64_t a_off(int g, int m) const { return (int64_t)g * x_bstride + (int64_t)m * nlon; }
   __device__ int64_t b_off(int, int n) const { return (int64_t)n * Wp; }
   struct Row { int64_t base; float a, d; };
-  __device__ Row row(int, int m) const {
-    int bc = m / nlat, k = m - bc * nlat;
-    int b = bc / C, c = bc - b * C;
+  __device__ Row row(int g, int m) const {
+    int c = m / nlat, k = m - c * nlat;
     Row r;
-    r.base = (int64_t)b * 2 * C * Kp + (int64_t)c * Kp + k;
-    r.a = aff_a ? aff_a[bc] : 1.0f;
-    r.d = aff_d ? aff_d[bc] * 6.28318530717958647692f : 0.0f;
+    r.base = (int64_t)g * 2 * C * Kp + (int64_t)c * Kp + k;
+    r.a = aff_a ? aff_a[g * C + c] : 1.0f;
+    r.d = aff_d ? aff_d[g * C + c] * 6.28318530717958647692f : 0.0f;
     return r;
   }
   __device__ void store(const Row& r, int, int, int n, float acc) const {

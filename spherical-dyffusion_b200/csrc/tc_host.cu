@@ -1,0 +1,32 @@
+// Host helpers of the tensor-core engine: driver entry point for tensor-map encoding (resolved at run time so the
+// library does not link against libcuda and loads on a machine without a driver), SM count.
+#include "gemm_tc.cuh"
+
+namespace sfno {
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+int tc_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+}  // namespace sfno

@@ -1,0 +1,30 @@
+"""Runs one device-vs-device engine cross-check (sfno_b200_selftest_gemm) in its own process so that a trap in a
+tensor-core kernel cannot poison the CUDA context of the test session.  Prints one JSON line."""
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "spherical-dyffusion_b200", "libsfno_b200.so")
+
+
+def main():
+    op = int(sys.argv[1])
+    dims = [int(v) for v in sys.argv[2:]]
+    dims += [0] * (6 - len(dims))
+    lib = ctypes.CDLL(LIB)
+    lib.sfno_b200_selftest_gemm.restype = ctypes.c_int
+    lib.sfno_b200_selftest_gemm.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    lib.sfno_b200_last_error.restype = ctypes.c_char_p
+    res = (ctypes.c_double * 5)()
+    arr = (ctypes.c_int * len(dims))(*dims)
+    st = lib.sfno_b200_selftest_gemm(op, arr, len(dims), res)
+    out = {"status": st, "error": lib.sfno_b200_last_error().decode() if st else "", "max_err": res[0], "max_ref": res[1],
+           "tc_used": res[2], "ms": res[3], "nonfinite": res[4], "op": op, "dims": dims}
+    print(json.dumps(out))
+    return 0 if st == 0 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

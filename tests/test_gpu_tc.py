@@ -1,0 +1,62 @@
+"""Tensor-core engine (tcgen05 + TMA) vs CUDA-core engine on identical bf16 operands, per op and per operand
+layout (K-major / MN-major SWIZZLE_128B descriptors, batched and shared operands, K / M / N tails)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+OPS = {"dft": 0, "leg": 1, "dhconv": 2, "ileg": 3, "idft": 4, "conv": 5}
+
+CASES = [
+    # op, dims, expect tensor-core engine
+    ("leg", [1, 8, 16, 16, 9, 0], True),        # single tile, K = 16
+    ("leg", [2, 64, 180, 180, 5, 0], True),     # ACE geometry, few m
+    ("leg", [8, 256, 180, 180, 181, 0], True),  # ACE full size
+    ("dft", [1, 8, 16, 32, 17, 0], True),
+    ("dft", [2, 32, 180, 360, 181, 0], True),
+    ("dft", [8, 256, 180, 360, 181, 0], True),
+    ("dft", [1, 8, 18, 36, 19, 0], False),      # nlon*2 bytes not 16-byte aligned -> CUDA-core engine
+    ("dhconv", [1, 16, 4, 5, 0, 0], True),
+    ("dhconv", [2, 64, 20, 21, 0, 0], True),
+    ("dhconv", [8, 256, 180, 181, 0, 0], True),
+    ("ileg", [1, 8, 16, 16, 9, 0], True),
+    ("ileg", [1, 8, 16, 16, 9, 1], True),       # X layout (residual path)
+    ("ileg", [2, 64, 180, 180, 7, 0], True),
+    ("ileg", [8, 256, 180, 180, 181, 0], True),
+    ("idft", [1, 8, 16, 32, 17, 0], True),
+    ("idft", [2, 16, 180, 360, 181, 1], True),
+    ("idft", [8, 256, 180, 360, 181, 1], True),
+    ("conv", [1, 16, 16, 288, 0, 0], True),
+    ("conv", [2, 36, 256, 64800, 0, 1], True),   # encoder0-like: K = 36 (tail), epilogue
+    ("conv", [2, 256, 512, 64800, 1, 1], True),  # fc1-like: per-sample folded weights, 2 N tiles
+    ("conv", [2, 512, 256, 64800, 0, 1], True),  # fc2-like: K = 512
+    ("conv", [2, 292, 256, 64800, 0, 0], True),  # decoder0-like: K = 292 (tail)
+    ("conv", [2, 256, 34, 64800, 0, 0], True),   # decoder1-like: N = 34
+    ("conv", [8, 256, 256, 64800, 1, 1], True),  # inner-skip at ACE size
+]
+
+
+@pytest.mark.parametrize("op,dims,expect_tc", CASES, ids=[f"{c[0]}-{'x'.join(map(str, c[1]))}" for c in CASES])
+def test_tc_engine_matches_cuda_core_engine(op, dims, expect_tc):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "tc_selftest_cli.py"), str(OPS[op])] + [str(d) for d in dims]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    line = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else ""
+    assert line, f"no output; stderr: {p.stderr[-2000:]}"
+    r = json.loads(line)
+    print(json.dumps(r))
+    assert r["status"] == 0, r["error"]
+    assert bool(r["tc_used"]) == expect_tc
+    assert r["nonfinite"] == 0
+    assert r["max_ref"] > 0
+    # both engines accumulate in fp32; outputs are bf16 (1 ulp = 2^-8 relative) or fp32 (conv case)
+    tol = 2e-5 if op == "conv" else 1.2e-2
+    assert r["max_err"] <= tol * r["max_ref"], r
