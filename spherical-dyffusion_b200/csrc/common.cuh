@@ -99,4 +99,14 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t offset, 
   return (v >> 8) * (1.0f / 16777216.0f);
 }
 
+// four uniforms for the aligned group idx .. idx+3 (idx % 4 == 0): identical values to philox_uniform
+__device__ __forceinline__ void philox_uniform4(uint64_t seed, uint64_t offset, uint64_t idx, float& u0, float& u1, float& u2, float& u3) {
+  uint4 c = make_uint4((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), (uint32_t)offset, (uint32_t)(offset >> 32));
+  uint4 r = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  u0 = (r.x >> 8) * (1.0f / 16777216.0f);
+  u1 = (r.y >> 8) * (1.0f / 16777216.0f);
+  u2 = (r.z >> 8) * (1.0f / 16777216.0f);
+  u3 = (r.w >> 8) * (1.0f / 16777216.0f);
+}
+
 }  // namespace sfno

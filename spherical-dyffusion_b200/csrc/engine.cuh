@@ -2,6 +2,8 @@
 // tcgen05/TMA engine when the problem meets its alignment rules (gemm_tc.cuh), otherwise on the
 // CUDA-core engine with bf16 storage.  Both are device paths of this library; there is no host path.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -18,6 +20,38 @@ int launch_gemm(const Op& op, cudaStream_t stream, const char* what) {
     if (!g_force_simt.load(std::memory_order_relaxed) && TcTraits<Op>::eligible(op)) return launch_gemm_tc(op, stream, what);
   }
   return launch_gemm_simt(op, stream, what);
+}
+
+// 1x1 convolutions and the inverse DFT carry an activation / dropout in their epilogue: the tensor-core engine gets
+// instantiations with those fixed at compile time (no per-element branches), everything else takes the generic op.
+template <class T, class TOut>
+int launch_conv(const ConvArgs<T, TOut>& a, cudaStream_t stream, const char* what) {
+  using Gen = OpConv<T, TOut, -1, -1>;
+  const Gen gen(a);
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (!g_force_simt.load(std::memory_order_relaxed) && TcTraits<Gen>::eligible(gen)) {
+      if (a.drop_p == 0.0f) {
+        if (a.act == SFNO_ACT_GELU) return launch_gemm_tc(OpConv<T, TOut, SFNO_ACT_GELU, 0>(a), stream, what);
+        if (a.act == SFNO_ACT_NONE) return launch_gemm_tc(OpConv<T, TOut, SFNO_ACT_NONE, 0>(a), stream, what);
+      }
+      return launch_gemm_tc(gen, stream, what);
+    }
+  }
+  return launch_gemm_simt(gen, stream, what);
+}
+
+template <class T, class TOut>
+int launch_idft(const IdftArgs<T, TOut>& a, cudaStream_t stream, const char* what) {
+  using Gen = OpIdft<T, TOut, -1>;
+  const Gen gen(a);
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (!g_force_simt.load(std::memory_order_relaxed) && TcTraits<Gen>::eligible(gen)) {
+      if (a.act == SFNO_ACT_GELU) return launch_gemm_tc(OpIdft<T, TOut, SFNO_ACT_GELU>(a), stream, what);
+      if (a.act == SFNO_ACT_NONE) return launch_gemm_tc(OpIdft<T, TOut, SFNO_ACT_NONE>(a), stream, what);
+      return launch_gemm_tc(gen, stream, what);
+    }
+  }
+  return launch_gemm_simt(gen, stream, what);
 }
 
 }  // namespace sfno

@@ -3,7 +3,8 @@
 //   persistent CTAs (one per SM), 128 x BN output tile, K in blocks of 64 bf16 (one 128-byte swizzle span)
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, 3-D maps {inner, outer, batch})
 //   warp 1      : MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM, 2 stages)
-//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> op.store(): lane = M index = contiguous output index)
+//   warps 2..17 : epilogue       (tcgen05.ld 32x32b.x16 -> fused op epilogue; 4 warps per TMEM sub-partition, each a
+//                                 column slice; compact rolled loops so the code stays inside the instruction cache)
 //   smem ring of kStages {A tile, B tile}, mbarrier full/empty; TMEM full/empty barriers decouple the MMA of
 //   tile i+1 from the epilogue of tile i.
 //
@@ -19,7 +20,7 @@ namespace sfno {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 struct TmaOperand {
@@ -113,6 +114,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -142,20 +151,48 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn_major, bool b_mn_maj
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-template <int BN>
+constexpr int TC_STAGE_PITCH = 128;                       // bytes per staged row (one pass of an epilogue warp)
+constexpr int TC_STAGING_PER_WARP = 32 * TC_STAGE_PITCH;  // 32 rows
+
+template <int BN, bool kStaging>
 struct TcSmem {
   static constexpr int kABytes = TC_BM * TC_BK * 2;
   static constexpr int kBBytes = BN * TC_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 6 ? 6 : (200 * 1024) / kStageBytes;
+  static constexpr int kStagingBytes = kStaging ? TC_EPI_WARPS * TC_STAGING_PER_WARP : 0;
+  static constexpr int kBudget = 226 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/ - kStagingBytes;
+  static constexpr int kStages = kBudget / kStageBytes > 6 ? 6 : kBudget / kStageBytes;
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + alignment slack
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + kStagingBytes + 1024;
+  static_assert(kStages >= 2, "not enough shared memory for a pipeline");
 };
+
+// 16-byte shared-memory accessors
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
 
 template <class Op, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Op op, const TcSched sc) {
-  using S = TcSmem<BN>;
+  using S = TcSmem<BN, Op::kColContig>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = 512;  // two accumulator stages of up to 256 fp32 columns
   extern __shared__ uint8_t smem_raw[];
@@ -166,6 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t staging_base = bar_base + S::kBarrierBytes;
   auto a_smem = [&](int s) { return smem_base + s * S::kStageBytes; };
   auto b_smem = [&](int s) { return smem_base + s * S::kStageBytes + S::kABytes; };
 
@@ -191,11 +229,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // consecutive tiles (= concurrently running CTAs) share the operand that is re-read: the N tiles of one M tile
+  // when the activations sit on the A side (kNFastest), the M tiles of one N tile when they sit on the B side
   auto decode = [&](int tile, int& g, int& mt, int& nt) {
-    mt = tile % sc.m_tiles;
-    const int r = tile / sc.m_tiles;
-    nt = r % sc.n_tiles;
-    g = r / sc.n_tiles;
+    if (Op::kNFastest) {
+      nt = tile % sc.n_tiles;
+      const int r = tile / sc.n_tiles;
+      mt = r % sc.m_tiles;
+      g = r / sc.m_tiles;
+    } else {
+      mt = tile % sc.m_tiles;
+      const int r = tile / sc.m_tiles;
+      nt = r % sc.n_tiles;
+      g = r / sc.n_tiles;
+    }
   };
 
   if (warp == 0) {
@@ -262,35 +309,125 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else {
     // ===================== epilogue =====================
-    const int ew = warp - 2;              // 0..7
+    const int ew = warp - 2;              // 0..15
     const int quad = warp & 3;            // TMEM sub-partition this warp may read: lanes [32*quad, 32*quad+32)
-    const int half = ew >> 2;             // two warps per sub-partition split the columns
+    const int part = ew >> 2;             // four warps per sub-partition, each owns a column slice
     constexpr int kColsPerWarp = BN / (TC_EPI_WARPS / 4);
+    static_assert(kColsPerWarp % 16 == 0, "column slice must be a multiple of the TMEM load width");
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x) {
       int g, mt, nt;
       decode(tile, g, mt, nt);
       const int m = mt * TC_BM + quad * 32 + lane;
-      const int n_base = nt * BN + half * kColsPerWarp;
-      ptx::mbar_wait(tfull_bar(acc), acc_phase);
-      ptx::tc_fence_after();
+      const int n_base = nt * BN + part * kColsPerWarp;
       const bool row_ok = m < op.M;
       typename Op::Row row{};
       if (row_ok) row = op.row(g, m);
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * kColsPerWarp);
-#pragma unroll 1
-      for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
-        if (n_base + c0 >= op.N) break;  // warp-uniform
-        uint32_t r[32];
-        ptx::tmem_ld32(t_row + (uint32_t)c0, r);
-        ptx::tmem_ld_wait();
-        if (row_ok) {
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kColsPerWarp);
+      if constexpr (Op::kColContig) {
+        // ---- column-contiguous output: warp-private swizzled smem transpose, fully coalesced global traffic ----
+        using OutT = typename Op::OutT;
+        constexpr int kEs = (int)sizeof(OutT);
+        constexpr int kPassCols = TC_STAGE_PITCH / kEs;                 // 64 (bf16) or 32 (fp32) columns per pass
+        constexpr int kPasses = (kColsPerWarp + kPassCols - 1) / kPassCols;
+        constexpr int kVec = 16 / kEs;                                   // output elements per 16-byte chunk
+        const uint32_t region = staging_base + (uint32_t)ew * TC_STAGING_PER_WARP;
+        const uint32_t my_row = region + (uint32_t)lane * TC_STAGE_PITCH;
+        const uint32_t sw = (uint32_t)(lane & 7);
+        const int srow0 = lane >> 3, cl = lane & 7;                      // staging copies: 4 rows x 128 B per instruction
+        const int n_end = op.n_store();
+        const bool has_res = (kEs == 2) && op.has_res();
+        const bool valid = row_ok && row.valid;
+        const unsigned long long out_ptr = (unsigned long long)row.out;
+        const unsigned long long res_ptr = (unsigned long long)row.res;
+        // residual / addend block (bf16 outputs only): 8 coalesced 16-byte loads per lane issued BEFORE waiting for
+        // the accumulator, so their latency hides behind the MMA of this tile
+        uint4 res_pf[8];
+        if (has_res) {
+          int nv0 = n_end - n_base;
+          nv0 = nv0 < kColsPerWarp ? nv0 : kColsPerWarp;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n_base + c0 + j;
-            if (n < op.N) op.store(row, g, m, n, __uint_as_float(r[j]));
+          for (int i = 0; i < 8; ++i) {
+            const int srow = 4 * i + srow0;
+            const unsigned long long p = __shfl_sync(0xffffffffu, res_ptr, srow);
+            const bool ok = __shfl_sync(0xffffffffu, (int)valid, srow) && (cl * 8 < nv0);
+            res_pf[i] = make_uint4(0, 0, 0, 0);
+            if (ok) res_pf[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p) + n_base + cl * 8);
           }
+        }
+        ptx::mbar_wait(tfull_bar(acc), acc_phase);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int pass = 0; pass < kPasses; ++pass) {
+          const int pn0 = n_base + pass * kPassCols;
+          const int pcols = (kColsPerWarp - pass * kPassCols) < kPassCols ? (kColsPerWarp - pass * kPassCols) : kPassCols;
+          int nvalid = n_end - pn0;
+          nvalid = nvalid < pcols ? nvalid : pcols;
+          if (nvalid <= 0) break;  // warp-uniform
+          if (has_res) {           // (kPasses == 1 whenever has_res)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              sts128(region + (uint32_t)(4 * i + srow0) * TC_STAGE_PITCH + (((uint32_t)cl ^ (uint32_t)((4 * i + srow0) & 7)) << 4), res_pf[i]);
+            __syncwarp();
+          }
+          const int nchunks = (nvalid + 15) >> 4;
+#pragma unroll 1
+          for (int ci = 0; ci < nchunks; ++ci) {
+            uint32_t r[16];
+            ptx::tmem_ld16(t_row + (uint32_t)(pass * kPassCols + 16 * ci), r);
+            ptx::tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const int cofs = 16 * ci + 8 * q;  // column offset inside the pass
+                if (cofs < nvalid) {
+                  float accv[8], resv[8], outv[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) { accv[i] = __uint_as_float(r[8 * q + i]); resv[i] = 0.0f; }
+                  if constexpr (kEs == 2) {
+                    const uint32_t slot = my_row + ((((uint32_t)cofs >> 3) ^ sw) << 4);
+                    if (has_res) unpack_bf16x8(lds128(slot), resv);
+                    op.compute8(row, pn0 + cofs, accv, resv, outv);
+                    sts128(slot, make_uint4(pack_bf16x2(outv[0], outv[1]), pack_bf16x2(outv[2], outv[3]),
+                                            pack_bf16x2(outv[4], outv[5]), pack_bf16x2(outv[6], outv[7])));
+                  } else {
+                    op.compute8(row, pn0 + cofs, accv, resv, outv);
+                    const uint32_t c4 = (uint32_t)cofs >> 2;  // 16-byte chunk index (4 floats)
+                    sts128(my_row + ((c4 ^ sw) << 4), make_uint4(__float_as_uint(outv[0]), __float_as_uint(outv[1]),
+                                                                 __float_as_uint(outv[2]), __float_as_uint(outv[3])));
+                    sts128(my_row + (((c4 + 1) ^ sw) << 4), make_uint4(__float_as_uint(outv[4]), __float_as_uint(outv[5]),
+                                                                       __float_as_uint(outv[6]), __float_as_uint(outv[7])));
+                  }
+                }
+              }
+            }
+          }
+          __syncwarp();
+          // staged rows -> global: 4 rows x 128 B per warp instruction
+#pragma unroll 2
+          for (int i = 0; i < 8; ++i) {
+            const int srow = 4 * i + srow0;
+            const unsigned long long p = __shfl_sync(0xffffffffu, out_ptr, srow);
+            const bool ok = __shfl_sync(0xffffffffu, (int)valid, srow) && (cl * kVec < nvalid);
+            const uint4 v = lds128(region + (uint32_t)srow * TC_STAGE_PITCH + (((uint32_t)cl ^ (uint32_t)(srow & 7)) << 4));
+            if (ok) *reinterpret_cast<uint4*>(reinterpret_cast<OutT*>(p) + pn0 + cl * kVec) = v;
+          }
+          __syncwarp();
+        }
+      } else {
+        // ---- row-contiguous output: for a fixed column the warp writes 32 consecutive elements ----
+        ptx::mbar_wait(tfull_bar(acc), acc_phase);
+        ptx::tc_fence_after();
+        const int n_end = op.N;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
+          const int n0 = n_base + c0;
+          if (n0 >= n_end) break;  // warp-uniform
+          uint32_t r[16];
+          ptx::tmem_ld16(t_row + (uint32_t)c0, r);
+          ptx::tmem_ld_wait();
+          if (row_ok) op.store16(row, g, m, n0, n_end - n0, r);
         }
       }
       ptx::tc_fence_before();
@@ -348,7 +485,7 @@ template <class Op>
 int launch_gemm_tc(const Op& op, cudaStream_t stream, const char* what) {
   using Tr = TcTraits<Op>;
   constexpr int BN = Tr::BN;
-  using S = TcSmem<BN>;
+  using S = TcSmem<BN, Op::kColContig>;
   if (op.M <= 0 || op.N <= 0 || op.G <= 0) return SFNO_OK;
   TmaOperand a, b;
   Tr::operands(op, a, b);

@@ -9,14 +9,16 @@ namespace sfno {
 template <class Op>
 struct TcTraitsBase {
   static constexpr bool kAvailable = true;
+  static bool extra_ok(const Op&) { return true; }  // vector-store alignment rules of the epilogue, if any
 };
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 template <class Derived, class Op>
 struct TcEligible {
   static bool eligible(const Op& op) {
     TmaOperand a, b;
     Derived::operands(op, a, b);
-    return tma_operand_ok(a) && tma_operand_ok(b) && op.M > 0 && op.N > 0 && op.K > 0;
+    return tma_operand_ok(a) && tma_operand_ok(b) && op.M > 0 && op.N > 0 && op.K > 0 && Derived::extra_ok(op);
   }
 };
 
@@ -55,35 +57,46 @@ struct TcTraits<OpDhconv<bf16>> : TcTraitsBase<OpDhconv<bf16>>, TcEligible<TcTra
 
 template <>
 struct TcTraits<OpIleg<bf16>> : TcTraitsBase<OpIleg<bf16>>, TcEligible<TcTraits<OpIleg<bf16>>, OpIleg<bf16>> {
-  static constexpr int BN = 256;
+  static constexpr int BN = 192;
   static void operands(const OpIleg<bf16>& op, TmaOperand& a, TmaOperand& b) {
-    a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.nlat; a.dims[2] = op.G;
-    a.strides[0] = (uint64_t)op.Lq * 2; a.strides[1] = (uint64_t)op.nlat * op.Lq * 2; a.batched = true;
-    b.base = op.Bm; b.dims[0] = op.N; b.dims[1] = op.K; b.dims[2] = op.G;  // N-contiguous: {n, l, m}
-    b.strides[0] = (uint64_t)op.b_sk * 2; b.strides[1] = (uint64_t)op.b_goff * 2; b.batched = true;
+    a.base = op.A; a.dims[0] = op.M; a.dims[1] = op.K; a.dims[2] = op.G;  // M-contiguous: {(b,ri,o), l, m}
+    a.strides[0] = (uint64_t)op.a_sk * 2; a.strides[1] = (uint64_t)op.a_goff * 2; a.batched = true;
+    b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.nlat; b.dims[2] = op.G;
+    b.strides[0] = (uint64_t)op.Lq * 2; b.strides[1] = (uint64_t)op.nlat * op.Lq * 2; b.batched = true;
+  }
+  static bool extra_ok(const OpIleg<bf16>& op) { return aligned16(op.g_out) && op.Kp % 8 == 0; }
+};
+
+template <class TOut, int ACT>
+struct TcTraits<OpIdft<bf16, TOut, ACT>> : TcTraitsBase<OpIdft<bf16, TOut, ACT>>,
+                                             TcEligible<TcTraits<OpIdft<bf16, TOut, ACT>>, OpIdft<bf16, TOut, ACT>> {
+  static constexpr int BN = 192;
+  static void operands(const OpIdft<bf16, TOut, ACT>& op, TmaOperand& a, TmaOperand& b) {
+    a.base = op.A; a.dims[0] = op.M; a.dims[1] = op.K; a.dims[2] = 1;  // M-contiguous: {(b,o,kp), (m,ri)}
+    a.strides[0] = (uint64_t)op.a_sk * 2; a.batched = false;
+    b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.N; b.dims[2] = 1;
+    b.strides[0] = (uint64_t)op.Kq2 * 2; b.batched = false;
+  }
+  static bool extra_ok(const OpIdft<bf16, TOut, ACT>& op) {
+    return op.nlon % 8 == 0 && op.out_bstride % 8 == 0 && aligned16(op.out) &&
+           (!op.add || (sizeof(TOut) == 2 && aligned16(op.add) && op.add_bstride % 8 == 0));
   }
 };
 
-template <class TOut>
-struct TcTraits<OpIdft<bf16, TOut>> : TcTraitsBase<OpIdft<bf16, TOut>>, TcEligible<TcTraits<OpIdft<bf16, TOut>>, OpIdft<bf16, TOut>> {
+template <class TOut, int ACT, int DROP>
+struct TcTraits<OpConv<bf16, TOut, ACT, DROP>> : TcTraitsBase<OpConv<bf16, TOut, ACT, DROP>>,
+                                                   TcEligible<TcTraits<OpConv<bf16, TOut, ACT, DROP>>, OpConv<bf16, TOut, ACT, DROP>> {
   static constexpr int BN = 256;
-  static void operands(const OpIdft<bf16, TOut>& op, TmaOperand& a, TmaOperand& b) {
-    a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.M; a.dims[2] = 1;
-    a.strides[0] = (uint64_t)op.Kq2 * 2; a.batched = false;
-    b.base = op.Bm; b.dims[0] = op.N; b.dims[1] = op.K; b.dims[2] = 1;  // N-contiguous: {(b,o,kp), (m,ri)}
-    b.strides[0] = (uint64_t)op.b_sk * 2; b.batched = false;
-  }
-};
-
-template <class TOut>
-struct TcTraits<OpConv<bf16, TOut>> : TcTraitsBase<OpConv<bf16, TOut>>, TcEligible<TcTraits<OpConv<bf16, TOut>>, OpConv<bf16, TOut>> {
-  static constexpr int BN = 256;
-  static void operands(const OpConv<bf16, TOut>& op, TmaOperand& a, TmaOperand& b) {
-    a.base = op.A; a.dims[0] = op.M; a.dims[1] = op.K; a.dims[2] = op.G;  // M-contiguous: {pixel, channel, sample}
-    a.strides[0] = (uint64_t)op.M * 2; a.strides[1] = (uint64_t)op.in_bstride * 2; a.batched = true;
+  static void operands(const OpConv<bf16, TOut, ACT, DROP>& op, TmaOperand& a, TmaOperand& b) {
     const bool wb = op.w_bstride != 0;
-    b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.N; b.dims[2] = wb ? op.G : 1;
-    b.strides[0] = (uint64_t)op.ldw * 2; b.strides[1] = (uint64_t)op.w_bstride * 2; b.batched = wb;
+    a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.M; a.dims[2] = wb ? op.G : 1;  // weights [o][c], K-contiguous
+    a.strides[0] = (uint64_t)op.ldw * 2; a.strides[1] = (uint64_t)op.w_bstride * 2; a.batched = wb;
+    b.base = op.Bm; b.dims[0] = op.N; b.dims[1] = op.K; b.dims[2] = op.G;  // N-contiguous: {pixel, channel, sample}
+    b.strides[0] = (uint64_t)op.N * 2; b.strides[1] = (uint64_t)op.in_bstride * 2; b.batched = true;
+  }
+  static bool extra_ok(const OpConv<bf16, TOut, ACT, DROP>& op) {
+    return op.N % 8 == 0 && op.out_bstride % 8 == 0 && aligned16(op.out) &&
+           (!op.res || (sizeof(TOut) == 2 && aligned16(op.res) && op.res_bstride % 8 == 0)) && (!op.pos || aligned16(op.pos));
   }
 };
 

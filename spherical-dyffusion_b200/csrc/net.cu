@@ -198,11 +198,11 @@ static int set_param_impl(sfno_net* n, const std::string& name, const float* v, 
 
 // ---- op builders ---------------------------------------------------------------------------------------------
 template <class T, class TOut>
-static OpConv<T, TOut> make_conv(int B, int P, int cin, int cout, const T* in, int64_t in_bs, const T* w, int64_t w_bs, int ldw,
+static ConvArgs<T, TOut> make_conv(int B, int P, int cin, int cout, const T* in, int64_t in_bs, const T* w, int64_t w_bs, int ldw,
                                  const float* bias, int64_t bias_bs, int act, TOut* out, int64_t out_bs) {
-  OpConv<T, TOut> op{};
-  op.G = B; op.M = P; op.N = cout; op.K = cin;
-  op.A = in; op.Bm = w; op.a_sk = P; op.b_sk = 1;
+  ConvArgs<T, TOut> op{};
+  op.G = B; op.M = cout; op.N = P; op.K = cin;
+  op.A = w; op.Bm = in; op.a_sk = 1; op.b_sk = P;
   op.in_bstride = in_bs; op.w_bstride = w_bs; op.ldw = ldw;
   op.bias = bias; op.bias_bstride = bias_bs; op.act = act;
   op.drop_p = 0.0f; op.seed = 0; op.offset = 0; op.branch_scale = nullptr;
@@ -231,22 +231,22 @@ static int run_leg(const sfno_net* n, const ShtDeviceTables& t, int B, const T* 
 template <class T>
 static int run_ileg(const sfno_net* n, const ShtDeviceTables& t, int B, const T* S, bool x_layout, T* G, cudaStream_t st) {
   OpIleg<T> op{};
-  op.G = t.mmax; op.M = t.nlat; op.N = B * 2 * n->C; op.K = t.lmax;
-  op.A = (const T*)t.pt; op.Bm = S; op.a_sk = 1;
-  if (x_layout) { op.b_goff = op.N; op.b_sk = (int64_t)t.mmax * op.N; }
-  else { op.b_goff = (int64_t)t.lmax * op.N; op.b_sk = op.N; }
+  op.G = t.mmax; op.M = B * 2 * n->C; op.N = t.nlat; op.K = t.lmax;
+  op.A = S; op.Bm = (const T*)t.pt; op.b_sk = 1;
+  if (x_layout) { op.a_goff = op.M; op.a_sk = (int64_t)t.mmax * op.M; }
+  else { op.a_goff = (int64_t)t.lmax * op.M; op.a_sk = op.M; }
   op.g_out = G; op.B = B; op.C = n->C; op.Kp = t.Kp; op.Lq = t.Lq; op.nlat = t.nlat;
   return launch_gemm(op, st, "legendre_inv");
 }
 template <class T>
 static int run_idft(const sfno_net* n, const ShtDeviceTables& t, int B, const T* G, const float* bias, const T* add, int64_t add_bs,
                     int act, T* out, int64_t out_bs, cudaStream_t st) {
-  OpIdft<T, T> op{};
-  op.G = 1; op.M = t.nlon; op.N = B * n->C * t.Kp; op.K = 2 * t.mmax;
-  op.A = (const T*)t.einv; op.Bm = G; op.a_sk = 1; op.b_sk = op.N;
+  IdftArgs<T, T> op{};
+  op.G = 1; op.M = B * n->C * t.Kp; op.N = t.nlon; op.K = 2 * t.mmax;
+  op.A = G; op.Bm = (const T*)t.einv; op.a_sk = op.M; op.b_sk = 1;
   op.out = out; op.out_bstride = out_bs; op.bias = bias; op.add = add; op.add_bstride = add_bs; op.act = act;
   op.C = n->C; op.nlat = t.nlat; op.nlon = t.nlon; op.Kp = t.Kp; op.Kq2 = t.Kq2;
-  return launch_gemm(op, st, "dft_inv");
+  return launch_idft(op, st, "dft_inv");
 }
 
 template <class T>
@@ -276,9 +276,6 @@ static int forward_impl(sfno_net* n, const float* x_in, const float* time, float
   const int64_t xcat_bs = (int64_t)n->Ccat * P;
   const int BC = B * C;
 
-  // pads of the longitude-spectral buffer must be finite zeros (they meet zero table entries)
-  SFNO_CUDA(cudaMemsetAsync(FG, 0, (size_t)n->M * B * 2 * C * n->lg_grid.Kp * sizeof(T), st));
-
   // ---- input: fp32 -> T, and into the tail channels of the big-skip concat buffer (sfnonet.py:804-805,832)
   {
     const int64_t per = (int64_t)n->Cin * P;
@@ -300,10 +297,10 @@ static int forward_impl(sfno_net* n, const float* x_in, const float* time, float
   // ---- encoder (sfnonet.py:610-618) + position embedding (sfnonet.py:824)
   {
     auto e0 = make_conv<T, T>(B, P, n->Cin, C, xin, (int64_t)n->Cin * P, (const T*)n->enc0_w, 0, n->Cin_p, n->enc0_b, 0, cfg.activation, t1, CP);
-    SFNO_TRY(launch_gemm(e0, st, "encoder0"));
+    SFNO_TRY(launch_conv(e0, st, "encoder0"));
     auto e1 = make_conv<T, T>(B, P, C, C, t1, CP, (const T*)n->enc1_w, 0, C, nullptr, 0, SFNO_ACT_NONE, cur, cur_bs);
     e1.pos = cfg.pos_embed ? (const T*)n->pos : nullptr;
-    SFNO_TRY(launch_gemm(e1, st, "encoder1"));
+    SFNO_TRY(launch_conv(e1, st, "encoder1"));
   }
   n->last_x_off = (size_t)((char*)cur - ws); n->last_x_bstride = cur_bs; n->last_batch = B;
   // ---- time embedding (misc.py:145-147) and all per-block time MLPs (sfnonet.py:210-213) up front
@@ -332,7 +329,7 @@ static int forward_impl(sfno_net* n, const float* x_in, const float* time, float
     // norm0 (+ time scale/shift before the filter) as a per-(b,c) affine  (sfnonet.py:290-299)
     const bool time_before = cfg.with_time_emb && cfg.time_scale_shift_before_filter;
     if (cfg.instance_norm) {
-      instance_stats_kernel<T><<<BC, 512, 0, st>>>(cur, cur_bs, C, P, cfg.norm_eps, mean, rstd);
+      launch_instance_stats<T>(cur, cur_bs, B, C, P, cfg.norm_eps, mean, rstd, st);
       SFNO_TRY(post_launch("instance_stats0"));
     }
     norm_affine_kernel<<<ceil_div(BC, 256), 256, 0, st>>>(cfg.instance_norm ? mean : nullptr, rstd, bp.norm0_g, bp.norm0_b,
@@ -364,18 +361,18 @@ static int forward_impl(sfno_net* n, const float* x_in, const float* time, float
     // folded into per-sample weights.  Output lands in t1, then the inverse DFT adds itself + bias, applies GELU.
     if (scale_residual) {
       auto sk = make_conv<T, T>(B, P, C, C, res, CP, (const T*)bp.skip_wT, 0, C, bp.skip_b, 0, SFNO_ACT_NONE, t1, CP);
-      SFNO_TRY(launch_gemm(sk, st, "inner_skip"));
+      SFNO_TRY(launch_conv(sk, st, "inner_skip"));
     } else {
       fold_affine_weight_kernel<T><<<B * C, 128, 0, st>>>(bp.skip_w32, bp.skip_b, a0, d0, C, C, C, skip_wb, skip_bb);
       SFNO_TRY(post_launch("fold_skip"));
       auto sk = make_conv<T, T>(B, P, C, C, cur, cur_bs, skip_wb, (int64_t)C * C, C, skip_bb, C, SFNO_ACT_NONE, t1, CP);
-      SFNO_TRY(launch_gemm(sk, st, "inner_skip"));
+      SFNO_TRY(launch_conv(sk, st, "inner_skip"));
     }
     SFNO_TRY(run_idft<T>(n, inv, B, FG, bp.spec_bias, t1, CP, cfg.activation, t1, CP, st));
 
     // norm1 (+ time scale/shift after the filter) folded into fc1  (sfnonet.py:313-323)
     if (cfg.instance_norm) {
-      instance_stats_kernel<T><<<BC, 512, 0, st>>>(t1, CP, C, P, cfg.norm_eps, mean, rstd);
+      launch_instance_stats<T>(t1, CP, B, C, P, cfg.norm_eps, mean, rstd, st);
       SFNO_TRY(post_launch("instance_stats1"));
     }
     const bool time_after = cfg.with_time_emb && !cfg.time_scale_shift_before_filter;
@@ -397,13 +394,13 @@ static int forward_impl(sfno_net* n, const float* x_in, const float* time, float
     SFNO_TRY(post_launch("fold_fc1"));
     auto f1 = make_conv<T, T>(B, P, C, hid, t1, CP, fc1_wb, (int64_t)hid * C, C, fc1_bb, hid, cfg.activation, hd, (int64_t)hid * P);
     f1.drop_p = pdrop; f1.seed = seed; f1.offset = offset + (uint64_t)i * 4 + 0;
-    SFNO_TRY(launch_gemm(f1, st, "mlp_fc1"));
+    SFNO_TRY(launch_conv(f1, st, "mlp_fc1"));
     auto f2 = make_conv<T, T>(B, P, hid, C, hd, (int64_t)hid * P, (const T*)bp.fc2_wT, 0, hid, bp.fc2_b, 0, SFNO_ACT_NONE, nxt, nxt_bs);
     f2.drop_p = pdrop; f2.seed = seed; f2.offset = offset + (uint64_t)i * 4 + 1;
     f2.branch_scale = use_dp ? dscale : nullptr;
     if (scale_residual) { f2.res = res; f2.res_bstride = CP; }
     else { f2.res = cur; f2.res_bstride = cur_bs; f2.res_a = a0; f2.res_d = d0; }
-    SFNO_TRY(launch_gemm(f2, st, "mlp_fc2"));
+    SFNO_TRY(launch_conv(f2, st, "mlp_fc2"));
 
     cur = nxt; cur_bs = nxt_bs;
     n->last_x_off = (size_t)((char*)cur - ws); n->last_x_bstride = cur_bs;
@@ -414,9 +411,9 @@ static int forward_impl(sfno_net* n, const float* x_in, const float* time, float
   {
     const int kin = cfg.big_skip ? n->Ccat : C;
     auto d0c = make_conv<T, T>(B, P, kin, C, cur, cur_bs, (const T*)n->dec0_w, 0, n->Ccat_p, n->dec0_b, 0, cfg.activation, t1, CP);
-    SFNO_TRY(launch_gemm(d0c, st, "decoder0"));
+    SFNO_TRY(launch_conv(d0c, st, "decoder0"));
     auto d1c = make_conv<T, float>(B, P, C, n->Cout, t1, CP, (const T*)n->dec1_w, 0, C, nullptr, 0, SFNO_ACT_NONE, y, (int64_t)n->Cout * P);
-    SFNO_TRY(launch_gemm(d1c, st, "decoder1"));
+    SFNO_TRY(launch_conv(d1c, st, "decoder1"));
   }
   return SFNO_OK;
 }

@@ -1,11 +1,18 @@
 // GEMM "ops": every contraction on the SFNO hot path expressed as a batched GEMM
 //     D[g][m][n] = sum_k A[g](m,k) * B[g](n,k)          (fp32 accumulate)
-// plus a fused epilogue.  An op describes operand addressing (row offset + k stride), the problem
-// size and the epilogue; the engines (gemm_simt.cuh: fp32 CUDA cores; gemm_tc.cuh: tcgen05 + TMA)
-// are templated on the op.  Orientation of each GEMM is chosen so that the M index (TMEM lane /
-// thread row) is the contiguous index of the OUTPUT tensor -> coalesced stores without staging.
+// plus a fused epilogue.  An op describes operand addressing (row offset + k stride), the problem size and the
+// epilogue; the engines (gemm_simt.cuh: fp32 CUDA cores; gemm_tc.cuh: tcgen05 + TMA) are templated on the op.
 //
-// Internal tensor layouts (T = float or bf16; Kp = nlat rounded up to 8; pads are kept zero):
+// In the tensor-core engine one thread owns one output row m (a TMEM lane) and walks the columns n.  Two epilogue
+// styles follow from the layout of the OUTPUT tensor:
+//   kColContig = false : the row index m is the contiguous output index -> for a fixed column the 32 lanes of a warp
+//                        write 32 consecutive elements (coalesced scalar stores); store16() walks the columns with
+//                        incremental addressing.  (forward DFT, forward Legendre, dhconv)
+//   kColContig = true  : the column index n is the contiguous output index -> the thread writes 16-byte vectors along
+//                        its own row and every per-row quantity (bias, affine, decoded indices) lives in registers;
+//                        compute8().  (inverse Legendre, inverse DFT, 1x1 convolutions)
+//
+// Internal tensor layouts (T = float or bf16; Kp = nlat rounded up to 8):
 //   grid   x  [B][C][nlat][nlon]                      (NCHW, as the reference)
 //   F, G      [mmax][B][2][C][Kp]   /  [mmax][2][B][C][Kp]     longitude-spectral, latitude contiguous
 //   X, Y      [lmax][mmax][B][2][C] /  [mmax][lmax][B][2][C]   spectral, channel contiguous
@@ -14,13 +21,66 @@
 
 namespace sfno {
 
+// GELU for the bf16 epilogues: 0.5 x (1 + tanh(x (a + b x^2))) with (a, b) fitted to the exact erf form (max abs
+// deviation 2.7e-4) and the MUFU tanh (rel. error 2^-11): together < 1/4 of a bf16 rounding step of the result, at
+// 7 instructions instead of ~20 for an erf evaluation.  The fp32 path keeps the exact erff form (gelu_exact).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float x2 = x * x;
+  const float u = x * fmaf(0.03470089f, x2, 0.80015708f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
+template <class T>
+__device__ __forceinline__ float act_for(int act, float x) {
+  if constexpr (sizeof(T) == 2) {
+    if (act == SFNO_ACT_GELU) return gelu_fast(x);
+  }
+  return apply_act(act, x);
+}
+// ACT >= 0: activation fixed at compile time (bf16 tensor-core instantiations); ACT < 0: runtime value
+template <class T, int ACT>
+__device__ __forceinline__ float act_ct(int act_rt, float x) {
+  if constexpr (ACT == SFNO_ACT_NONE) return x;
+  else if constexpr (ACT == SFNO_ACT_GELU) return sizeof(T) == 2 ? gelu_fast(x) : gelu_exact(x);
+  else return act_for<T>(act_rt, x);
+}
+
+// pack 8 floats -> 8 x T and store as one (bf16) or two (fp32) 16-byte vectors; p must be 16-byte aligned
+__device__ __forceinline__ void store_vec8(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void store_vec8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void load_vec8(const bf16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void load_vec8(const float* p, float (&v)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 // ------------------------------------------------------------------------------------------------
-// forward longitude DFT (K1 of SURVEY 2.3): rows (b,c,k) x nlon -> F, fused InstanceNorm/time affine:
-//   F = a[b,c] * DFT(x) + d[b,c] * 2*pi * [m==0, re]       (DFT is linear; DFT(1) = 2*pi*delta_m0)
+// forward longitude DFT (K1 of SURVEY 2.3), one GEMM per sample: rows (c,k) x nlon -> F, fused
+// InstanceNorm/time affine:   F = a[b,c] * DFT(x) + d[b,c] * 2*pi * [m==0, re]   (DFT(1) = 2*pi*delta_m0)
 // ------------------------------------------------------------------------------------------------
 template <class T>
 struct OpDft {
-  static constexpr bool A_KCONTIG = true, B_KCONTIG = true;
+  static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = false, kNFastest = true;
   int G, M, N, K;  // G = B, M = C*nlat (rows (c,k) of one sample), N = 2*mmax, K = nlon
   const T* A; const T* Bm; int64_t a_sk, b_sk;
   T* f;
@@ -44,6 +104,17 @@ struct OpDft {
     float v = r.a * acc + (n == 0 ? r.d : 0.0f);
     f[(int64_t)mm * B * 2 * C * Kp + (int64_t)ri * C * Kp + r.base] = from_f32<T>(v);
   }
+  // columns n0 .. n0+15 (n0 even): n = 2*mm + ri -> alternate strides
+  __device__ void store16(const Row& r, int, int, int n0, int nvalid, const uint32_t (&acc)[16]) const {
+    const int64_t s_m = (int64_t)B * 2 * C * Kp, s_ri = (int64_t)C * Kp;
+    T* p = f + r.base + (int64_t)(n0 >> 1) * s_m;
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      if (j < nvalid) p[0] = from_f32<T>(fmaf(r.a, __uint_as_float(acc[j]), (n0 + j) == 0 ? r.d : 0.0f));
+      if (j + 1 < nvalid) p[s_ri] = from_f32<T>(r.a * __uint_as_float(acc[j + 1]));
+      p += s_m;
+    }
+  }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -51,7 +122,7 @@ struct OpDft {
 // ------------------------------------------------------------------------------------------------
 template <class T>
 struct OpLeg {
-  static constexpr bool A_KCONTIG = true, B_KCONTIG = true;
+  static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = false, kNFastest = false;
   int G, M, N, K;  // G = mmax, M = B*2*C, N = lmax, K = nlat
   const T* A; const T* Bm; int64_t a_sk, b_sk;
   T* x;
@@ -63,6 +134,15 @@ struct OpLeg {
   __device__ void store(const Row& r, int, int, int n, float acc) const {
     x[(int64_t)n * mmax * M + r.base] = from_f32<T>(acc);
   }
+  __device__ void store16(const Row& r, int, int, int n0, int nvalid, const uint32_t (&acc)[16]) const {
+    const int64_t s_l = (int64_t)mmax * M;
+    T* p = x + r.base + (int64_t)n0 * s_l;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < nvalid) *p = from_f32<T>(__uint_as_float(acc[j]));
+      p += s_l;
+    }
+  }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -72,7 +152,7 @@ struct OpLeg {
 // ------------------------------------------------------------------------------------------------
 template <class T>
 struct OpDhconv {
-  static constexpr bool A_KCONTIG = true, B_KCONTIG = true;
+  static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = false, kNFastest = false;
   int G, M, N, K;  // G = lmax, M = 2*Cout, N = mmax*B, K = 2*Cin
   const T* A; const T* Bm; int64_t a_sk, b_sk;
   T* y;
@@ -85,73 +165,111 @@ struct OpDhconv {
     int mm = n / B, b = n - mm * B;
     y[(int64_t)mm * lmax * B * M + (int64_t)b * M + r.base] = from_f32<T>(acc);
   }
-};
-
-// ------------------------------------------------------------------------------------------------
-// inverse Legendre (K4), flipped so latitude k is the M index: per m,
-//   D[k, (b,ri,o)] = sum_l Pt[m][k][l] * Y[m][l][(b,ri,o)]  -> G[m][ri][b][o][k]
-// ------------------------------------------------------------------------------------------------
-template <class T>
-struct OpIleg {
-  static constexpr bool A_KCONTIG = true, B_KCONTIG = false;
-  int G, M, N, K;  // G = mmax, M = nlat, N = B*2*C, K = lmax
-  const T* A; const T* Bm; int64_t a_sk, b_sk;
-  T* g_out;
-  int B, C, Kp, Lq, nlat;
-  int64_t b_goff;  // Y layout [m][l][n]: b_goff = lmax*N, b_sk = N;  X layout [l][m][n]: b_goff = N, b_sk = mmax*N
-  __device__ int64_t a_off(int g, int m) const { return ((int64_t)g * nlat + m) * Lq; }
-  __device__ int64_t b_off(int g, int n) const { return (int64_t)g * b_goff + n; }  // + l * b_sk
-  struct Row { int64_t base; };
-  __device__ Row row(int g, int m) const { return Row{(int64_t)g * 2 * B * C * Kp + m}; }
-  __device__ void store(const Row& r, int, int, int n, float acc) const {
-    int b = n / (2 * C), rem = n - b * 2 * C;
-    int ri = rem / C, o = rem - ri * C;
-    g_out[r.base + (int64_t)ri * B * C * Kp + ((int64_t)b * C + o) * Kp] = from_f32<T>(acc);
+  __device__ void store16(const Row& r, int, int, int n0, int nvalid, const uint32_t (&acc)[16]) const {
+    const int64_t s_m = (int64_t)lmax * B * M;
+    int mm = n0 / B, b = n0 - mm * B;
+    T* p = y + r.base + (int64_t)mm * s_m + (int64_t)b * M;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < nvalid) *p = from_f32<T>(__uint_as_float(acc[j]));
+      p += M;
+      if (++b == B) { b = 0; p += s_m - (int64_t)B * M; }
+    }
   }
 };
 
 // ------------------------------------------------------------------------------------------------
-// inverse longitude DFT (K5), flipped so longitude j is the M index:
-//   D[j, (b,o,kp)] = sum_(m,ri) Einv[j][(m,ri)] * G[(m,ri)][(b,o,kp)]
-//   epilogue: + bias[o] + add[b][o][k][j] -> act -> out[b][o][k][j]   (bias of SpectralConvS2,
-//   inner-skip sum and GELU of FourierNeuralOperatorBlock.forward fused: sfnonet.py:308-311)
+// inverse Legendre (K4): per m, rows (b,ri,o), columns = latitude k (contiguous in G):
+//   D[(b,ri,o), k] = sum_l S[m][l][(b,ri,o)] * Pt[m][k][l]  -> G[m][ri][b][o][k]
+//   S is Y [m][l][rows] (a_goff = lmax*rows, a_sk = rows) or X [l][m][rows] (a_goff = rows, a_sk = mmax*rows)
+// ------------------------------------------------------------------------------------------------
+template <class T>
+struct OpIleg {
+  static constexpr bool A_KCONTIG = false, B_KCONTIG = true, kColContig = true, kNFastest = true;
+  using OutT = T;
+  int G, M, N, K;  // G = mmax, M = B*2*C, N = nlat, K = lmax
+  const T* A; const T* Bm; int64_t a_sk, b_sk;
+  int64_t a_goff;
+  T* g_out;
+  int B, C, Kp, Lq, nlat;
+  __device__ int64_t a_off(int g, int m) const { return (int64_t)g * a_goff + m; }   // + l * a_sk
+  __device__ int64_t b_off(int g, int n) const { return ((int64_t)g * nlat + n) * Lq; }
+  __device__ int n_store() const { return Kp; }  // columns [nlat, Kp) are exact zeros (zero-filled table rows)
+  __device__ bool has_res() const { return false; }
+  struct Row { T* out; const T* res; bool valid; };
+  __device__ Row row(int g, int m) const {
+    int b = m / (2 * C), rem = m - b * 2 * C;
+    int ri = rem / C, o = rem - ri * C;
+    return Row{g_out + (int64_t)g * 2 * B * C * Kp + (int64_t)ri * B * C * Kp + ((int64_t)b * C + o) * Kp, nullptr, true};
+  }
+  __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = from_f32<T>(acc); }
+  __device__ void compute8(const Row&, int, const float (&acc)[8], const float (&)[8], float (&o)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = acc[i];
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// inverse longitude DFT (K5): rows (b,o,kp), columns = longitude j (contiguous in the output):
+//   D[(b,o,kp), j] = sum_(m,ri) G[(m,ri)][(b,o,kp)] * Einv[j][(m,ri)]
+//   epilogue: + bias[o] + add[b][o][k][j] -> act -> out[b][o][k][j]   (bias of SpectralConvS2, inner-skip sum and
+//   GELU of FourierNeuralOperatorBlock.forward fused: s2convolutions.py:188-189, sfnonet.py:308-311)
 // ------------------------------------------------------------------------------------------------
 template <class T, class TOut>
-struct OpIdft {
-  static constexpr bool A_KCONTIG = true, B_KCONTIG = false;
-  int G, M, N, K;  // G = 1, M = nlon, N = B*C*Kp, K = 2*mmax
+struct IdftArgs {
+  int G, M, N, K;  // G = 1, M = B*C*Kp, N = nlon, K = 2*mmax
   const T* A; const T* Bm; int64_t a_sk, b_sk;
   TOut* out; int64_t out_bstride;
   const float* bias;                      // [C] or nullptr
   const T* add; int64_t add_bstride;      // [B][C][nlat][nlon] or nullptr
   int act;
   int C, nlat, nlon, Kp, Kq2;
-  __device__ int64_t a_off(int, int m) const { return (int64_t)m * Kq2; }
-  __device__ int64_t b_off(int, int n) const { return n; }  // + kk * N
-  struct Row { int j; };
-  __device__ Row row(int, int m) const { return Row{m}; }
+};
+template <class T, class TOut, int ACT = -1>
+struct OpIdft : IdftArgs<T, TOut> {
+  static constexpr bool A_KCONTIG = false, B_KCONTIG = true, kColContig = true, kNFastest = true;
+  using OutT = TOut;
+  using Args = IdftArgs<T, TOut>;
+  OpIdft() = default;
+  __host__ __device__ explicit OpIdft(const Args& a) : Args(a) {}
+  __device__ int64_t a_off(int, int m) const { return m; }  // + kk * a_sk
+  __device__ int64_t b_off(int, int n) const { return (int64_t)n * this->Kq2; }
+  __device__ int n_store() const { return this->N; }
+  __device__ bool has_res() const { return this->add != nullptr; }
+  struct Row { TOut* out; const T* res; bool valid; float bias; };
+  __device__ Row row(int, int m) const {
+    int bo = m / this->Kp, k = m - bo * this->Kp;
+    int b = bo / this->C, o = bo - b * this->C;
+    Row r;
+    r.valid = k < this->nlat;
+    const int64_t pix = ((int64_t)o * this->nlat + k) * this->nlon;
+    r.out = this->out + (int64_t)b * this->out_bstride + pix;
+    r.res = this->add ? this->add + (int64_t)b * this->add_bstride + pix : nullptr;
+    r.bias = this->bias ? this->bias[o] : 0.0f;
+    return r;
+  }
   __device__ void store(const Row& r, int, int, int n, float acc) const {
-    int bo = n / Kp, k = n - bo * Kp;
-    if (k >= nlat) return;
-    int b = bo / C, o = bo - b * C;
-    int64_t pix = ((int64_t)o * nlat + k) * nlon + r.j;
-    float v = acc + (bias ? bias[o] : 0.0f);
-    if (add) v += to_f32(add[(int64_t)b * add_bstride + pix]);
-    v = apply_act(act, v);
-    out[(int64_t)b * out_bstride + pix] = from_f32<TOut>(v);
+    if (!r.valid) return;
+    float v = acc + r.bias;
+    if (r.res) v += to_f32(r.res[n]);
+    r.out[n] = from_f32<TOut>(act_ct<T, ACT>(this->act, v));
+  }
+  __device__ void compute8(const Row& r, int, const float (&acc)[8], const float (&res)[8], float (&o)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = act_ct<T, ACT>(this->act, acc[i] + r.bias + res[i]);
   }
 };
 
 // ------------------------------------------------------------------------------------------------
-// 1x1 convolution (K6) per sample: D[p, o] = sum_c in[b][c][p] * w[(b)][o][c], pixel index p is M.
+// 1x1 convolution (K6) per sample, output channel o is the row, pixel p the (contiguous) column:
+//   D[o, p] = sum_c w[(b)][o][c] * in[b][c][p]
 // epilogue (all optional): + bias[(b)][o] -> act -> dropout -> * branch_scale[b]
 //                          + residual (optionally affine: ra[b,o]*res + rd[b,o]) + pos[o][p]
 // ------------------------------------------------------------------------------------------------
 template <class T, class TOut>
-struct OpConv {
-  static constexpr bool A_KCONTIG = false, B_KCONTIG = true;
-  int G, M, N, K;  // G = batch, M = hw, N = cout, K = cin
-  const T* A; const T* Bm; int64_t a_sk, b_sk;
+struct ConvArgs {
+  int G, M, N, K;  // G = batch, M = cout, N = hw, K = cin
+  const T* A; const T* Bm; int64_t a_sk, b_sk;   // A = weights, Bm = input activations (b_sk = hw)
   int64_t in_bstride;
   int64_t w_bstride; int ldw;            // w_bstride = 0 for shared weights
   const float* bias; int64_t bias_bstride;
@@ -162,26 +280,68 @@ struct OpConv {
   const float* res_a; const float* res_d; // [batch*cout] affine on the residual or nullptr
   const T* pos;                           // [cout][hw] or nullptr
   TOut* out; int64_t out_bstride;
-  __device__ int64_t a_off(int g, int m) const { return (int64_t)g * in_bstride + m; }  // + c * hw
-  __device__ int64_t b_off(int g, int n) const { return (int64_t)g * w_bstride + (int64_t)n * ldw; }
-  struct Row { int p; };
-  __device__ Row row(int, int m) const { return Row{m}; }
-  __device__ void store(const Row& r, int g, int, int n, float acc) const {
-    float v = acc + (bias ? bias[(int64_t)g * bias_bstride + n] : 0.0f);
-    v = apply_act(act, v);
-    int64_t pix = (int64_t)n * M + r.p;
-    if (drop_p > 0.0f) {
-      float u = philox_uniform(seed, offset, (uint64_t)g * N * M + pix);
-      v = (u >= drop_p) ? v * (1.0f / (1.0f - drop_p)) : 0.0f;
+};
+// ACT / DROP < 0: decided at run time (CUDA-core engine and rarely used combinations)
+template <class T, class TOut, int ACT = -1, int DROP = -1>
+struct OpConv : ConvArgs<T, TOut> {
+  static constexpr bool A_KCONTIG = true, B_KCONTIG = false, kColContig = true, kNFastest = false;
+  using OutT = TOut;
+  using Args = ConvArgs<T, TOut>;
+  OpConv() = default;
+  __host__ __device__ explicit OpConv(const Args& a) : Args(a) {}
+  __device__ int64_t a_off(int g, int m) const { return (int64_t)g * this->w_bstride + (int64_t)m * this->ldw; }
+  __device__ int64_t b_off(int g, int n) const { return (int64_t)g * this->in_bstride + n; }  // + c * hw
+  __device__ int n_store() const { return this->N; }
+  __device__ bool has_res() const { return this->res != nullptr; }
+  struct Row { TOut* out; const T* res; bool valid; const T* pos; float bias, ra, rd, scale; uint64_t rng_base; };
+  __device__ Row row(int g, int m) const {
+    Row r;
+    const int64_t off = (int64_t)m * this->N;
+    r.valid = true;
+    r.out = this->out + (int64_t)g * this->out_bstride + off;
+    r.res = this->res ? this->res + (int64_t)g * this->res_bstride + off : nullptr;
+    r.pos = this->pos ? this->pos + off : nullptr;
+    r.bias = this->bias ? this->bias[(int64_t)g * this->bias_bstride + m] : 0.0f;
+    r.ra = this->res_a ? this->res_a[g * this->M + m] : 1.0f;
+    r.rd = this->res_d ? this->res_d[g * this->M + m] : 0.0f;
+    r.scale = this->branch_scale ? this->branch_scale[g] : 1.0f;
+    r.rng_base = ((uint64_t)g * this->M + m) * (uint64_t)this->N;
+    return r;
+  }
+  __device__ bool dropping() const {
+    if constexpr (DROP == 0) return false;
+    else return this->drop_p > 0.0f;
+  }
+  __device__ float finish_value(const Row& r, float acc, float u) const {
+    float v = act_ct<T, ACT>(this->act, acc + r.bias);
+    if (dropping()) v = (u >= this->drop_p) ? __fdividef(v, 1.0f - this->drop_p) : 0.0f;
+    return v * r.scale;
+  }
+  __device__ void store(const Row& r, int, int, int n, float acc) const {
+    const float u = dropping() ? philox_uniform(this->seed, this->offset, r.rng_base + n) : 1.0f;
+    float v = finish_value(r, acc, u);
+    if (r.res) v += fmaf(r.ra, to_f32(r.res[n]), r.rd);
+    if (r.pos) v += to_f32(r.pos[n]);
+    r.out[n] = from_f32<TOut>(v);
+  }
+  __device__ void compute8(const Row& r, int n, const float (&acc)[8], const float (&res)[8], float (&o)[8]) const {
+    float u[8];
+    if (dropping()) {
+      philox_uniform4(this->seed, this->offset, r.rng_base + n, u[0], u[1], u[2], u[3]);
+      philox_uniform4(this->seed, this->offset, r.rng_base + n + 4, u[4], u[5], u[6], u[7]);
     }
-    if (branch_scale) v *= branch_scale[g];
-    if (res) {
-      float rv = to_f32(res[(int64_t)g * res_bstride + pix]);
-      if (res_a) rv = res_a[g * N + n] * rv + res_d[g * N + n];
-      v += rv;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = finish_value(r, acc[i], dropping() ? u[i] : 1.0f);
+    if (r.res) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += fmaf(r.ra, res[i], r.rd);
     }
-    if (pos) v += to_f32(pos[pix]);
-    out[(int64_t)g * out_bstride + pix] = from_f32<TOut>(v);
+    if (r.pos) {
+      float t[8];
+      load_vec8(r.pos + n, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += t[i];
+    }
   }
 };
 

@@ -32,19 +32,51 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
   return sh[32];
 }
 
-// ---- InstanceNorm statistics: one CTA per (b, c) plane, two passes (second pass hits L2) ----------------
-// nn.InstanceNorm2d semantics (sfnonet.py:641-647): biased variance over H*W.
-template <class T>
-static __global__ void __launch_bounds__(512) instance_stats_kernel(const T* __restrict__ x, int64_t bstride, int C,
+// ---- InstanceNorm statistics: one CTA per (b, c) plane ------------------------------------------------------
+// nn.InstanceNorm2d semantics (sfnonet.py:641-647): biased variance over H*W, exact two-pass (mean, then centred
+// sum of squares).  The plane is read from HBM ONCE: each thread keeps its 16-byte vectors in registers between the
+// passes (kVecs x 16 B x blockDim covers planes up to 64 Ki bf16 / 32 Ki fp32 elements per 512 threads); larger or
+// unaligned planes take the second pass from L2 / HBM.
+template <class T, int kVecs>
+__global__ void __launch_bounds__(512) instance_stats_kernel(const T* __restrict__ x, int64_t bstride, int C,
                                                               int64_t hw, float eps, float* __restrict__ mean_out,
                                                               float* __restrict__ rstd_out) {
   __shared__ float sh[33];
+  constexpr int kPer = 16 / (int)sizeof(T);
   const int bc = blockIdx.x, b = bc / C, c = bc - b * C;
   const T* p = x + (int64_t)b * bstride + (int64_t)c * hw;
-  float s = 0.0f;
+  const bool in_regs = (hw % kPer == 0) && (((uintptr_t)p & 15) == 0) && (hw <= (int64_t)kVecs * kPer * blockDim.x);
+  float s = 0.0f, q = 0.0f;
+  if (in_regs) {
+    const int64_t nvec = hw / kPer;
+    uint4 v[kVecs];
+#pragma unroll
+    for (int i = 0; i < kVecs; ++i) {
+      const int64_t idx = (int64_t)i * blockDim.x + threadIdx.x;
+      v[i] = idx < nvec ? reinterpret_cast<const uint4*>(p)[idx] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < kVecs; ++i) {
+      const T* e = reinterpret_cast<const T*>(&v[i]);
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) s += to_f32(e[k]);  // padding vectors are zeros
+    }
+    const float mean = block_sum(s, sh) / (float)hw;
+#pragma unroll
+    for (int i = 0; i < kVecs; ++i) {
+      const int64_t idx = (int64_t)i * blockDim.x + threadIdx.x;
+      if (idx < nvec) {
+        const T* e = reinterpret_cast<const T*>(&v[i]);
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) { const float d = to_f32(e[k]) - mean; q = fmaf(d, d, q); }
+      }
+    }
+    const float var = block_sum(q, sh) / (float)hw;
+    if (threadIdx.x == 0) { mean_out[bc] = mean; rstd_out[bc] = rsqrtf(var + eps); }
+    return;
+  }
   for (int64_t i = threadIdx.x; i < hw; i += blockDim.x) s += to_f32(p[i]);
   const float mean = block_sum(s, sh) / (float)hw;
-  float q = 0.0f;
   for (int64_t i = threadIdx.x; i < hw; i += blockDim.x) {
     float d = to_f32(p[i]) - mean;
     q = fmaf(d, d, q);
@@ -54,6 +86,11 @@ static __global__ void __launch_bounds__(512) instance_stats_kernel(const T* __r
     mean_out[bc] = mean;
     rstd_out[bc] = rsqrtf(var + eps);
   }
+}
+template <class T>
+inline void launch_instance_stats(const T* x, int64_t bstride, int B, int C, int64_t hw, float eps, float* mean, float* rstd, cudaStream_t st) {
+  // bf16: 16 vectors x 8 elements x 512 threads = 65536 elements; fp32: 32 vectors x 4 x 512 = 65536 elements
+  instance_stats_kernel<T, (sizeof(T) == 2 ? 16 : 32)><<<B * C, 512, 0, st>>>(x, bstride, C, hw, eps, mean, rstd);
 }
 
 // ---- per-(b,c) affine of "InstanceNorm -> time_scale_shift" (sfnonet.py:280-287,292-299) -----------------

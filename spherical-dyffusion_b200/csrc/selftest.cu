@@ -61,8 +61,13 @@ struct Scratch {
   }
 };
 
-template <class Op, class TOut, class SetOut>
-static int run_both(Op op, int64_t out_elems, SetOut set_out, Scratch& s, double* res) {
+template <class Op>
+struct DefaultTc {
+  int operator()(const Op& op) const { return launch_gemm_tc(op, 0, "selftest_tc"); }
+};
+
+template <class Op, class TOut, class SetOut, class TcLaunch = DefaultTc<Op>>
+static int run_both(Op op, int64_t out_elems, SetOut set_out, Scratch& s, double* res, TcLaunch tc_launch = TcLaunch()) {
   TOut* o0 = s.get<TOut>(out_elems, true);
   TOut* o1 = s.get<TOut>(out_elems, true);
   unsigned int* stats = s.get<unsigned int>(2, true);
@@ -77,9 +82,9 @@ static int run_both(Op op, int64_t out_elems, SetOut set_out, Scratch& s, double
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   float ms = 0.0f;
   if (tc_ok) {
-    SFNO_TRY(launch_gemm_tc(op, 0, "selftest_tc"));      // warm-up (+ correctness run)
+    SFNO_TRY(tc_launch(op));      // warm-up (+ correctness run)
     cudaEventRecord(e0, 0);
-    for (int i = 0; i < 5; ++i) SFNO_TRY(launch_gemm_tc(op, 0, "selftest_tc"));
+    for (int i = 0; i < 5; ++i) SFNO_TRY(tc_launch(op));
     cudaEventRecord(e1, 0);
   } else {
     SFNO_TRY(launch_gemm_simt(op, 0, "selftest_simt"));
@@ -139,39 +144,64 @@ extern "C" int sfno_b200_selftest_gemm(int op_kind, const int* d, int nd, double
       const int B = d[0], C = d[1], nlat = d[2], lmax = d[3], mmax = d[4], xl = d[5];
       const int Kp = round_up(nlat, Kr), Lq = round_up(lmax, Kr);
       OpIleg<bf16> op{};
-      op.G = mmax; op.M = nlat; op.N = B * 2 * C; op.K = lmax;
-      op.A = s.rnd((int64_t)mmax * nlat * Lq, 9, 0.1f); op.Bm = s.rnd((int64_t)lmax * mmax * op.N, 10); op.a_sk = 1;
-      if (xl) { op.b_goff = op.N; op.b_sk = (int64_t)mmax * op.N; } else { op.b_goff = (int64_t)lmax * op.N; op.b_sk = op.N; }
+      op.G = mmax; op.M = B * 2 * C; op.N = nlat; op.K = lmax;
+      op.A = s.rnd((int64_t)lmax * mmax * op.M, 10); op.Bm = s.rnd((int64_t)mmax * nlat * Lq, 9, 0.1f); op.b_sk = 1;
+      if (xl) { op.a_goff = op.M; op.a_sk = (int64_t)mmax * op.M; } else { op.a_goff = (int64_t)lmax * op.M; op.a_sk = op.M; }
       op.B = B; op.C = C; op.Kp = Kp; op.Lq = Lq; op.nlat = nlat;
       return run_both<OpIleg<bf16>, bf16>(op, (int64_t)mmax * 2 * B * C * Kp, [](OpIleg<bf16>& o, bf16* p) { o.g_out = p; }, s, res);
     }
-    case 4: {  // IDFT: B, C, nlat, nlon, mmax, with_epilogue
+    case 4: {  // IDFT: B, C, nlat, nlon, mmax, epilogue bitmask (1 bias, 2 gelu, 4 add)
       const int B = d[0], C = d[1], nlat = d[2], nlon = d[3], mmax = d[4], epi = d[5];
       const int Kp = round_up(nlat, Kr), Kq2 = round_up(2 * mmax, Kr);
       OpIdft<bf16, bf16> op{};
-      op.G = 1; op.M = nlon; op.N = B * C * Kp; op.K = 2 * mmax;
-      op.A = s.rnd((int64_t)nlon * Kq2, 11, 0.1f); op.Bm = s.rnd((int64_t)2 * mmax * op.N, 12); op.a_sk = 1; op.b_sk = op.N;
+      op.G = 1; op.M = B * C * Kp; op.N = nlon; op.K = 2 * mmax;
+      op.A = s.rnd((int64_t)2 * mmax * op.M, 12); op.Bm = s.rnd((int64_t)nlon * Kq2, 11, 0.1f); op.a_sk = op.M; op.b_sk = 1;
       op.out_bstride = (int64_t)C * nlat * nlon;
-      op.bias = epi ? s.rndf(C, 13) : nullptr;
-      op.add = epi ? s.rnd((int64_t)B * C * nlat * nlon, 14) : nullptr; op.add_bstride = op.out_bstride;
-      op.act = epi ? SFNO_ACT_GELU : SFNO_ACT_NONE;
+      op.bias = (epi & 1) ? s.rndf(C, 13) : nullptr;
+      op.add = (epi & 4) ? s.rnd((int64_t)B * C * nlat * nlon, 14) : nullptr; op.add_bstride = op.out_bstride;
+      op.act = (epi & 2) ? SFNO_ACT_GELU : SFNO_ACT_NONE;
       op.C = C; op.nlat = nlat; op.nlon = nlon; op.Kp = Kp; op.Kq2 = Kq2;
-      return run_both<OpIdft<bf16, bf16>, bf16>(op, (int64_t)B * C * nlat * nlon, [](OpIdft<bf16, bf16>& o, bf16* p) { o.out = p; }, s, res);
+      auto tc = [](const OpIdft<bf16, bf16>& o) {  // same compile-time specialisation as launch_idft
+        const IdftArgs<bf16, bf16>& a = o;
+        if (a.act == SFNO_ACT_GELU) return launch_gemm_tc(OpIdft<bf16, bf16, SFNO_ACT_GELU>(a), 0, "selftest_tc");
+        return launch_gemm_tc(OpIdft<bf16, bf16, SFNO_ACT_NONE>(a), 0, "selftest_tc");
+      };
+      return run_both<OpIdft<bf16, bf16>, bf16>(op, (int64_t)B * C * nlat * nlon, [](OpIdft<bf16, bf16>& o, bf16* p) { o.out = p; }, s, res, tc);
     }
-    case 5: {  // CONV: B, cin, cout, P, batched_w, epilogue
+    case 5: case 6: {  // CONV: B, cin, cout, P, batched_w, epilogue bitmask (1 bias, 2 gelu, 4 res+affine, 8 pos, 16 dropout); 6: bf16 out
       const int B = d[0], cin = d[1], cout = d[2], P = d[3], bw = d[4], epi = d[5];
       const int ldw = round_up(cin, Kr);
-      OpConv<bf16, float> op{};
-      op.G = B; op.M = P; op.N = cout; op.K = cin;
-      op.A = s.rnd((int64_t)B * cin * P, 15); op.Bm = s.rnd((int64_t)(bw ? B : 1) * cout * ldw, 16, 0.1f); op.a_sk = P; op.b_sk = 1;
-      op.in_bstride = (int64_t)cin * P; op.w_bstride = bw ? (int64_t)cout * ldw : 0; op.ldw = ldw;
-      op.bias = epi ? s.rndf((int64_t)B * cout, 17) : nullptr; op.bias_bstride = cout;
-      op.act = epi ? SFNO_ACT_GELU : SFNO_ACT_NONE;
-      op.drop_p = 0.0f; op.branch_scale = nullptr;
-      op.res = epi ? s.rnd((int64_t)B * cout * P, 18) : nullptr; op.res_bstride = (int64_t)cout * P;
-      op.res_a = epi ? s.rndf((int64_t)B * cout, 19) : nullptr; op.res_d = epi ? s.rndf((int64_t)B * cout, 20) : nullptr;
-      op.pos = nullptr; op.out_bstride = (int64_t)cout * P;
-      return run_both<OpConv<bf16, float>, float>(op, (int64_t)B * cout * P, [](OpConv<bf16, float>& o, float* p) { o.out = p; }, s, res);
+      auto fill = [&](auto& op) {
+        op.G = B; op.M = cout; op.N = P; op.K = cin;
+        op.A = s.rnd((int64_t)(bw ? B : 1) * cout * ldw, 16, 0.1f); op.Bm = s.rnd((int64_t)B * cin * P, 15); op.a_sk = 1; op.b_sk = P;
+        op.in_bstride = (int64_t)cin * P; op.w_bstride = bw ? (int64_t)cout * ldw : 0; op.ldw = ldw;
+        op.bias = (epi & 1) ? s.rndf((int64_t)B * cout, 17) : nullptr; op.bias_bstride = cout;
+        op.act = (epi & 2) ? SFNO_ACT_GELU : SFNO_ACT_NONE;
+        op.drop_p = (epi & 16) ? 0.1f : 0.0f; op.seed = 1234; op.offset = 77; op.branch_scale = nullptr;
+        op.res = (epi & 4) ? s.rnd((int64_t)B * cout * P, 18) : nullptr; op.res_bstride = (int64_t)cout * P;
+        op.res_a = (epi & 4) ? s.rndf((int64_t)B * cout, 19) : nullptr; op.res_d = (epi & 4) ? s.rndf((int64_t)B * cout, 20) : nullptr;
+        op.pos = (epi & 8) ? s.rnd((int64_t)cout * P, 21) : nullptr; op.out_bstride = (int64_t)cout * P;
+      };
+      if (op_kind == 5) {
+        OpConv<bf16, float> op{};
+        fill(op);
+        auto tc = [](const OpConv<bf16, float>& o) {
+          const ConvArgs<bf16, float>& a = o;
+          if (a.drop_p == 0.0f && a.act == SFNO_ACT_GELU) return launch_gemm_tc(OpConv<bf16, float, SFNO_ACT_GELU, 0>(a), 0, "selftest_tc");
+          if (a.drop_p == 0.0f && a.act == SFNO_ACT_NONE) return launch_gemm_tc(OpConv<bf16, float, SFNO_ACT_NONE, 0>(a), 0, "selftest_tc");
+          return launch_gemm_tc(o, 0, "selftest_tc");
+        };
+        return run_both<OpConv<bf16, float>, float>(op, (int64_t)B * cout * P, [](OpConv<bf16, float>& o, float* p) { o.out = p; }, s, res, tc);
+      }
+      OpConv<bf16, bf16> op{};
+      fill(op);
+      auto tc = [](const OpConv<bf16, bf16>& o) {
+        const ConvArgs<bf16, bf16>& a = o;
+        if (a.drop_p == 0.0f && a.act == SFNO_ACT_GELU) return launch_gemm_tc(OpConv<bf16, bf16, SFNO_ACT_GELU, 0>(a), 0, "selftest_tc");
+        if (a.drop_p == 0.0f && a.act == SFNO_ACT_NONE) return launch_gemm_tc(OpConv<bf16, bf16, SFNO_ACT_NONE, 0>(a), 0, "selftest_tc");
+        return launch_gemm_tc(o, 0, "selftest_tc");
+      };
+      return run_both<OpConv<bf16, bf16>, bf16>(op, (int64_t)B * cout * P, [](OpConv<bf16, bf16>& o, bf16* p) { o.out = p; }, s, res, tc);
     }
     default:
       return fail(SFNO_ERR_INVALID_ARGUMENT, "unknown selftest op %d", op_kind);

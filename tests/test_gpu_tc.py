@@ -12,8 +12,9 @@ from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 
-OPS = {"dft": 0, "leg": 1, "dhconv": 2, "ileg": 3, "idft": 4, "conv": 5}
+OPS = {"dft": 0, "leg": 1, "dhconv": 2, "ileg": 3, "idft": 4, "conv": 5, "convb": 6}
 
+# conv / idft epilogue bitmask: 1 bias, 2 gelu, 4 residual (+ per-row affine), 8 pos-embed, 16 dropout
 CASES = [
     # op, dims, expect tensor-core engine
     ("leg", [1, 8, 16, 16, 9, 0], True),        # single tile, K = 16
@@ -31,15 +32,23 @@ CASES = [
     ("ileg", [2, 64, 180, 180, 7, 0], True),
     ("ileg", [8, 256, 180, 180, 181, 0], True),
     ("idft", [1, 8, 16, 32, 17, 0], True),
-    ("idft", [2, 16, 180, 360, 181, 1], True),
-    ("idft", [8, 256, 180, 360, 181, 1], True),
+    ("idft", [2, 16, 180, 360, 181, 7], True),
+    ("idft", [8, 256, 180, 360, 181, 7], True),   # block epilogue: + bias + inner-skip -> GELU
+    ("idft", [8, 256, 180, 360, 181, 0], True),   # residual path: plain inverse
     ("conv", [1, 16, 16, 288, 0, 0], True),
-    ("conv", [2, 36, 256, 64800, 0, 1], True),   # encoder0-like: K = 36 (tail), epilogue
-    ("conv", [2, 256, 512, 64800, 1, 1], True),  # fc1-like: per-sample folded weights, 2 N tiles
-    ("conv", [2, 512, 256, 64800, 0, 1], True),  # fc2-like: K = 512
-    ("conv", [2, 292, 256, 64800, 0, 0], True),  # decoder0-like: K = 292 (tail)
-    ("conv", [2, 256, 34, 64800, 0, 0], True),   # decoder1-like: N = 34
-    ("conv", [8, 256, 256, 64800, 1, 1], True),  # inner-skip at ACE size
+    ("conv", [2, 36, 256, 64800, 0, 3], True),    # fp32 output, K = 36 (tail), bias + GELU
+    ("conv", [2, 292, 256, 64800, 0, 0], True),   # decoder0-like: K = 292 (tail)
+    ("conv", [2, 256, 34, 64800, 0, 0], True),    # decoder1: cout = 34 rows, fp32 output
+    ("conv", [2, 256, 64, 64800, 0, 5], False),   # fp32 output with a residual -> CUDA-core engine (not on the hot path)
+    ("conv", [2, 64, 96, 1024, 0, 19], True),     # dropout epilogue: identical Philox masks in both engines
+    ("convb", [2, 36, 256, 64800, 0, 3], True),   # encoder0
+    ("convb", [2, 256, 256, 64800, 0, 8], True),  # encoder1: + pos-embed
+    ("convb", [8, 256, 256, 64800, 1, 1], True),  # inner skip: per-sample folded weights + bias
+    ("convb", [8, 256, 512, 64800, 1, 3], True),  # fc1 at ACE size: folded weights, bias, GELU
+    ("convb", [8, 512, 256, 64800, 0, 5], True),  # fc2 at ACE size: bias + affine residual
+    ("convb", [2, 512, 256, 64800, 0, 21], True), # fc2 with dropout (interpolator)
+    ("convb", [2, 256, 256, 64800, 1, 15], True), # everything but dropout
+    ("convb", [1, 16, 16, 300, 0, 0], False),     # hw not a multiple of 8 -> CUDA-core engine
 ]
 
 
@@ -59,4 +68,5 @@ def test_tc_engine_matches_cuda_core_engine(op, dims, expect_tc):
     assert r["max_ref"] > 0
     # both engines accumulate in fp32; outputs are bf16 (1 ulp = 2^-8 relative) or fp32 (conv case)
     tol = 2e-5 if op == "conv" else 1.2e-2
+
     assert r["max_err"] <= tol * r["max_ref"], r
