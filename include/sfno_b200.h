@@ -158,6 +158,12 @@ size_t sfno_net_workspace_bytes(const sfno_net* net, int batch);
 int sfno_net_forward(sfno_net* net, const float* x_dev, const float* time_dev, float* y_dev, int batch,
                      int dropout_enabled, uint64_t seed, uint64_t offset,
                      void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Same forward with the channel concat of BaseModel.concat_condition_if_needed (_base_model.py:166-192) fused into the
+ * input conversion: parts_dev[k] is fp32 [batch][part_channels[k]][nlat][nlon] (inputs, condition, static_condition in
+ * that order; 1 <= nparts <= 3, channel counts must add up to in_chans). */
+int sfno_net_forward_parts(sfno_net* net, const float* const* parts_dev, const int* part_channels, int nparts,
+                           const float* time_dev, float* y_dev, int batch, int dropout_enabled, uint64_t seed, uint64_t offset,
+                           void* workspace_dev, size_t workspace_bytes, void* stream);
 /* Per-net test switch: "stop_after_block" = -2 run everything (default), -1 stop after encoder + pos-embed,
  * i stop after block i (the output tensor is then left untouched; read the state with sfno_net_debug_tap). */
 int sfno_net_set_option(sfno_net* net, const char* key, int64_t value);

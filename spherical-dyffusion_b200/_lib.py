@@ -64,6 +64,8 @@ _SIGNATURES = {
     "sfno_net_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "sfno_net_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_uint64, c_uint64, c_void_p,
                                  c_size_t, c_void_p]),
+    "sfno_net_forward_parts": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int), c_int, c_void_p, c_void_p, c_int, c_int,
+                                       c_uint64, c_uint64, c_void_p, c_size_t, c_void_p]),
     "sfno_net_set_option": (c_int, [c_void_p, c_char_p, c_int64]),
     "sfno_net_debug_tap": (c_int64, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "sfno_ensemble_accumulate": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),

@@ -24,6 +24,25 @@ int launch_gemm(const Op& op, cudaStream_t stream, const char* what) {
 
 // 1x1 convolutions and the inverse DFT carry an activation / dropout in their epilogue: the tensor-core engine gets
 // instantiations with those fixed at compile time (no per-element branches), everything else takes the generic op.
+// true when launch_conv / launch_idft will take the tensor-core engine (which can fuse InstanceNorm statistics)
+template <class T, class TOut>
+bool conv_uses_tc(const ConvArgs<T, TOut>& a) {
+  if constexpr (std::is_same<T, bf16>::value) {
+    using Gen = OpConv<T, TOut, -1, -1>;
+    return !g_force_simt.load(std::memory_order_relaxed) && TcTraits<Gen>::eligible(Gen(a));
+  }
+  return false;
+}
+template <class T, class TOut>
+bool idft_uses_tc(const IdftArgs<T, TOut>& a) {
+  if constexpr (std::is_same<T, bf16>::value) {
+    using Gen = OpIdft<T, TOut, -1>;
+    return !g_force_simt.load(std::memory_order_relaxed) && TcTraits<Gen>::eligible(Gen(a));
+  }
+  return false;
+}
+constexpr int kConvStatSlicesPerTile = TC_EPI_WARPS / 4;
+
 template <class T, class TOut>
 int launch_conv(const ConvArgs<T, TOut>& a, cudaStream_t stream, const char* what) {
   using Gen = OpConv<T, TOut, -1, -1>;

@@ -415,6 +415,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           __syncwarp();
         }
+        if (row_ok) op.finish(row, g, m, nt * (TC_EPI_WARPS / 4) + part);  // fused statistics partials (if enabled)
       } else {
         // ---- row-contiguous output: for a fixed column the warp writes 32 consecutive elements ----
         ptx::mbar_wait(tfull_bar(acc), acc_phase);

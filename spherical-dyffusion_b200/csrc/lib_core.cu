@@ -166,7 +166,7 @@ static int sht_inverse_impl(const ShtDeviceTables& t, const float* coeffs, float
   id.G = 1; id.M = C * t.Kp; id.N = t.nlon; id.K = 2 * t.mmax;
   id.A = Gb; id.Bm = (const T*)t.einv; id.a_sk = id.M; id.b_sk = 1;
   id.out = x; id.out_bstride = 0; id.bias = nullptr; id.add = nullptr; id.add_bstride = 0; id.act = SFNO_ACT_NONE;
-  id.C = C; id.nlat = t.nlat; id.nlon = t.nlon; id.Kp = t.Kp; id.Kq2 = t.Kq2;
+  id.C = C; id.nlat = t.nlat; id.nlon = t.nlon; id.Kp = t.Kp; id.Kq2 = t.Kq2; id.stat_part = nullptr;
   (void)xt;
   return launch_idft(id, st, "dft_inv");
 }
@@ -357,7 +357,7 @@ int sfno_conv1x1(const float* x_dev, const float* weight_dev, const float* bias_
   op.bias = bias_dev; op.bias_bstride = 0; op.act = activation;
   op.drop_p = 0.0f; op.seed = 0; op.offset = 0; op.branch_scale = nullptr;
   op.res = residual_dev; op.res_bstride = (int64_t)cout * hw; op.res_a = nullptr; op.res_d = nullptr; op.pos = nullptr;
-  op.out = y_dev; op.out_bstride = (int64_t)cout * hw;
+  op.out = y_dev; op.out_bstride = (int64_t)cout * hw; op.stat_part = nullptr;
   return launch_conv(op, (cudaStream_t)stream, "conv1x1");
 }
 

@@ -31,7 +31,7 @@ struct BlockParams {
 
 struct WsLayout {
   size_t xin, buf0, xcat, t1, res, hid, fg, X, Y;
-  size_t mean, rstd, a0, d0, a1, d1, tsin, th, trepr, ts, skip_wb, skip_bb, fc1_wb, fc1_bb, dscale;
+  size_t mean, rstd, a0, d0, a1, d1, tsin, th, trepr, ts, skip_wb, skip_bb, fc1_wb, fc1_bb, dscale, stat_part;
   size_t total;
 };
 
@@ -100,6 +100,12 @@ static WsLayout ws_layout(const sfno_net* n, int B) {
   w.fc1_wb = take((size_t)B * std::max(n->hid, 1) * n->C * e);
   w.fc1_bb = take((size_t)B * std::max(n->hid, 1) * sizeof(float));
   w.dscale = take((size_t)B * sizeof(float));
+  {  // per-slice partial sums of the fused InstanceNorm statistics (tensor-core epilogues)
+    const size_t conv_slices = (size_t)ceil_div(n->P, 256) * kConvStatSlicesPerTile;
+    const size_t idft_slices = (size_t)ceil_div(n->cfg.nlon, 192) * kConvStatSlicesPerTile;
+    const size_t conv_f = conv_slices * 2 * (size_t)B * n->C, idft_f = idft_slices * 2 * (size_t)B * n->C * Kp;
+    w.stat_part = take(std::max(conv_f, idft_f) * sizeof(float));
+  }
   w.total = off;
   return w;
 }
@@ -207,7 +213,7 @@ static ConvArgs<T, TOut> make_conv(int B, int P, int cin, int cout, const T* in,
   op.bias = bias; op.bias_bstride = bias_bs; op.act = act;
   op.drop_p = 0.0f; op.seed = 0; op.offset = 0; op.branch_scale = nullptr;
   op.res = nullptr; op.res_bstride = 0; op.res_a = nullptr; op.res_d = nullptr; op.pos = nullptr;
-  op.out = out; op.out_bstride = out_bs;
+  op.out = out; op.out_bstride = out_bs; op.stat_part = nullptr;
   return op;
 }
 
@@ -238,19 +244,23 @@ static int run_ileg(const sfno_net* n, const ShtDeviceTables& t, int B, const T*
   op.g_out = G; op.B = B; op.C = n->C; op.Kp = t.Kp; op.Lq = t.Lq; op.nlat = t.nlat;
   return launch_gemm(op, st, "legendre_inv");
 }
+// stat_part != nullptr: ask for fused output statistics; *fused reports whether the engine could provide them
 template <class T>
 static int run_idft(const sfno_net* n, const ShtDeviceTables& t, int B, const T* G, const float* bias, const T* add, int64_t add_bs,
-                    int act, T* out, int64_t out_bs, cudaStream_t st) {
+                    int act, T* out, int64_t out_bs, float* stat_part, bool* fused, cudaStream_t st) {
   IdftArgs<T, T> op{};
   op.G = 1; op.M = B * n->C * t.Kp; op.N = t.nlon; op.K = 2 * t.mmax;
   op.A = G; op.Bm = (const T*)t.einv; op.a_sk = op.M; op.b_sk = 1;
   op.out = out; op.out_bstride = out_bs; op.bias = bias; op.add = add; op.add_bstride = add_bs; op.act = act;
   op.C = n->C; op.nlat = t.nlat; op.nlon = t.nlon; op.Kp = t.Kp; op.Kq2 = t.Kq2;
+  op.stat_part = nullptr;
+  if (fused) *fused = false;
+  if (stat_part && idft_uses_tc(op)) { op.stat_part = stat_part; *fused = true; }
   return launch_idft(op, st, "dft_inv");
 }
 
 template <class T>
-static int forward_impl(sfno_net* n, const float* x_in, const float* time, float* y, int B, int dropout, uint64_t seed,
+static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time, float* y, int B, int dropout, uint64_t seed,
                         uint64_t offset, char* ws, cudaStream_t st) {
   const sfno_net_config& cfg = n->cfg;
   const WsLayout w = ws_layout(n, B);
@@ -278,12 +288,11 @@ static int forward_impl(sfno_net* n, const float* x_in, const float* time, float
 
   // ---- input: fp32 -> T, and into the tail channels of the big-skip concat buffer (sfnonet.py:804-805,832)
   {
-    const int64_t per = (int64_t)n->Cin * P;
-    dim3 grid((unsigned)std::min<int64_t>(ceil_div64(per, 256), 2048), B);
-    convert_planes_kernel<float, T><<<grid, 256, 0, st>>>(x_in, per, xin, per, per);
+    dim3 grid(1184 / std::max(1, std::min(B, 8)) + 1, B);
+    concat_convert_kernel<T><<<grid, 256, 0, st>>>(parts, (int64_t)P, xin, (int64_t)n->Cin * P);
     SFNO_TRY(post_launch("convert_input"));
     if (cfg.big_skip) {
-      convert_planes_kernel<float, T><<<grid, 256, 0, st>>>(x_in, per, xcat + CP, xcat_bs, per);
+      concat_convert_kernel<T><<<grid, 256, 0, st>>>(parts, (int64_t)P, xcat + CP, xcat_bs);
       SFNO_TRY(post_launch("convert_input_skip"));
     }
   }
@@ -293,6 +302,9 @@ static int forward_impl(sfno_net* n, const float* x_in, const float* time, float
   };
   T* cur; int64_t cur_bs;
   buf_of(nl, &cur, &cur_bs);
+  float* stat_part = (float*)(ws + w.stat_part);
+  bool x_stats_fused = false;  // statistics of `cur` already sit in stat_part (written by the producing conv)
+  const int conv_slices = ceil_div(P, 256) * kConvStatSlicesPerTile;
 
   // ---- encoder (sfnonet.py:610-618) + position embedding (sfnonet.py:824)
   {
@@ -300,6 +312,7 @@ static int forward_impl(sfno_net* n, const float* x_in, const float* time, float
     SFNO_TRY(launch_conv(e0, st, "encoder0"));
     auto e1 = make_conv<T, T>(B, P, C, C, t1, CP, (const T*)n->enc1_w, 0, C, nullptr, 0, SFNO_ACT_NONE, cur, cur_bs);
     e1.pos = cfg.pos_embed ? (const T*)n->pos : nullptr;
+    if (cfg.instance_norm && conv_uses_tc(e1)) { e1.stat_part = stat_part; x_stats_fused = true; }
     SFNO_TRY(launch_conv(e1, st, "encoder1"));
   }
   n->last_x_off = (size_t)((char*)cur - ws); n->last_x_bstride = cur_bs; n->last_batch = B;
@@ -328,20 +341,26 @@ static int forward_impl(sfno_net* n, const float* x_in, const float* time, float
 
     // norm0 (+ time scale/shift before the filter) as a per-(b,c) affine  (sfnonet.py:290-299)
     const bool time_before = cfg.with_time_emb && cfg.time_scale_shift_before_filter;
-    if (cfg.instance_norm) {
-      launch_instance_stats<T>(cur, cur_bs, B, C, P, cfg.norm_eps, mean, rstd, st);
-      SFNO_TRY(post_launch("instance_stats0"));
+    if (cfg.instance_norm && x_stats_fused) {
+      norm_affine_partials_kernel<<<ceil_div(BC * 32, 256), 256, 0, st>>>(stat_part, conv_slices, (int64_t)BC, 1, (float)P, cfg.norm_eps,
+                                                                     bp.norm0_g, bp.norm0_b, time_before ? ts_i : nullptr, ts_bs, B, C, a0, d0);
+      SFNO_TRY(post_launch("norm_affine0"));
+    } else {
+      if (cfg.instance_norm) {
+        launch_instance_stats<T>(cur, cur_bs, B, C, P, cfg.norm_eps, mean, rstd, st);
+        SFNO_TRY(post_launch("instance_stats0"));
+      }
+      norm_affine_kernel<<<ceil_div(BC, 256), 256, 0, st>>>(cfg.instance_norm ? mean : nullptr, rstd, bp.norm0_g, bp.norm0_b,
+                                                            time_before ? ts_i : nullptr, ts_bs, B, C, a0, d0);
+      SFNO_TRY(post_launch("norm_affine0"));
     }
-    norm_affine_kernel<<<ceil_div(BC, 256), 256, 0, st>>>(cfg.instance_norm ? mean : nullptr, rstd, bp.norm0_g, bp.norm0_b,
-                                                          time_before ? ts_i : nullptr, ts_bs, B, C, a0, d0);
-    SFNO_TRY(post_launch("norm_affine0"));
 
     // SpectralConvS2.forward (s2convolutions.py:158-193)
     SFNO_TRY(run_dft<T>(n, fwd, B, cur, cur_bs, a0, d0, FG, st));
     SFNO_TRY(run_leg<T>(n, fwd, B, FG, X, st));
     if (scale_residual) {  // residual = inverse_transform(forward_transform(x_norm))
       SFNO_TRY(run_ileg<T>(n, inv, B, X, /*x_layout=*/true, FG, st));
-      SFNO_TRY(run_idft<T>(n, inv, B, FG, nullptr, nullptr, 0, SFNO_ACT_NONE, res, CP, st));
+      SFNO_TRY(run_idft<T>(n, inv, B, FG, nullptr, nullptr, 0, SFNO_ACT_NONE, res, CP, nullptr, nullptr, st));
     }
     if (cfg.operator_type == SFNO_OP_DHCONV) {
       OpDhconv<T> op{};
@@ -368,17 +387,27 @@ static int forward_impl(sfno_net* n, const float* x_in, const float* time, float
       auto sk = make_conv<T, T>(B, P, C, C, cur, cur_bs, skip_wb, (int64_t)C * C, C, skip_bb, C, SFNO_ACT_NONE, t1, CP);
       SFNO_TRY(launch_conv(sk, st, "inner_skip"));
     }
-    SFNO_TRY(run_idft<T>(n, inv, B, FG, bp.spec_bias, t1, CP, cfg.activation, t1, CP, st));
+    bool t1_stats_fused = false;
+    SFNO_TRY(run_idft<T>(n, inv, B, FG, bp.spec_bias, t1, CP, cfg.activation, t1, CP, cfg.instance_norm ? stat_part : nullptr,
+                         &t1_stats_fused, st));
 
     // norm1 (+ time scale/shift after the filter) folded into fc1  (sfnonet.py:313-323)
-    if (cfg.instance_norm) {
-      launch_instance_stats<T>(t1, CP, B, C, P, cfg.norm_eps, mean, rstd, st);
-      SFNO_TRY(post_launch("instance_stats1"));
-    }
     const bool time_after = cfg.with_time_emb && !cfg.time_scale_shift_before_filter;
-    norm_affine_kernel<<<ceil_div(BC, 256), 256, 0, st>>>(cfg.instance_norm ? mean : nullptr, rstd, bp.norm1_g, bp.norm1_b,
-                                                          time_after ? ts_i : nullptr, ts_bs, B, C, a1, d1);
-    SFNO_TRY(post_launch("norm_affine1"));
+    if (cfg.instance_norm && t1_stats_fused) {
+      const int idft_slices = ceil_div(inv.nlon, 192) * kConvStatSlicesPerTile;
+      norm_affine_partials_kernel<<<ceil_div(BC * 32, 256), 256, 0, st>>>(stat_part, idft_slices, (int64_t)BC * inv.Kp, inv.Kp, (float)P,
+                                                                     cfg.norm_eps, bp.norm1_g, bp.norm1_b, time_after ? ts_i : nullptr,
+                                                                     ts_bs, B, C, a1, d1);
+      SFNO_TRY(post_launch("norm_affine1"));
+    } else {
+      if (cfg.instance_norm) {
+        launch_instance_stats<T>(t1, CP, B, C, P, cfg.norm_eps, mean, rstd, st);
+        SFNO_TRY(post_launch("instance_stats1"));
+      }
+      norm_affine_kernel<<<ceil_div(BC, 256), 256, 0, st>>>(cfg.instance_norm ? mean : nullptr, rstd, bp.norm1_g, bp.norm1_b,
+                                                            time_after ? ts_i : nullptr, ts_bs, B, C, a1, d1);
+      SFNO_TRY(post_launch("norm_affine1"));
+    }
 
     // stochastic depth factor (drop_path.py:5-22); block 0 has rate 0 (sfnonet.py:622)
     const float dp = nl > 1 ? cfg.drop_path_rate * (float)i / (float)(nl - 1) : 0.0f;
@@ -400,6 +429,8 @@ static int forward_impl(sfno_net* n, const float* x_in, const float* time, float
     f2.branch_scale = use_dp ? dscale : nullptr;
     if (scale_residual) { f2.res = res; f2.res_bstride = CP; }
     else { f2.res = cur; f2.res_bstride = cur_bs; f2.res_a = a0; f2.res_d = d0; }
+    x_stats_fused = false;
+    if (cfg.instance_norm && i + 1 < nl && conv_uses_tc(f2)) { f2.stat_part = stat_part; x_stats_fused = true; }
     SFNO_TRY(launch_conv(f2, st, "mlp_fc2"));
 
     cur = nxt; cur_bs = nxt_bs;
@@ -530,17 +561,42 @@ size_t sfno_net_workspace_bytes(const sfno_net* n, int batch) {
   return ws_layout(n, batch).total;
 }
 
-int sfno_net_forward(sfno_net* n, const float* x_dev, const float* time_dev, float* y_dev, int batch, int dropout_enabled,
-                     uint64_t seed, uint64_t offset, void* workspace_dev, size_t workspace_bytes, void* stream) {
-  SFNO_CHECK_ARG(n && x_dev && y_dev && workspace_dev, "NULL argument");
+static int forward_dispatch(sfno_net* n, const ConcatParts& parts, const float* time_dev, float* y_dev, int batch, int dropout_enabled,
+                            uint64_t seed, uint64_t offset, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  SFNO_CHECK_ARG(n && y_dev && workspace_dev, "NULL argument");
   SFNO_CHECK_ARG(batch > 0 && batch <= n->cfg.max_batch, "batch %d outside (0, max_batch=%d]", batch, n->cfg.max_batch);
   SFNO_CHECK_ARG((time_dev != nullptr) == (n->cfg.with_time_emb != 0), "time must be given iff with_time_emb");
   SFNO_CHECK_ARG(((uintptr_t)workspace_dev & 1023) == 0, "workspace must be 1024-byte aligned");
+  int csum = 0;
+  for (int k = 0; k < parts.nparts; ++k) {
+    SFNO_CHECK_ARG(parts.src[k] != nullptr && parts.channels[k] > 0, "input part %d is empty", k);
+    csum += parts.channels[k];
+  }
+  if (csum != n->Cin) return fail(SFNO_ERR_SHAPE_MISMATCH, "input parts have %d channels in total, the net expects %d", csum, n->Cin);
   if (workspace_bytes < ws_layout(n, batch).total) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small: %zu < %zu", workspace_bytes, ws_layout(n, batch).total);
   cudaStream_t st = (cudaStream_t)stream;
   return n->cfg.precision == SFNO_PREC_BF16
-             ? forward_impl<bf16>(n, x_dev, time_dev, y_dev, batch, dropout_enabled, seed, offset, (char*)workspace_dev, st)
-             : forward_impl<float>(n, x_dev, time_dev, y_dev, batch, dropout_enabled, seed, offset, (char*)workspace_dev, st);
+             ? forward_impl<bf16>(n, parts, time_dev, y_dev, batch, dropout_enabled, seed, offset, (char*)workspace_dev, st)
+             : forward_impl<float>(n, parts, time_dev, y_dev, batch, dropout_enabled, seed, offset, (char*)workspace_dev, st);
+}
+
+int sfno_net_forward(sfno_net* n, const float* x_dev, const float* time_dev, float* y_dev, int batch, int dropout_enabled,
+                     uint64_t seed, uint64_t offset, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  SFNO_CHECK_ARG(n && x_dev, "NULL argument");
+  ConcatParts parts{};
+  parts.src[0] = x_dev; parts.channels[0] = n->Cin; parts.nparts = 1;
+  return forward_dispatch(n, parts, time_dev, y_dev, batch, dropout_enabled, seed, offset, workspace_dev, workspace_bytes, stream);
+}
+
+int sfno_net_forward_parts(sfno_net* n, const float* const* parts_dev, const int* part_channels, int nparts, const float* time_dev,
+                           float* y_dev, int batch, int dropout_enabled, uint64_t seed, uint64_t offset, void* workspace_dev,
+                           size_t workspace_bytes, void* stream) {
+  SFNO_CHECK_ARG(n && parts_dev && part_channels, "NULL argument");
+  SFNO_CHECK_ARG(nparts >= 1 && nparts <= 3, "between 1 and 3 input parts, got %d", nparts);
+  ConcatParts parts{};
+  parts.nparts = nparts;
+  for (int k = 0; k < nparts; ++k) { parts.src[k] = parts_dev[k]; parts.channels[k] = part_channels[k]; }
+  return forward_dispatch(n, parts, time_dev, y_dev, batch, dropout_enabled, seed, offset, workspace_dev, workspace_bytes, stream);
 }
 
 int64_t sfno_net_debug_tap(sfno_net* n, const char* name, float* dst_dev, int64_t capacity, void* workspace_dev, void* stream) {

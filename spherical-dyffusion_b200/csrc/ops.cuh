@@ -203,10 +203,11 @@ struct OpIleg {
     return Row{g_out + (int64_t)g * 2 * B * C * Kp + (int64_t)ri * B * C * Kp + ((int64_t)b * C + o) * Kp, nullptr, true};
   }
   __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = from_f32<T>(acc); }
-  __device__ void compute8(const Row&, int, const float (&acc)[8], const float (&)[8], float (&o)[8]) const {
+  __device__ void compute8(Row&, int, const float (&acc)[8], const float (&)[8], float (&o)[8]) const {
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = acc[i];
   }
+  __device__ void finish(const Row&, int, int, int) const {}
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -224,6 +225,9 @@ struct IdftArgs {
   const T* add; int64_t add_bstride;      // [B][C][nlat][nlon] or nullptr
   int act;
   int C, nlat, nlon, Kp, Kq2;
+  // optional fused InstanceNorm statistics of the OUTPUT: per (column slice, row) partial sum / sum of squares,
+  // stat_part[(slice*2 + {0,1}) * M + row]; reduced in a fixed order by norm_affine_partials_kernel (deterministic)
+  float* stat_part;
 };
 template <class T, class TOut, int ACT = -1>
 struct OpIdft : IdftArgs<T, TOut> {
@@ -236,11 +240,12 @@ struct OpIdft : IdftArgs<T, TOut> {
   __device__ int64_t b_off(int, int n) const { return (int64_t)n * this->Kq2; }
   __device__ int n_store() const { return this->N; }
   __device__ bool has_res() const { return this->add != nullptr; }
-  struct Row { TOut* out; const T* res; bool valid; float bias; };
+  struct Row { TOut* out; const T* res; bool valid; float bias; float s, q; };
   __device__ Row row(int, int m) const {
     int bo = m / this->Kp, k = m - bo * this->Kp;
     int b = bo / this->C, o = bo - b * this->C;
     Row r;
+    r.s = 0.0f; r.q = 0.0f;
     r.valid = k < this->nlat;
     const int64_t pix = ((int64_t)o * this->nlat + k) * this->nlon;
     r.out = this->out + (int64_t)b * this->out_bstride + pix;
@@ -254,9 +259,20 @@ struct OpIdft : IdftArgs<T, TOut> {
     if (r.res) v += to_f32(r.res[n]);
     r.out[n] = from_f32<TOut>(act_ct<T, ACT>(this->act, v));
   }
-  __device__ void compute8(const Row& r, int, const float (&acc)[8], const float (&res)[8], float (&o)[8]) const {
+  __device__ void compute8(Row& r, int, const float (&acc)[8], const float (&res)[8], float (&o)[8]) const {
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = act_ct<T, ACT>(this->act, acc[i] + r.bias + res[i]);
+    if (this->stat_part) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { r.s += o[i]; r.q = fmaf(o[i], o[i], r.q); }
+    }
+  }
+  // called once per (tile, column slice) by every in-range row, valid or not (invalid rows contribute zeros)
+  __device__ void finish(const Row& r, int, int m, int slice) const {
+    if (this->stat_part) {
+      this->stat_part[((int64_t)slice * 2) * this->M + m] = r.valid ? r.s : 0.0f;
+      this->stat_part[((int64_t)slice * 2 + 1) * this->M + m] = r.valid ? r.q : 0.0f;
+    }
   }
 };
 
@@ -280,6 +296,8 @@ struct ConvArgs {
   const float* res_a; const float* res_d; // [batch*cout] affine on the residual or nullptr
   const T* pos;                           // [cout][hw] or nullptr
   TOut* out; int64_t out_bstride;
+  // optional fused InstanceNorm statistics of the OUTPUT: stat_part[(slice*2 + {0,1}) * (G*M) + g*M + m]
+  float* stat_part;
 };
 // ACT / DROP < 0: decided at run time (CUDA-core engine and rarely used combinations)
 template <class T, class TOut, int ACT = -1, int DROP = -1>
@@ -293,11 +311,12 @@ struct OpConv : ConvArgs<T, TOut> {
   __device__ int64_t b_off(int g, int n) const { return (int64_t)g * this->in_bstride + n; }  // + c * hw
   __device__ int n_store() const { return this->N; }
   __device__ bool has_res() const { return this->res != nullptr; }
-  struct Row { TOut* out; const T* res; bool valid; const T* pos; float bias, ra, rd, scale; uint64_t rng_base; };
+  struct Row { TOut* out; const T* res; bool valid; const T* pos; float bias, ra, rd, scale; uint64_t rng_base; float s, q; };
   __device__ Row row(int g, int m) const {
     Row r;
     const int64_t off = (int64_t)m * this->N;
     r.valid = true;
+    r.s = 0.0f; r.q = 0.0f;
     r.out = this->out + (int64_t)g * this->out_bstride + off;
     r.res = this->res ? this->res + (int64_t)g * this->res_bstride + off : nullptr;
     r.pos = this->pos ? this->pos + off : nullptr;
@@ -324,7 +343,7 @@ struct OpConv : ConvArgs<T, TOut> {
     if (r.pos) v += to_f32(r.pos[n]);
     r.out[n] = from_f32<TOut>(v);
   }
-  __device__ void compute8(const Row& r, int n, const float (&acc)[8], const float (&res)[8], float (&o)[8]) const {
+  __device__ void compute8(Row& r, int n, const float (&acc)[8], const float (&res)[8], float (&o)[8]) const {
     float u[8];
     if (dropping()) {
       philox_uniform4(this->seed, this->offset, r.rng_base + n, u[0], u[1], u[2], u[3]);
@@ -341,6 +360,17 @@ struct OpConv : ConvArgs<T, TOut> {
       load_vec8(r.pos + n, t);
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] += t[i];
+    }
+    if (this->stat_part) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { r.s += o[i]; r.q = fmaf(o[i], o[i], r.q); }
+    }
+  }
+  __device__ void finish(const Row& r, int g, int m, int slice) const {
+    if (this->stat_part) {
+      const int64_t rows = (int64_t)this->G * this->M, idx = (int64_t)g * this->M + m;
+      this->stat_part[((int64_t)slice * 2) * rows + idx] = r.s;
+      this->stat_part[((int64_t)slice * 2 + 1) * rows + idx] = r.q;
     }
   }
 };

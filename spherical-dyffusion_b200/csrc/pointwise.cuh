@@ -118,6 +118,44 @@ static __global__ void norm_affine_kernel(const float* __restrict__ mean, const 
   d_out[i] = d;
 }
 
+// Same affine, with mean / variance reduced (fixed order, fp64) from the per-slice partial sums written by the
+// tensor-core epilogues: part[(slice*2 + {0,1}) * rows + row]; one (b,c) has `rows_per_bc` consecutive rows
+// (1 for the convolutions, Kp latitude rows for the inverse DFT).  count = number of pixels per (b,c).
+static __global__ void __launch_bounds__(256) norm_affine_partials_kernel(
+    const float* __restrict__ part, int slices, int64_t rows, int rows_per_bc, float count, float eps,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ts, int64_t ts_bstride, int B,
+    int C, float* __restrict__ a_out, float* __restrict__ d_out) {
+  // one warp per (b,c): lanes stride over the (slice, row) partials, fp64 accumulation, fixed-order shuffle tree
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  double s = 0.0, q = 0.0;
+  const int total = slices * rows_per_bc;
+  for (int t = lane; t < total; t += 32) {
+    const int sl = t / rows_per_bc, r = t - sl * rows_per_bc;
+    const float* ps = part + ((int64_t)sl * 2) * rows + (int64_t)i * rows_per_bc + r;
+    s += (double)ps[0];
+    q += (double)ps[rows];
+  }
+  s = warp_sum_d(s);
+  q = warp_sum_d(q);
+  if (lane != 0) return;
+  const double mean = s / (double)count;
+  double var = q / (double)count - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  const float rstd = rsqrtf((float)var + eps);
+  const float g = gamma ? gamma[c] : 1.0f, be = beta ? beta[c] : 0.0f;
+  float a = g * rstd;
+  float d = be - g * (float)mean * rstd;
+  if (ts) {
+    const float sc = ts[(int64_t)b * ts_bstride + c] + 1.0f, sf = ts[(int64_t)b * ts_bstride + C + c];
+    a *= sc;
+    d = d * sc + sf;
+  }
+  a_out[i] = a;
+  d_out[i] = d;
+}
+
 // compose a time scale/shift given as separate [B*C] arrays onto an existing affine
 static __global__ void time_affine_compose_kernel(float* __restrict__ a, float* __restrict__ d, const float* __restrict__ scale,
                                            const float* __restrict__ shift, int n) {
@@ -200,6 +238,59 @@ static __global__ void convert_planes_kernel(const TS* __restrict__ src, int64_t
   const int b = blockIdx.y;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += (int64_t)gridDim.x * blockDim.x)
     dst[(int64_t)b * dst_bstride + i] = from_f32<TD>(to_f32(src[(int64_t)b * src_bstride + i]));
+}
+
+// fp32 -> bf16, 8 elements per thread (two float4 loads, one 16-byte store); per_sample % 8 == 0, 16-byte aligned
+static __global__ void convert_planes_vec8_kernel(const float* __restrict__ src, int64_t src_bstride, bf16* __restrict__ dst,
+                                                  int64_t dst_bstride, int64_t per_sample) {
+  const int b = blockIdx.y;
+  const float4* s4 = reinterpret_cast<const float4*>(src + (int64_t)b * src_bstride);
+  uint4* d4 = reinterpret_cast<uint4*>(dst + (int64_t)b * dst_bstride);
+  const int64_t nvec = per_sample >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = s4[2 * i], c = s4[2 * i + 1];
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(c.x, c.y), h3 = __floats2bfloat162_rn(c.z, c.w);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+    d4[i] = u;
+  }
+}
+
+// Fused concat + convert (BaseModel.concat_condition_if_needed, _base_model.py:166-192): up to 3 fp32 sources
+// [B][c_k][hw] are written as channels [coff_k, coff_k + c_k) of dst [B][..][hw] (dst_bstride elements per sample).
+struct ConcatParts {
+  const float* src[3];
+  int channels[3];
+  int nparts;
+};
+template <class T>
+static __global__ void concat_convert_kernel(ConcatParts parts, int64_t hw, T* __restrict__ dst, int64_t dst_bstride) {
+  const int b = blockIdx.y;
+  int coff = 0;
+  for (int k = 0; k < parts.nparts; ++k) {
+    const int64_t per = (int64_t)parts.channels[k] * hw;
+    const float* s = parts.src[k] + (int64_t)b * per;
+    T* d = dst + (int64_t)b * dst_bstride + (int64_t)coff * hw;
+    if (sizeof(T) == 2 && per % 8 == 0 && ((((uintptr_t)s) | ((uintptr_t)d)) & 15) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(s);
+      uint4* d4 = reinterpret_cast<uint4*>(d);
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (per >> 3); i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 a = s4[2 * i], c = s4[2 * i + 1];
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(c.x, c.y), h3 = __floats2bfloat162_rn(c.z, c.w);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+        d4[i] = u;
+      }
+    } else {
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x)
+        d[i] = from_f32<T>(s[i]);
+    }
+    coff += parts.channels[k];
+  }
 }
 
 // fp32 row-major [rows][cols] -> T [rows][ld] with zero padding (conv / linear weights)

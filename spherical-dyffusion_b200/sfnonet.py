@@ -416,14 +416,37 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
         return any(m.training for m in self.modules() if isinstance(m, ALL_DROPOUT_LAYERS))
 
     # ---- forward ------------------------------------------------------------------------------------------------------
+    def _input_parts(self, inputs, condition, static_condition):
+        """The tensors ``concat_condition_if_needed`` (``_base_model.py:166-192``) would concatenate, validated the same
+        way but NOT concatenated: the channel concat is fused into the library's input conversion."""
+        if self.num_conditional_channels > 0:
+            if condition is None and static_condition is None:
+                raise ValueError(
+                    f"condition and static_condition are both None but num_conditional_channels is {self.num_conditional_channels}")
+            parts = [inputs] + [t for t in (condition, static_condition) if t is not None]
+            if hasattr(self, "upsample_condition"):
+                parts = [inputs, self.upsample_condition(torch.cat(parts[1:], dim=1))]
+        else:
+            assert condition is None, "condition is not None but num_conditional_channels is 0"
+            assert static_condition is None, "static_condition is not None but num_conditional_channels is 0"
+            parts = [inputs]
+        B = inputs.shape[0]
+        for t in parts:
+            if t.dim() != 4 or t.shape[0] != B or tuple(t.shape[2:]) != tuple(self.img_shape):
+                cond_shape = parts[1].shape if len(parts) > 1 else None
+                raise RuntimeError(f"inputs.shape: {inputs.shape}, condition.shape: {cond_shape}")
+        if sum(t.shape[1] for t in parts) != self.in_chans:
+            raise RuntimeError(f"expected {self.in_chans} input channels in total "
+                               f"[B,{self.in_chans},{self.img_shape[0]},{self.img_shape[1]}], got {[tuple(t.shape) for t in parts]}")
+        return parts
+
     def forward(self, inputs, time=None, condition=None, static_condition=None, return_time_emb: bool = False, **kwargs):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
             raise NotImplementedError("the B200 path is inference-only; call under torch.no_grad()/inference_mode() and .eval()")
-        x = self.concat_condition_if_needed(inputs, condition, static_condition)
-        in_dtype = x.dtype
-        x = require_cuda_f32(x, "inputs")
-        if x.dim() != 4 or x.shape[1] != self.in_chans or tuple(x.shape[2:]) != tuple(self.img_shape):
-            raise RuntimeError(f"expected input [B,{self.in_chans},{self.img_shape[0]},{self.img_shape[1]}], got {tuple(x.shape)}")
+        parts = self._input_parts(inputs, condition, static_condition)
+        in_dtype = inputs.dtype
+        parts = [require_cuda_f32(t, "inputs") for t in parts]
+        x = parts[0]
         B = x.shape[0]
         device = x.device
         t_ptr = None
@@ -451,9 +474,11 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
             ws = workspace(device, L.sfno_net_workspace_bytes(self._net, B), "net")
             drop = self.dropout_active()
             self._calls += 1
-            _lib.check(L.sfno_net_forward(self._net, x.data_ptr(), t_ptr, out.data_ptr(), B, int(drop),
-                                          int(self.dropout_seed), int(self._calls) * 4096, ws.data_ptr(), ws.numel(),
-                                          stream_ptr(device)), "sfno_net_forward")
+            ptrs = (ctypes.c_void_p * len(parts))(*[t.data_ptr() for t in parts])
+            chans = (ctypes.c_int * len(parts))(*[int(t.shape[1]) for t in parts])
+            _lib.check(L.sfno_net_forward_parts(self._net, ptrs, chans, len(parts), t_ptr, out.data_ptr(), B, int(drop),
+                                                int(self.dropout_seed), int(self._calls) * 4096, ws.data_ptr(), ws.numel(),
+                                                stream_ptr(device)), "sfno_net_forward_parts")
             t_repr = None
             if return_time_emb and self.with_time_emb:
                 t_repr = torch.empty(B, self.time_dim, dtype=torch.float32, device=device)
@@ -467,7 +492,7 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
     # ---- test hook: activation after the encoder (-1) or after block i ----------------------------------------------------
     def debug_activation(self, stop_after_block: int, inputs, time=None, condition=None, static_condition=None):
         L = _lib.lib()
-        x = require_cuda_f32(self.concat_condition_if_needed(inputs, condition, static_condition), "inputs")
+        x = require_cuda_f32(inputs, "inputs")
         device = x.device
         with torch.cuda.device(device):
             self._ensure_net(device)
