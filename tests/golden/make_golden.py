@@ -113,3 +113,86 @@ def make_case(name, spec):
 if __name__ == "__main__":
     for name, spec in CASES.items():
         make_case(name, spec)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# DYffusion sampling window: the reference's own sampler (src/diffusion/dyffusion.py:457-567) driving the reference's
+# own SFNO forecaster + interpolator (interpolator dropout off so the window is deterministic).
+# ---------------------------------------------------------------------------------------------------------------
+SAMPLER_CASES = {
+    "dyffusion_window_12x24_h4": dict(horizon=4, channels=3, forcing=2, spatial_shape=(12, 24), embed_dim=16, num_layers=2,
+                                      batch=2, seed=10, forward_conditioning="none", condition_kind="static"),
+    "dyffusion_window_12x24_h3_dyn": dict(horizon=3, channels=2, forcing=1, spatial_shape=(12, 24), embed_dim=16, num_layers=2,
+                                          batch=2, seed=11, forward_conditioning="data", condition_kind="dynamical"),
+}
+
+
+class _InterpolatorHandle(torch.nn.Module):
+    """Duck-typed stand-in for InterpolationExperiment: only what DYffusion touches."""
+
+    def __init__(self, model, horizon):
+        super().__init__()
+        self.model = model
+        self.window, self.true_horizon = 1, horizon
+        self.ema_scope = None
+
+    def predict_packed(self, *inputs, **kwargs):
+        out = self.model.predict_forward(*inputs, **kwargs)
+        return {"preds": out}
+
+    def inference_dropout_scope(self, condition, context=None):
+        return self.model.inference_dropout_scope(condition=condition, context=context)
+
+    def get_dynamical_condition(self, dynamical_condition, target_time):
+        if dynamical_condition is None:
+            return None
+        if isinstance(target_time, int):
+            return dynamical_condition[:, target_time, ...]
+        return dynamical_condition[torch.arange(dynamical_condition.shape[0]), target_time.long(), ...]
+
+
+def make_sampler_case(name, spec):
+    ref_shim.install()
+    from src.diffusion.dyffusion import DYffusion
+
+    h, C, F = spec["horizon"], spec["channels"], spec["forcing"]
+    shape = spec["spatial_shape"]
+    fc_cond = F + (C if spec["forward_conditioning"] == "data" else 0)
+    common = dict(spatial_shape=shape, embed_dim=spec["embed_dim"], num_layers=spec["num_layers"], operator_type="dhconv",
+                  data_grid="equiangular")
+    fcfg = SFNOConfig(num_input_channels=C, num_output_channels=C, num_conditional_channels=fc_cond, min_time=0.0,
+                      max_time=float(h - 1), **common)
+    icfg = SFNOConfig(num_input_channels=2 * C, num_output_channels=C, num_conditional_channels=F, min_time=1.0,
+                      max_time=float(h - 1), **common)
+    forecaster = ref_shim.build_reference_sfno(num_input_channels=C, num_output_channels=C, num_conditional_channels=fc_cond,
+                                               spatial_shape=shape, seed=spec["seed"], min_max_time=(0, h - 1), **fcfg.model_kwargs())
+    interp = ref_shim.build_reference_sfno(num_input_channels=2 * C, num_output_channels=C, num_conditional_channels=F,
+                                           spatial_shape=shape, seed=spec["seed"] + 100, min_max_time=(1, h - 1), **icfg.model_kwargs())
+    perturb(forecaster, spec["seed"])
+    perturb(interp, spec["seed"] + 100)
+    dy = DYffusion(model=forecaster, timesteps=h, interpolator=_InterpolatorHandle(interp, h), interpolator_local_checkpoint_path=None,
+                   forward_conditioning=spec["forward_conditioning"], time_encoding="dynamics", enable_interpolator_dropout=False,
+                   sampling_type="cold")
+    g = torch.Generator().manual_seed(3000 + spec["seed"])
+    B = spec["batch"]
+    x0 = torch.randn(B, C, *shape, generator=g)
+    kwargs = {}
+    if spec["condition_kind"] == "static":
+        kwargs["static_condition"] = torch.randn(B, F, *shape, generator=g)
+    else:
+        kwargs["dynamical_condition"] = torch.randn(B, h + 1, F, *shape, generator=g)
+    with torch.inference_mode():
+        preds = dy.sample(x0, **kwargs)
+    fixture = dict(spec=spec, forecaster_cfg={k: v for k, v in fcfg.__dict__.items()}, interpolator_cfg={k: v for k, v in icfg.__dict__.items()},
+                   forecaster_sd={k: v.clone() for k, v in forecaster.state_dict().items()},
+                   interpolator_sd={k: v.clone() for k, v in interp.state_dict().items()},
+                   x0=x0, kwargs=kwargs, preds={k: v.clone() for k, v in preds.items() if k.endswith("_preds")},
+                   torch_version=torch.__version__)
+    path = os.path.join(OUT, f"{name}.pt")
+    torch.save(fixture, path)
+    print(f"{name}: keys {sorted(fixture['preds'])} -> {path} ({os.path.getsize(path) / 1024:.0f} kB)")
+
+
+if __name__ == "__main__":
+    for name, spec in SAMPLER_CASES.items():
+        make_sampler_case(name, spec)

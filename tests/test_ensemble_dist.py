@@ -1,0 +1,94 @@
+"""Multi-rank host logic on CPU: member sharding and the statistics collectives (world_size 2, gloo).
+The local arithmetic is replaced by a torch stand-in (the product's CudaEnsembleOps needs a GPU); what is under
+test is the sharding, padding, all-reduce / all-gather plumbing and the metric definitions of metrics.py."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from spherical_dyffusion_b200.ensemble import EnsembleStatistics, area_weights, max_local_members, member_shard
+
+
+class TorchOps:
+    def accumulate(self, members, sums):
+        sums[0] += members.sum(0)
+        sums[1] += (members * members).sum(0)
+
+    def finalize(self, sums, total):
+        mean = sums[0] / total
+        var = (sums[1] - total * mean * mean) / (total - 1)
+        return mean, var.clamp_min(0)
+
+    def crps(self, members, truth):
+        E = members.shape[0]
+        skill = (members - truth).abs().mean(0)
+        spread = (members[None] - members[:, None]).abs().sum((0, 1)) / (E * (E - 1))
+        return skill - 0.5 * spread
+
+
+def test_member_shard_partition():
+    for E in (1, 5, 25, 32):
+        for G in (1, 2, 4, 8):
+            shards = [member_shard(E, G, r) for r in range(G)]
+            assert sorted(sum(shards, [])) == list(range(E))
+            assert max(len(s) for s in shards) == max_local_members(E, G)
+    assert [len(member_shard(25, 8, r)) for r in range(8)] == [4, 3, 3, 3, 3, 3, 3, 3]
+
+
+def _reference_metrics(members, truth, weights):
+    # metrics.py:166-246 restated with torch for the comparison
+    def wmean(x):
+        return (x * weights).sum((-2, -1)) / weights.expand(x.shape).sum((-2, -1))
+    E = members.shape[0]
+    mean = members.mean(0)
+    spread = torch.sqrt(wmean(members.var(dim=0)))
+    rmse = torch.sqrt(wmean((mean - truth) ** 2))
+    skill = (members - truth).abs().mean(0)
+    sp = (members[None] - members[:, None]).abs().sum((0, 1)) / (E * (E - 1))
+    return dict(mean=mean, spread=spread, rmse=rmse, ssr=spread * ((E + 1) / E) ** 0.5 / rmse, crps=wmean(skill - 0.5 * sp))
+
+
+def _worker(rank, world, port, E, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        members = torch.randn(E, 3, 6, 12, generator=g) * 2 + 1
+        truth = torch.randn(3, 6, 12, generator=g)
+        weights = area_weights(torch.linspace(-80, 80, 6), 12)
+        stats = EnsembleStatistics(E, ops=TorchOps())
+        local = members[stats.local_ids]
+        out = stats.step(local, truth=truth, weights=weights)
+        ref = _reference_metrics(members, truth, weights)
+        ok = all(torch.allclose(out[k], ref[k], rtol=1e-4, atol=1e-5) for k in ref)
+        gathered = stats.gather_members(local)
+        ok = ok and torch.equal(gathered, members)
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("E", [5, 8])
+def test_statistics_two_ranks_gloo(E):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(2, port, E, results), nprocs=2, join=True)
+    assert dict(results) == {0: True, 1: True}
+
+
+def test_statistics_single_process_matches_metrics():
+    g = torch.Generator().manual_seed(1)
+    members = torch.randn(7, 2, 5, 10, generator=g)
+    truth = torch.randn(2, 5, 10, generator=g)
+    weights = area_weights(torch.linspace(-60, 60, 5), 10)
+    out = EnsembleStatistics(7, ops=TorchOps()).step(members, truth=truth, weights=weights)
+    ref = _reference_metrics(members, truth, weights)
+    for k in ref:
+        assert torch.allclose(out[k], ref[k], rtol=1e-4, atol=1e-5), k

@@ -335,3 +335,39 @@ def test_ensemble_statistics(dev, E):
     skill = (mem - truth).abs().mean(0)
     spread = (mem[None] - mem[:, None]).abs().sum((0, 1)) / (E * (E - 1))
     assert rel_l2(crps, skill - 0.5 * spread) < 1e-5
+
+
+def test_ensemble_statistics_module_and_rollout(dev):
+    """EnsembleStatistics with the CUDA kernels (single rank) against the metric definitions, and a tiny rollout."""
+    from spherical_dyffusion_b200.dyffusion import DYffusion
+    from spherical_dyffusion_b200.ensemble import EnsembleStatistics, area_weights
+    from spherical_dyffusion_b200.rollout import EnsembleRollout
+
+    g = torch.Generator().manual_seed(2)
+    E, C, H, W = 6, 4, 16, 32
+    members = (torch.randn(E, C, H, W, generator=g) * 2 + 1).to(dev)
+    truth = torch.randn(C, H, W, generator=g).to(dev)
+    weights = area_weights(torch.linspace(-84, 84, H), W).to(dev)
+    out = EnsembleStatistics(E).step(members, truth=truth, weights=weights)
+    wm = lambda x: (x * weights).sum((-2, -1)) / weights.expand(x.shape).sum((-2, -1))
+    mean = members.mean(0)
+    assert rel_l2(out["spread"], torch.sqrt(wm(members.var(dim=0)))) < 1e-5
+    assert rel_l2(out["rmse"], torch.sqrt(wm((mean - truth) ** 2))) < 1e-5
+    skill = (members - truth).abs().mean(0)
+    sp = (members[None] - members[:, None]).abs().sum((0, 1)) / (E * (E - 1))
+    assert rel_l2(out["crps"], wm(skill - 0.5 * sp)) < 1e-5
+
+    hcfg = dict(spatial_shape=(H, W), embed_dim=16, num_layers=2)
+    fcfg = SFNOConfig(num_input_channels=C, num_output_channels=C, num_conditional_channels=2, min_time=0.0, max_time=2.0, **hcfg)
+    icfg = SFNOConfig(num_input_channels=2 * C, num_output_channels=C, num_conditional_channels=2, min_time=1.0, max_time=2.0,
+                      dropout_mlp=0.1, drop_path_rate=0.1, **hcfg)
+    fore = module_from_cfg(fcfg, perturb_affine_and_biases(random_state_dict(fcfg, seed=5)), dev)
+    ipol = module_from_cfg(icfg, perturb_affine_and_biases(random_state_dict(icfg, seed=6)), dev)
+    dy = DYffusion(fore, ipol, timesteps=3)
+    stats = EnsembleStatistics(5)
+    ro = EnsembleRollout(dy, stats, forcing_fn=lambda s, n, d: torch.zeros(n, 2, H, W, device=d) + 0.01 * s,
+                         truth_fn=lambda s, d: torch.zeros(C, H, W, device=d), weights=weights)
+    hist = ro.run(torch.randn(C, H, W, generator=g).to(dev), n_steps=7)
+    assert len(hist["crps"]) == 7 and len(hist["spread"]) == 7
+    assert all(torch.isfinite(v).all() for v in hist["crps"])
+    assert float(hist["spread"][-1].mean()) > 0.0  # members diverge through the interpolator's dropout stream
