@@ -17,7 +17,9 @@ __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(const Op op) {
   const int g = blockIdx.z;
   const int m0 = blockIdx.x * SIMT_BM, n0 = blockIdx.y * SIMT_BN;
   const int t = threadIdx.x;
-  const int M = op.M, N = op.N, K = op.K;
+  const int M = op.M, K = op.K;
+  const int N = op.n_end(g), n_lo = op.n_begin(g);   // per-group column range actually produced
+  if (n0 >= N || n0 + SIMT_BN <= n_lo) return;       // block-uniform
   const auto* __restrict__ A = op.A;
   const auto* __restrict__ Bm = op.Bm;
 
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(const Op op) {
 
   const int tx = t % 16, ty = t / 16;
 
-  for (int k0 = 0; k0 < K; k0 += SIMT_BK) {
+  for (int k0 = op.k_begin(g); k0 < K; k0 += SIMT_BK) {
     if (Op::A_KCONTIG) {
       const int k = k0 + a_kk;
 #pragma unroll
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(const Op op) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int n = n0 + ty + 16 * j;
-      if (n < N) op.store(r, g, m, n, acc[i][j]);
+      if (n < N && n >= n_lo) op.store(r, g, m, n, acc[i][j]);
     }
   }
 }

@@ -245,6 +245,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   };
 
+  // tiles whose column range lies outside the group's [n_begin, n_end) carry no information: all roles skip them
+  auto tile_skipped = [&](int g, int nt) { return nt * BN >= op.n_end(g) || (nt + 1) * BN <= op.n_begin(g); };
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -253,9 +256,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x) {
         int g, mt, nt;
         decode(tile, g, mt, nt);
+        if (tile_skipped(g, nt)) continue;
         const int m0 = mt * TC_BM, n0 = nt * BN;
         const int ga = sc.a_batched ? g : 0, gb = sc.b_batched ? g : 0;
-        for (int kb = 0; kb < sc.k_blocks; ++kb) {
+        for (int kb = op.k_begin(g) / TC_BK; kb < sc.k_blocks; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           ptx::mbar_expect_tx(full_bar(stage), S::kStageBytes);
           const int k0 = kb * TC_BK;
@@ -288,17 +292,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x) {
+        int g, mt, nt;
+        decode(tile, g, mt, nt);
+        if (tile_skipped(g, nt)) continue;
+        const int kb0 = op.k_begin(g) / TC_BK;
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < sc.k_blocks; ++kb) {
+        for (int kb = kb0; kb < sc.k_blocks; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
           const int nk = (kb == sc.k_blocks - 1) ? sc.k16_last : TC_BK / 16;
           for (int k = 0; k < nk; ++k) {
             const uint64_t ad = make_smem_desc(a_smem(stage) + k * a_kstep, a_lbo, 1024u);
             const uint64_t bd = make_smem_desc(b_smem(stage) + k * b_kstep, b_lbo, 1024u);
-            ptx::mma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::mma_bf16(d_tmem, ad, bd, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           ptx::mma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -319,6 +327,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x) {
       int g, mt, nt;
       decode(tile, g, mt, nt);
+      if (tile_skipped(g, nt)) continue;
       const int m = mt * TC_BM + quad * 32 + lane;
       const int n_base = nt * BN + part * kColsPerWarp;
       const bool row_ok = m < op.M;
@@ -420,11 +429,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // ---- row-contiguous output: for a fixed column the warp writes 32 consecutive elements ----
         ptx::mbar_wait(tfull_bar(acc), acc_phase);
         ptx::tc_fence_after();
-        const int n_end = op.N;
+        const int n_end = op.n_end(g), n_lo = op.n_begin(g);
 #pragma unroll 1
         for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
           const int n0 = n_base + c0;
-          if (n0 >= n_end) break;  // warp-uniform
+          if (n0 >= n_end) break;         // warp-uniform
+          if (n0 + 16 <= n_lo) continue;  // below the group's first column (n_begin is a multiple of 16)
           uint32_t r[16];
           ptx::tmem_ld16(t_row + (uint32_t)c0, r);
           ptx::tmem_ld_wait();

@@ -139,7 +139,7 @@ static int sht_forward_impl(const ShtDeviceTables& t, const float* x, float* coe
   OpLeg<T> leg{};
   leg.G = t.mmax; leg.M = 2 * C; leg.N = t.lmax; leg.K = t.nlat;
   leg.A = F; leg.Bm = (const T*)t.wq; leg.a_sk = 1; leg.b_sk = 1;
-  leg.x = X; leg.Kp = t.Kp; leg.lmax = t.lmax; leg.mmax = t.mmax;
+  leg.x = X; leg.Kp = t.Kp; leg.lmax = t.lmax; leg.mmax = t.mmax; leg.triangular = 0;
   SFNO_TRY(launch_gemm(leg, st, "legendre_fwd"));
   const int64_t total = fields * t.lmax * t.mmax * 2;
   internal_to_coeffs_kernel<T><<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 8192), 256, 0, st>>>(X, coeffs, C, t.lmax, t.mmax);
@@ -160,7 +160,7 @@ static int sht_inverse_impl(const ShtDeviceTables& t, const float* coeffs, float
   il.G = t.mmax; il.M = 2 * C; il.N = t.nlat; il.K = t.lmax;
   il.A = X; il.Bm = (const T*)t.pt; il.b_sk = 1;
   il.a_goff = il.M; il.a_sk = (int64_t)t.mmax * il.M;  // X layout [l][m][rows]
-  il.g_out = Gb; il.B = 1; il.C = C; il.Kp = t.Kp; il.Lq = t.Lq; il.nlat = t.nlat;
+  il.g_out = Gb; il.B = 1; il.C = C; il.Kp = t.Kp; il.Lq = t.Lq; il.nlat = t.nlat; il.triangular = 0;
   SFNO_TRY(launch_gemm(il, st, "legendre_inv"));
   IdftArgs<T, float> id{};
   id.G = 1; id.M = C * t.Kp; id.N = t.nlon; id.K = 2 * t.mmax;

@@ -55,6 +55,8 @@ struct sfno_net {
   int stop_after_block = -2;  // -2: run everything; -1: stop after encoder(+pos); i: stop after block i
   // bookkeeping of the last forward for debug taps
   size_t last_x_off = 0; int64_t last_x_bstride = 0; int last_batch = 0;
+  // the spectral buffers were zero-filled for this (workspace, batch): entries skipped by the triangular ranges stay finite
+  const void* zeroed_ws = nullptr; int zeroed_batch = 0;
 };
 
 namespace sfno {
@@ -232,6 +234,7 @@ static int run_leg(const sfno_net* n, const ShtDeviceTables& t, int B, const T* 
   op.G = t.mmax; op.M = B * 2 * n->C; op.N = t.lmax; op.K = t.nlat;
   op.A = F; op.Bm = (const T*)t.wq; op.a_sk = 1; op.b_sk = 1;
   op.x = X; op.Kp = t.Kp; op.lmax = t.lmax; op.mmax = t.mmax;
+  op.triangular = n->cfg.operator_type == SFNO_OP_DHCONV;
   return launch_gemm(op, st, "legendre_fwd");
 }
 template <class T>
@@ -242,6 +245,7 @@ static int run_ileg(const sfno_net* n, const ShtDeviceTables& t, int B, const T*
   if (x_layout) { op.a_goff = op.M; op.a_sk = (int64_t)t.mmax * op.M; }
   else { op.a_goff = (int64_t)t.lmax * op.M; op.a_sk = op.M; }
   op.g_out = G; op.B = B; op.C = n->C; op.Kp = t.Kp; op.Lq = t.Lq; op.nlat = t.nlat;
+  op.triangular = n->cfg.operator_type == SFNO_OP_DHCONV;
   return launch_gemm(op, st, "legendre_inv");
 }
 // stat_part != nullptr: ask for fused output statistics; *fused reports whether the engine could provide them
@@ -285,6 +289,13 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
   float* dscale = (float*)(ws + w.dscale);
   const int64_t xcat_bs = (int64_t)n->Ccat * P;
   const int BC = B * C;
+  if (n->zeroed_ws != (const void*)ws || n->zeroed_batch != B) {
+    // X / Y entries outside the triangular ranges are never written; they only ever meet exact table zeros, so they
+    // just have to be finite: zero them once per (workspace, batch)
+    SFNO_CUDA(cudaMemsetAsync(X, 0, (size_t)n->L * n->M * B * 2 * C * sizeof(T), st));
+    SFNO_CUDA(cudaMemsetAsync(Y, 0, (size_t)n->L * n->M * B * 2 * C * sizeof(T), st));
+    n->zeroed_ws = (const void*)ws; n->zeroed_batch = B;
+  }
 
   // ---- input: fp32 -> T, and into the tail channels of the big-skip concat buffer (sfnonet.py:804-805,832)
   {
@@ -366,7 +377,7 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
       OpDhconv<T> op{};
       op.G = n->L; op.M = 2 * C; op.N = n->M * B; op.K = 2 * C;
       op.A = (const T*)bp.wpack; op.Bm = X; op.a_sk = 1; op.b_sk = 1;
-      op.y = Y; op.B = B; op.lmax = n->L; op.mmax = n->M;
+      op.y = Y; op.B = B; op.lmax = n->L; op.mmax = n->M; op.triangular = 1;
       SFNO_TRY(launch_gemm(op, st, "dhconv"));
     } else {
       const int64_t total = (int64_t)n->L * n->M * B * C;

@@ -74,13 +74,24 @@ __device__ __forceinline__ void load_vec8(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
+// Per-group index ranges.  The Legendre tables are exactly zero for l < m, so for the zonal
+// wavenumber m only degrees l >= m carry information: the forward transform stores only those columns, dhconv
+// visits only m <= l and the inverse transform contracts only over l >= m (ranges are rounded to the engines'
+// granularity inside the ops so that both engines skip exactly the same work).  Skipped entries of X / Y are never
+// read as anything but a factor of an exact table zero; the executor keeps those buffers finite (zero-filled once).
+struct FullRanges {
+  __device__ int n_begin(int) const { return 0; }
+  __device__ int k_begin(int) const { return 0; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // forward longitude DFT (K1 of SURVEY 2.3), one GEMM per sample: rows (c,k) x nlon -> F, fused
 // InstanceNorm/time affine:   F = a[b,c] * DFT(x) + d[b,c] * 2*pi * [m==0, re]   (DFT(1) = 2*pi*delta_m0)
 // ------------------------------------------------------------------------------------------------
 template <class T>
-struct OpDft {
+struct OpDft : FullRanges {
   static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = false, kNFastest = true;
+  __device__ int n_end(int) const { return N; }
   int G, M, N, K;  // G = B, M = C*nlat (rows (c,k) of one sample), N = 2*mmax, K = nlon
   const T* A; const T* Bm; int64_t a_sk, b_sk;
   T* f;
@@ -123,6 +134,10 @@ struct OpDft {
 template <class T>
 struct OpLeg {
   static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = false, kNFastest = false;
+  int triangular;  // 1: store only degrees l >= m (rounded down to 16)
+  __device__ int n_begin(int g) const { return triangular ? (g & ~15) : 0; }
+  __device__ int n_end(int) const { return N; }
+  __device__ int k_begin(int) const { return 0; }
   int G, M, N, K;  // G = mmax, M = B*2*C, N = lmax, K = nlat
   const T* A; const T* Bm; int64_t a_sk, b_sk;
   T* x;
@@ -153,6 +168,10 @@ struct OpLeg {
 template <class T>
 struct OpDhconv {
   static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = false, kNFastest = false;
+  int triangular;  // 1: only wavenumbers m <= l
+  __device__ int n_begin(int) const { return 0; }
+  __device__ int n_end(int g) const { int e = (g + 1) * B; return (triangular && e < N) ? e : N; }
+  __device__ int k_begin(int) const { return 0; }
   int G, M, N, K;  // G = lmax, M = 2*Cout, N = mmax*B, K = 2*Cin
   const T* A; const T* Bm; int64_t a_sk, b_sk;
   T* y;
@@ -187,6 +206,10 @@ template <class T>
 struct OpIleg {
   static constexpr bool A_KCONTIG = false, B_KCONTIG = true, kColContig = true, kNFastest = true;
   using OutT = T;
+  int triangular;  // 1: contract only over degrees l >= m (rounded down to the 64-wide K block)
+  __device__ int n_begin(int) const { return 0; }
+  __device__ int n_end(int) const { return N; }
+  __device__ int k_begin(int g) const { int k = g & ~63; return triangular ? (k < K ? k : (K > 0 ? ((K - 1) & ~63) : 0)) : 0; }
   int G, M, N, K;  // G = mmax, M = B*2*C, N = nlat, K = lmax
   const T* A; const T* Bm; int64_t a_sk, b_sk;
   int64_t a_goff;
@@ -230,8 +253,9 @@ struct IdftArgs {
   float* stat_part;
 };
 template <class T, class TOut, int ACT = -1>
-struct OpIdft : IdftArgs<T, TOut> {
+struct OpIdft : IdftArgs<T, TOut>, FullRanges {
   static constexpr bool A_KCONTIG = false, B_KCONTIG = true, kColContig = true, kNFastest = true;
+  __device__ int n_end(int) const { return this->N; }
   using OutT = TOut;
   using Args = IdftArgs<T, TOut>;
   OpIdft() = default;
@@ -301,8 +325,9 @@ struct ConvArgs {
 };
 // ACT / DROP < 0: decided at run time (CUDA-core engine and rarely used combinations)
 template <class T, class TOut, int ACT = -1, int DROP = -1>
-struct OpConv : ConvArgs<T, TOut> {
+struct OpConv : ConvArgs<T, TOut>, FullRanges {
   static constexpr bool A_KCONTIG = true, B_KCONTIG = false, kColContig = true, kNFastest = false;
+  __device__ int n_end(int) const { return this->N; }
   using OutT = TOut;
   using Args = ConvArgs<T, TOut>;
   OpConv() = default;

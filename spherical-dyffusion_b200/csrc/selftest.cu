@@ -129,7 +129,7 @@ extern "C" int sfno_b200_selftest_gemm(int op_kind, const int* d, int nd, double
       OpLeg<bf16> op{};
       op.G = mmax; op.M = B * 2 * C; op.N = lmax; op.K = nlat;
       op.A = s.rnd((int64_t)mmax * op.M * Kp, 5); op.Bm = s.rnd((int64_t)mmax * lmax * Kp, 6, 0.1f); op.a_sk = 1; op.b_sk = 1;
-      op.Kp = Kp; op.lmax = lmax; op.mmax = mmax;
+      op.Kp = Kp; op.lmax = lmax; op.mmax = mmax; op.triangular = d[5];
       return run_both<OpLeg<bf16>, bf16>(op, (int64_t)lmax * mmax * op.M, [](OpLeg<bf16>& o, bf16* p) { o.x = p; }, s, res);
     }
     case 2: {  // DHCONV: B, C, lmax, mmax
@@ -137,13 +137,14 @@ extern "C" int sfno_b200_selftest_gemm(int op_kind, const int* d, int nd, double
       OpDhconv<bf16> op{};
       op.G = lmax; op.M = 2 * C; op.N = mmax * B; op.K = 2 * C;
       op.A = s.rnd((int64_t)lmax * 4 * C * C, 7, 0.1f); op.Bm = s.rnd((int64_t)lmax * mmax * B * 2 * C, 8); op.a_sk = 1; op.b_sk = 1;
-      op.B = B; op.lmax = lmax; op.mmax = mmax;
+      op.B = B; op.lmax = lmax; op.mmax = mmax; op.triangular = d[4];
       return run_both<OpDhconv<bf16>, bf16>(op, (int64_t)lmax * mmax * B * 2 * C, [](OpDhconv<bf16>& o, bf16* p) { o.y = p; }, s, res);
     }
     case 3: {  // ILEG: B, C, nlat, lmax, mmax, x_layout
-      const int B = d[0], C = d[1], nlat = d[2], lmax = d[3], mmax = d[4], xl = d[5];
+      const int B = d[0], C = d[1], nlat = d[2], lmax = d[3], mmax = d[4], xl = d[5] & 1;
       const int Kp = round_up(nlat, Kr), Lq = round_up(lmax, Kr);
       OpIleg<bf16> op{};
+      op.triangular = (d[5] >> 1) & 1;
       op.G = mmax; op.M = B * 2 * C; op.N = nlat; op.K = lmax;
       op.A = s.rnd((int64_t)lmax * mmax * op.M, 10); op.Bm = s.rnd((int64_t)mmax * nlat * Lq, 9, 0.1f); op.b_sk = 1;
       if (xl) { op.a_goff = op.M; op.a_sk = (int64_t)mmax * op.M; } else { op.a_goff = (int64_t)lmax * op.M; op.a_sk = op.M; }

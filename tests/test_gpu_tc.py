@@ -20,6 +20,7 @@ CASES = [
     ("leg", [1, 8, 16, 16, 9, 0], True),        # single tile, K = 16
     ("leg", [2, 64, 180, 180, 5, 0], True),     # ACE geometry, few m
     ("leg", [8, 256, 180, 180, 181, 0], True),  # ACE full size
+    ("leg", [8, 256, 180, 180, 181, 1], True),  # ... storing only degrees l >= m (triangular)
     ("dft", [1, 8, 16, 32, 17, 0], True),
     ("dft", [2, 32, 180, 360, 181, 0], True),
     ("dft", [8, 256, 180, 360, 181, 0], True),
@@ -27,10 +28,14 @@ CASES = [
     ("dhconv", [1, 16, 4, 5, 0, 0], True),
     ("dhconv", [2, 64, 20, 21, 0, 0], True),
     ("dhconv", [8, 256, 180, 181, 0, 0], True),
+    ("dhconv", [8, 256, 180, 181, 1, 0], True),  # only wavenumbers m <= l (triangular)
+    ("dhconv", [3, 32, 20, 21, 1, 0], True),
     ("ileg", [1, 8, 16, 16, 9, 0], True),
     ("ileg", [1, 8, 16, 16, 9, 1], True),       # X layout (residual path)
     ("ileg", [2, 64, 180, 180, 7, 0], True),
     ("ileg", [8, 256, 180, 180, 181, 0], True),
+    ("ileg", [8, 256, 180, 180, 181, 2], True),  # contraction over l >= m only (triangular, Y layout)
+    ("ileg", [2, 64, 180, 180, 181, 3], True),   # triangular, X layout
     ("idft", [1, 8, 16, 32, 17, 0], True),
     ("idft", [2, 16, 180, 360, 181, 7], True),
     ("idft", [8, 256, 180, 360, 181, 7], True),   # block epilogue: + bias + inner-skip -> GELU
