@@ -202,19 +202,47 @@ def run_b200(args):
         launches = _lib.launch_count() - n0
         clocks = sampler.stop() if rank == 0 else None
 
-        # ---- end to end through the public call: pinned host -> device -> forward -> host ----------------------
-        def e2e_step():
-            xi = x_pin.to(dev, non_blocking=True)
-            ci = c_pin.to(dev, non_blocking=True)
-            y = model(xi, time=td, condition=ci)
-            y_pin.copy_(y, non_blocking=True)
+        # ---- end to end through the public call: pinned host -> device -> forward -> host, every step --------------
+        # The copies run on their own streams and are double-buffered, so step i+1's upload and step i-1's download
+        # overlap step i's forward (what a serving loop does); every step still moves all its bytes inside the timed
+        # region, and the region ends only when the last result has landed in host memory.
+        compute = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        x_buf = [torch.empty_like(xd) for _ in range(2)]
+        c_buf = [torch.empty_like(cd) for _ in range(2)]
+        y_pins = [y_pin, torch.empty_like(y_pin).pin_memory()]
+        free_ev = [torch.cuda.Event() for _ in range(2)]
+        ready_ev = [torch.cuda.Event() for _ in range(2)]
+        out_ev = [torch.cuda.Event() for _ in range(2)]
+        for ev in free_ev + out_ev:
+            ev.record(compute)
 
-        for _ in range(3):
-            e2e_step()
+        def e2e_step(i):
+            k = i & 1
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(free_ev[k])
+                x_buf[k].copy_(x_pin, non_blocking=True)
+                c_buf[k].copy_(c_pin, non_blocking=True)
+                ready_ev[k].record(s_in)
+            compute.wait_event(ready_ev[k])
+            y = model(x_buf[k], time=td, condition=c_buf[k])
+            free_ev[k].record(compute)
+            done = torch.cuda.Event()
+            done.record(compute)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                s_out.wait_event(out_ev[k])
+                y_pins[k].copy_(y, non_blocking=True)
+                y.record_stream(s_out)
+                out_ev[k].record(s_out)
+
+        for i in range(4):
+            e2e_step(i)
         barrier()
         e0.record()
-        for _ in range(args.steps):
-            e2e_step()
+        for i in range(args.steps):
+            e2e_step(i)
+        compute.wait_stream(s_out)
         e1.record()
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))

@@ -41,7 +41,7 @@ bool idft_uses_tc(const IdftArgs<T, TOut>& a) {
   }
   return false;
 }
-constexpr int kConvStatSlicesPerTile = TC_EPI_WARPS / 4;
+constexpr int kConvStatSlicesPerTile = TC_EPI_WARPS / 4;  // statistics partials per (row, N tile): one per column slice
 
 template <class T, class TOut>
 int launch_conv(const ConvArgs<T, TOut>& a, cudaStream_t stream, const char* what) {

@@ -424,7 +424,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           __syncwarp();
         }
-        if (row_ok) op.finish(row, g, m, nt * (TC_EPI_WARPS / 4) + part);  // fused statistics partials (if enabled)
+        // the accumulator has been drained: hand the TMEM stage back to the MMA warp before any further work
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+        // fused InstanceNorm statistics: one partial per (row, N tile, column slice); no cross-warp synchronisation
+        if (op.wants_stats() && row_ok)
+          op.finish(g, m, nt * (TC_EPI_WARPS / 4) + part, valid ? row.s : 0.0f, valid ? row.q : 0.0f);
       } else {
         // ---- row-contiguous output: for a fixed column the warp writes 32 consecutive elements ----
         ptx::mbar_wait(tfull_bar(acc), acc_phase);
@@ -440,10 +446,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           ptx::tmem_ld_wait();
           if (row_ok) op.store16(row, g, m, n0, n_end - n0, r);
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }

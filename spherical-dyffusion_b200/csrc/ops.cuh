@@ -219,18 +219,19 @@ struct OpIleg {
   __device__ int64_t b_off(int g, int n) const { return ((int64_t)g * nlat + n) * Lq; }
   __device__ int n_store() const { return Kp; }  // columns [nlat, Kp) are exact zeros (zero-filled table rows)
   __device__ bool has_res() const { return false; }
-  struct Row { T* out; const T* res; bool valid; };
+  struct Row { T* out; const T* res; bool valid; float s, q; };
   __device__ Row row(int g, int m) const {
     int b = m / (2 * C), rem = m - b * 2 * C;
     int ri = rem / C, o = rem - ri * C;
-    return Row{g_out + (int64_t)g * 2 * B * C * Kp + (int64_t)ri * B * C * Kp + ((int64_t)b * C + o) * Kp, nullptr, true};
+    return Row{g_out + (int64_t)g * 2 * B * C * Kp + (int64_t)ri * B * C * Kp + ((int64_t)b * C + o) * Kp, nullptr, true, 0.0f, 0.0f};
   }
   __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = from_f32<T>(acc); }
   __device__ void compute8(Row&, int, const float (&acc)[8], const float (&)[8], float (&o)[8]) const {
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = acc[i];
   }
-  __device__ void finish(const Row&, int, int, int) const {}
+  __device__ bool wants_stats() const { return false; }
+  __device__ void finish(int, int, int, float, float) const {}
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -291,12 +292,11 @@ struct OpIdft : IdftArgs<T, TOut>, FullRanges {
       for (int i = 0; i < 8; ++i) { r.s += o[i]; r.q = fmaf(o[i], o[i], r.q); }
     }
   }
-  // called once per (tile, column slice) by every in-range row, valid or not (invalid rows contribute zeros)
-  __device__ void finish(const Row& r, int, int m, int slice) const {
-    if (this->stat_part) {
-      this->stat_part[((int64_t)slice * 2) * this->M + m] = r.valid ? r.s : 0.0f;
-      this->stat_part[((int64_t)slice * 2 + 1) * this->M + m] = r.valid ? r.q : 0.0f;
-    }
+  __device__ bool wants_stats() const { return this->stat_part != nullptr; }
+  // called once per (row, N tile) with the row's sums over that tile's columns (zeros for pad rows)
+  __device__ void finish(int, int m, int slice, float s, float q) const {
+    this->stat_part[((int64_t)slice * 2) * this->M + m] = s;
+    this->stat_part[((int64_t)slice * 2 + 1) * this->M + m] = q;
   }
 };
 
@@ -391,12 +391,11 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
       for (int i = 0; i < 8; ++i) { r.s += o[i]; r.q = fmaf(o[i], o[i], r.q); }
     }
   }
-  __device__ void finish(const Row& r, int g, int m, int slice) const {
-    if (this->stat_part) {
-      const int64_t rows = (int64_t)this->G * this->M, idx = (int64_t)g * this->M + m;
-      this->stat_part[((int64_t)slice * 2) * rows + idx] = r.s;
-      this->stat_part[((int64_t)slice * 2 + 1) * rows + idx] = r.q;
-    }
+  __device__ bool wants_stats() const { return this->stat_part != nullptr; }
+  __device__ void finish(int g, int m, int slice, float s, float q) const {
+    const int64_t rows = (int64_t)this->G * this->M, idx = (int64_t)g * this->M + m;
+    this->stat_part[((int64_t)slice * 2) * rows + idx] = s;
+    this->stat_part[((int64_t)slice * 2 + 1) * rows + idx] = q;
   }
 };
 

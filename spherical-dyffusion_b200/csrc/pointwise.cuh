@@ -156,6 +156,46 @@ static __global__ void __launch_bounds__(256) norm_affine_partials_kernel(
   d_out[i] = d;
 }
 
+// rows_per_bc == 1 (convolution partials, layout [slice][{s,q}][B*C]): 32 consecutive (b,c) per CTA so that every
+// read is a coalesced 128-byte row; 32 warps stride over the slices, fixed-order smem reduction (deterministic)
+static __global__ void __launch_bounds__(1024) norm_affine_partials_conv_kernel(
+    const float* __restrict__ part, int slices, int64_t rows, float count, float eps, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const float* __restrict__ ts, int64_t ts_bstride, int B, int C, float* __restrict__ a_out,
+    float* __restrict__ d_out) {
+  __shared__ double sh_s[32][32], sh_q[32][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;  // 32 warps stride over the slices
+  const int i = blockIdx.x * 32 + lane;
+  double s = 0.0, q = 0.0;
+  if (i < B * C) {
+#pragma unroll 4
+    for (int sl = w; sl < slices; sl += 32) {
+      const float* ps = part + ((int64_t)sl * 2) * rows + i;
+      s += (double)ps[0];
+      q += (double)ps[rows];
+    }
+  }
+  sh_s[w][lane] = s; sh_q[w][lane] = q;
+  __syncthreads();
+  if (w != 0 || i >= B * C) return;
+#pragma unroll
+  for (int k = 1; k < 32; ++k) { s += sh_s[k][lane]; q += sh_q[k][lane]; }
+  const int b = i / C, c = i - b * C;
+  const double mean = s / (double)count;
+  double var = q / (double)count - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  const float rstd = rsqrtf((float)var + eps);
+  const float g = gamma ? gamma[c] : 1.0f, be = beta ? beta[c] : 0.0f;
+  float a = g * rstd;
+  float d = be - g * (float)mean * rstd;
+  if (ts) {
+    const float sc = ts[(int64_t)b * ts_bstride + c] + 1.0f, sf = ts[(int64_t)b * ts_bstride + C + c];
+    a *= sc;
+    d = d * sc + sf;
+  }
+  a_out[i] = a;
+  d_out[i] = d;
+}
+
 // compose a time scale/shift given as separate [B*C] arrays onto an existing affine
 static __global__ void time_affine_compose_kernel(float* __restrict__ a, float* __restrict__ d, const float* __restrict__ scale,
                                            const float* __restrict__ shift, int n) {

@@ -91,4 +91,16 @@ def roofline_from_profile(recs, pk, model=None, batch=None):
             out["algorithmic_bytes_per_launch"] = nbytes
             out["tflops_achieved"] = flops / sec / 1e12
             out["traffic"] = None
+        # every GEMM-shaped kernel against its own bound (all of them sit below the ridge at ACE size -> HBM)
+        table = {}
+        for name, (flops, nbytes) in algorithmic_work(model, batch).items():
+            if name in recs and recs[name]["launches"] > 0 and nbytes > 0:
+                sec = recs[name]["ms_total"] / recs[name]["launches"] * 1e-3
+                table[name] = {"ms_per_launch": round(sec * 1e3, 4), "GBps": round(nbytes / sec / 1e9, 1),
+                               "frac_hbm": round(nbytes / sec / 1e9 / pk["hbm_gbs"], 3),
+                               "TFLOPs": round(flops / sec / 1e12, 1),
+                               "frac_tensor": round(flops / sec / 1e12 / pk["bf16_tflops_sustained"], 3)}
+        out["per_kernel_roofline"] = table
+        out["per_kernel_roofline_note"] = ("DENSE algorithmic bytes / flops per launch (SURVEY 8d); the Legendre and dhconv "
+                                           "kernels execute only the l >= m half, so their fractions are upper bounds on the traffic actually moved")
     return out
