@@ -55,8 +55,6 @@ struct sfno_net {
   int stop_after_block = -2;  // -2: run everything; -1: stop after encoder(+pos); i: stop after block i
   // bookkeeping of the last forward for debug taps
   size_t last_x_off = 0; int64_t last_x_bstride = 0; int last_batch = 0;
-  // the spectral buffers were zero-filled for this (workspace, batch): entries skipped by the triangular ranges stay finite
-  const void* zeroed_ws = nullptr; int zeroed_batch = 0;
 };
 
 namespace sfno {
@@ -289,14 +287,6 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
   float* dscale = (float*)(ws + w.dscale);
   const int64_t xcat_bs = (int64_t)n->Ccat * P;
   const int BC = B * C;
-  if (n->zeroed_ws != (const void*)ws || n->zeroed_batch != B) {
-    // X / Y entries outside the triangular ranges are never written; they only ever meet exact table zeros, so they
-    // just have to be finite: zero them once per (workspace, batch)
-    SFNO_CUDA(cudaMemsetAsync(X, 0, (size_t)n->L * n->M * B * 2 * C * sizeof(T), st));
-    SFNO_CUDA(cudaMemsetAsync(Y, 0, (size_t)n->L * n->M * B * 2 * C * sizeof(T), st));
-    n->zeroed_ws = (const void*)ws; n->zeroed_batch = B;
-  }
-
   // ---- input: fp32 -> T, and into the tail channels of the big-skip concat buffer (sfnonet.py:804-805,832)
   {
     dim3 grid(1184 / std::max(1, std::min(B, 8)) + 1, B);

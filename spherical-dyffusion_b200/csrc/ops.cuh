@@ -75,10 +75,11 @@ __device__ __forceinline__ void load_vec8(const float* p, float (&v)[8]) {
 }
 
 // Per-group index ranges.  The Legendre tables are exactly zero for l < m, so for the zonal
-// wavenumber m only degrees l >= m carry information: the forward transform stores only those columns, dhconv
-// visits only m <= l and the inverse transform contracts only over l >= m (ranges are rounded to the engines'
-// granularity inside the ops so that both engines skip exactly the same work).  Skipped entries of X / Y are never
-// read as anything but a factor of an exact table zero; the executor keeps those buffers finite (zero-filled once).
+// wavenumber m only degrees l >= m carry information.  All three spectral ops use the SAME predicate
+//     (l, m) is live  <=>  l >= (m & ~63)          (the triangle, rounded to the 64-wide K block of the engine)
+// the forward transform stores exactly the live columns, dhconv visits exactly the live wavenumbers of a degree
+// (m <= l | 63) and the inverse transform contracts over exactly the live degrees.  Hence every X / Y entry that is
+// ever read was written in the same forward: nothing depends on the previous contents of the workspace.
 struct FullRanges {
   __device__ int n_begin(int) const { return 0; }
   __device__ int k_begin(int) const { return 0; }
@@ -134,8 +135,8 @@ struct OpDft : FullRanges {
 template <class T>
 struct OpLeg {
   static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = false, kNFastest = false;
-  int triangular;  // 1: store only degrees l >= m (rounded down to 16)
-  __device__ int n_begin(int g) const { return triangular ? (g & ~15) : 0; }
+  int triangular;  // 1: store only the live degrees l >= (m & ~63)
+  __device__ int n_begin(int g) const { return triangular ? (g & ~63) : 0; }
   __device__ int n_end(int) const { return N; }
   __device__ int k_begin(int) const { return 0; }
   int G, M, N, K;  // G = mmax, M = B*2*C, N = lmax, K = nlat
@@ -168,9 +169,9 @@ struct OpLeg {
 template <class T>
 struct OpDhconv {
   static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = false, kNFastest = false;
-  int triangular;  // 1: only wavenumbers m <= l
+  int triangular;  // 1: only the live wavenumbers m <= (l | 63)
   __device__ int n_begin(int) const { return 0; }
-  __device__ int n_end(int g) const { int e = (g + 1) * B; return (triangular && e < N) ? e : N; }
+  __device__ int n_end(int g) const { int e = ((g | 63) + 1) * B; return (triangular && e < N) ? e : N; }
   __device__ int k_begin(int) const { return 0; }
   int G, M, N, K;  // G = lmax, M = 2*Cout, N = mmax*B, K = 2*Cin
   const T* A; const T* Bm; int64_t a_sk, b_sk;
@@ -206,7 +207,7 @@ template <class T>
 struct OpIleg {
   static constexpr bool A_KCONTIG = false, B_KCONTIG = true, kColContig = true, kNFastest = true;
   using OutT = T;
-  int triangular;  // 1: contract only over degrees l >= m (rounded down to the 64-wide K block)
+  int triangular;  // 1: contract only over the live degrees l >= (m & ~63)
   __device__ int n_begin(int) const { return 0; }
   __device__ int n_end(int) const { return N; }
   __device__ int k_begin(int g) const { int k = g & ~63; return triangular ? (k < K ? k : (K > 0 ? ((K - 1) & ~63) : 0)) : 0; }

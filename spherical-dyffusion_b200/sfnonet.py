@@ -349,7 +349,10 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
         self._param_versions = {}
 
     def __del__(self):
-        self._destroy_net()
+        try:
+            self._destroy_net()
+        except Exception:  # interpreter shutdown
+            pass
 
     def net_config(self, max_batch: int = 1 << 20) -> "_lib.NetConfig":
         c = _lib.NetConfig()

@@ -371,3 +371,28 @@ def test_ensemble_statistics_module_and_rollout(dev):
     assert len(hist["crps"]) == 7 and len(hist["spread"]) == 7
     assert all(torch.isfinite(v).all() for v in hist["crps"])
     assert float(hist["spread"][-1].mean()) > 0.0  # members diverge through the interpolator's dropout stream
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_does_not_depend_on_workspace_contents(dev, precision, load_golden):
+    """The scratch arena is shared between nets and never cleared: poisoning it with NaN bit patterns before a
+    forward must not change the result (every scratch entry that is read is written in the same forward)."""
+    from spherical_dyffusion_b200 import _util
+
+    cfg = SFNOConfig(num_input_channels=6, num_output_channels=6, num_conditional_channels=2, spatial_shape=(96, 192),
+                     embed_dim=64, num_layers=3)
+    sd = perturb_affine_and_biases(random_state_dict(cfg, seed=3, spectral_gain=64.0))
+    m = module_from_cfg(cfg, sd, dev, precision)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(3, 6, 96, 192, generator=g).to(dev)
+    c = torch.randn(3, 2, 96, 192, generator=g).to(dev)
+    t = torch.tensor([0.0, 2.0, 5.0], device=dev)
+    with torch.inference_mode():
+        y0 = m(x, time=t, condition=c).clone()
+        for buf in _util._workspaces.values():
+            buf.fill_(0xFF)  # 0xFFFF = bf16 NaN, 0xFFFFFFFF = fp32 NaN
+        y1 = m(x, time=t, condition=c)
+    assert torch.isfinite(y1).all()
+    assert rel_l2(y1, y0) < 1e-6
+    ref = SFNOOracle(cfg, sd)(x.cpu(), time=t.cpu(), condition=c.cpu())
+    assert rel_l2(y1, ref) < (FP32_TOL if precision == "fp32" else BF16_BOUND)
