@@ -93,7 +93,8 @@ def run_rollout(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     fore, ipol = _ace_pair(dev, args.precision)
     dy = DYffusion(fore, ipol, timesteps=6, forward_conditioning="none", time_encoding="dynamics")
