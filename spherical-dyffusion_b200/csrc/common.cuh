@@ -109,4 +109,13 @@ __device__ __forceinline__ void philox_uniform4(uint64_t seed, uint64_t offset, 
   u3 = (r.w >> 8) * (1.0f / 16777216.0f);
 }
 
+// Optional epilogue features.  The tensor-core engine instantiates its drain loop for the op's two most frequent
+// feature sets (kFast0, kFast1: compile-time masks, no per-element tests) plus, if kGeneral, a run-time tested one (F < 0).
+enum : int { F_RES = 1, F_STATS = 2, F_POS = 4, F_SCALE = 8 };
+template <int F, int BIT>
+__device__ __forceinline__ bool feat_on(bool runtime_value) {
+  if constexpr (F < 0) return runtime_value;
+  else return (F & BIT) != 0;
+}
+
 }  // namespace sfno

@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(const Op op) {
   const int t = threadIdx.x;
   const int M = op.M, K = op.K;
   const int N = op.n_end(g), n_lo = op.n_begin(g);   // per-group column range actually produced
-  if (n0 >= N || n0 + SIMT_BN <= n_lo) return;       // block-uniform
+  const int m_hi = op.m_end(g), m_lo = op.m_begin(g);  // per-group row range actually produced
+  if (n0 >= N || n0 + SIMT_BN <= n_lo || m0 >= m_hi || m0 + SIMT_BM <= m_lo) return;  // block-uniform
   const auto* __restrict__ A = op.A;
   const auto* __restrict__ Bm = op.Bm;
 
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(const Op op) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = m0 + tx + 16 * i;
-    if (m >= M) continue;
+    if (m >= m_hi || m < m_lo) continue;
     const typename Op::Row r = op.row(g, m);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {

@@ -1,10 +1,12 @@
 // tcgen05 / TMA / TMEM engine for the bf16 batched-GEMM ops (SFNO_PREC_BF16), sm_100a only.
 //
 //   persistent CTAs (one per SM), 128 x BN output tile, K in blocks of 64 bf16 (one 128-byte swizzle span)
-//   warp 0      : TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, 3-D maps {inner, outer, batch})
+//   warp 0      : TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, 4-D maps {inner, outer, batch, batch_hi})
 //   warp 1      : MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM, 2 stages)
 //   warps 2..17 : epilogue       (tcgen05.ld 32x32b.x16 -> fused op epilogue; 4 warps per TMEM sub-partition, each a
 //                                 column slice; compact rolled loops so the code stays inside the instruction cache)
+//   (576 threads cap the kernel at 96 registers per thread; moving registers between roles with setmaxnreg was
+//    tried -- 640 threads, 56/104 -- and lost: ptxas spilled the residual prefetch block)
 //   smem ring of kStages {A tile, B tile}, mbarrier full/empty; TMEM full/empty barriers decouple the MMA of
 //   tile i+1 from the epilogue of tile i.
 //
@@ -14,6 +16,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sfno {
@@ -22,17 +26,40 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_WARP_TMA = 0, TC_WARP_MMA = 1;
 
 struct TmaOperand {
   const void* base = nullptr;
-  uint64_t dims[3] = {1, 1, 1};      // {inner, outer, batch} in elements
-  uint64_t strides[2] = {0, 0};      // byte strides of dims[1], dims[2]
+  uint64_t dims[4] = {1, 1, 1, 1};   // {inner, outer, batch, batch_hi} in elements
+  uint64_t strides[3] = {0, 0, 0};   // byte strides of dims[1..3]
   bool batched = false;
+  int group_lo = 0;                  // > 0: group g addresses {g % group_lo, g / group_lo} in dims[2], dims[3]
 };
 
 struct TcSched {
   int m_tiles, n_tiles, groups, num_tiles, k_blocks, k16_last;  // k16_last: MMAs (K=16) in the last k block
   int a_batched, b_batched;
+  int a_glo, b_glo;  // > 0: the operand's group index splits into {g % glo, g / glo} (4-D tensor map)
+  // experiment switch (sfno_b200_set_option("tc_debug")), WRONG results, timing only: bit0 skip A loads, bit1 skip B
+  // loads, bit2 skip global stores, bit3 skip the fused epilogue math, bit4 skip the MMAs, bit5 skip the TMEM loads
+  int dbg;
+};
+
+extern std::atomic<int> g_tc_debug;
+
+// Tile walk of a persistent CTA without per-tile divisions: tile = (c * J + b) * I + a advances by a fixed step.
+struct TileIter {
+  int a, b, c, da, db, dc, I, J;
+  __device__ void init(int tile0, int step, int I_, int J_) {
+    I = I_; J = J_;
+    a = tile0 % I; int r = tile0 / I; b = r % J; c = r / J;
+    da = step % I; r = step / I; db = r % J; dc = r / J;
+  }
+  __device__ void next() {
+    a += da; int carry = a >= I; a -= carry ? I : 0;
+    b += db + carry; carry = b >= J; b -= carry ? J : 0;
+    c += dc + carry;
+  }
 };
 
 template <class Op>
@@ -65,18 +92,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Blocking wait with a watchdog: a pipeline bug traps (-> CUDA error) after ~2 s instead of hanging the GPU.
+template <bool kBackoff = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (kBackoff) __nanosleep(64);  // single-thread roles with slack: do not compete with the epilogue warps for issue slots
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -209,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == TC_WARP_TMA && lane == 0) {
     ptx::prefetch_tmap(&tma_a);
     ptx::prefetch_tmap(&tma_b);
     for (int s = 0; s < kStages; ++s) {
@@ -222,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == TC_WARP_MMA) ptx::tmem_alloc(tmem_slot, kTmemCols);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -231,57 +260,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   // consecutive tiles (= concurrently running CTAs) share the operand that is re-read: the N tiles of one M tile
   // when the activations sit on the A side (kNFastest), the M tiles of one N tile when they sit on the B side
-  auto decode = [&](int tile, int& g, int& mt, int& nt) {
-    if (Op::kNFastest) {
-      nt = tile % sc.n_tiles;
-      const int r = tile / sc.n_tiles;
-      mt = r % sc.m_tiles;
-      g = r / sc.m_tiles;
-    } else {
-      mt = tile % sc.m_tiles;
-      const int r = tile / sc.m_tiles;
-      nt = r % sc.n_tiles;
-      g = r / sc.n_tiles;
-    }
+  TileIter it;
+  it.init(blockIdx.x, gridDim.x, Op::kNFastest ? sc.n_tiles : sc.m_tiles, Op::kNFastest ? sc.m_tiles : sc.n_tiles);
+  auto decode = [&](int& g, int& mt, int& nt) {
+    g = it.c;
+    if (Op::kNFastest) { nt = it.a; mt = it.b; } else { mt = it.a; nt = it.b; }
   };
 
-  // tiles whose column range lies outside the group's [n_begin, n_end) carry no information: all roles skip them
-  auto tile_skipped = [&](int g, int nt) { return nt * BN >= op.n_end(g) || (nt + 1) * BN <= op.n_begin(g); };
+  // tiles outside the group's live row / column ranges carry no information: all roles skip them
+  auto tile_skipped = [&](int g, int mt, int nt) {
+    if constexpr (!Op::kRanged) return false;
+    else return nt * BN >= op.n_end(g) || (nt + 1) * BN <= op.n_begin(g) || mt * TC_BM >= op.m_end(g) || (mt + 1) * TC_BM <= op.m_begin(g);
+  };
 
-  if (warp == 0) {
+  if (warp == TC_WARP_TMA) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, it.next()) {
         int g, mt, nt;
-        decode(tile, g, mt, nt);
-        if (tile_skipped(g, nt)) continue;
+        decode(g, mt, nt);
+        if (tile_skipped(g, mt, nt)) continue;
         const int m0 = mt * TC_BM, n0 = nt * BN;
-        const int ga = sc.a_batched ? g : 0, gb = sc.b_batched ? g : 0;
+        int ga = sc.a_batched ? g : 0, gb = sc.b_batched ? g : 0, ga_hi = 0, gb_hi = 0;
+        if (sc.a_glo) { ga_hi = ga / sc.a_glo; ga -= ga_hi * sc.a_glo; }
+        if (sc.b_glo) { gb_hi = gb / sc.b_glo; gb -= gb_hi * sc.b_glo; }
         for (int kb = op.k_begin(g) / TC_BK; kb < sc.k_blocks; ++kb) {
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          ptx::mbar_expect_tx(full_bar(stage), S::kStageBytes);
+          ptx::mbar_wait<true>(empty_bar(stage), phase ^ 1u);
+          const bool load_a = !(sc.dbg & 1), load_b = !(sc.dbg & 2);
+          ptx::mbar_expect_tx(full_bar(stage), (load_a ? S::kABytes : 0) + (load_b ? S::kBBytes : 0));
           const int k0 = kb * TC_BK;
-          if (Op::A_KCONTIG) {
-            ptx::tma_load_3d(a_smem(stage), &tma_a, full_bar(stage), k0, m0, ga);
+          if (!load_a) {
+          } else if (Op::A_KCONTIG) {
+            ptx::tma_load_4d(a_smem(stage), &tma_a, full_bar(stage), k0, m0, ga, ga_hi);
           } else {
 #pragma unroll
             for (int h = 0; h < TC_BM / 64; ++h)
-              ptx::tma_load_3d(a_smem(stage) + h * (64 * TC_BK * 2), &tma_a, full_bar(stage), m0 + 64 * h, k0, ga);
+              ptx::tma_load_4d(a_smem(stage) + h * (64 * TC_BK * 2), &tma_a, full_bar(stage), m0 + 64 * h, k0, ga, ga_hi);
           }
-          if (Op::B_KCONTIG) {
-            ptx::tma_load_3d(b_smem(stage), &tma_b, full_bar(stage), k0, n0, gb);
+          if (!load_b) {
+          } else if (Op::B_KCONTIG) {
+            ptx::tma_load_4d(b_smem(stage), &tma_b, full_bar(stage), k0, n0, gb, gb_hi);
           } else {
 #pragma unroll
             for (int h = 0; h < BN / 64; ++h)
-              ptx::tma_load_3d(b_smem(stage) + h * (64 * TC_BK * 2), &tma_b, full_bar(stage), n0 + 64 * h, k0, gb);
+              ptx::tma_load_4d(b_smem(stage) + h * (64 * TC_BK * 2), &tma_b, full_bar(stage), n0 + 64 * h, k0, gb, gb_hi);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == TC_WARP_MMA) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(!Op::A_KCONTIG, !Op::B_KCONTIG, BN);
@@ -291,22 +321,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       constexpr uint32_t b_lbo = Op::B_KCONTIG ? 16u : (uint32_t)(TC_BK * 128), b_kstep = Op::B_KCONTIG ? 32u : 2048u;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, it.next()) {
         int g, mt, nt;
-        decode(tile, g, mt, nt);
-        if (tile_skipped(g, nt)) continue;
+        decode(g, mt, nt);
+        if (tile_skipped(g, mt, nt)) continue;
         const int kb0 = op.k_begin(g) / TC_BK;
-        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::mbar_wait<true>(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = kb0; kb < sc.k_blocks; ++kb) {
-          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::mbar_wait<true>(full_bar(stage), phase);
           ptx::tc_fence_after();
           const int nk = (kb == sc.k_blocks - 1) ? sc.k16_last : TC_BK / 16;
           for (int k = 0; k < nk; ++k) {
             const uint64_t ad = make_smem_desc(a_smem(stage) + k * a_kstep, a_lbo, 1024u);
             const uint64_t bd = make_smem_desc(b_smem(stage) + k * b_kstep, b_lbo, 1024u);
-            ptx::mma_bf16(d_tmem, ad, bd, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            if (!(sc.dbg & 16)) ptx::mma_bf16(d_tmem, ad, bd, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           ptx::mma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -324,51 +354,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     static_assert(kColsPerWarp % 16 == 0, "column slice must be a multiple of the TMEM load width");
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, it.next()) {
       int g, mt, nt;
-      decode(tile, g, mt, nt);
-      if (tile_skipped(g, nt)) continue;
+      decode(g, mt, nt);
+      if (tile_skipped(g, mt, nt)) continue;
       const int m = mt * TC_BM + quad * 32 + lane;
       const int n_base = nt * BN + part * kColsPerWarp;
-      const bool row_ok = m < op.M;
-      typename Op::Row row{};
-      if (row_ok) row = op.row(g, m);
+      const bool row_ok = m < op.m_end(g) && m >= op.m_begin(g);
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kColsPerWarp);
-      if constexpr (Op::kColContig) {
-        // ---- column-contiguous output: warp-private swizzled smem transpose, fully coalesced global traffic ----
+      static_assert(Op::kColContig, "the tensor-core epilogue writes along the row: the column index must be the contiguous output index");
+      // ---- drain: TMEM -> registers -> fused epilogue -> warp-private swizzled smem transpose -> coalesced 16-byte
+      //      global stores (and, for residual / addend blocks, coalesced loads through the same staging rows) ----
+      auto drain = [&](auto feat_c) {
+        constexpr int F = decltype(feat_c)::value;   // compile-time feature mask, or < 0: tested at run time
+        typename Op::Row row{};
+        if (row_ok) row = op.template row_f<F>(g, m);
         using OutT = typename Op::OutT;
         constexpr int kEs = (int)sizeof(OutT);
         constexpr int kPassCols = TC_STAGE_PITCH / kEs;                 // 64 (bf16) or 32 (fp32) columns per pass
         constexpr int kPasses = (kColsPerWarp + kPassCols - 1) / kPassCols;
         constexpr int kVec = 16 / kEs;                                   // output elements per 16-byte chunk
+        constexpr bool kGuardRows = F < 0 || (F & F_POS) != 0;           // compute8 may dereference per-row pointers
         const uint32_t region = staging_base + (uint32_t)ew * TC_STAGING_PER_WARP;
         const uint32_t my_row = region + (uint32_t)lane * TC_STAGE_PITCH;
         const uint32_t sw = (uint32_t)(lane & 7);
         const int srow0 = lane >> 3, cl = lane & 7;                      // staging copies: 4 rows x 128 B per instruction
         const int n_end = op.n_store();
-        const bool has_res = (kEs == 2) && op.has_res();
+        const bool has_res = (kEs == 2) && feat_on<F, F_RES>(op.has_res());
         const bool valid = row_ok && row.valid;
-        const unsigned long long out_ptr = (unsigned long long)row.out;
-        const unsigned long long res_ptr = (unsigned long long)row.res;
+        // row starts as 16-byte units relative to the tensor base: ONE 32-bit shuffle per staged row (~0 = no row)
+        const uint32_t out16 = valid ? (uint32_t)(((const char*)row.out - (const char*)op.out_base()) >> 4) : 0xFFFFFFFFu;
         // residual / addend block (bf16 outputs only): 8 coalesced 16-byte loads per lane issued BEFORE waiting for
         // the accumulator, so their latency hides behind the MMA of this tile
         uint4 res_pf[8];
         if (has_res) {
+          const uint32_t res16 = valid ? (uint32_t)(((const char*)row.res - (const char*)op.res_base()) >> 4) : 0xFFFFFFFFu;
+          const uint4* rb = reinterpret_cast<const uint4*>(op.res_base()) + (n_base >> 3) + cl;
           int nv0 = n_end - n_base;
           nv0 = nv0 < kColsPerWarp ? nv0 : kColsPerWarp;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int srow = 4 * i + srow0;
-            const unsigned long long p = __shfl_sync(0xffffffffu, res_ptr, srow);
-            const bool ok = __shfl_sync(0xffffffffu, (int)valid, srow) && (cl * 8 < nv0);
-            res_pf[i] = make_uint4(0, 0, 0, 0);
-            if (ok) res_pf[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p) + n_base + cl * 8);
+            const uint32_t o = __shfl_sync(0xffffffffu, res16, 4 * i + srow0);
+            res_pf[i] = (o != 0xFFFFFFFFu && cl * 8 < nv0) ? rb[o] : make_uint4(0, 0, 0, 0);
           }
         }
+        const bool warp_live = __any_sync(0xffffffffu, valid);  // all 32 rows outside the live range: nothing to drain
         ptx::mbar_wait(tfull_bar(acc), acc_phase);
         ptx::tc_fence_after();
 #pragma unroll 1
-        for (int pass = 0; pass < kPasses; ++pass) {
+        for (int pass = 0; pass < (warp_live ? kPasses : 0); ++pass) {
           const int pn0 = n_base + pass * kPassCols;
           const int pcols = (kColsPerWarp - pass * kPassCols) < kPassCols ? (kColsPerWarp - pass * kPassCols) : kPassCols;
           int nvalid = n_end - pn0;
@@ -384,9 +418,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll 1
           for (int ci = 0; ci < nchunks; ++ci) {
             uint32_t r[16];
-            ptx::tmem_ld16(t_row + (uint32_t)(pass * kPassCols + 16 * ci), r);
-            ptx::tmem_ld_wait();
-            if (valid) {
+            if (!(sc.dbg & 32)) {
+              ptx::tmem_ld16(t_row + (uint32_t)(pass * kPassCols + 16 * ci), r);
+              ptx::tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = 0x3f800000u + (uint32_t)ci;
+            }
+            if (!kGuardRows || valid) {
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
                 const int cofs = 16 * ci + 8 * q;  // column offset inside the pass
@@ -397,11 +436,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                   if constexpr (kEs == 2) {
                     const uint32_t slot = my_row + ((((uint32_t)cofs >> 3) ^ sw) << 4);
                     if (has_res) unpack_bf16x8(lds128(slot), resv);
-                    op.compute8(row, pn0 + cofs, accv, resv, outv);
+                    if (!(sc.dbg & 8)) op.template compute8<F>(row, pn0 + cofs, accv, resv, outv);
+                    else {
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) outv[i] = accv[i] + resv[i];
+                    }
                     sts128(slot, make_uint4(pack_bf16x2(outv[0], outv[1]), pack_bf16x2(outv[2], outv[3]),
                                             pack_bf16x2(outv[4], outv[5]), pack_bf16x2(outv[6], outv[7])));
                   } else {
-                    op.compute8(row, pn0 + cofs, accv, resv, outv);
+                    op.template compute8<F>(row, pn0 + cofs, accv, resv, outv);
                     const uint32_t c4 = (uint32_t)cofs >> 2;  // 16-byte chunk index (4 floats)
                     sts128(my_row + ((c4 ^ sw) << 4), make_uint4(__float_as_uint(outv[0]), __float_as_uint(outv[1]),
                                                                  __float_as_uint(outv[2]), __float_as_uint(outv[3])));
@@ -414,13 +457,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           __syncwarp();
           // staged rows -> global: 4 rows x 128 B per warp instruction
+          uint4* ob = reinterpret_cast<uint4*>(const_cast<void*>(op.out_base())) + ((pn0 * kEs) >> 4) + cl;
 #pragma unroll 2
           for (int i = 0; i < 8; ++i) {
             const int srow = 4 * i + srow0;
-            const unsigned long long p = __shfl_sync(0xffffffffu, out_ptr, srow);
-            const bool ok = __shfl_sync(0xffffffffu, (int)valid, srow) && (cl * kVec < nvalid);
+            const uint32_t o = __shfl_sync(0xffffffffu, out16, srow);
             const uint4 v = lds128(region + (uint32_t)srow * TC_STAGE_PITCH + (((uint32_t)cl ^ (uint32_t)(srow & 7)) << 4));
-            if (ok) *reinterpret_cast<uint4*>(reinterpret_cast<OutT*>(p) + pn0 + cl * kVec) = v;
+            if (o != 0xFFFFFFFFu && cl * kVec < nvalid && !(sc.dbg & 4)) ob[o] = v;
           }
           __syncwarp();
         }
@@ -429,26 +472,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
         // fused InstanceNorm statistics: one partial per (row, N tile, column slice); no cross-warp synchronisation
-        if (op.wants_stats() && row_ok)
+        if (feat_on<F, F_STATS>(op.wants_stats()) && row_ok)
           op.finish(g, m, nt * (TC_EPI_WARPS / 4) + part, valid ? row.s : 0.0f, valid ? row.q : 0.0f);
+      };
+      if constexpr (!Op::kGeneral && Op::kFast0 == Op::kFast1) {
+        drain(std::integral_constant<int, Op::kFast0>{});
       } else {
-        // ---- row-contiguous output: for a fixed column the warp writes 32 consecutive elements ----
-        ptx::mbar_wait(tfull_bar(acc), acc_phase);
-        ptx::tc_fence_after();
-        const int n_end = op.n_end(g), n_lo = op.n_begin(g);
-#pragma unroll 1
-        for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
-          const int n0 = n_base + c0;
-          if (n0 >= n_end) break;         // warp-uniform
-          if (n0 + 16 <= n_lo) continue;  // below the group's first column (n_begin is a multiple of 16)
-          uint32_t r[16];
-          ptx::tmem_ld16(t_row + (uint32_t)c0, r);
-          ptx::tmem_ld_wait();
-          if (row_ok) op.store16(row, g, m, n0, n_end - n0, r);
-        }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+        const int feat = op.feat();
+        if (feat == Op::kFast0) drain(std::integral_constant<int, Op::kFast0>{});
+        else if (feat == Op::kFast1) drain(std::integral_constant<int, Op::kFast1>{});
+        else drain(std::integral_constant<int, -1>{});
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -456,7 +489,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == TC_WARP_MMA) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -472,28 +505,31 @@ int tc_num_sms();
 inline int encode_operand(const TmaOperand& o, bool k_contig, int rows_box, CUtensorMap* map, const char* what) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return fail(SFNO_ERR_CUDA, "%s: cuTensorMapEncodeTiled unavailable", what);
-  cuuint64_t dims[3] = {o.dims[0], o.dims[1], o.dims[2]};
-  cuuint64_t strides[2] = {o.strides[0], o.strides[1]};
-  if (dims[2] == 1) strides[1] = strides[0] * dims[1];  // any valid multiple of 16
-  cuuint32_t box[3];
-  if (k_contig) { box[0] = TC_BK; box[1] = (cuuint32_t)rows_box; box[2] = 1; }
-  else { box[0] = 64; box[1] = TC_BK; box[2] = 1; }
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(o.base), dims, strides, box, estr,
+  cuuint64_t dims[4] = {o.dims[0], o.dims[1], o.dims[2], o.dims[3]};
+  cuuint64_t strides[3] = {o.strides[0], o.strides[1], o.strides[2]};
+  for (int i = 1; i < 3; ++i)
+    if (dims[i + 1] == 1) strides[i] = strides[i - 1] * dims[i];  // extent-1 dimension: any valid multiple of 16
+  cuuint32_t box[4] = {1, 1, 1, 1};
+  if (k_contig) { box[0] = TC_BK; box[1] = (cuuint32_t)rows_box; }
+  else { box[0] = 64; box[1] = TC_BK; }
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(o.base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return fail(SFNO_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d): base=%p dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u,%u)",
+    return fail(SFNO_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d): base=%p dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) box=(%u,%u)",
                 what, (int)r, o.base, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
-                (unsigned long long)strides[0], (unsigned long long)strides[1], box[0], box[1], box[2]);
+                (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
+                (unsigned long long)strides[2], box[0], box[1]);
   return SFNO_OK;
 }
 
 inline bool tma_operand_ok(const TmaOperand& o) {
   if (((uintptr_t)o.base & 15) != 0) return false;
   if (o.strides[0] % 16 != 0 || o.strides[0] == 0) return false;
-  if (o.dims[2] > 1 && (o.strides[1] % 16 != 0 || o.strides[1] == 0)) return false;
-  for (int i = 0; i < 3; ++i)
+  for (int i = 1; i < 3; ++i)
+    if (o.dims[i + 1] > 1 && (o.strides[i] % 16 != 0 || o.strides[i] == 0)) return false;
+  for (int i = 0; i < 4; ++i)
     if (o.dims[i] == 0 || o.dims[i] > (1ull << 31)) return false;
   return true;
 }
@@ -521,6 +557,9 @@ int launch_gemm_tc(const Op& op, cudaStream_t stream, const char* what) {
   sc.k16_last = ceil_div(k_rem, 16);
   sc.a_batched = a.batched ? 1 : 0;
   sc.b_batched = b.batched ? 1 : 0;
+  sc.a_glo = a.group_lo;
+  sc.b_glo = b.group_lo;
+  sc.dbg = g_tc_debug.load(std::memory_order_relaxed);
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<Op, BN>;
   if (!attr_set) {

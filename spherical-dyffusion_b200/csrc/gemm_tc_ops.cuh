@@ -26,33 +26,37 @@ template <>
 struct TcTraits<OpDft<bf16>> : TcTraitsBase<OpDft<bf16>>, TcEligible<TcTraits<OpDft<bf16>>, OpDft<bf16>> {
   static constexpr int BN = 192;
   static void operands(const OpDft<bf16>& op, TmaOperand& a, TmaOperand& b) {
-    a.base = op.A; a.dims[0] = op.nlon; a.dims[1] = op.M; a.dims[2] = op.G;
-    a.strides[0] = (uint64_t)op.nlon * 2; a.strides[1] = (uint64_t)op.x_bstride * 2; a.batched = true;
-    b.base = op.Bm; b.dims[0] = op.nlon; b.dims[1] = op.N; b.dims[2] = 1;
-    b.strides[0] = (uint64_t)op.Wp * 2; b.batched = false;
+    a.base = op.A; a.dims[0] = op.nlon; a.dims[1] = op.M;                 // basis rows (m,ri), K-contiguous, shared
+    a.strides[0] = (uint64_t)op.Wp * 2; a.batched = false;
+    b.base = op.Bm; b.dims[0] = op.nlon; b.dims[1] = op.nlat; b.dims[2] = op.C; b.dims[3] = op.B;  // {j, k, c, b}
+    b.strides[0] = (uint64_t)op.nlon * 2; b.strides[1] = (uint64_t)op.nlat * op.nlon * 2; b.strides[2] = (uint64_t)op.x_bstride * 2;
+    b.batched = true; b.group_lo = op.C;
   }
+  static bool extra_ok(const OpDft<bf16>& op) { return aligned16(op.f) && op.Kp % 8 == 0; }
 };
 
 template <>
 struct TcTraits<OpLeg<bf16>> : TcTraitsBase<OpLeg<bf16>>, TcEligible<TcTraits<OpLeg<bf16>>, OpLeg<bf16>> {
-  static constexpr int BN = 192;
+  static constexpr int BN = 256;
   static void operands(const OpLeg<bf16>& op, TmaOperand& a, TmaOperand& b) {
-    a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.M; a.dims[2] = op.G;
-    a.strides[0] = (uint64_t)op.Kp * 2; a.strides[1] = (uint64_t)op.M * op.Kp * 2; a.batched = true;
-    b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.lmax; b.dims[2] = op.G;
-    b.strides[0] = (uint64_t)op.Kp * 2; b.strides[1] = (uint64_t)op.lmax * op.Kp * 2; b.batched = true;
+    a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.lmax; a.dims[2] = op.G;   // table rows l of wavenumber m
+    a.strides[0] = (uint64_t)op.Kp * 2; a.strides[1] = (uint64_t)op.lmax * op.Kp * 2; a.batched = true;
+    b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.N; b.dims[2] = op.G;      // F rows (b,ri,c) of wavenumber m
+    b.strides[0] = (uint64_t)op.Kp * 2; b.strides[1] = (uint64_t)op.N * op.Kp * 2; b.batched = true;
   }
+  static bool extra_ok(const OpLeg<bf16>& op) { return aligned16(op.x) && op.N % 8 == 0; }
 };
 
 template <>
 struct TcTraits<OpDhconv<bf16>> : TcTraitsBase<OpDhconv<bf16>>, TcEligible<TcTraits<OpDhconv<bf16>>, OpDhconv<bf16>> {
   static constexpr int BN = 256;
   static void operands(const OpDhconv<bf16>& op, TmaOperand& a, TmaOperand& b) {
-    a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.M; a.dims[2] = op.G;
+    a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.M; a.dims[2] = op.G;       // X rows (m,b) of degree l
     a.strides[0] = (uint64_t)op.K * 2; a.strides[1] = (uint64_t)op.M * op.K * 2; a.batched = true;
-    b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.N; b.dims[2] = op.G;
+    b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.N; b.dims[2] = op.G;       // packed weight rows (ri',o) of degree l
     b.strides[0] = (uint64_t)op.K * 2; b.strides[1] = (uint64_t)op.N * op.K * 2; b.batched = true;
   }
+  static bool extra_ok(const OpDhconv<bf16>& op) { return aligned16(op.y) && op.N % 8 == 0; }
 };
 
 template <>

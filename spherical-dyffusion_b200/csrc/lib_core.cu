@@ -131,14 +131,14 @@ static int sht_forward_impl(const ShtDeviceTables& t, const float* x, float* coe
     xin = xt;
   }
   OpDft<T> dft{};
-  dft.G = 1; dft.M = C * t.nlat; dft.N = 2 * t.mmax; dft.K = t.nlon;
-  dft.A = xin; dft.Bm = (const T*)t.efwd; dft.a_sk = 1; dft.b_sk = 1;
+  dft.G = C; dft.M = 2 * t.mmax; dft.N = t.nlat; dft.K = t.nlon;
+  dft.A = (const T*)t.efwd; dft.Bm = xin; dft.a_sk = 1; dft.b_sk = 1;
   dft.f = F; dft.aff_a = nullptr; dft.aff_d = nullptr;
   dft.B = 1; dft.C = C; dft.nlat = t.nlat; dft.nlon = t.nlon; dft.Kp = t.Kp; dft.Wp = t.Wp; dft.x_bstride = 0;
   SFNO_TRY(launch_gemm(dft, st, "dft_fwd"));
   OpLeg<T> leg{};
-  leg.G = t.mmax; leg.M = 2 * C; leg.N = t.lmax; leg.K = t.nlat;
-  leg.A = F; leg.Bm = (const T*)t.wq; leg.a_sk = 1; leg.b_sk = 1;
+  leg.G = t.mmax; leg.M = t.lmax; leg.N = 2 * C; leg.K = t.nlat;
+  leg.A = (const T*)t.wq; leg.Bm = F; leg.a_sk = 1; leg.b_sk = 1;
   leg.x = X; leg.Kp = t.Kp; leg.lmax = t.lmax; leg.mmax = t.mmax; leg.triangular = 0;
   SFNO_TRY(launch_gemm(leg, st, "legendre_fwd"));
   const int64_t total = fields * t.lmax * t.mmax * 2;

@@ -220,8 +220,8 @@ static ConvArgs<T, TOut> make_conv(int B, int P, int cin, int cout, const T* in,
 template <class T>
 static int run_dft(const sfno_net* n, const ShtDeviceTables& t, int B, const T* x, int64_t x_bs, const float* a, const float* d, T* F, cudaStream_t st) {
   OpDft<T> op{};
-  op.G = B; op.M = n->C * t.nlat; op.N = 2 * t.mmax; op.K = t.nlon;
-  op.A = x; op.Bm = (const T*)t.efwd; op.a_sk = 1; op.b_sk = 1;
+  op.G = B * n->C; op.M = 2 * t.mmax; op.N = t.nlat; op.K = t.nlon;
+  op.A = (const T*)t.efwd; op.Bm = x; op.a_sk = 1; op.b_sk = 1;
   op.f = F; op.aff_a = a; op.aff_d = d;
   op.B = B; op.C = n->C; op.nlat = t.nlat; op.nlon = t.nlon; op.Kp = t.Kp; op.Wp = t.Wp; op.x_bstride = x_bs;
   return launch_gemm(op, st, "dft_fwd");
@@ -229,8 +229,8 @@ static int run_dft(const sfno_net* n, const ShtDeviceTables& t, int B, const T* 
 template <class T>
 static int run_leg(const sfno_net* n, const ShtDeviceTables& t, int B, const T* F, T* X, cudaStream_t st) {
   OpLeg<T> op{};
-  op.G = t.mmax; op.M = B * 2 * n->C; op.N = t.lmax; op.K = t.nlat;
-  op.A = F; op.Bm = (const T*)t.wq; op.a_sk = 1; op.b_sk = 1;
+  op.G = t.mmax; op.M = t.lmax; op.N = B * 2 * n->C; op.K = t.nlat;
+  op.A = (const T*)t.wq; op.Bm = F; op.a_sk = 1; op.b_sk = 1;
   op.x = X; op.Kp = t.Kp; op.lmax = t.lmax; op.mmax = t.mmax;
   op.triangular = n->cfg.operator_type == SFNO_OP_DHCONV;
   return launch_gemm(op, st, "legendre_fwd");
@@ -365,8 +365,8 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
     }
     if (cfg.operator_type == SFNO_OP_DHCONV) {
       OpDhconv<T> op{};
-      op.G = n->L; op.M = 2 * C; op.N = n->M * B; op.K = 2 * C;
-      op.A = (const T*)bp.wpack; op.Bm = X; op.a_sk = 1; op.b_sk = 1;
+      op.G = n->L; op.M = n->M * B; op.N = 2 * C; op.K = 2 * C;
+      op.A = X; op.Bm = (const T*)bp.wpack; op.a_sk = 1; op.b_sk = 1;
       op.y = Y; op.B = B; op.lmax = n->L; op.mmax = n->M; op.triangular = 1;
       SFNO_TRY(launch_gemm(op, st, "dhconv"));
     } else {
@@ -457,6 +457,7 @@ extern "C" {
 int sfno_b200_set_option(const char* key, int64_t value) {
   if (!key) return fail(SFNO_ERR_INVALID_ARGUMENT, "key is NULL");
   if (strcmp(key, "force_simt") == 0) { g_force_simt.store((int)value); return SFNO_OK; }
+  if (strcmp(key, "tc_debug") == 0) { g_tc_debug.store((int)value); return SFNO_OK; }
   return fail(SFNO_ERR_INVALID_ARGUMENT, "unknown option %s", key);
 }
 

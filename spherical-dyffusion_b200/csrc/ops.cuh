@@ -7,10 +7,10 @@
 // styles follow from the layout of the OUTPUT tensor:
 //   kColContig = false : the row index m is the contiguous output index -> for a fixed column the 32 lanes of a warp
 //                        write 32 consecutive elements (coalesced scalar stores); store16() walks the columns with
-//                        incremental addressing.  (forward DFT, forward Legendre, dhconv)
+//                        incremental addressing.  (forward Legendre, dhconv)
 //   kColContig = true  : the column index n is the contiguous output index -> the thread writes 16-byte vectors along
 //                        its own row and every per-row quantity (bias, affine, decoded indices) lives in registers;
-//                        compute8().  (inverse Legendre, inverse DFT, 1x1 convolutions)
+//                        compute8().  (forward DFT, inverse Legendre, inverse DFT, 1x1 convolutions)
 //
 // Internal tensor layouts (T = float or bf16; Kp = nlat rounded up to 8):
 //   grid   x  [B][C][nlat][nlon]                      (NCHW, as the reference)
@@ -47,6 +47,16 @@ __device__ __forceinline__ float act_ct(int act_rt, float x) {
   else return act_for<T>(act_rt, x);
 }
 
+struct NoFeatures {
+  static constexpr int kFast0 = 0, kFast1 = 0;
+  static constexpr bool kGeneral = false;
+  __device__ int feat() const { return 0; }
+  __device__ bool has_res() const { return false; }
+  __device__ const void* res_base() const { return nullptr; }
+  __device__ bool wants_stats() const { return false; }
+  __device__ void finish(int, int, int, float, float) const {}
+};
+
 // pack 8 floats -> 8 x T and store as one (bf16) or two (fp32) 16-byte vectors; p must be 16-byte aligned
 __device__ __forceinline__ void store_vec8(bf16* p, const float (&v)[8]) {
   uint4 u;
@@ -76,125 +86,145 @@ __device__ __forceinline__ void load_vec8(const float* p, float (&v)[8]) {
 
 // Per-group index ranges.  The Legendre tables are exactly zero for l < m, so for the zonal
 // wavenumber m only degrees l >= m carry information.  All three spectral ops use the SAME predicate
-//     (l, m) is live  <=>  l >= (m & ~63)          (the triangle, rounded to the 64-wide K block of the engine)
-// the forward transform stores exactly the live columns, dhconv visits exactly the live wavenumbers of a degree
+//     (l, m) is live  <=>  l >= live_l0(m)        (the triangle, rounded to the 64-wide K block of the engine)
+// the forward transform stores exactly the live degrees (rows), dhconv visits exactly the live wavenumbers of a degree
 // (m <= l | 63) and the inverse transform contracts over exactly the live degrees.  Hence every X / Y entry that is
 // ever read was written in the same forward: nothing depends on the previous contents of the workspace.
+// first live degree of wavenumber m, clamped to the last 64-block of degrees so that at least one block is live
+__host__ __device__ inline int live_l0(int m, int lmax) {
+  const int l0 = m & ~63, last = lmax > 0 ? ((lmax - 1) & ~63) : 0;
+  return l0 < last ? l0 : last;
+}
 struct FullRanges {
+  static constexpr bool kRanged = false;  // every tile of the M x N x G grid is live
   __device__ int n_begin(int) const { return 0; }
   __device__ int k_begin(int) const { return 0; }
+  __device__ int m_begin(int) const { return 0; }
 };
 
 // ------------------------------------------------------------------------------------------------
-// forward longitude DFT (K1 of SURVEY 2.3), one GEMM per sample: rows (c,k) x nlon -> F, fused
-// InstanceNorm/time affine:   F = a[b,c] * DFT(x) + d[b,c] * 2*pi * [m==0, re]   (DFT(1) = 2*pi*delta_m0)
+// forward longitude DFT (K1 of SURVEY 2.3), one GEMM per (sample, channel): the basis rows (m,ri) are the GEMM
+// rows, the latitudes k of one channel plane the columns, so the contiguous index of F (the latitude) is the
+// column index and the InstanceNorm/time affine of the plane is a pair of tile-wide scalars:
+//   F[m][b][ri][c][k] = a[b,c] * sum_j E[(m,ri)][j] x[b][c][k][j] + d[b,c] * 2*pi * [m==0, re]   (DFT(1) = 2*pi*delta_m0)
 // ------------------------------------------------------------------------------------------------
 template <class T>
-struct OpDft : FullRanges {
-  static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = false, kNFastest = true;
+struct OpDft : FullRanges, NoFeatures {
+  static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = true, kNFastest = false;
+  using OutT = T;
   __device__ int n_end(int) const { return N; }
-  int G, M, N, K;  // G = B, M = C*nlat (rows (c,k) of one sample), N = 2*mmax, K = nlon
-  const T* A; const T* Bm; int64_t a_sk, b_sk;
+  __device__ int m_end(int) const { return M; }
+  int G, M, N, K;  // G = B*C, M = 2*mmax, N = nlat, K = nlon
+  const T* A; const T* Bm; int64_t a_sk, b_sk;   // A = basis [2*mmax][Wp], Bm = x [B][C][nlat][nlon]
   T* f;
   const float* aff_a; const float* aff_d;  // [B*C] or nullptr
   int B, C, nlat, nlon, Kp, Wp;
   int64_t x_bstride;
 
-  __device__ int64_t a_off(int g, int m) const { return (int64_t)g * x_bstride + (int64_t)m * nlon; }
-  __device__ int64_t b_off(int, int n) const { return (int64_t)n * Wp; }
-  struct Row { int64_t base; float a, d; };
+  __device__ int64_t a_off(int, int m) const { return (int64_t)m * Wp; }
+  __device__ int64_t b_off(int g, int n) const {
+    const int b = g / C, c = g - b * C;
+    return (int64_t)b * x_bstride + ((int64_t)c * nlat + n) * nlon;
+  }
+  __device__ int n_store() const { return Kp; }
+  __device__ const void* out_base() const { return f; }
+  struct Row { T* out; const T* res; bool valid; float a, d, s, q; };
   __device__ Row row(int g, int m) const {
-    int c = m / nlat, k = m - c * nlat;
+    const int b = g / C, c = g - b * C, mm = m >> 1, ri = m & 1;
     Row r;
-    r.base = (int64_t)g * 2 * C * Kp + (int64_t)c * Kp + k;
-    r.a = aff_a ? aff_a[g * C + c] : 1.0f;
-    r.d = aff_d ? aff_d[g * C + c] * 6.28318530717958647692f : 0.0f;
+    r.out = f + (((int64_t)mm * B + b) * 2 + ri) * C * Kp + (int64_t)c * Kp;
+    r.res = nullptr; r.valid = true; r.s = 0.0f; r.q = 0.0f;
+    r.a = aff_a ? aff_a[g] : 1.0f;
+    r.d = (aff_d && m == 0) ? aff_d[g] * 6.28318530717958647692f : 0.0f;
     return r;
   }
-  __device__ void store(const Row& r, int, int, int n, float acc) const {
-    int mm = n >> 1, ri = n & 1;
-    float v = r.a * acc + (n == 0 ? r.d : 0.0f);
-    f[(int64_t)mm * B * 2 * C * Kp + (int64_t)ri * C * Kp + r.base] = from_f32<T>(v);
-  }
-  // columns n0 .. n0+15 (n0 even): n = 2*mm + ri -> alternate strides
-  __device__ void store16(const Row& r, int, int, int n0, int nvalid, const uint32_t (&acc)[16]) const {
-    const int64_t s_m = (int64_t)B * 2 * C * Kp, s_ri = (int64_t)C * Kp;
-    T* p = f + r.base + (int64_t)(n0 >> 1) * s_m;
+  template <int F> __device__ Row row_f(int g, int m) const { return row(g, m); }
+  __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = from_f32<T>(fmaf(r.a, acc, r.d)); }
+  template <int F>
+  __device__ void compute8(Row& r, int n, const float (&acc)[8], const float (&)[8], float (&o)[8]) const {
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-      if (j < nvalid) p[0] = from_f32<T>(fmaf(r.a, __uint_as_float(acc[j]), (n0 + j) == 0 ? r.d : 0.0f));
-      if (j + 1 < nvalid) p[s_ri] = from_f32<T>(r.a * __uint_as_float(acc[j + 1]));
-      p += s_m;
+    for (int i = 0; i < 8; ++i) o[i] = r.a * acc[i];
+    if (r.d != 0.0f) {  // the single (m = 0, re) row; the pad latitudes [nlat, Kp) stay zero
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += (n + i < nlat) ? r.d : 0.0f;
     }
   }
 };
 
 // ------------------------------------------------------------------------------------------------
-// forward Legendre (K2): per m, rows (b,ri,c) x nlat -> X[l][m][b][ri][c]
+// forward Legendre (K2): per m, table rows l x latitude  times  F rows (b,ri,c) x latitude -> X[l][m][b][ri][c]
+//   (degree l = GEMM row, the channel-contiguous index (b,ri,c) = GEMM column = contiguous output index)
 // ------------------------------------------------------------------------------------------------
 template <class T>
-struct OpLeg {
-  static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = false, kNFastest = false;
-  int triangular;  // 1: store only the live degrees l >= (m & ~63)
-  __device__ int n_begin(int g) const { return triangular ? (g & ~63) : 0; }
+struct OpLeg : NoFeatures {
+  static constexpr bool kRanged = true;
+  static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = true, kNFastest = false;
+  using OutT = T;
+  int triangular;  // 1: store only the live degrees l >= live_l0(m)
+  __device__ int m_begin(int g) const { return triangular ? live_l0(g, M) : 0; }
+  __device__ int m_end(int) const { return M; }
+  __device__ int n_begin(int) const { return 0; }
   __device__ int n_end(int) const { return N; }
   __device__ int k_begin(int) const { return 0; }
-  int G, M, N, K;  // G = mmax, M = B*2*C, N = lmax, K = nlat
-  const T* A; const T* Bm; int64_t a_sk, b_sk;
+  int G, M, N, K;  // G = mmax, M = lmax, N = B*2*C, K = nlat
+  const T* A; const T* Bm; int64_t a_sk, b_sk;   // A = wq [mmax][lmax][Kp], Bm = F [mmax][(b,ri,c)][Kp]
   T* x;
   int Kp, lmax, mmax;
-  __device__ int64_t a_off(int g, int m) const { return ((int64_t)g * M + m) * Kp; }
-  __device__ int64_t b_off(int g, int n) const { return ((int64_t)g * lmax + n) * Kp; }
-  struct Row { int64_t base; };
-  __device__ Row row(int g, int m) const { return Row{(int64_t)g * M + m}; }
-  __device__ void store(const Row& r, int, int, int n, float acc) const {
-    x[(int64_t)n * mmax * M + r.base] = from_f32<T>(acc);
-  }
-  __device__ void store16(const Row& r, int, int, int n0, int nvalid, const uint32_t (&acc)[16]) const {
-    const int64_t s_l = (int64_t)mmax * M;
-    T* p = x + r.base + (int64_t)n0 * s_l;
+  __device__ int64_t a_off(int g, int m) const { return ((int64_t)g * lmax + m) * Kp; }
+  __device__ int64_t b_off(int g, int n) const { return ((int64_t)g * N + n) * Kp; }
+  __device__ int n_store() const { return N; }
+  __device__ const void* out_base() const { return x; }
+  struct Row { T* out; const T* res; bool valid; float s, q; };
+  __device__ Row row(int g, int m) const { return Row{x + ((int64_t)m * mmax + g) * N, nullptr, true, 0.0f, 0.0f}; }
+  template <int F> __device__ Row row_f(int g, int m) const { return row(g, m); }
+  __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = from_f32<T>(acc); }
+  template <int F>
+  __device__ void compute8(Row&, int, const float (&acc)[8], const float (&)[8], float (&o)[8]) const {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (j < nvalid) *p = from_f32<T>(__uint_as_float(acc[j]));
-      p += s_l;
-    }
+    for (int i = 0; i < 8; ++i) o[i] = acc[i];
   }
 };
 
 // ------------------------------------------------------------------------------------------------
 // dhconv channel contraction (K3) as a REAL GEMM on the packed complex weight, per degree l:
-//   D[(ri',o), (m,b)] = sum_(ri,c) Wp[l][(ri',o)][(ri,c)] * X[l][m][b][(ri,c)]  -> Y[m][l][b][ri'][o]
+//   D[(m,b), (ri',o)] = sum_(ri,c) X[l][m][b][(ri,c)] * Wp[l][(ri',o)][(ri,c)]  -> Y[m][l][b][ri'][o]
 //   Wp = [[wr, -wi], [wi, wr]] (rows = output re/im, cols = input re/im)
 // ------------------------------------------------------------------------------------------------
 template <class T>
-struct OpDhconv {
-  static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = false, kNFastest = false;
-  int triangular;  // 1: only the live wavenumbers m <= (l | 63)
+struct OpDhconv : NoFeatures {
+  static constexpr bool kRanged = true;
+  static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = true, kNFastest = true;
+  using OutT = T;
+  int triangular;  // 1: only the live wavenumbers of degree l
+  __device__ int m_begin(int) const { return 0; }
+  __device__ int m_end(int g) const {
+    const int last = lmax > 0 ? ((lmax - 1) & ~63) : 0;  // degrees of the last block see every wavenumber (live_l0 clamp)
+    if (!triangular || g >= last) return M;
+    const int e = ((g | 63) + 1) * B;
+    return e < M ? e : M;
+  }
   __device__ int n_begin(int) const { return 0; }
-  __device__ int n_end(int g) const { int e = ((g | 63) + 1) * B; return (triangular && e < N) ? e : N; }
+  __device__ int n_end(int) const { return N; }
   __device__ int k_begin(int) const { return 0; }
-  int G, M, N, K;  // G = lmax, M = 2*Cout, N = mmax*B, K = 2*Cin
-  const T* A; const T* Bm; int64_t a_sk, b_sk;
+  int G, M, N, K;  // G = lmax, M = mmax*B, N = 2*Cout, K = 2*Cin
+  const T* A; const T* Bm; int64_t a_sk, b_sk;   // A = X [lmax][(m,b)][2Cin], Bm = Wp [lmax][2Cout][2Cin]
   T* y;
   int B, lmax, mmax;
   __device__ int64_t a_off(int g, int m) const { return ((int64_t)g * M + m) * K; }
   __device__ int64_t b_off(int g, int n) const { return ((int64_t)g * N + n) * K; }
-  struct Row { int64_t base; };
-  __device__ Row row(int g, int m) const { return Row{(int64_t)g * B * M + m}; }
-  __device__ void store(const Row& r, int, int, int n, float acc) const {
-    int mm = n / B, b = n - mm * B;
-    y[(int64_t)mm * lmax * B * M + (int64_t)b * M + r.base] = from_f32<T>(acc);
+  __device__ int n_store() const { return N; }
+  __device__ const void* out_base() const { return y; }
+  struct Row { T* out; const T* res; bool valid; float s, q; };
+  __device__ Row row(int g, int m) const {
+    const int mm = m / B, b = m - mm * B;
+    return Row{y + (((int64_t)mm * lmax + g) * B + b) * N, nullptr, true, 0.0f, 0.0f};
   }
-  __device__ void store16(const Row& r, int, int, int n0, int nvalid, const uint32_t (&acc)[16]) const {
-    const int64_t s_m = (int64_t)lmax * B * M;
-    int mm = n0 / B, b = n0 - mm * B;
-    T* p = y + r.base + (int64_t)mm * s_m + (int64_t)b * M;
+  template <int F> __device__ Row row_f(int g, int m) const { return row(g, m); }
+  __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = from_f32<T>(acc); }
+  template <int F>
+  __device__ void compute8(Row&, int, const float (&acc)[8], const float (&)[8], float (&o)[8]) const {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (j < nvalid) *p = from_f32<T>(__uint_as_float(acc[j]));
-      p += M;
-      if (++b == B) { b = 0; p += s_m - (int64_t)B * M; }
-    }
+    for (int i = 0; i < 8; ++i) o[i] = acc[i];
   }
 };
 
@@ -204,13 +234,16 @@ struct OpDhconv {
 //   S is Y [m][l][rows] (a_goff = lmax*rows, a_sk = rows) or X [l][m][rows] (a_goff = rows, a_sk = mmax*rows)
 // ------------------------------------------------------------------------------------------------
 template <class T>
-struct OpIleg {
+struct OpIleg : NoFeatures {
+  static constexpr bool kRanged = true;
   static constexpr bool A_KCONTIG = false, B_KCONTIG = true, kColContig = true, kNFastest = true;
   using OutT = T;
   int triangular;  // 1: contract only over the live degrees l >= (m & ~63)
   __device__ int n_begin(int) const { return 0; }
   __device__ int n_end(int) const { return N; }
-  __device__ int k_begin(int g) const { int k = g & ~63; return triangular ? (k < K ? k : (K > 0 ? ((K - 1) & ~63) : 0)) : 0; }
+  __device__ int k_begin(int g) const { return triangular ? live_l0(g, K) : 0; }
+  __device__ int m_begin(int) const { return 0; }
+  __device__ int m_end(int) const { return M; }
   int G, M, N, K;  // G = mmax, M = B*2*C, N = nlat, K = lmax
   const T* A; const T* Bm; int64_t a_sk, b_sk;
   int64_t a_goff;
@@ -219,20 +252,20 @@ struct OpIleg {
   __device__ int64_t a_off(int g, int m) const { return (int64_t)g * a_goff + m; }   // + l * a_sk
   __device__ int64_t b_off(int g, int n) const { return ((int64_t)g * nlat + n) * Lq; }
   __device__ int n_store() const { return Kp; }  // columns [nlat, Kp) are exact zeros (zero-filled table rows)
-  __device__ bool has_res() const { return false; }
+  __device__ const void* out_base() const { return g_out; }
   struct Row { T* out; const T* res; bool valid; float s, q; };
   __device__ Row row(int g, int m) const {
     int b = m / (2 * C), rem = m - b * 2 * C;
     int ri = rem / C, o = rem - ri * C;
     return Row{g_out + (int64_t)g * 2 * B * C * Kp + (int64_t)ri * B * C * Kp + ((int64_t)b * C + o) * Kp, nullptr, true, 0.0f, 0.0f};
   }
+  template <int F> __device__ Row row_f(int g, int m) const { return row(g, m); }
   __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = from_f32<T>(acc); }
+  template <int F>
   __device__ void compute8(Row&, int, const float (&acc)[8], const float (&)[8], float (&o)[8]) const {
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = acc[i];
   }
-  __device__ bool wants_stats() const { return false; }
-  __device__ void finish(int, int, int, float, float) const {}
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -258,6 +291,7 @@ template <class T, class TOut, int ACT = -1>
 struct OpIdft : IdftArgs<T, TOut>, FullRanges {
   static constexpr bool A_KCONTIG = false, B_KCONTIG = true, kColContig = true, kNFastest = true;
   __device__ int n_end(int) const { return this->N; }
+  __device__ int m_end(int) const { return this->M; }
   using OutT = TOut;
   using Args = IdftArgs<T, TOut>;
   OpIdft() = default;
@@ -266,6 +300,11 @@ struct OpIdft : IdftArgs<T, TOut>, FullRanges {
   __device__ int64_t b_off(int, int n) const { return (int64_t)n * this->Kq2; }
   __device__ int n_store() const { return this->N; }
   __device__ bool has_res() const { return this->add != nullptr; }
+  static constexpr int kFast0 = 0, kFast1 = F_RES | F_STATS;
+  static constexpr bool kGeneral = true;
+  __device__ int feat() const { return (this->add ? F_RES : 0) | (this->stat_part ? F_STATS : 0); }
+  __device__ const void* out_base() const { return this->out; }
+  __device__ const void* res_base() const { return this->add; }
   struct Row { TOut* out; const T* res; bool valid; float bias; float s, q; };
   __device__ Row row(int, int m) const {
     int bo = m / this->Kp, k = m - bo * this->Kp;
@@ -279,16 +318,23 @@ struct OpIdft : IdftArgs<T, TOut>, FullRanges {
     r.bias = this->bias ? this->bias[o] : 0.0f;
     return r;
   }
+  template <int F> __device__ Row row_f(int g, int m) const { return row(g, m); }
   __device__ void store(const Row& r, int, int, int n, float acc) const {
     if (!r.valid) return;
     float v = acc + r.bias;
     if (r.res) v += to_f32(r.res[n]);
     r.out[n] = from_f32<TOut>(act_ct<T, ACT>(this->act, v));
   }
+  template <int F>
   __device__ void compute8(Row& r, int, const float (&acc)[8], const float (&res)[8], float (&o)[8]) const {
+    if (feat_on<F, F_RES>(true)) {  // (res[] is zero when no addend is staged)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = act_ct<T, ACT>(this->act, acc[i] + r.bias + res[i]);
-    if (this->stat_part) {
+      for (int i = 0; i < 8; ++i) o[i] = act_ct<T, ACT>(this->act, acc[i] + r.bias + res[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = act_ct<T, ACT>(this->act, acc[i] + r.bias);
+    }
+    if (feat_on<F, F_STATS>(this->stat_part != nullptr)) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) { r.s += o[i]; r.q = fmaf(o[i], o[i], r.q); }
     }
@@ -329,6 +375,7 @@ template <class T, class TOut, int ACT = -1, int DROP = -1>
 struct OpConv : ConvArgs<T, TOut>, FullRanges {
   static constexpr bool A_KCONTIG = true, B_KCONTIG = false, kColContig = true, kNFastest = false;
   __device__ int n_end(int) const { return this->N; }
+  __device__ int m_end(int) const { return this->M; }
   using OutT = TOut;
   using Args = ConvArgs<T, TOut>;
   OpConv() = default;
@@ -337,22 +384,34 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
   __device__ int64_t b_off(int g, int n) const { return (int64_t)g * this->in_bstride + n; }  // + c * hw
   __device__ int n_store() const { return this->N; }
   __device__ bool has_res() const { return this->res != nullptr; }
+  static constexpr int kFast0 = 0, kFast1 = F_RES | F_STATS;
+  static constexpr bool kGeneral = true;
+  __device__ int feat() const {
+    return (this->res ? F_RES : 0) | (this->stat_part ? F_STATS : 0) | (this->pos ? F_POS : 0) | (this->branch_scale ? F_SCALE : 0);
+  }
+  __device__ const void* out_base() const { return this->out; }
+  __device__ const void* res_base() const { return this->res; }
   struct Row { TOut* out; const T* res; bool valid; const T* pos; float bias, ra, rd, scale; uint64_t rng_base; float s, q; };
-  __device__ Row row(int g, int m) const {
+  template <int F>
+  __device__ Row row_f(int g, int m) const {
     Row r;
     const int64_t off = (int64_t)m * this->N;
     r.valid = true;
     r.s = 0.0f; r.q = 0.0f;
     r.out = this->out + (int64_t)g * this->out_bstride + off;
-    r.res = this->res ? this->res + (int64_t)g * this->res_bstride + off : nullptr;
-    r.pos = this->pos ? this->pos + off : nullptr;
     r.bias = this->bias ? this->bias[(int64_t)g * this->bias_bstride + m] : 0.0f;
-    r.ra = this->res_a ? this->res_a[g * this->M + m] : 1.0f;
-    r.rd = this->res_d ? this->res_d[g * this->M + m] : 0.0f;
-    r.scale = this->branch_scale ? this->branch_scale[g] : 1.0f;
-    r.rng_base = ((uint64_t)g * this->M + m) * (uint64_t)this->N;
+    r.res = nullptr; r.ra = 1.0f; r.rd = 0.0f; r.pos = nullptr; r.scale = 1.0f; r.rng_base = 0;
+    if (feat_on<F, F_RES>(this->res != nullptr)) {
+      r.res = this->res + (int64_t)g * this->res_bstride + off;
+      if (this->res_a) r.ra = this->res_a[g * this->M + m];
+      if (this->res_d) r.rd = this->res_d[g * this->M + m];
+    }
+    if (feat_on<F, F_POS>(this->pos != nullptr)) r.pos = this->pos + off;
+    if (feat_on<F, F_SCALE>(this->branch_scale != nullptr)) r.scale = this->branch_scale[g];
+    if (dropping()) r.rng_base = ((uint64_t)g * this->M + m) * (uint64_t)this->N;
     return r;
   }
+  __device__ Row row(int g, int m) const { return row_f<-1>(g, m); }
   __device__ bool dropping() const {
     if constexpr (DROP == 0) return false;
     else return this->drop_p > 0.0f;
@@ -369,6 +428,7 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
     if (r.pos) v += to_f32(r.pos[n]);
     r.out[n] = from_f32<TOut>(v);
   }
+  template <int F>
   __device__ void compute8(Row& r, int n, const float (&acc)[8], const float (&res)[8], float (&o)[8]) const {
     float u[8];
     if (dropping()) {
@@ -376,18 +436,22 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
       philox_uniform4(this->seed, this->offset, r.rng_base + n + 4, u[4], u[5], u[6], u[7]);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = finish_value(r, acc[i], dropping() ? u[i] : 1.0f);
-    if (r.res) {
+    for (int i = 0; i < 8; ++i) {
+      float v = act_ct<T, ACT>(this->act, acc[i] + r.bias);
+      if (dropping()) v = (u[i] >= this->drop_p) ? __fdividef(v, 1.0f - this->drop_p) : 0.0f;
+      o[i] = feat_on<F, F_SCALE>(true) ? v * r.scale : v;   // (r.scale = 1 without DropPath)
+    }
+    if (feat_on<F, F_RES>(r.res != nullptr)) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] += fmaf(r.ra, res[i], r.rd);
     }
-    if (r.pos) {
+    if (feat_on<F, F_POS>(r.pos != nullptr)) {
       float t[8];
       load_vec8(r.pos + n, t);
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] += t[i];
     }
-    if (this->stat_part) {
+    if (feat_on<F, F_STATS>(this->stat_part != nullptr)) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) { r.s += o[i]; r.q = fmaf(o[i], o[i], r.q); }
     }

@@ -117,8 +117,8 @@ extern "C" int sfno_b200_selftest_gemm(int op_kind, const int* d, int nd, double
       const int B = d[0], C = d[1], nlat = d[2], nlon = d[3], mmax = d[4];
       const int Kp = round_up(nlat, Kr), Wp = round_up(nlon, Kr);
       OpDft<bf16> op{};
-      op.G = B; op.M = C * nlat; op.N = 2 * mmax; op.K = nlon;
-      op.A = s.rnd((int64_t)B * C * nlat * nlon, 1); op.Bm = s.rnd((int64_t)2 * mmax * Wp, 2, 0.1f); op.a_sk = 1; op.b_sk = 1;
+      op.G = B * C; op.M = 2 * mmax; op.N = nlat; op.K = nlon;
+      op.Bm = s.rnd((int64_t)B * C * nlat * nlon, 1); op.A = s.rnd((int64_t)2 * mmax * Wp, 2, 0.1f); op.a_sk = 1; op.b_sk = 1;
       op.aff_a = s.rndf((int64_t)B * C, 3); op.aff_d = s.rndf((int64_t)B * C, 4);
       op.B = B; op.C = C; op.nlat = nlat; op.nlon = nlon; op.Kp = Kp; op.Wp = Wp; op.x_bstride = (int64_t)C * nlat * nlon;
       return run_both<OpDft<bf16>, bf16>(op, (int64_t)mmax * B * 2 * C * Kp, [](OpDft<bf16>& o, bf16* p) { o.f = p; }, s, res);
@@ -127,16 +127,16 @@ extern "C" int sfno_b200_selftest_gemm(int op_kind, const int* d, int nd, double
       const int B = d[0], C = d[1], nlat = d[2], lmax = d[3], mmax = d[4];
       const int Kp = round_up(nlat, Kr);
       OpLeg<bf16> op{};
-      op.G = mmax; op.M = B * 2 * C; op.N = lmax; op.K = nlat;
-      op.A = s.rnd((int64_t)mmax * op.M * Kp, 5); op.Bm = s.rnd((int64_t)mmax * lmax * Kp, 6, 0.1f); op.a_sk = 1; op.b_sk = 1;
+      op.G = mmax; op.M = lmax; op.N = B * 2 * C; op.K = nlat;
+      op.Bm = s.rnd((int64_t)mmax * op.N * Kp, 5); op.A = s.rnd((int64_t)mmax * lmax * Kp, 6, 0.1f); op.a_sk = 1; op.b_sk = 1;
       op.Kp = Kp; op.lmax = lmax; op.mmax = mmax; op.triangular = d[5];
-      return run_both<OpLeg<bf16>, bf16>(op, (int64_t)lmax * mmax * op.M, [](OpLeg<bf16>& o, bf16* p) { o.x = p; }, s, res);
+      return run_both<OpLeg<bf16>, bf16>(op, (int64_t)lmax * mmax * op.N, [](OpLeg<bf16>& o, bf16* p) { o.x = p; }, s, res);
     }
     case 2: {  // DHCONV: B, C, lmax, mmax
       const int B = d[0], C = d[1], lmax = d[2], mmax = d[3];
       OpDhconv<bf16> op{};
-      op.G = lmax; op.M = 2 * C; op.N = mmax * B; op.K = 2 * C;
-      op.A = s.rnd((int64_t)lmax * 4 * C * C, 7, 0.1f); op.Bm = s.rnd((int64_t)lmax * mmax * B * 2 * C, 8); op.a_sk = 1; op.b_sk = 1;
+      op.G = lmax; op.M = mmax * B; op.N = 2 * C; op.K = 2 * C;
+      op.Bm = s.rnd((int64_t)lmax * 4 * C * C, 7, 0.1f); op.A = s.rnd((int64_t)lmax * mmax * B * 2 * C, 8); op.a_sk = 1; op.b_sk = 1;
       op.B = B; op.lmax = lmax; op.mmax = mmax; op.triangular = d[4];
       return run_both<OpDhconv<bf16>, bf16>(op, (int64_t)lmax * mmax * B * 2 * C, [](OpDhconv<bf16>& o, bf16* p) { o.y = p; }, s, res);
     }

@@ -4,6 +4,8 @@
 
 namespace sfno {
 
+std::atomic<int> g_tc_debug{0};
+
 PFN_encodeTiled get_encode_tiled() {
   static PFN_encodeTiled fn = nullptr;
   static bool tried = false;

@@ -17,6 +17,9 @@ def main():
     lib.sfno_b200_selftest_gemm.restype = ctypes.c_int
     lib.sfno_b200_selftest_gemm.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     lib.sfno_b200_last_error.restype = ctypes.c_char_p
+    if os.environ.get("SFNO_TC_DEBUG"):
+        lib.sfno_b200_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
+        lib.sfno_b200_set_option(b"tc_debug", int(os.environ["SFNO_TC_DEBUG"]))
     res = (ctypes.c_double * 5)()
     arr = (ctypes.c_int * len(dims))(*dims)
     st = lib.sfno_b200_selftest_gemm(op, arr, len(dims), res)
