@@ -49,8 +49,19 @@ const char* sfno_b200_last_error(void);
 /* Number of kernels this library has launched since load (monotonic; used by bench.py). */
 int64_t sfno_b200_launch_count(void);
 
-/* Library-wide switches for tests: "force_simt" = 1 routes bf16 ops to the CUDA-core engine. */
+/* Library-wide switches for tests: "force_simt" = 1 routes bf16 ops to the CUDA-core engine.
+ * "tc_debug" = bit mask of TIMING-ONLY experiment switches of the tensor-core engine (results are wrong while any of
+ * bits 0-5 is set): 1 skip A-operand loads, 2 skip B-operand loads, 4 skip global stores, 8 skip the fused epilogue
+ * math, 16 skip the MMAs, 32 skip the TMEM loads; 64 = epilogue I/O by LDS/STG instead of TMA (correct results);
+ * 128 = accumulate the role-wait counters read by sfno_b200_tc_counters (correct results). */
 int sfno_b200_set_option(const char* key, int64_t value);
+
+/* Measurement hook: cycles summed over the CTAs of all tensor-core launches since the last call (tc_debug bit 7):
+ * out12 = {TMA producer blocked on a free stage, MMA issuer blocked on operands, MMA issuer blocked on a free
+ * accumulator, epilogue warp 0 blocked on the accumulator, epilogue warp 0 blocked on the residual block,
+ * CTA lifetime, epilogue warp 0 busy, number of CTAs, epilogue warp 0: per-tile set-up, drain loop, store + hand-over,
+ * reserved}.  Synchronises the device and clears the counters. */
+int sfno_b200_tc_counters(unsigned long long* out12);
 
 /* Per-launch device timing for bench.py: between _begin and _end every kernel launched by this library on
  * `stream` is followed by a CUDA event; _end synchronises the stream and returns the number of launches, their

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "sfno_b200_last_error": (c_char_p, []),
     "sfno_b200_launch_count": (c_int64, []),
     "sfno_b200_set_option": (c_int, [c_char_p, c_int64]),
+    "sfno_b200_tc_counters": (c_int, [c_void_p]),
     "sfno_b200_profile_begin": (c_int, [c_void_p]),
     "sfno_b200_profile_end": (c_int, [c_void_p, c_size_t, c_void_p, c_int]),
     "sfno_b200_selftest_gemm": (c_int, [c_int, POINTER(c_int), c_int, POINTER(c_double)]),

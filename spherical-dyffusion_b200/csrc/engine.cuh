@@ -41,7 +41,10 @@ bool idft_uses_tc(const IdftArgs<T, TOut>& a) {
   }
   return false;
 }
-constexpr int kConvStatSlicesPerTile = TC_EPI_WARPS / 4;  // statistics partials per (row, N tile): one per column slice
+// statistics partials per row: one per 64-column slice of every N tile
+constexpr int kConvBN = 192, kIdftBN = 192;
+inline int conv_stat_slices(int64_t hw) { return (int)ceil_div64(hw, kConvBN) * (kConvBN / TC_SLICE_COLS); }
+inline int idft_stat_slices(int nlon) { return ceil_div(nlon, kIdftBN) * (kIdftBN / TC_SLICE_COLS); }
 
 template <class T, class TOut>
 int launch_conv(const ConvArgs<T, TOut>& a, cudaStream_t stream, const char* what) {

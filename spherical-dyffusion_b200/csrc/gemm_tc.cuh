@@ -3,10 +3,11 @@
 //   persistent CTAs (one per SM), 128 x BN output tile, K in blocks of 64 bf16 (one 128-byte swizzle span)
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, 4-D maps {inner, outer, batch, batch_hi})
 //   warp 1      : MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM, 2 stages)
-//   warps 2..17 : epilogue       (tcgen05.ld 32x32b.x16 -> fused op epilogue; 4 warps per TMEM sub-partition, each a
-//                                 column slice; compact rolled loops so the code stays inside the instruction cache)
-//   (576 threads cap the kernel at 96 registers per thread; moving registers between roles with setmaxnreg was
-//    tried -- 640 threads, 56/104 -- and lost: ptxas spilled the residual prefetch block)
+//   warps 2..   : epilogue       (tcgen05.ld 32x32b.x16 -> fused op epilogue; BN/64 warps per TMEM sub-partition, each
+//                                 a 64-column slice = one 128-byte staging row of bf16; compact rolled loops so the
+//                                 code stays inside the instruction cache)
+//   (BN = 256: 576 threads cap the kernel at 96 registers per thread; moving registers between roles with
+//    setmaxnreg was tried -- 640 threads, 56/104 -- and lost: ptxas spilled the residual prefetch block)
 //   smem ring of kStages {A tile, B tile}, mbarrier full/empty; TMEM full/empty barriers decouple the MMA of
 //   tile i+1 from the epilogue of tile i.
 //
@@ -24,8 +25,9 @@ namespace sfno {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_EPI_WARPS = 16;
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_SLICE_COLS = 64;  // accumulator columns drained by one epilogue warp
+constexpr int tc_epi_warps(int bn) { return 4 * (bn / TC_SLICE_COLS); }   // 4 TMEM sub-partitions x column slices
+constexpr int tc_threads(int bn) { return 64 + 32 * tc_epi_warps(bn); }
 constexpr int TC_WARP_TMA = 0, TC_WARP_MMA = 1;
 
 struct TmaOperand {
@@ -36,16 +38,34 @@ struct TmaOperand {
   int group_lo = 0;                  // > 0: group g addresses {g % group_lo, g / group_lo} in dims[2], dims[3]
 };
 
+// Epilogue I/O through TMA: the output (and the residual / addend block) as a 5-D tensor whose 128-byte x 8-row
+// boxes are exactly the 1024-byte groups of a warp's swizzled staging rows.  Eight consecutive GEMM rows must map to
+// a box of the tensor (box_rows = extents of dims[1..4], product 8); ops that cannot guarantee it keep the LDS/STG path.
+struct TmaIo {
+  const void* base = nullptr;
+  int es = 2;                               // element size: 2 (bf16) or 4 (fp32)
+  uint64_t dims[5] = {1, 1, 1, 1, 1};
+  uint64_t strides[4] = {0, 0, 0, 0};       // byte strides of dims[1..4]
+  uint32_t box_rows[4] = {8, 1, 1, 1};
+  bool ok = false;
+};
+
 struct TcSched {
   int m_tiles, n_tiles, groups, num_tiles, k_blocks, k16_last;  // k16_last: MMAs (K=16) in the last k block
   int a_batched, b_batched;
   int a_glo, b_glo;  // > 0: the operand's group index splits into {g % glo, g / glo} (4-D tensor map)
+  int io;            // bit0: output stored by TMA, bit1: residual / addend loaded by TMA
+  // role-wait profile (tc_debug bit7) or nullptr: cycles summed over CTAs {producer waits for a free stage, MMA waits
+  // for operands, MMA waits for a free accumulator, epilogue warp 0 waits for the accumulator, epilogue warp 0 waits
+  // for the residual block, CTA lifetime, epilogue warp 0 busy, CTAs}
+  unsigned long long* prof;
   // experiment switch (sfno_b200_set_option("tc_debug")), WRONG results, timing only: bit0 skip A loads, bit1 skip B
   // loads, bit2 skip global stores, bit3 skip the fused epilogue math, bit4 skip the MMAs, bit5 skip the TMEM loads
   int dbg;
 };
 
 extern std::atomic<int> g_tc_debug;
+unsigned long long* tc_prof_buffer();  // 12 device counters (allocated on first use)
 
 // Tile walk of a persistent CTA without per-tile divisions: tile = (c * J + b) * I + a advances by a fixed step.
 struct TileIter {
@@ -93,13 +113,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Blocking wait with a watchdog: a pipeline bug traps (-> CUDA error) after ~2 s instead of hanging the GPU.
 template <bool kBackoff = false>
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+__device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();  // (try_wait itself may block for a while: it has to be inside the timed region)
   while (!mbar_try_wait(bar, parity)) {
     if (kBackoff) __nanosleep(64);  // single-thread roles with slack: do not compete with the epilogue warps for issue slots
     if (clock64() - t0 > 4000000000LL) __trap();
   }
+  return clock64() - t0;  // cycles spent blocked (role-wait profile, tc_debug bit7)
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -108,6 +128,20 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, const int (&c)[5]) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, const int (&c)[5]) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map), "r"(src),
+               "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -188,10 +222,10 @@ struct TcSmem {
   static constexpr int kABytes = TC_BM * TC_BK * 2;
   static constexpr int kBBytes = BN * TC_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kStaging ? TC_EPI_WARPS * TC_STAGING_PER_WARP : 0;
-  static constexpr int kBudget = 226 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/ - kStagingBytes;
+  static constexpr int kStagingBytes = kStaging ? tc_epi_warps(BN) * TC_STAGING_PER_WARP : 0;
+  static constexpr int kBudget = 226 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - kStagingBytes;
   static constexpr int kStages = kBudget / kStageBytes > 6 ? 6 : kBudget / kStageBytes;
-  static constexpr int kBarrierBytes = 256;
+  static constexpr int kBarrierBytes = 512;
   static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + kStagingBytes + 1024;
   static_assert(kStages >= 2, "not enough shared memory for a pipeline");
 };
@@ -219,20 +253,22 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&v)[8]) {
 }
 
 template <class Op, int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Op op, const TcSched sc) {
+__global__ void __launch_bounds__(tc_threads(BN), 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res, const Op op, const TcSched sc) {
   using S = TcSmem<BN, Op::kColContig>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = 512;  // two accumulator stages of up to 256 fp32 columns
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
-  const uint32_t bar_base = smem_base + kStages * S::kStageBytes;
+  const uint32_t staging_base = smem_base + kStages * S::kStageBytes;  // 1024-byte aligned: TMA boxes of 8 staged rows
+  const uint32_t bar_base = staging_base + S::kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
-  const uint32_t staging_base = bar_base + S::kBarrierBytes;
+  auto res_bar = [&](int w) { return bar_base + 8u * (2 * kStages + 6 + w); };  // one per epilogue warp (TMA residual loads)
   auto a_smem = [&](int s) { return smem_base + s * S::kStageBytes; };
   auto b_smem = [&](int s) { return smem_base + s * S::kStageBytes + S::kABytes; };
 
@@ -247,8 +283,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), TC_EPI_WARPS);
+      ptx::mbar_init(tempty_bar(a), tc_epi_warps(BN));
     }
+    for (int w = 0; w < tc_epi_warps(BN); ++w) ptx::mbar_init(res_bar(w), 1);
     ptx::fence_barrier_init();
   }
   if (warp == TC_WARP_MMA) ptx::tmem_alloc(tmem_slot, kTmemCols);
@@ -278,6 +315,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0;
+      const long long t_cta = clock64();
       for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, it.next()) {
         int g, mt, nt;
         decode(g, mt, nt);
@@ -287,7 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (sc.a_glo) { ga_hi = ga / sc.a_glo; ga -= ga_hi * sc.a_glo; }
         if (sc.b_glo) { gb_hi = gb / sc.b_glo; gb -= gb_hi * sc.b_glo; }
         for (int kb = op.k_begin(g) / TC_BK; kb < sc.k_blocks; ++kb) {
-          ptx::mbar_wait<true>(empty_bar(stage), phase ^ 1u);
+          w_empty += ptx::mbar_wait<true>(empty_bar(stage), phase ^ 1u);
           const bool load_a = !(sc.dbg & 1), load_b = !(sc.dbg & 2);
           ptx::mbar_expect_tx(full_bar(stage), (load_a ? S::kABytes : 0) + (load_b ? S::kBBytes : 0));
           const int k0 = kb * TC_BK;
@@ -310,6 +349,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
+      if (sc.prof) {
+        atomicAdd(sc.prof + 0, (unsigned long long)w_empty);
+        atomicAdd(sc.prof + 5, (unsigned long long)(clock64() - t_cta));
+        atomicAdd(sc.prof + 7, 1ull);
+      }
     }
   } else if (warp == TC_WARP_MMA) {
     // ===================== MMA issuer =====================
@@ -321,16 +365,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       constexpr uint32_t b_lbo = Op::B_KCONTIG ? 16u : (uint32_t)(TC_BK * 128), b_kstep = Op::B_KCONTIG ? 32u : 2048u;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      long long w_full = 0, w_tempty = 0;
       for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, it.next()) {
         int g, mt, nt;
         decode(g, mt, nt);
         if (tile_skipped(g, mt, nt)) continue;
         const int kb0 = op.k_begin(g) / TC_BK;
-        ptx::mbar_wait<true>(tempty_bar(acc), acc_phase ^ 1u);
+        w_tempty += ptx::mbar_wait<true>(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = kb0; kb < sc.k_blocks; ++kb) {
-          ptx::mbar_wait<true>(full_bar(stage), phase);
+          w_full += ptx::mbar_wait<true>(full_bar(stage), phase);
           ptx::tc_fence_after();
           const int nk = (kb == sc.k_blocks - 1) ? sc.k16_last : TC_BK / 16;
           for (int k = 0; k < nk; ++k) {
@@ -344,20 +389,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         ptx::mma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
+      if (sc.prof) {
+        atomicAdd(sc.prof + 1, (unsigned long long)w_full);
+        atomicAdd(sc.prof + 2, (unsigned long long)w_tempty);
+      }
     }
   } else {
     // ===================== epilogue =====================
-    const int ew = warp - 2;              // 0..15
+    const int ew = warp - 2;              // 0 .. tc_epi_warps(BN)-1
     const int quad = warp & 3;            // TMEM sub-partition this warp may read: lanes [32*quad, 32*quad+32)
-    const int part = ew >> 2;             // four warps per sub-partition, each owns a column slice
-    constexpr int kColsPerWarp = BN / (TC_EPI_WARPS / 4);
-    static_assert(kColsPerWarp % 16 == 0, "column slice must be a multiple of the TMEM load width");
+    const int part = ew >> 2;             // BN/64 warps per sub-partition, each owns a 64-column slice
+    constexpr int kColsPerWarp = TC_SLICE_COLS;
+    static_assert(BN % TC_SLICE_COLS == 0, "BN must be a whole number of column slices");
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, res_phase = 0;
+    long long w_tfull = 0, w_res = 0, c_pro = 0, c_loop = 0, c_tail = 0;
+    const long long t_epi = clock64();
     for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, it.next()) {
       int g, mt, nt;
       decode(g, mt, nt);
       if (tile_skipped(g, mt, nt)) continue;
+      const long long t_tile = clock64();
       const int m = mt * TC_BM + quad * 32 + lane;
       const int n_base = nt * BN + part * kColsPerWarp;
       const bool row_ok = m < op.m_end(g) && m >= op.m_begin(g);
@@ -382,25 +434,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int n_end = op.n_store();
         const bool has_res = (kEs == 2) && feat_on<F, F_RES>(op.has_res());
         const bool valid = row_ok && row.valid;
+        // all 32 rows outside the live range, or the column slice beyond the last column: nothing to drain
+        const bool warp_live = __any_sync(0xffffffffu, valid) && n_base < n_end;
+        const bool tma_st = (sc.io & 1) != 0, tma_ld = (sc.io & 2) != 0;
+        // TMA epilogue I/O: lanes 0..3 each own one 8-row x 128-byte group (1024 B) of the warp's staging rows
+        const int grow0 = mt * TC_BM + quad * 32 + 8 * lane;   // first GEMM row of this lane's group (lanes 0..3)
+        const bool gissue = lane < 4 && grow0 < op.m_end(g) && grow0 >= op.m_begin(g);
         // row starts as 16-byte units relative to the tensor base: ONE 32-bit shuffle per staged row (~0 = no row)
-        const uint32_t out16 = valid ? (uint32_t)(((const char*)row.out - (const char*)op.out_base()) >> 4) : 0xFFFFFFFFu;
-        // residual / addend block (bf16 outputs only): 8 coalesced 16-byte loads per lane issued BEFORE waiting for
-        // the accumulator, so their latency hides behind the MMA of this tile
+        uint32_t out16 = 0xFFFFFFFFu;
+        if (!tma_st && valid) out16 = (uint32_t)(((const char*)row.out - (const char*)op.out_base()) >> 4);
+        // residual / addend block (bf16 outputs only), fetched BEFORE waiting for the accumulator so that its latency
+        // hides behind the MMA of this tile: by TMA straight into the staging rows, or 8 coalesced 16-byte loads per lane
         uint4 res_pf[8];
-        if (has_res) {
-          const uint32_t res16 = valid ? (uint32_t)(((const char*)row.res - (const char*)op.res_base()) >> 4) : 0xFFFFFFFFu;
-          const uint4* rb = reinterpret_cast<const uint4*>(op.res_base()) + (n_base >> 3) + cl;
-          int nv0 = n_end - n_base;
-          nv0 = nv0 < kColsPerWarp ? nv0 : kColsPerWarp;
+        if (has_res && warp_live) {
+          if (tma_ld) {
+            if (tma_st && lane < 4) ptx::bulk_wait_read();   // the previous tile's stores have left the staging rows
+            __syncwarp();
+            if (lane == 0) ptx::mbar_expect_tx(res_bar(ew), 4 * 1024);
+            __syncwarp();
+            if (lane < 4) {
+              int c[5];
+              op.io_coords(g, grow0, n_base, c);
+              ptx::tma_load_5d(region + (uint32_t)lane * 1024u, &tma_res, res_bar(ew), c);
+            }
+          } else {
+            const uint32_t res16 = valid ? (uint32_t)(((const char*)row.res - (const char*)op.res_base()) >> 4) : 0xFFFFFFFFu;
+            const uint4* rb = reinterpret_cast<const uint4*>(op.res_base()) + (n_base >> 3) + cl;
+            int nv0 = n_end - n_base;
+            nv0 = nv0 < kColsPerWarp ? nv0 : kColsPerWarp;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t o = __shfl_sync(0xffffffffu, res16, 4 * i + srow0);
-            res_pf[i] = (o != 0xFFFFFFFFu && cl * 8 < nv0) ? rb[o] : make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t o = __shfl_sync(0xffffffffu, res16, 4 * i + srow0);
+              res_pf[i] = (o != 0xFFFFFFFFu && cl * 8 < nv0) ? rb[o] : make_uint4(0, 0, 0, 0);
+            }
           }
         }
-        const bool warp_live = __any_sync(0xffffffffu, valid);  // all 32 rows outside the live range: nothing to drain
-        ptx::mbar_wait(tfull_bar(acc), acc_phase);
+        const long long w0 = ptx::mbar_wait(tfull_bar(acc), acc_phase);
+        w_tfull += w0;
         ptx::tc_fence_after();
+        long long t_ph = clock64();
+        c_pro += t_ph - t_tile - w0;
 #pragma unroll 1
         for (int pass = 0; pass < (warp_live ? kPasses : 0); ++pass) {
           const int pn0 = n_base + pass * kPassCols;
@@ -409,26 +482,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           nvalid = nvalid < pcols ? nvalid : pcols;
           if (nvalid <= 0) break;  // warp-uniform
           if (has_res) {           // (kPasses == 1 whenever has_res)
+            if (tma_ld) {
+              w_res += ptx::mbar_wait(res_bar(ew), res_phase);
+              res_phase ^= 1u;
+            } else {
+              if (tma_st && lane < 4) ptx::bulk_wait_read();
+              __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              sts128(region + (uint32_t)(4 * i + srow0) * TC_STAGE_PITCH + (((uint32_t)cl ^ (uint32_t)((4 * i + srow0) & 7)) << 4), res_pf[i]);
+              for (int i = 0; i < 8; ++i)
+                sts128(region + (uint32_t)(4 * i + srow0) * TC_STAGE_PITCH + (((uint32_t)cl ^ (uint32_t)((4 * i + srow0) & 7)) << 4), res_pf[i]);
+              __syncwarp();
+            }
+          } else if (tma_st) {
+            if (lane < 4) ptx::bulk_wait_read();   // staging rows free again (previous tile / previous pass)
             __syncwarp();
           }
-          const int nchunks = (nvalid + 15) >> 4;
+          // 32 accumulator columns per iteration: four independent 8-column groups give the scheduler the
+          // instruction-level parallelism that the few resident warps (3-4 per sub-partition) cannot
+          const int nchunks = (nvalid + 31) >> 5;
 #pragma unroll 1
           for (int ci = 0; ci < nchunks; ++ci) {
-            uint32_t r[16];
+            uint32_t r[32];
             if (!(sc.dbg & 32)) {
-              ptx::tmem_ld16(t_row + (uint32_t)(pass * kPassCols + 16 * ci), r);
+              ptx::tmem_ld32(t_row + (uint32_t)(pass * kPassCols + 32 * ci), r);
               ptx::tmem_ld_wait();
             } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) r[i] = 0x3f800000u + (uint32_t)ci;
+              for (int i = 0; i < 32; ++i) r[i] = 0x3f800000u + (uint32_t)ci;
             }
             if (!kGuardRows || valid) {
 #pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const int cofs = 16 * ci + 8 * q;  // column offset inside the pass
+              for (int q = 0; q < 4; ++q) {
+                const int cofs = 32 * ci + 8 * q;  // column offset inside the pass
                 if (cofs < nvalid) {
                   float accv[8], resv[8], outv[8];
 #pragma unroll
@@ -455,17 +540,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               }
             }
           }
-          __syncwarp();
-          // staged rows -> global: 4 rows x 128 B per warp instruction
-          uint4* ob = reinterpret_cast<uint4*>(const_cast<void*>(op.out_base())) + ((pn0 * kEs) >> 4) + cl;
+          { const long long t = clock64(); c_loop += t - t_ph; t_ph = t; }
+          if (tma_st) {
+            // staged rows -> global: one TMA store per 8-row group; rows / columns outside the tensor are clipped
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (gissue && !(sc.dbg & 4)) {
+              int c[5];
+              op.io_coords(g, grow0, pn0, c);
+              ptx::tma_store_5d(&tma_out, region + (uint32_t)lane * 1024u, c);
+            }
+            if (lane < 4) ptx::bulk_commit();
+          } else {
+            __syncwarp();
+            // staged rows -> global: 4 rows x 128 B per warp instruction
+            uint4* ob = reinterpret_cast<uint4*>(const_cast<void*>(op.out_base())) + ((pn0 * kEs) >> 4) + cl;
 #pragma unroll 2
-          for (int i = 0; i < 8; ++i) {
-            const int srow = 4 * i + srow0;
-            const uint32_t o = __shfl_sync(0xffffffffu, out16, srow);
-            const uint4 v = lds128(region + (uint32_t)srow * TC_STAGE_PITCH + (((uint32_t)cl ^ (uint32_t)(srow & 7)) << 4));
-            if (o != 0xFFFFFFFFu && cl * kVec < nvalid && !(sc.dbg & 4)) ob[o] = v;
+            for (int i = 0; i < 8; ++i) {
+              const int srow = 4 * i + srow0;
+              const uint32_t o = __shfl_sync(0xffffffffu, out16, srow);
+              const uint4 v = lds128(region + (uint32_t)srow * TC_STAGE_PITCH + (((uint32_t)cl ^ (uint32_t)(srow & 7)) << 4));
+              if (o != 0xFFFFFFFFu && cl * kVec < nvalid && !(sc.dbg & 4)) ob[o] = v;
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
         // the accumulator has been drained: hand the TMEM stage back to the MMA warp before any further work
         ptx::tc_fence_before();
@@ -473,7 +571,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
         // fused InstanceNorm statistics: one partial per (row, N tile, column slice); no cross-warp synchronisation
         if (feat_on<F, F_STATS>(op.wants_stats()) && row_ok)
-          op.finish(g, m, nt * (TC_EPI_WARPS / 4) + part, valid ? row.s : 0.0f, valid ? row.q : 0.0f);
+          op.finish(g, m, nt * (BN / TC_SLICE_COLS) + part, valid ? row.s : 0.0f, valid ? row.q : 0.0f);
+        c_tail += clock64() - t_ph;
       };
       if constexpr (!Op::kGeneral && Op::kFast0 == Op::kFast1) {
         drain(std::integral_constant<int, Op::kFast0>{});
@@ -484,6 +583,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         else drain(std::integral_constant<int, -1>{});
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if ((sc.io & 1) && lane < 4) ptx::bulk_wait_read();  // outstanding TMA stores still read this CTA's shared memory
+    if (sc.prof && ew == 0 && lane == 0) {
+      atomicAdd(sc.prof + 3, (unsigned long long)w_tfull);
+      atomicAdd(sc.prof + 4, (unsigned long long)w_res);
+      atomicAdd(sc.prof + 6, (unsigned long long)(clock64() - t_epi - w_tfull - w_res));
+      atomicAdd(sc.prof + 8, (unsigned long long)c_pro);
+      atomicAdd(sc.prof + 9, (unsigned long long)c_loop);
+      atomicAdd(sc.prof + 10, (unsigned long long)c_tail);
     }
   }
 
@@ -524,6 +632,39 @@ inline int encode_operand(const TmaOperand& o, bool k_contig, int rows_box, CUte
   return SFNO_OK;
 }
 
+inline int encode_io(const TmaIo& o, CUtensorMap* map, const char* what) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return fail(SFNO_ERR_CUDA, "%s: cuTensorMapEncodeTiled unavailable", what);
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 5; ++i) dims[i] = o.dims[i];
+  for (int i = 0; i < 4; ++i) strides[i] = o.strides[i];
+  for (int i = 1; i < 4; ++i)
+    if (dims[i + 1] == 1) strides[i] = strides[i - 1] * dims[i];  // extent-1 dimension: any valid multiple of 16
+  box[0] = (cuuint32_t)(TC_STAGE_PITCH / o.es);
+  for (int i = 0; i < 4; ++i) box[i + 1] = o.box_rows[i];
+  CUresult r = enc(map, o.es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(o.base),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SFNO_ERR_CUDA, "%s: cuTensorMapEncodeTiled (epilogue I/O) failed (%d): base=%p dims=(%llu,%llu,%llu,%llu,%llu)", what, (int)r,
+                o.base, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                (unsigned long long)dims[3], (unsigned long long)dims[4]);
+  return SFNO_OK;
+}
+
+inline bool tma_io_ok(const TmaIo& o) {
+  if (!o.ok || !o.base || ((uintptr_t)o.base & 15) != 0) return false;
+  uint32_t rows = 1;
+  for (int i = 0; i < 4; ++i) {
+    rows *= o.box_rows[i];
+    if (o.dims[i + 1] > 1 && (o.strides[i] % 16 != 0 || o.strides[i] == 0 || o.strides[i] >= (1ull << 40))) return false;
+  }
+  for (int i = 0; i < 5; ++i)
+    if (o.dims[i] == 0 || o.dims[i] > (1ull << 31)) return false;
+  return rows == 8;
+}
+
 inline bool tma_operand_ok(const TmaOperand& o) {
   if (((uintptr_t)o.base & 15) != 0) return false;
   if (o.strides[0] % 16 != 0 || o.strides[0] == 0) return false;
@@ -542,9 +683,18 @@ int launch_gemm_tc(const Op& op, cudaStream_t stream, const char* what) {
   if (op.M <= 0 || op.N <= 0 || op.G <= 0) return SFNO_OK;
   TmaOperand a, b;
   Tr::operands(op, a, b);
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mo, mr;
   SFNO_TRY(encode_operand(a, Op::A_KCONTIG, TC_BM, &ma, what));
   SFNO_TRY(encode_operand(b, Op::B_KCONTIG, BN, &mb, what));
+  TmaIo io_out, io_res;
+  Tr::io(op, io_out, io_res);
+  int io = 0;
+  if (!(g_tc_debug.load(std::memory_order_relaxed) & 64)) {  // tc_debug bit6: force the LDS/STG epilogue (A/B comparison)
+    if (tma_io_ok(io_out)) io |= 1;
+    if (tma_io_ok(io_res)) io |= 2;
+  }
+  if (io & 1) SFNO_TRY(encode_io(io_out, &mo, what)); else mo = ma;
+  if (io & 2) SFNO_TRY(encode_io(io_res, &mr, what)); else mr = ma;
   TcSched sc;
   sc.m_tiles = ceil_div(op.M, TC_BM);
   sc.n_tiles = ceil_div(op.N, BN);
@@ -560,6 +710,8 @@ int launch_gemm_tc(const Op& op, cudaStream_t stream, const char* what) {
   sc.a_glo = a.group_lo;
   sc.b_glo = b.group_lo;
   sc.dbg = g_tc_debug.load(std::memory_order_relaxed);
+  sc.io = io;
+  sc.prof = (sc.dbg & 128) ? tc_prof_buffer() : nullptr;
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<Op, BN>;
   if (!attr_set) {
@@ -567,7 +719,7 @@ int launch_gemm_tc(const Op& op, cudaStream_t stream, const char* what) {
     attr_set = true;
   }
   const int grid = std::min(sc.num_tiles, tc_num_sms());
-  kern<<<grid, TC_THREADS, S::kTotal, stream>>>(ma, mb, op, sc);
+  kern<<<grid, tc_threads(BN), S::kTotal, stream>>>(ma, mb, mo, mr, op, sc);
   return post_launch(what);
 }
 

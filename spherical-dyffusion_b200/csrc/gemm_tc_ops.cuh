@@ -10,6 +10,7 @@ template <class Op>
 struct TcTraitsBase {
   static constexpr bool kAvailable = true;
   static bool extra_ok(const Op&) { return true; }  // vector-store alignment rules of the epilogue, if any
+  static void io(const Op&, TmaIo&, TmaIo&) {}       // TMA views of the output / residual tensors (default: none)
 };
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
@@ -33,6 +34,13 @@ struct TcTraits<OpDft<bf16>> : TcTraitsBase<OpDft<bf16>>, TcEligible<TcTraits<Op
     b.batched = true; b.group_lo = op.C;
   }
   static bool extra_ok(const OpDft<bf16>& op) { return aligned16(op.f) && op.Kp % 8 == 0; }
+  static void io(const OpDft<bf16>& op, TmaIo& o, TmaIo&) {
+    const uint64_t kp = (uint64_t)op.Kp * 2;
+    o.base = op.f; o.es = 2; o.ok = true;
+    o.dims[0] = op.Kp; o.dims[1] = op.C; o.dims[2] = 2; o.dims[3] = op.B; o.dims[4] = op.M / 2;
+    o.strides[0] = kp; o.strides[1] = kp * op.C; o.strides[2] = kp * op.C * 2; o.strides[3] = kp * op.C * 2 * op.B;
+    o.box_rows[0] = 1; o.box_rows[1] = 2; o.box_rows[2] = 1; o.box_rows[3] = 4;
+  }
 };
 
 template <>
@@ -45,6 +53,12 @@ struct TcTraits<OpLeg<bf16>> : TcTraitsBase<OpLeg<bf16>>, TcEligible<TcTraits<Op
     b.strides[0] = (uint64_t)op.Kp * 2; b.strides[1] = (uint64_t)op.N * op.Kp * 2; b.batched = true;
   }
   static bool extra_ok(const OpLeg<bf16>& op) { return aligned16(op.x) && op.N % 8 == 0; }
+  static void io(const OpLeg<bf16>& op, TmaIo& o, TmaIo&) {
+    o.base = op.x; o.es = 2; o.ok = true;
+    o.dims[0] = op.N; o.dims[1] = op.mmax; o.dims[2] = op.lmax;
+    o.strides[0] = (uint64_t)op.N * 2; o.strides[1] = (uint64_t)op.mmax * op.N * 2;
+    o.box_rows[0] = 1; o.box_rows[1] = 8;
+  }
 };
 
 template <>
@@ -57,6 +71,13 @@ struct TcTraits<OpDhconv<bf16>> : TcTraitsBase<OpDhconv<bf16>>, TcEligible<TcTra
     b.strides[0] = (uint64_t)op.K * 2; b.strides[1] = (uint64_t)op.N * op.K * 2; b.batched = true;
   }
   static bool extra_ok(const OpDhconv<bf16>& op) { return aligned16(op.y) && op.N % 8 == 0; }
+  static void io(const OpDhconv<bf16>& op, TmaIo& o, TmaIo&) {
+    o.base = op.y; o.es = 2;
+    o.dims[0] = op.N; o.dims[1] = op.B; o.dims[2] = op.lmax; o.dims[3] = op.mmax;
+    o.strides[0] = (uint64_t)op.N * 2; o.strides[1] = (uint64_t)op.B * op.N * 2; o.strides[2] = (uint64_t)op.lmax * op.B * op.N * 2;
+    if (op.B % 8 == 0) { o.ok = true; }
+    else if (8 % op.B == 0) { o.ok = true; o.box_rows[0] = op.B; o.box_rows[2] = 8 / op.B; }
+  }
 };
 
 template <>
@@ -69,6 +90,12 @@ struct TcTraits<OpIleg<bf16>> : TcTraitsBase<OpIleg<bf16>>, TcEligible<TcTraits<
     b.strides[0] = (uint64_t)op.Lq * 2; b.strides[1] = (uint64_t)op.nlat * op.Lq * 2; b.batched = true;
   }
   static bool extra_ok(const OpIleg<bf16>& op) { return aligned16(op.g_out) && op.Kp % 8 == 0; }
+  static void io(const OpIleg<bf16>& op, TmaIo& o, TmaIo&) {
+    const uint64_t kp = (uint64_t)op.Kp * 2;
+    o.base = op.g_out; o.es = 2; o.ok = op.C % 8 == 0;
+    o.dims[0] = op.Kp; o.dims[1] = op.C; o.dims[2] = op.B; o.dims[3] = 2; o.dims[4] = op.G;
+    o.strides[0] = kp; o.strides[1] = kp * op.C; o.strides[2] = kp * op.C * op.B; o.strides[3] = kp * op.C * op.B * 2;
+  }
 };
 
 template <class TOut, int ACT>
@@ -85,12 +112,23 @@ struct TcTraits<OpIdft<bf16, TOut, ACT>> : TcTraitsBase<OpIdft<bf16, TOut, ACT>>
     return op.nlon % 8 == 0 && op.out_bstride % 8 == 0 && aligned16(op.out) &&
            (!op.add || (sizeof(TOut) == 2 && aligned16(op.add) && op.add_bstride % 8 == 0));
   }
+  static void io(const OpIdft<bf16, TOut, ACT>& op, TmaIo& o, TmaIo& r) {
+    const uint64_t es = sizeof(TOut);
+    const int B = op.M / (op.C * op.Kp);
+    o.base = op.out; o.es = (int)es; o.ok = op.Kp % 8 == 0;
+    o.dims[0] = op.nlon; o.dims[1] = op.nlat; o.dims[2] = op.C; o.dims[3] = B;
+    o.strides[0] = (uint64_t)op.nlon * es; o.strides[1] = (uint64_t)op.nlat * op.nlon * es; o.strides[2] = (uint64_t)op.out_bstride * es;
+    if (op.add && es == 2) {
+      r = o;
+      r.base = op.add; r.strides[2] = (uint64_t)op.add_bstride * 2;
+    }
+  }
 };
 
 template <class TOut, int ACT, int DROP>
 struct TcTraits<OpConv<bf16, TOut, ACT, DROP>> : TcTraitsBase<OpConv<bf16, TOut, ACT, DROP>>,
                                                    TcEligible<TcTraits<OpConv<bf16, TOut, ACT, DROP>>, OpConv<bf16, TOut, ACT, DROP>> {
-  static constexpr int BN = 256;
+  static constexpr int BN = 192;
   static void operands(const OpConv<bf16, TOut, ACT, DROP>& op, TmaOperand& a, TmaOperand& b) {
     const bool wb = op.w_bstride != 0;
     a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.M; a.dims[2] = wb ? op.G : 1;  // weights [o][c], K-contiguous
@@ -101,6 +139,16 @@ struct TcTraits<OpConv<bf16, TOut, ACT, DROP>> : TcTraitsBase<OpConv<bf16, TOut,
   static bool extra_ok(const OpConv<bf16, TOut, ACT, DROP>& op) {
     return op.N % 8 == 0 && op.out_bstride % 8 == 0 && aligned16(op.out) &&
            (!op.res || (sizeof(TOut) == 2 && aligned16(op.res) && op.res_bstride % 8 == 0)) && (!op.pos || aligned16(op.pos));
+  }
+  static void io(const OpConv<bf16, TOut, ACT, DROP>& op, TmaIo& o, TmaIo& r) {
+    const uint64_t es = sizeof(TOut);
+    o.base = op.out; o.es = (int)es; o.ok = true;
+    o.dims[0] = op.N; o.dims[1] = op.M; o.dims[2] = op.G;
+    o.strides[0] = (uint64_t)op.N * es; o.strides[1] = (uint64_t)op.out_bstride * es;
+    if (op.res && es == 2) {
+      r = o;
+      r.base = op.res; r.strides[1] = (uint64_t)op.res_bstride * 2;
+    }
   }
 };
 

@@ -101,8 +101,8 @@ static WsLayout ws_layout(const sfno_net* n, int B) {
   w.fc1_bb = take((size_t)B * std::max(n->hid, 1) * sizeof(float));
   w.dscale = take((size_t)B * sizeof(float));
   {  // per-slice partial sums of the fused InstanceNorm statistics (tensor-core epilogues)
-    const size_t conv_slices = (size_t)ceil_div(n->P, 256) * kConvStatSlicesPerTile;
-    const size_t idft_slices = (size_t)ceil_div(n->cfg.nlon, 192) * kConvStatSlicesPerTile;
+    const size_t conv_slices = (size_t)conv_stat_slices(n->P);
+    const size_t idft_slices = (size_t)idft_stat_slices(n->cfg.nlon);
     const size_t conv_f = conv_slices * 2 * (size_t)B * n->C, idft_f = idft_slices * 2 * (size_t)B * n->C * Kp;
     w.stat_part = take(std::max(conv_f, idft_f) * sizeof(float));
   }
@@ -305,14 +305,16 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
   buf_of(nl, &cur, &cur_bs);
   float* stat_part = (float*)(ws + w.stat_part);
   bool x_stats_fused = false;  // statistics of `cur` already sit in stat_part (written by the producing conv)
-  const int conv_slices = ceil_div(P, 256) * kConvStatSlicesPerTile;
+  const int conv_slices = conv_stat_slices(P);
 
   // ---- encoder (sfnonet.py:610-618) + position embedding (sfnonet.py:824)
   {
     auto e0 = make_conv<T, T>(B, P, n->Cin, C, xin, (int64_t)n->Cin * P, (const T*)n->enc0_w, 0, n->Cin_p, n->enc0_b, 0, cfg.activation, t1, CP);
     SFNO_TRY(launch_conv(e0, st, "encoder0"));
     auto e1 = make_conv<T, T>(B, P, C, C, t1, CP, (const T*)n->enc1_w, 0, C, nullptr, 0, SFNO_ACT_NONE, cur, cur_bs);
-    e1.pos = cfg.pos_embed ? (const T*)n->pos : nullptr;
+    // position embedding [C][P] (sfnonet.py:824) enters as a residual block with sample stride 0: the conv then runs
+    // the residual + statistics fast path of the epilogue
+    if (cfg.pos_embed) { e1.res = (const T*)n->pos; e1.res_bstride = 0; }
     if (cfg.instance_norm && conv_uses_tc(e1)) { e1.stat_part = stat_part; x_stats_fused = true; }
     SFNO_TRY(launch_conv(e1, st, "encoder1"));
   }
@@ -395,7 +397,7 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
     // norm1 (+ time scale/shift after the filter) folded into fc1  (sfnonet.py:313-323)
     const bool time_after = cfg.with_time_emb && !cfg.time_scale_shift_before_filter;
     if (cfg.instance_norm && t1_stats_fused) {
-      const int idft_slices = ceil_div(inv.nlon, 192) * kConvStatSlicesPerTile;
+      const int idft_slices = idft_stat_slices(inv.nlon);
       norm_affine_partials_kernel<<<ceil_div(BC * 32, 256), 256, 0, st>>>(stat_part, idft_slices, (int64_t)BC * inv.Kp, inv.Kp, (float)P,
                                                                      cfg.norm_eps, bp.norm1_g, bp.norm1_b, time_after ? ts_i : nullptr,
                                                                      ts_bs, B, C, a1, d1);

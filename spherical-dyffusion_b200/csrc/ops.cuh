@@ -128,6 +128,11 @@ struct OpDft : FullRanges, NoFeatures {
   }
   __device__ int n_store() const { return Kp; }
   __device__ const void* out_base() const { return f; }
+  // TMA view of F: {k, c, ri, b, m}; eight GEMM rows (m,ri) = 4 wavenumbers x {re, im} of one (b, c) plane
+  __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const {
+    const int b = g / C;
+    c[0] = col0; c[1] = g - b * C; c[2] = 0; c[3] = b; c[4] = row0 >> 1;
+  }
   struct Row { T* out; const T* res; bool valid; float a, d, s, q; };
   __device__ Row row(int g, int m) const {
     const int b = g / C, c = g - b * C, mm = m >> 1, ri = m & 1;
@@ -174,6 +179,8 @@ struct OpLeg : NoFeatures {
   __device__ int64_t b_off(int g, int n) const { return ((int64_t)g * N + n) * Kp; }
   __device__ int n_store() const { return N; }
   __device__ const void* out_base() const { return x; }
+  // TMA view of X: {(b,ri,c), m, l}; eight GEMM rows = eight degrees of wavenumber g
+  __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const { c[0] = col0; c[1] = g; c[2] = row0; c[3] = 0; c[4] = 0; }
   struct Row { T* out; const T* res; bool valid; float s, q; };
   __device__ Row row(int g, int m) const { return Row{x + ((int64_t)m * mmax + g) * N, nullptr, true, 0.0f, 0.0f}; }
   template <int F> __device__ Row row_f(int g, int m) const { return row(g, m); }
@@ -214,6 +221,12 @@ struct OpDhconv : NoFeatures {
   __device__ int64_t b_off(int g, int n) const { return ((int64_t)g * N + n) * K; }
   __device__ int n_store() const { return N; }
   __device__ const void* out_base() const { return y; }
+  // TMA view of Y: {(ri',o), b, l, m}; eight GEMM rows (m,b) = eight samples of one wavenumber (B % 8 == 0) or
+  // 8/B wavenumbers x B samples (B divides 8)
+  __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const {
+    const int mm = row0 / B;
+    c[0] = col0; c[1] = row0 - mm * B; c[2] = g; c[3] = mm; c[4] = 0;
+  }
   struct Row { T* out; const T* res; bool valid; float s, q; };
   __device__ Row row(int g, int m) const {
     const int mm = m / B, b = m - mm * B;
@@ -253,6 +266,11 @@ struct OpIleg : NoFeatures {
   __device__ int64_t b_off(int g, int n) const { return ((int64_t)g * nlat + n) * Lq; }
   __device__ int n_store() const { return Kp; }  // columns [nlat, Kp) are exact zeros (zero-filled table rows)
   __device__ const void* out_base() const { return g_out; }
+  // TMA view of G: {k, o, b, ri, m}; eight GEMM rows (b,ri,o) = eight channels (C % 8 == 0)
+  __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const {
+    const int b = row0 / (2 * C), rem = row0 - b * 2 * C, ri = rem / C;
+    c[0] = col0; c[1] = rem - ri * C; c[2] = b; c[3] = ri; c[4] = g;
+  }
   struct Row { T* out; const T* res; bool valid; float s, q; };
   __device__ Row row(int g, int m) const {
     int b = m / (2 * C), rem = m - b * 2 * C;
@@ -305,6 +323,12 @@ struct OpIdft : IdftArgs<T, TOut>, FullRanges {
   __device__ int feat() const { return (this->add ? F_RES : 0) | (this->stat_part ? F_STATS : 0); }
   __device__ const void* out_base() const { return this->out; }
   __device__ const void* res_base() const { return this->add; }
+  // TMA view of the grid tensor: {j, k, o, b}; eight GEMM rows (b,o,kp) = eight latitudes of one plane (Kp % 8 == 0);
+  // the pad latitudes kp >= nlat are clipped by the tensor extent
+  __device__ void io_coords(int, int row0, int col0, int (&c)[5]) const {
+    const int bo = row0 / this->Kp, b = bo / this->C;
+    c[0] = col0; c[1] = row0 - bo * this->Kp; c[2] = bo - b * this->C; c[3] = b; c[4] = 0;
+  }
   struct Row { TOut* out; const T* res; bool valid; float bias; float s, q; };
   __device__ Row row(int, int m) const {
     int bo = m / this->Kp, k = m - bo * this->Kp;
@@ -391,6 +415,8 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
   }
   __device__ const void* out_base() const { return this->out; }
   __device__ const void* res_base() const { return this->res; }
+  // TMA view of the activation tensor: {pixel, channel, sample}
+  __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const { c[0] = col0; c[1] = row0; c[2] = g; c[3] = 0; c[4] = 0; }
   struct Row { TOut* out; const T* res; bool valid; const T* pos; float bias, ra, rd, scale; uint64_t rng_base; float s, q; };
   template <int F>
   __device__ Row row_f(int g, int m) const {

@@ -21,6 +21,15 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+unsigned long long* tc_prof_buffer() {
+  static unsigned long long* buf = nullptr;
+  if (!buf) {
+    if (cudaMalloc(&buf, 12 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); buf = nullptr; }
+    else cudaMemset(buf, 0, 12 * sizeof(unsigned long long));
+  }
+  return buf;
+}
+
 int tc_num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -32,3 +41,14 @@ int tc_num_sms() {
 }
 
 }  // namespace sfno
+
+// measurement hook: read (and clear) the role-wait counters filled by tensor-core launches while tc_debug bit7 is set
+extern "C" int sfno_b200_tc_counters(unsigned long long* out12) {
+  if (!out12) return SFNO_ERR_INVALID_ARGUMENT;
+  unsigned long long* buf = sfno::tc_prof_buffer();
+  if (!buf) return SFNO_ERR_CUDA;
+  if (cudaDeviceSynchronize() != cudaSuccess) return SFNO_ERR_CUDA;
+  if (cudaMemcpy(out12, buf, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return SFNO_ERR_CUDA;
+  cudaMemset(buf, 0, 12 * sizeof(unsigned long long));
+  return SFNO_OK;
+}
