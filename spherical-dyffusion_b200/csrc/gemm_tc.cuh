@@ -307,7 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   // tiles outside the group's live row / column ranges carry no information: all roles skip them
   auto tile_skipped = [&](int g, int mt, int nt) {
     if constexpr (!Op::kRanged) return false;
-    else return nt * BN >= op.n_end(g) || (nt + 1) * BN <= op.n_begin(g) || mt * TC_BM >= op.m_end(g) || (mt + 1) * TC_BM <= op.m_begin(g);
+    else return nt * BN >= op.n_end(g) || (nt + 1) * BN <= op.n_begin(g) || op.m_begin(g) + mt * TC_BM >= op.m_end(g);
   };
 
   if (warp == TC_WARP_TMA) {
@@ -321,7 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         int g, mt, nt;
         decode(g, mt, nt);
         if (tile_skipped(g, mt, nt)) continue;
-        const int m0 = mt * TC_BM, n0 = nt * BN;
+        const int m0 = op.m_begin(g) + mt * TC_BM, n0 = nt * BN;   // M tiles start at the group's first live row
         int ga = sc.a_batched ? g : 0, gb = sc.b_batched ? g : 0, ga_hi = 0, gb_hi = 0;
         if (sc.a_glo) { ga_hi = ga / sc.a_glo; ga -= ga_hi * sc.a_glo; }
         if (sc.b_glo) { gb_hi = gb / sc.b_glo; gb -= gb_hi * sc.b_glo; }
@@ -410,9 +410,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       decode(g, mt, nt);
       if (tile_skipped(g, mt, nt)) continue;
       const long long t_tile = clock64();
-      const int m = mt * TC_BM + quad * 32 + lane;
+      const int m_tile0 = op.m_begin(g) + mt * TC_BM;
+      const int m = m_tile0 + quad * 32 + lane;
       const int n_base = nt * BN + part * kColsPerWarp;
-      const bool row_ok = m < op.m_end(g) && m >= op.m_begin(g);
+      const bool row_ok = m < op.m_end(g);
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kColsPerWarp);
       static_assert(Op::kColContig, "the tensor-core epilogue writes along the row: the column index must be the contiguous output index");
       // ---- drain: TMEM -> registers -> fused epilogue -> warp-private swizzled smem transpose -> coalesced 16-byte
@@ -438,8 +439,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const bool warp_live = __any_sync(0xffffffffu, valid) && n_base < n_end;
         const bool tma_st = (sc.io & 1) != 0, tma_ld = (sc.io & 2) != 0;
         // TMA epilogue I/O: lanes 0..3 each own one 8-row x 128-byte group (1024 B) of the warp's staging rows
-        const int grow0 = mt * TC_BM + quad * 32 + 8 * lane;   // first GEMM row of this lane's group (lanes 0..3)
-        const bool gissue = lane < 4 && grow0 < op.m_end(g) && grow0 >= op.m_begin(g);
+        const int grow0 = m_tile0 + quad * 32 + 8 * lane;   // first GEMM row of this lane's group (lanes 0..3)
+        const bool gissue = lane < 4 && grow0 < op.m_end(g);
         // row starts as 16-byte units relative to the tensor base: ONE 32-bit shuffle per staged row (~0 = no row)
         uint32_t out16 = 0xFFFFFFFFu;
         if (!tma_st && valid) out16 = (uint32_t)(((const char*)row.out - (const char*)op.out_base()) >> 4);
