@@ -85,6 +85,7 @@ struct TileIter {
 template <class Op>
 struct TcTraits {
   static constexpr bool kAvailable = false;
+  static constexpr bool kDualM = false;
   static bool eligible(const Op&) { return false; }
 };
 
@@ -217,9 +218,10 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn_major, bool b_mn_maj
 constexpr int TC_STAGE_PITCH = 128;                       // bytes per staged row (one pass of an epilogue warp)
 constexpr int TC_STAGING_PER_WARP = 32 * TC_STAGE_PITCH;  // 32 rows
 
-template <int BN, bool kStaging>
+template <int BN, bool kStaging, bool kDual = false>
 struct TcSmem {
-  static constexpr int kABytes = TC_BM * TC_BK * 2;
+  static constexpr int kAHalfBytes = TC_BM * TC_BK * 2;
+  static constexpr int kABytes = (kDual ? 2 : 1) * kAHalfBytes;   // dual-M: two 128-row A tiles share one B tile
   static constexpr int kBBytes = BN * TC_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = kStaging ? tc_epi_warps(BN) * TC_STAGING_PER_WARP : 0;
@@ -252,13 +254,15 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&v)[8]) {
   }
 }
 
-template <class Op, int BN>
+template <class Op, int BN, bool kDual>
 __global__ void __launch_bounds__(tc_threads(BN), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res, const Op op, const TcSched sc) {
-  using S = TcSmem<BN, Op::kColContig>;
+  using S = TcSmem<BN, Op::kColContig, kDual>;
   constexpr int kStages = S::kStages;
-  constexpr uint32_t kTmemCols = 512;  // two accumulator stages of up to 256 fp32 columns
+  constexpr uint32_t kTmemCols = 512;  // two accumulator stages of up to 256 fp32 columns, or (dual-M) one stage of two
+  constexpr int kBMT = kDual ? 2 * TC_BM : TC_BM;   // rows per tile
+  constexpr int kAccStages = kDual ? 1 : 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
   const uint32_t staging_base = smem_base + kStages * S::kStageBytes;  // 1024-byte aligned: TMA boxes of 8 staged rows
@@ -269,7 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   auto res_bar = [&](int w) { return bar_base + 8u * (2 * kStages + 6 + w); };  // one per epilogue warp (TMA residual loads)
-  auto a_smem = [&](int s) { return smem_base + s * S::kStageBytes; };
+  auto a_smem = [&](int s, int h = 0) { return smem_base + s * S::kStageBytes + h * S::kAHalfBytes; };
   auto b_smem = [&](int s) { return smem_base + s * S::kStageBytes + S::kABytes; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -307,7 +311,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   // tiles outside the group's live row / column ranges carry no information: all roles skip them
   auto tile_skipped = [&](int g, int mt, int nt) {
     if constexpr (!Op::kRanged) return false;
-    else return nt * BN >= op.n_end(g) || (nt + 1) * BN <= op.n_begin(g) || op.m_begin(g) + mt * TC_BM >= op.m_end(g);
+    else return nt * BN >= op.n_end(g) || (nt + 1) * BN <= op.n_begin(g) || op.m_begin(g) + mt * kBMT >= op.m_end(g);
   };
 
   if (warp == TC_WARP_TMA) {
@@ -321,22 +325,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         int g, mt, nt;
         decode(g, mt, nt);
         if (tile_skipped(g, mt, nt)) continue;
-        const int m0 = op.m_begin(g) + mt * TC_BM, n0 = nt * BN;   // M tiles start at the group's first live row
+        const int m0 = op.m_begin(g) + mt * kBMT, n0 = nt * BN;   // M tiles start at the group's first live row
+        const int halves = (kDual && m0 + TC_BM < op.m_end(g)) ? 2 : 1;
         int ga = sc.a_batched ? g : 0, gb = sc.b_batched ? g : 0, ga_hi = 0, gb_hi = 0;
         if (sc.a_glo) { ga_hi = ga / sc.a_glo; ga -= ga_hi * sc.a_glo; }
         if (sc.b_glo) { gb_hi = gb / sc.b_glo; gb -= gb_hi * sc.b_glo; }
         for (int kb = op.k_begin(g) / TC_BK; kb < sc.k_blocks; ++kb) {
           w_empty += ptx::mbar_wait<true>(empty_bar(stage), phase ^ 1u);
           const bool load_a = !(sc.dbg & 1), load_b = !(sc.dbg & 2);
-          ptx::mbar_expect_tx(full_bar(stage), (load_a ? S::kABytes : 0) + (load_b ? S::kBBytes : 0));
+          ptx::mbar_expect_tx(full_bar(stage), (load_a ? halves * S::kAHalfBytes : 0) + (load_b ? S::kBBytes : 0));
           const int k0 = kb * TC_BK;
-          if (!load_a) {
-          } else if (Op::A_KCONTIG) {
-            ptx::tma_load_4d(a_smem(stage), &tma_a, full_bar(stage), k0, m0, ga, ga_hi);
-          } else {
+          for (int hf = 0; hf < (load_a ? halves : 0); ++hf) {
+            const int mh = m0 + hf * TC_BM;
+            if (Op::A_KCONTIG) {
+              ptx::tma_load_4d(a_smem(stage, hf), &tma_a, full_bar(stage), k0, mh, ga, ga_hi);
+            } else {
 #pragma unroll
-            for (int h = 0; h < TC_BM / 64; ++h)
-              ptx::tma_load_4d(a_smem(stage) + h * (64 * TC_BK * 2), &tma_a, full_bar(stage), m0 + 64 * h, k0, ga, ga_hi);
+              for (int h = 0; h < TC_BM / 64; ++h)
+                ptx::tma_load_4d(a_smem(stage, hf) + h * (64 * TC_BK * 2), &tma_a, full_bar(stage), mh + 64 * h, k0, ga, ga_hi);
+            }
           }
           if (!load_b) {
           } else if (Op::B_KCONTIG) {
@@ -371,23 +378,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         decode(g, mt, nt);
         if (tile_skipped(g, mt, nt)) continue;
         const int kb0 = op.k_begin(g) / TC_BK;
+        const int halves = (kDual && op.m_begin(g) + mt * kBMT + TC_BM < op.m_end(g)) ? 2 : 1;
         w_tempty += ptx::mbar_wait<true>(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(kDual ? 0 : acc * BN);
         for (int kb = kb0; kb < sc.k_blocks; ++kb) {
           w_full += ptx::mbar_wait<true>(full_bar(stage), phase);
           ptx::tc_fence_after();
           const int nk = (kb == sc.k_blocks - 1) ? sc.k16_last : TC_BK / 16;
           for (int k = 0; k < nk; ++k) {
-            const uint64_t ad = make_smem_desc(a_smem(stage) + k * a_kstep, a_lbo, 1024u);
             const uint64_t bd = make_smem_desc(b_smem(stage) + k * b_kstep, b_lbo, 1024u);
-            if (!(sc.dbg & 16)) ptx::mma_bf16(d_tmem, ad, bd, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            for (int hf = 0; hf < halves; ++hf) {
+              const uint64_t ad = make_smem_desc(a_smem(stage, hf) + k * a_kstep, a_lbo, 1024u);
+              if (!(sc.dbg & 16)) ptx::mma_bf16(d_tmem + (uint32_t)(hf * BN), ad, bd, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            }
           }
           ptx::mma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         ptx::mma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
       }
       if (sc.prof) {
         atomicAdd(sc.prof + 1, (unsigned long long)w_full);
@@ -409,12 +419,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int g, mt, nt;
       decode(g, mt, nt);
       if (tile_skipped(g, mt, nt)) continue;
+      const int halves = (kDual && op.m_begin(g) + mt * kBMT + TC_BM < op.m_end(g)) ? 2 : 1;
+      for (int hf = 0; hf < halves; ++hf) {   // dual-M: the two 128-row halves of the tile are drained one after the other
+      const bool first_half = hf == 0, last_half = hf == halves - 1;
       const long long t_tile = clock64();
-      const int m_tile0 = op.m_begin(g) + mt * TC_BM;
+      const int m_tile0 = op.m_begin(g) + mt * kBMT + hf * TC_BM;
       const int m = m_tile0 + quad * 32 + lane;
       const int n_base = nt * BN + part * kColsPerWarp;
       const bool row_ok = m < op.m_end(g);
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kColsPerWarp);
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((kDual ? hf : acc) * BN + part * kColsPerWarp);
       static_assert(Op::kColContig, "the tensor-core epilogue writes along the row: the column index must be the contiguous output index");
       // ---- drain: TMEM -> registers -> fused epilogue -> warp-private swizzled smem transpose -> coalesced 16-byte
       //      global stores (and, for residual / addend blocks, coalesced loads through the same staging rows) ----
@@ -470,9 +483,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
         }
-        const long long w0 = ptx::mbar_wait(tfull_bar(acc), acc_phase);
-        w_tfull += w0;
-        ptx::tc_fence_after();
+        long long w0 = 0;
+        if (first_half) {
+          w0 = ptx::mbar_wait(tfull_bar(acc), acc_phase);
+          w_tfull += w0;
+          ptx::tc_fence_after();
+        }
         long long t_ph = clock64();
         c_pro += t_ph - t_tile - w0;
 #pragma unroll 1
@@ -567,9 +583,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
         // the accumulator has been drained: hand the TMEM stage back to the MMA warp before any further work
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+        if (last_half) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+        }
         // fused InstanceNorm statistics: one partial per (row, N tile, column slice); no cross-warp synchronisation
         if (feat_on<F, F_STATS>(op.wants_stats()) && row_ok)
           op.finish(g, m, nt * (BN / TC_SLICE_COLS) + part, valid ? row.s : 0.0f, valid ? row.q : 0.0f);
@@ -583,7 +601,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         else if (feat == Op::kFast1) drain(std::integral_constant<int, Op::kFast1>{});
         else drain(std::integral_constant<int, -1>{});
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }  // halves
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
     }
     if ((sc.io & 1) && lane < 4) ptx::bulk_wait_read();  // outstanding TMA stores still read this CTA's shared memory
     if (sc.prof && ew == 0 && lane == 0) {
@@ -676,11 +695,12 @@ inline bool tma_operand_ok(const TmaOperand& o) {
   return true;
 }
 
-template <class Op>
-int launch_gemm_tc(const Op& op, cudaStream_t stream, const char* what) {
+template <class Op, bool kDual>
+int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what) {
   using Tr = TcTraits<Op>;
   constexpr int BN = Tr::BN;
-  using S = TcSmem<BN, Op::kColContig>;
+  static_assert(!kDual || 2 * BN <= 512, "dual-M needs both accumulators in TMEM");
+  using S = TcSmem<BN, Op::kColContig, kDual>;
   if (op.M <= 0 || op.N <= 0 || op.G <= 0) return SFNO_OK;
   TmaOperand a, b;
   Tr::operands(op, a, b);
@@ -697,7 +717,7 @@ int launch_gemm_tc(const Op& op, cudaStream_t stream, const char* what) {
   if (io & 1) SFNO_TRY(encode_io(io_out, &mo, what)); else mo = ma;
   if (io & 2) SFNO_TRY(encode_io(io_res, &mr, what)); else mr = ma;
   TcSched sc;
-  sc.m_tiles = ceil_div(op.M, TC_BM);
+  sc.m_tiles = ceil_div(op.M, kDual ? 2 * TC_BM : TC_BM);
   sc.n_tiles = ceil_div(op.N, BN);
   sc.groups = op.G;
   const int64_t tiles = (int64_t)sc.m_tiles * sc.n_tiles * sc.groups;
@@ -714,7 +734,7 @@ int launch_gemm_tc(const Op& op, cudaStream_t stream, const char* what) {
   sc.io = io;
   sc.prof = (sc.dbg & 128) ? tc_prof_buffer() : nullptr;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<Op, BN>;
+  auto kern = gemm_tc_kernel<Op, BN, kDual>;
   if (!attr_set) {
     SFNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
@@ -722,6 +742,17 @@ int launch_gemm_tc(const Op& op, cudaStream_t stream, const char* what) {
   const int grid = std::min(sc.num_tiles, tc_num_sms());
   kern<<<grid, tc_threads(BN), S::kTotal, stream>>>(ma, mb, mo, mr, op, sc);
   return post_launch(what);
+}
+
+// dual-M (two 128-row A tiles per B tile, single-buffered accumulators) for the ops whose traits ask for it:
+// less L2->SMEM operand traffic per output element; tc_debug bit8 forces the single-tile kernel (A/B comparison)
+template <class Op>
+int launch_gemm_tc(const Op& op, cudaStream_t stream, const char* what) {
+  if constexpr (TcTraits<Op>::kDualM) {
+    if (TcTraits<Op>::use_dual(op) && !(g_tc_debug.load(std::memory_order_relaxed) & 256))
+      return launch_gemm_tc_impl<Op, true>(op, stream, what);
+  }
+  return launch_gemm_tc_impl<Op, false>(op, stream, what);
 }
 
 }  // namespace sfno

@@ -9,6 +9,8 @@ namespace sfno {
 template <class Op>
 struct TcTraitsBase {
   static constexpr bool kAvailable = true;
+  static constexpr bool kDualM = false;
+  static bool use_dual(const Op&) { return true; }
   static bool extra_ok(const Op&) { return true; }  // vector-store alignment rules of the epilogue, if any
   static void io(const Op&, TmaIo&, TmaIo&) {}       // TMA views of the output / residual tensors (default: none)
 };
@@ -45,6 +47,12 @@ struct TcTraits<OpDft<bf16>> : TcTraitsBase<OpDft<bf16>>, TcEligible<TcTraits<Op
 
 template <>
 struct TcTraits<OpLeg<bf16>> : TcTraitsBase<OpLeg<bf16>>, TcEligible<TcTraits<OpLeg<bf16>>, OpLeg<bf16>> {
+  // dual-M (two 128-row A tiles per B tile, single-buffered accumulators): the 180 degrees of a wavenumber fit ONE
+  // 256-row tile, which halves the F traffic.  Measured (profiles/r01_j_tc_dual_ab.txt): -8 % for the triangular
+  // Legendre; +30 % / +9 % / +28 % for DFT / dhconv / inverse Legendre (losing the second accumulator stage costs
+  // more than the saved L2 traffic), so only this op uses it, and only with the triangular ranges.
+  static constexpr bool kDualM = true;
+  static bool use_dual(const OpLeg<bf16>& op) { return op.triangular != 0; }
   static constexpr int BN = 256;
   static void operands(const OpLeg<bf16>& op, TmaOperand& a, TmaOperand& b) {
     a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.lmax; a.dims[2] = op.G;   // table rows l of wavenumber m

@@ -67,6 +67,18 @@ def algorithmic_work(model, batch: int):
     return w
 
 
+def _ncu_traffic(kernel_name):
+    """DRAM bytes per launch of `kernel_name` from the committed ncu capture (profiles/ncu_traffic.json), else None."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["kernels"][kernel_name]["traffic_bytes"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def roofline_from_profile(recs, pk, model=None, batch=None):
     total = sum(r["ms_total"] for r in recs.values())
     top_name, top = max(recs.items(), key=lambda kv: kv[1]["ms_total"])
@@ -90,7 +102,8 @@ def roofline_from_profile(recs, pk, model=None, batch=None):
             out["algorithmic_flops_per_launch"] = flops
             out["algorithmic_bytes_per_launch"] = nbytes
             out["tflops_achieved"] = flops / sec / 1e12
-            out["traffic"] = None
+            out["traffic"] = _ncu_traffic(top_name)
+            out["traffic_source"] = "profiles/ncu_traffic.json (ncu --set full, dram read + write bytes of one launch)" if out["traffic"] else None
         # every GEMM-shaped kernel against its own bound (all of them sit below the ridge at ACE size -> HBM)
         table = {}
         for name, (flops, nbytes) in algorithmic_work(model, batch).items():
