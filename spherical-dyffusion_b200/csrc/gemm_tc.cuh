@@ -142,6 +142,7 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -218,13 +219,15 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn_major, bool b_mn_maj
 constexpr int TC_STAGE_PITCH = 128;                       // bytes per staged row (one pass of an epilogue warp)
 constexpr int TC_STAGING_PER_WARP = 32 * TC_STAGE_PITCH;  // 32 rows
 
-template <int BN, bool kStaging, bool kDual = false>
+template <int BN, bool kStaging, bool kDual = false, int kBufs = 1>
 struct TcSmem {
   static constexpr int kAHalfBytes = TC_BM * TC_BK * 2;
   static constexpr int kABytes = (kDual ? 2 : 1) * kAHalfBytes;   // dual-M: two 128-row A tiles share one B tile
   static constexpr int kBBytes = BN * TC_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kStaging ? tc_epi_warps(BN) * TC_STAGING_PER_WARP : 0;
+  // kBufs = 2: the TMA store of one tile reads staging buffer b while the next tile fills b^1 (epilogue-bound ops);
+  // kBufs = 1 leaves the shared memory to the operand ring (load-bound ops)
+  static constexpr int kStagingBytes = kStaging ? kBufs * tc_epi_warps(BN) * TC_STAGING_PER_WARP : 0;
   static constexpr int kBudget = 226 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - kStagingBytes;
   static constexpr int kStages = kBudget / kStageBytes > 6 ? 6 : kBudget / kStageBytes;
   static constexpr int kBarrierBytes = 512;
@@ -258,7 +261,7 @@ template <class Op, int BN, bool kDual>
 __global__ void __launch_bounds__(tc_threads(BN), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res, const Op op, const TcSched sc) {
-  using S = TcSmem<BN, Op::kColContig, kDual>;
+  using S = TcSmem<BN, Op::kColContig, kDual, Op::kStagingBufs>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = 512;  // two accumulator stages of up to 256 fp32 columns, or (dual-M) one stage of two
   constexpr int kBMT = kDual ? 2 * TC_BM : TC_BM;   // rows per tile
@@ -412,7 +415,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     constexpr int kColsPerWarp = TC_SLICE_COLS;
     static_assert(BN % TC_SLICE_COLS == 0, "BN must be a whole number of column slices");
     int acc = 0;
-    uint32_t acc_phase = 0, res_phase = 0;
+    uint32_t acc_phase = 0, res_phase = 0, sbuf = 0;
     long long w_tfull = 0, w_res = 0, c_pro = 0, c_loop = 0, c_tail = 0;
     const long long t_epi = clock64();
     for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, it.next()) {
@@ -441,8 +444,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         constexpr int kPasses = (kColsPerWarp + kPassCols - 1) / kPassCols;
         constexpr int kVec = 16 / kEs;                                   // output elements per 16-byte chunk
         constexpr bool kGuardRows = F < 0 || (F & F_POS) != 0;           // compute8 may dereference per-row pointers
-        const uint32_t region = staging_base + (uint32_t)ew * TC_STAGING_PER_WARP;
-        const uint32_t my_row = region + (uint32_t)lane * TC_STAGE_PITCH;
+        constexpr uint32_t kBufs = Op::kStagingBufs;
+        uint32_t region = staging_base + ((uint32_t)ew * kBufs + sbuf) * TC_STAGING_PER_WARP;
+        uint32_t my_row = region + (uint32_t)lane * TC_STAGE_PITCH;
         const uint32_t sw = (uint32_t)(lane & 7);
         const int srow0 = lane >> 3, cl = lane & 7;                      // staging copies: 4 rows x 128 B per instruction
         const int n_end = op.n_store();
@@ -462,7 +466,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         uint4 res_pf[8];
         if (has_res && warp_live) {
           if (tma_ld) {
-            if (tma_st && lane < 4) ptx::bulk_wait_read();   // the previous tile's stores have left the staging rows
+            if (tma_st && lane < 4) { if (kBufs == 2) ptx::bulk_wait_read1(); else ptx::bulk_wait_read(); }  // the buffer's last store has left it
             __syncwarp();
             if (lane == 0) ptx::mbar_expect_tx(res_bar(ew), 4 * 1024);
             __syncwarp();
@@ -503,7 +507,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               w_res += ptx::mbar_wait(res_bar(ew), res_phase);
               res_phase ^= 1u;
             } else {
-              if (tma_st && lane < 4) ptx::bulk_wait_read();
+              if (tma_st && lane < 4) { if (kBufs == 2) ptx::bulk_wait_read1(); else ptx::bulk_wait_read(); }
               __syncwarp();
 #pragma unroll
               for (int i = 0; i < 8; ++i)
@@ -511,7 +515,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               __syncwarp();
             }
           } else if (tma_st) {
-            if (lane < 4) ptx::bulk_wait_read();   // staging rows free again (previous tile / previous pass)
+            if (lane < 4) { if (kBufs == 2) ptx::bulk_wait_read1(); else ptx::bulk_wait_read(); }  // this buffer is free again
             __syncwarp();
           }
           // 32 accumulator columns per iteration: four independent 8-column groups give the scheduler the
@@ -568,6 +572,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               ptx::tma_store_5d(&tma_out, region + (uint32_t)lane * 1024u, c);
             }
             if (lane < 4) ptx::bulk_commit();
+            sbuf = (kBufs == 2) ? (sbuf ^ 1u) : 0u;
+            region = staging_base + ((uint32_t)ew * kBufs + sbuf) * TC_STAGING_PER_WARP;
+            my_row = region + (uint32_t)lane * TC_STAGE_PITCH;
           } else {
             __syncwarp();
             // staged rows -> global: 4 rows x 128 B per warp instruction
@@ -700,7 +707,7 @@ int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what) {
   using Tr = TcTraits<Op>;
   constexpr int BN = Tr::BN;
   static_assert(!kDual || 2 * BN <= 512, "dual-M needs both accumulators in TMEM");
-  using S = TcSmem<BN, Op::kColContig, kDual>;
+  using S = TcSmem<BN, Op::kColContig, kDual, Op::kStagingBufs>;
   if (op.M <= 0 || op.N <= 0 || op.G <= 0) return SFNO_OK;
   TmaOperand a, b;
   Tr::operands(op, a, b);

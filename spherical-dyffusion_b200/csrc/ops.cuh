@@ -48,6 +48,7 @@ __device__ __forceinline__ float act_ct(int act_rt, float x) {
 }
 
 struct NoFeatures {
+  static constexpr int kStagingBufs = 1;   // load-bound ops: shared memory goes to the operand ring
   static constexpr int kFast0 = 0, kFast1 = 0;
   static constexpr bool kGeneral = false;
   __device__ int feat() const { return 0; }
@@ -320,6 +321,10 @@ struct OpIdft : IdftArgs<T, TOut>, FullRanges {
   __device__ bool has_res() const { return this->add != nullptr; }
   static constexpr int kFast0 = 0, kFast1 = F_RES | F_STATS;
   static constexpr bool kGeneral = true;
+  // 2 = the TMA store of one tile reads staging buffer b while the next tile fills b^1.  Measured slower (fc1 0.22 ->
+  // 0.255 ms, inverse DFT 0.20 -> 0.246 ms): the second buffer costs one operand stage (4 -> 3) and these kernels do
+  // wait for operands 8-20 % of the time, which outweighs the hidden store latency.
+  static constexpr int kStagingBufs = 1;
   __device__ int feat() const { return (this->add ? F_RES : 0) | (this->stat_part ? F_STATS : 0); }
   __device__ const void* out_base() const { return this->out; }
   __device__ const void* res_base() const { return this->add; }
@@ -410,6 +415,10 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
   __device__ bool has_res() const { return this->res != nullptr; }
   static constexpr int kFast0 = 0, kFast1 = F_RES | F_STATS;
   static constexpr bool kGeneral = true;
+  // 2 = the TMA store of one tile reads staging buffer b while the next tile fills b^1.  Measured slower (fc1 0.22 ->
+  // 0.255 ms, inverse DFT 0.20 -> 0.246 ms): the second buffer costs one operand stage (4 -> 3) and these kernels do
+  // wait for operands 8-20 % of the time, which outweighs the hidden store latency.
+  static constexpr int kStagingBufs = 1;
   __device__ int feat() const {
     return (this->res ? F_RES : 0) | (this->stat_part ? F_STATS : 0) | (this->pos ? F_POS : 0) | (this->branch_scale ? F_SCALE : 0);
   }
