@@ -109,6 +109,25 @@ __device__ __forceinline__ void philox_uniform4(uint64_t seed, uint64_t offset, 
   u3 = (r.w >> 8) * (1.0f / 16777216.0f);
 }
 
+// Dropout decisions: one Philox4x32-10 block serves EIGHT consecutive elements (16 random bits each, idx8 % 8 == 0):
+// element idx8 + j is kept iff its 16-bit value >= thr16 = round(p * 65536).  Bit j of the result = keep.
+__device__ __forceinline__ uint32_t dropout_threshold16(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+__device__ __forceinline__ float dropout_keep_scale(uint32_t thr16) { return 65536.0f / (float)(65536u - thr16); }
+__device__ __forceinline__ uint32_t dropout_keep_mask8(uint64_t seed, uint64_t offset, uint64_t idx8, uint32_t thr16) {
+  const uint64_t blk = idx8 >> 3;
+  const uint4 c = make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)offset, (uint32_t)(offset >> 32));
+  const uint4 r = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  uint32_t m = 0;
+  m |= ((r.x & 0xffffu) >= thr16) ? 1u : 0u;   m |= ((r.x >> 16) >= thr16) ? 2u : 0u;
+  m |= ((r.y & 0xffffu) >= thr16) ? 4u : 0u;   m |= ((r.y >> 16) >= thr16) ? 8u : 0u;
+  m |= ((r.z & 0xffffu) >= thr16) ? 16u : 0u;  m |= ((r.z >> 16) >= thr16) ? 32u : 0u;
+  m |= ((r.w & 0xffffu) >= thr16) ? 64u : 0u;  m |= ((r.w >> 16) >= thr16) ? 128u : 0u;
+  return m;
+}
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t offset, uint64_t idx, uint32_t thr16) {
+  return (dropout_keep_mask8(seed, offset, idx & ~7ull, thr16) >> (uint32_t)(idx & 7ull)) & 1u;
+}
+
 // Optional epilogue features.  The tensor-core engine instantiates its drain loop for the op's two most frequent
 // feature sets (kFast0, kFast1: compile-time masks, no per-element tests) plus, if kGeneral, a run-time tested one (F < 0).
 enum : int { F_RES = 1, F_STATS = 2, F_POS = 4, F_SCALE = 8 };

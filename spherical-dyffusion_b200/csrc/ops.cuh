@@ -443,7 +443,10 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
     }
     if (feat_on<F, F_POS>(this->pos != nullptr)) r.pos = this->pos + off;
     if (feat_on<F, F_SCALE>(this->branch_scale != nullptr)) r.scale = this->branch_scale[g];
-    if (dropping()) r.rng_base = ((uint64_t)g * this->M + m) * (uint64_t)this->N;
+    if (dropping()) {   // the 1/keep factor of the dropout rides on the DropPath scale
+      r.rng_base = ((uint64_t)g * this->M + m) * (uint64_t)this->N;
+      r.scale *= dropout_keep_scale(dropout_threshold16(this->drop_p));
+    }
     return r;
   }
   __device__ Row row(int g, int m) const { return row_f<-1>(g, m); }
@@ -451,30 +454,22 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
     if constexpr (DROP == 0) return false;
     else return this->drop_p > 0.0f;
   }
-  __device__ float finish_value(const Row& r, float acc, float u) const {
-    float v = act_ct<T, ACT>(this->act, acc + r.bias);
-    if (dropping()) v = (u >= this->drop_p) ? __fdividef(v, 1.0f - this->drop_p) : 0.0f;
-    return v * r.scale;
-  }
   __device__ void store(const Row& r, int, int, int n, float acc) const {
-    const float u = dropping() ? philox_uniform(this->seed, this->offset, r.rng_base + n) : 1.0f;
-    float v = finish_value(r, acc, u);
+    float v = act_ct<T, ACT>(this->act, acc + r.bias) * r.scale;
+    if (dropping() && !dropout_keep(this->seed, this->offset, r.rng_base + n, dropout_threshold16(this->drop_p))) v = 0.0f;
     if (r.res) v += fmaf(r.ra, to_f32(r.res[n]), r.rd);
     if (r.pos) v += to_f32(r.pos[n]);
     r.out[n] = from_f32<TOut>(v);
   }
   template <int F>
   __device__ void compute8(Row& r, int n, const float (&acc)[8], const float (&res)[8], float (&o)[8]) const {
-    float u[8];
-    if (dropping()) {
-      philox_uniform4(this->seed, this->offset, r.rng_base + n, u[0], u[1], u[2], u[3]);
-      philox_uniform4(this->seed, this->offset, r.rng_base + n + 4, u[4], u[5], u[6], u[7]);
-    }
+    uint32_t keep = 0xffu;
+    if (dropping()) keep = dropout_keep_mask8(this->seed, this->offset, r.rng_base + n, dropout_threshold16(this->drop_p));
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float v = act_ct<T, ACT>(this->act, acc[i] + r.bias);
-      if (dropping()) v = (u[i] >= this->drop_p) ? __fdividef(v, 1.0f - this->drop_p) : 0.0f;
-      o[i] = feat_on<F, F_SCALE>(true) ? v * r.scale : v;   // (r.scale = 1 without DropPath)
+      const float v = act_ct<T, ACT>(this->act, acc[i] + r.bias);
+      if (dropping()) o[i] = ((keep >> i) & 1u) ? v * r.scale : 0.0f;
+      else o[i] = feat_on<F, F_SCALE>(true) ? v * r.scale : v;   // (r.scale = 1 without DropPath)
     }
     if (feat_on<F, F_RES>(r.res != nullptr)) {
 #pragma unroll

@@ -57,15 +57,53 @@ CASES = [
 ]
 
 
+def _run_case(op, dims, tc_debug=0):
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "tc_selftest_cli.py"), str(OPS[op])] + [str(d) for d in dims]
+    env = dict(os.environ)
+    env.pop("SFNO_TC_DEBUG", None)
+    if tc_debug:
+        env["SFNO_TC_DEBUG"] = str(tc_debug)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    line = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else ""
+    assert line, f"no output; stderr: {p.stderr[-2000:]}"
+    return json.loads(line)
+
+
+# engine variants selected by the correct-result tc_debug bits: 64 = epilogue I/O by LDS/STG instead of TMA boxes,
+# 256 = single 128-row tiles where the op would use dual-M tiles, 128 = role-wait counters on
+VARIANTS = [
+    ("leg", [8, 256, 180, 180, 181, 1], 256),
+    ("leg", [2, 64, 180, 180, 5, 1], 64),
+    ("dft", [2, 32, 180, 360, 181, 0], 64),
+    ("dhconv", [8, 256, 180, 181, 1, 0], 64),
+    ("ileg", [2, 64, 180, 180, 181, 3], 64),
+    ("idft", [2, 16, 180, 360, 181, 7], 64),
+    ("conv", [2, 256, 34, 64800, 0, 0], 64),
+    ("convb", [2, 512, 256, 64800, 0, 21], 64),
+    ("convb", [2, 256, 256, 64800, 1, 15], 64 + 128),
+]
+
+
+@pytest.mark.parametrize("op,dims,tc_debug", VARIANTS, ids=[f"{c[0]}-{'x'.join(map(str, c[1]))}-dbg{c[2]}" for c in VARIANTS])
+def test_tc_engine_variants_match_cuda_core_engine(op, dims, tc_debug):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    r = _run_case(op, dims, tc_debug)
+    print(json.dumps(r))
+    assert r["status"] == 0, r["error"]
+    assert r["tc_used"] and r["nonfinite"] == 0 and r["max_ref"] > 0
+    tol = 2e-5 if op == "conv" else 1.2e-2
+    assert r["max_err"] <= tol * r["max_ref"], r
+    if tc_debug & 128:
+        c = r["counters"]
+        assert c["ctas"] > 0 and 0.0 < c["epi_busy"] <= 1.5 and c["cta_cycles"] > 0
+
+
 @pytest.mark.parametrize("op,dims,expect_tc", CASES, ids=[f"{c[0]}-{'x'.join(map(str, c[1]))}" for c in CASES])
 def test_tc_engine_matches_cuda_core_engine(op, dims, expect_tc):
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
-    cmd = [sys.executable, os.path.join(ROOT, "tests", "tc_selftest_cli.py"), str(OPS[op])] + [str(d) for d in dims]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
-    line = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else ""
-    assert line, f"no output; stderr: {p.stderr[-2000:]}"
-    r = json.loads(line)
+    r = _run_case(op, dims)
     print(json.dumps(r))
     assert r["status"] == 0, r["error"]
     assert bool(r["tc_used"]) == expect_tc
