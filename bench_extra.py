@@ -162,10 +162,14 @@ def run_scaled(args):
         ms = _timeit(lambda: m(x, time=t, condition=c), args.steps, args.warmup)
         y = m(x, time=t, condition=c)
     flop = 66.78e12 * B
+    from spherical_dyffusion_b200.profile import profile_forward
+    recs = profile_forward(m, x, t, c, repeats=1)
+    per_kernel = {k: [round(v["ms_total"], 3), v["launches"]] for k, v in sorted(recs.items(), key=lambda kv: -kv[1]["ms_total"])[:10]}
     print(json.dumps({
         "workload": f"scaled SFNO forward: embed 512, 12 blocks, 720x1440, lmax 720, batch {B}, {args.precision} (random-init, synthetic)",
         "params": m.num_params, "ms_per_forward": ms, "samples_per_s": B / (ms * 1e-3), "model_tflops": flop / (ms * 1e-3) / 1e12,
-        "finite": bool(torch.isfinite(y).all()), "mem_GB": torch.cuda.max_memory_allocated() / 2**30}), flush=True)
+        "finite": bool(torch.isfinite(y).all()), "mem_GB": torch.cuda.max_memory_allocated() / 2**30,
+        "per_kernel_ms_and_launches": per_kernel}), flush=True)
 
 
 def run_sht(args):

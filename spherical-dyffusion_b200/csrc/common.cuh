@@ -99,15 +99,16 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t offset, 
   return (v >> 8) * (1.0f / 16777216.0f);
 }
 
-// four uniforms for the aligned group idx .. idx+3 (idx % 4 == 0): identical values to philox_uniform
-__device__ __forceinline__ void philox_uniform4(uint64_t seed, uint64_t offset, uint64_t idx, float& u0, float& u1, float& u2, float& u3) {
-  uint4 c = make_uint4((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), (uint32_t)offset, (uint32_t)(offset >> 32));
-  uint4 r = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  u0 = (r.x >> 8) * (1.0f / 16777216.0f);
-  u1 = (r.y >> 8) * (1.0f / 16777216.0f);
-  u2 = (r.z >> 8) * (1.0f / 16777216.0f);
-  u3 = (r.w >> 8) * (1.0f / 16777216.0f);
-}
+// Packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per issued instruction).  The epilogues
+// of the tensor-core engine are bound by instruction issue, not by the fp32 pipe, so the element-wise math runs on pairs.
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 f2_make(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 f2_splat(float a) { return f2_make(a, a); }
+__device__ __forceinline__ void f2_get(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ float f2_hsum(f2 a) { float lo, hi; f2_get(a, lo, hi); return lo + hi; }
 
 // Dropout decisions: one Philox4x32-10 block serves EIGHT consecutive elements (16 random bits each, idx8 % 8 == 0):
 // element idx8 + j is kept iff its 16-bit value >= thr16 = round(p * 65536).  Bit j of the result = keep.

@@ -597,7 +597,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         // fused InstanceNorm statistics: one partial per (row, N tile, column slice); no cross-warp synchronisation
         if (feat_on<F, F_STATS>(op.wants_stats()) && row_ok)
-          op.finish(g, m, nt * (BN / TC_SLICE_COLS) + part, valid ? row.s : 0.0f, valid ? row.q : 0.0f);
+          op.finish(g, m, nt * (BN / TC_SLICE_COLS) + part, valid ? row.stat_s() : 0.0f, valid ? row.stat_q() : 0.0f);
         c_tail += clock64() - t_ph;
       };
       if constexpr (!Op::kGeneral && Op::kFast0 == Op::kFast1) {

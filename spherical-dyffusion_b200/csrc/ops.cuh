@@ -3,14 +3,10 @@
 // plus a fused epilogue.  An op describes operand addressing (row offset + k stride), the problem size and the
 // epilogue; the engines (gemm_simt.cuh: fp32 CUDA cores; gemm_tc.cuh: tcgen05 + TMA) are templated on the op.
 //
-// In the tensor-core engine one thread owns one output row m (a TMEM lane) and walks the columns n.  Two epilogue
-// styles follow from the layout of the OUTPUT tensor:
-//   kColContig = false : the row index m is the contiguous output index -> for a fixed column the 32 lanes of a warp
-//                        write 32 consecutive elements (coalesced scalar stores); store16() walks the columns with
-//                        incremental addressing.  (forward Legendre, dhconv)
-//   kColContig = true  : the column index n is the contiguous output index -> the thread writes 16-byte vectors along
-//                        its own row and every per-row quantity (bias, affine, decoded indices) lives in registers;
-//                        compute8().  (forward DFT, inverse Legendre, inverse DFT, 1x1 convolutions)
+// In the tensor-core engine one thread owns one output row m (a TMEM lane) and walks the columns n.  Every op is
+// oriented so that the COLUMN index n is the contiguous index of the output tensor: the thread produces 16-byte vectors
+// along its own row, every per-row quantity (bias, affine, decoded indices) lives in registers, the element-wise math
+// runs on packed fp32 pairs (compute8()), and eight consecutive rows form one box of a TMA store (io_coords()).
 //
 // Internal tensor layouts (T = float or bf16; Kp = nlat rounded up to 8):
 //   grid   x  [B][C][nlat][nlon]                      (NCHW, as the reference)
@@ -47,6 +43,28 @@ __device__ __forceinline__ float act_ct(int act_rt, float x) {
   else return act_for<T>(act_rt, x);
 }
 
+// packed-pair forms of gelu_fast / act_ct (same formula, two elements per instruction)
+__device__ __forceinline__ f2 gelu_fast2(f2 x) {
+  const f2 x2 = f2_mul(x, x);
+  const f2 u = f2_mul(x, f2_fma(f2_splat(0.03470089f), x2, f2_splat(0.80015708f)));
+  float u0, u1, t0, t1;
+  f2_get(u, u0, u1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  const f2 h = f2_mul(x, f2_splat(0.5f));
+  return f2_fma(h, f2_make(t0, t1), h);
+}
+template <class T, int ACT>
+__device__ __forceinline__ f2 act_ct2(int act_rt, f2 v) {
+  if constexpr (ACT == SFNO_ACT_NONE) return v;
+  else if constexpr (ACT == SFNO_ACT_GELU && sizeof(T) == 2) return gelu_fast2(v);
+  else {
+    float lo, hi;
+    f2_get(v, lo, hi);
+    return f2_make(act_ct<T, ACT>(act_rt, lo), act_ct<T, ACT>(act_rt, hi));
+  }
+}
+
 struct NoFeatures {
   static constexpr int kStagingBufs = 1;   // load-bound ops: shared memory goes to the operand ring
   static constexpr int kFast0 = 0, kFast1 = 0;
@@ -58,19 +76,6 @@ struct NoFeatures {
   __device__ void finish(int, int, int, float, float) const {}
 };
 
-// pack 8 floats -> 8 x T and store as one (bf16) or two (fp32) 16-byte vectors; p must be 16-byte aligned
-__device__ __forceinline__ void store_vec8(bf16* p, const float (&v)[8]) {
-  uint4 u;
-  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
-  u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-  u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-  *reinterpret_cast<uint4*>(p) = u;
-}
-__device__ __forceinline__ void store_vec8(float* p, const float (&v)[8]) {
-  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
-}
 __device__ __forceinline__ void load_vec8(const bf16* p, float (&v)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -134,12 +139,12 @@ struct OpDft : FullRanges, NoFeatures {
     const int b = g / C;
     c[0] = col0; c[1] = g - b * C; c[2] = 0; c[3] = b; c[4] = row0 >> 1;
   }
-  struct Row { T* out; const T* res; bool valid; float a, d, s, q; };
+  struct Row { T* out; const T* res; bool valid; float a, d; __device__ float stat_s() const { return 0.0f; } __device__ float stat_q() const { return 0.0f; } };
   __device__ Row row(int g, int m) const {
     const int b = g / C, c = g - b * C, mm = m >> 1, ri = m & 1;
     Row r;
     r.out = f + (((int64_t)mm * B + b) * 2 + ri) * C * Kp + (int64_t)c * Kp;
-    r.res = nullptr; r.valid = true; r.s = 0.0f; r.q = 0.0f;
+    r.res = nullptr; r.valid = true;
     r.a = aff_a ? aff_a[g] : 1.0f;
     r.d = (aff_d && m == 0) ? aff_d[g] * 6.28318530717958647692f : 0.0f;
     return r;
@@ -148,8 +153,9 @@ struct OpDft : FullRanges, NoFeatures {
   __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = from_f32<T>(fmaf(r.a, acc, r.d)); }
   template <int F>
   __device__ void compute8(Row& r, int n, const float (&acc)[8], const float (&)[8], float (&o)[8]) const {
+    const f2 a2 = f2_splat(r.a);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = r.a * acc[i];
+    for (int j = 0; j < 4; ++j) f2_get(f2_mul(a2, f2_make(acc[2 * j], acc[2 * j + 1])), o[2 * j], o[2 * j + 1]);
     if (r.d != 0.0f) {  // the single (m = 0, re) row; the pad latitudes [nlat, Kp) stay zero
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] += (n + i < nlat) ? r.d : 0.0f;
@@ -182,8 +188,8 @@ struct OpLeg : NoFeatures {
   __device__ const void* out_base() const { return x; }
   // TMA view of X: {(b,ri,c), m, l}; eight GEMM rows = eight degrees of wavenumber g
   __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const { c[0] = col0; c[1] = g; c[2] = row0; c[3] = 0; c[4] = 0; }
-  struct Row { T* out; const T* res; bool valid; float s, q; };
-  __device__ Row row(int g, int m) const { return Row{x + ((int64_t)m * mmax + g) * N, nullptr, true, 0.0f, 0.0f}; }
+  struct Row { T* out; const T* res; bool valid; __device__ float stat_s() const { return 0.0f; } __device__ float stat_q() const { return 0.0f; } };
+  __device__ Row row(int g, int m) const { return Row{x + ((int64_t)m * mmax + g) * N, nullptr, true}; }
   template <int F> __device__ Row row_f(int g, int m) const { return row(g, m); }
   __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = from_f32<T>(acc); }
   template <int F>
@@ -228,10 +234,10 @@ struct OpDhconv : NoFeatures {
     const int mm = row0 / B;
     c[0] = col0; c[1] = row0 - mm * B; c[2] = g; c[3] = mm; c[4] = 0;
   }
-  struct Row { T* out; const T* res; bool valid; float s, q; };
+  struct Row { T* out; const T* res; bool valid; __device__ float stat_s() const { return 0.0f; } __device__ float stat_q() const { return 0.0f; } };
   __device__ Row row(int g, int m) const {
     const int mm = m / B, b = m - mm * B;
-    return Row{y + (((int64_t)mm * lmax + g) * B + b) * N, nullptr, true, 0.0f, 0.0f};
+    return Row{y + (((int64_t)mm * lmax + g) * B + b) * N, nullptr, true};
   }
   template <int F> __device__ Row row_f(int g, int m) const { return row(g, m); }
   __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = from_f32<T>(acc); }
@@ -272,11 +278,11 @@ struct OpIleg : NoFeatures {
     const int b = row0 / (2 * C), rem = row0 - b * 2 * C, ri = rem / C;
     c[0] = col0; c[1] = rem - ri * C; c[2] = b; c[3] = ri; c[4] = g;
   }
-  struct Row { T* out; const T* res; bool valid; float s, q; };
+  struct Row { T* out; const T* res; bool valid; __device__ float stat_s() const { return 0.0f; } __device__ float stat_q() const { return 0.0f; } };
   __device__ Row row(int g, int m) const {
     int b = m / (2 * C), rem = m - b * 2 * C;
     int ri = rem / C, o = rem - ri * C;
-    return Row{g_out + (int64_t)g * 2 * B * C * Kp + (int64_t)ri * B * C * Kp + ((int64_t)b * C + o) * Kp, nullptr, true, 0.0f, 0.0f};
+    return Row{g_out + (int64_t)g * 2 * B * C * Kp + (int64_t)ri * B * C * Kp + ((int64_t)b * C + o) * Kp, nullptr, true};
   }
   template <int F> __device__ Row row_f(int g, int m) const { return row(g, m); }
   __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = from_f32<T>(acc); }
@@ -334,12 +340,16 @@ struct OpIdft : IdftArgs<T, TOut>, FullRanges {
     const int bo = row0 / this->Kp, b = bo / this->C;
     c[0] = col0; c[1] = row0 - bo * this->Kp; c[2] = bo - b * this->C; c[3] = b; c[4] = 0;
   }
-  struct Row { TOut* out; const T* res; bool valid; float bias; float s, q; };
+  struct Row {
+    TOut* out; const T* res; bool valid; float bias; f2 s2, q2;   // s2 / q2: packed partial sum / sum of squares
+    __device__ float stat_s() const { return f2_hsum(s2); }
+    __device__ float stat_q() const { return f2_hsum(q2); }
+  };
   __device__ Row row(int, int m) const {
     int bo = m / this->Kp, k = m - bo * this->Kp;
     int b = bo / this->C, o = bo - b * this->C;
     Row r;
-    r.s = 0.0f; r.q = 0.0f;
+    r.s2 = f2_splat(0.0f); r.q2 = f2_splat(0.0f);
     r.valid = k < this->nlat;
     const int64_t pix = ((int64_t)o * this->nlat + k) * this->nlon;
     r.out = this->out + (int64_t)b * this->out_bstride + pix;
@@ -356,16 +366,14 @@ struct OpIdft : IdftArgs<T, TOut>, FullRanges {
   }
   template <int F>
   __device__ void compute8(Row& r, int, const float (&acc)[8], const float (&res)[8], float (&o)[8]) const {
-    if (feat_on<F, F_RES>(true)) {  // (res[] is zero when no addend is staged)
+    const f2 b2 = f2_splat(r.bias);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = act_ct<T, ACT>(this->act, acc[i] + r.bias + res[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = act_ct<T, ACT>(this->act, acc[i] + r.bias);
-    }
-    if (feat_on<F, F_STATS>(this->stat_part != nullptr)) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { r.s += o[i]; r.q = fmaf(o[i], o[i], r.q); }
+    for (int j = 0; j < 4; ++j) {
+      f2 v = f2_add(f2_make(acc[2 * j], acc[2 * j + 1]), b2);
+      if (feat_on<F, F_RES>(true)) v = f2_add(v, f2_make(res[2 * j], res[2 * j + 1]));  // (res[] is zero when no addend is staged)
+      v = act_ct2<T, ACT>(this->act, v);
+      if (feat_on<F, F_STATS>(this->stat_part != nullptr)) { r.s2 = f2_add(r.s2, v); r.q2 = f2_fma(v, v, r.q2); }
+      f2_get(v, o[2 * j], o[2 * j + 1]);
     }
   }
   __device__ bool wants_stats() const { return this->stat_part != nullptr; }
@@ -426,13 +434,17 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
   __device__ const void* res_base() const { return this->res; }
   // TMA view of the activation tensor: {pixel, channel, sample}
   __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const { c[0] = col0; c[1] = row0; c[2] = g; c[3] = 0; c[4] = 0; }
-  struct Row { TOut* out; const T* res; bool valid; const T* pos; float bias, ra, rd, scale; uint64_t rng_base; float s, q; };
+  struct Row {
+    TOut* out; const T* res; bool valid; const T* pos; float bias, ra, rd, scale; uint64_t rng_base; f2 s2, q2;
+    __device__ float stat_s() const { return f2_hsum(s2); }
+    __device__ float stat_q() const { return f2_hsum(q2); }
+  };
   template <int F>
   __device__ Row row_f(int g, int m) const {
     Row r;
     const int64_t off = (int64_t)m * this->N;
     r.valid = true;
-    r.s = 0.0f; r.q = 0.0f;
+    r.s2 = f2_splat(0.0f); r.q2 = f2_splat(0.0f);
     r.out = this->out + (int64_t)g * this->out_bstride + off;
     r.bias = this->bias ? this->bias[(int64_t)g * this->bias_bstride + m] : 0.0f;
     r.res = nullptr; r.ra = 1.0f; r.rd = 0.0f; r.pos = nullptr; r.scale = 1.0f; r.rng_base = 0;
@@ -465,25 +477,19 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
   __device__ void compute8(Row& r, int n, const float (&acc)[8], const float (&res)[8], float (&o)[8]) const {
     uint32_t keep = 0xffu;
     if (dropping()) keep = dropout_keep_mask8(this->seed, this->offset, r.rng_base + n, dropout_threshold16(this->drop_p));
+    const f2 b2 = f2_splat(r.bias), sc2 = f2_splat(r.scale), ra2 = f2_splat(r.ra), rd2 = f2_splat(r.rd);
+    float t[8];
+    if (feat_on<F, F_POS>(r.pos != nullptr)) load_vec8(r.pos + n, t);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float v = act_ct<T, ACT>(this->act, acc[i] + r.bias);
-      if (dropping()) o[i] = ((keep >> i) & 1u) ? v * r.scale : 0.0f;
-      else o[i] = feat_on<F, F_SCALE>(true) ? v * r.scale : v;   // (r.scale = 1 without DropPath)
-    }
-    if (feat_on<F, F_RES>(r.res != nullptr)) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += fmaf(r.ra, res[i], r.rd);
-    }
-    if (feat_on<F, F_POS>(r.pos != nullptr)) {
-      float t[8];
-      load_vec8(r.pos + n, t);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += t[i];
-    }
-    if (feat_on<F, F_STATS>(this->stat_part != nullptr)) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { r.s += o[i]; r.q = fmaf(o[i], o[i], r.q); }
+    for (int j = 0; j < 4; ++j) {
+      f2 v = act_ct2<T, ACT>(this->act, f2_add(f2_make(acc[2 * j], acc[2 * j + 1]), b2));
+      if (dropping())   // (r.scale carries 1/keep and the DropPath factor)
+        v = f2_mul(v, f2_make(((keep >> (2 * j)) & 1u) ? r.scale : 0.0f, ((keep >> (2 * j + 1)) & 1u) ? r.scale : 0.0f));
+      else if (feat_on<F, F_SCALE>(true)) v = f2_mul(v, sc2);   // (r.scale = 1 without DropPath)
+      if (feat_on<F, F_RES>(r.res != nullptr)) v = f2_add(v, f2_fma(ra2, f2_make(res[2 * j], res[2 * j + 1]), rd2));
+      if (feat_on<F, F_POS>(r.pos != nullptr)) v = f2_add(v, f2_make(t[2 * j], t[2 * j + 1]));
+      if (feat_on<F, F_STATS>(this->stat_part != nullptr)) { r.s2 = f2_add(r.s2, v); r.q2 = f2_fma(v, v, r.q2); }
+      f2_get(v, o[2 * j], o[2 * j + 1]);
     }
   }
   __device__ bool wants_stats() const { return this->stat_part != nullptr; }
