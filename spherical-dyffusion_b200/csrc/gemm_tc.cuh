@@ -40,7 +40,8 @@ struct TmaOperand {
 
 // Epilogue I/O through TMA: the output (and the residual / addend block) as a 5-D tensor whose 128-byte x 8-row
 // boxes are exactly the 1024-byte groups of a warp's swizzled staging rows.  Eight consecutive GEMM rows must map to
-// a box of the tensor (box_rows = extents of dims[1..4], product 8); ops that cannot guarantee it keep the LDS/STG path.
+// a box of the tensor (box_rows = extents of dims[1..4], product 8); shapes that cannot guarantee it are not eligible
+// for this engine.
 struct TmaIo {
   const void* base = nullptr;
   int es = 2;                               // element size: 2 (bf16) or 4 (fp32)
@@ -54,13 +55,13 @@ struct TcSched {
   int m_tiles, n_tiles, groups, num_tiles, k_blocks, k16_last;  // k16_last: MMAs (K=16) in the last k block
   int a_batched, b_batched;
   int a_glo, b_glo;  // > 0: the operand's group index splits into {g % glo, g / glo} (4-D tensor map)
-  int io;            // bit0: output stored by TMA, bit1: residual / addend loaded by TMA
   // role-wait profile (tc_debug bit7) or nullptr: cycles summed over CTAs {producer waits for a free stage, MMA waits
   // for operands, MMA waits for a free accumulator, epilogue warp 0 waits for the accumulator, epilogue warp 0 waits
   // for the residual block, CTA lifetime, epilogue warp 0 busy, CTAs}
   unsigned long long* prof;
   // experiment switch (sfno_b200_set_option("tc_debug")), WRONG results, timing only: bit0 skip A loads, bit1 skip B
-  // loads, bit2 skip global stores, bit3 skip the fused epilogue math, bit4 skip the MMAs, bit5 skip the TMEM loads
+  // loads, bit2 skip global stores, bit4 skip the MMAs (bits 3 and 5 -- epilogue math, TMEM loads -- were removed
+  // from the drain loop once measured: profiles/r01_j_tc_dbg_sweep.txt)
   int dbg;
 };
 
@@ -114,13 +115,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Blocking wait with a watchdog: a pipeline bug traps (-> CUDA error) after ~2 s instead of hanging the GPU.
 template <bool kBackoff = false>
-__device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity) {
-  const long long t0 = clock64();  // (try_wait itself may block for a while: it has to be inside the timed region)
+__device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity, bool timed = false) {
+  if (!timed) {
+    if (mbar_try_wait(bar, parity)) return 0;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+      if (kBackoff) __nanosleep(64);  // single-thread roles with slack: do not compete with the epilogue warps for issue slots
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
+    return 0;
+  }
+  // role-wait profile (tc_debug bit7): try_wait itself may block for a while, so it sits inside the timed region
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (kBackoff) __nanosleep(64);  // single-thread roles with slack: do not compete with the epilogue warps for issue slots
+    if (kBackoff) __nanosleep(64);
     if (clock64() - t0 > 4000000000LL) __trap();
   }
-  return clock64() - t0;  // cycles spent blocked (role-wait profile, tc_debug bit7)
+  return clock64() - t0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -280,6 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   auto b_smem = [&](int s) { return smem_base + s * S::kStageBytes + S::kABytes; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool timed = sc.prof != nullptr;   // role-wait / phase timers only when somebody reads them
 
   if (warp == TC_WARP_TMA && lane == 0) {
     ptx::prefetch_tmap(&tma_a);
@@ -323,7 +335,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       long long w_empty = 0;
-      const long long t_cta = clock64();
+      const long long t_cta = timed ? clock64() : 0;
       for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, it.next()) {
         int g, mt, nt;
         decode(g, mt, nt);
@@ -334,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (sc.a_glo) { ga_hi = ga / sc.a_glo; ga -= ga_hi * sc.a_glo; }
         if (sc.b_glo) { gb_hi = gb / sc.b_glo; gb -= gb_hi * sc.b_glo; }
         for (int kb = op.k_begin(g) / TC_BK; kb < sc.k_blocks; ++kb) {
-          w_empty += ptx::mbar_wait<true>(empty_bar(stage), phase ^ 1u);
+          w_empty += ptx::mbar_wait<true>(empty_bar(stage), phase ^ 1u, timed);
           const bool load_a = !(sc.dbg & 1), load_b = !(sc.dbg & 2);
           ptx::mbar_expect_tx(full_bar(stage), (load_a ? halves * S::kAHalfBytes : 0) + (load_b ? S::kBBytes : 0));
           const int k0 = kb * TC_BK;
@@ -382,11 +394,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (tile_skipped(g, mt, nt)) continue;
         const int kb0 = op.k_begin(g) / TC_BK;
         const int halves = (kDual && op.m_begin(g) + mt * kBMT + TC_BM < op.m_end(g)) ? 2 : 1;
-        w_tempty += ptx::mbar_wait<true>(tempty_bar(acc), acc_phase ^ 1u);
+        w_tempty += ptx::mbar_wait<true>(tempty_bar(acc), acc_phase ^ 1u, timed);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(kDual ? 0 : acc * BN);
         for (int kb = kb0; kb < sc.k_blocks; ++kb) {
-          w_full += ptx::mbar_wait<true>(full_bar(stage), phase);
+          w_full += ptx::mbar_wait<true>(full_bar(stage), phase, timed);
           ptx::tc_fence_after();
           const int nk = (kb == sc.k_blocks - 1) ? sc.k16_last : TC_BK / 16;
           for (int k = 0; k < nk; ++k) {
@@ -417,7 +429,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0, res_phase = 0, sbuf = 0;
     long long w_tfull = 0, w_res = 0, c_pro = 0, c_loop = 0, c_tail = 0;
-    const long long t_epi = clock64();
+    const long long t_epi = timed ? clock64() : 0;
     for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, it.next()) {
       int g, mt, nt;
       decode(g, mt, nt);
@@ -425,7 +437,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int halves = (kDual && op.m_begin(g) + mt * kBMT + TC_BM < op.m_end(g)) ? 2 : 1;
       for (int hf = 0; hf < halves; ++hf) {   // dual-M: the two 128-row halves of the tile are drained one after the other
       const bool first_half = hf == 0, last_half = hf == halves - 1;
-      const long long t_tile = clock64();
+      const long long t_tile = timed ? clock64() : 0;
       const int m_tile0 = op.m_begin(g) + mt * kBMT + hf * TC_BM;
       const int m = m_tile0 + quad * 32 + lane;
       const int n_base = nt * BN + part * kColsPerWarp;
@@ -442,59 +454,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         constexpr int kEs = (int)sizeof(OutT);
         constexpr int kPassCols = TC_STAGE_PITCH / kEs;                 // 64 (bf16) or 32 (fp32) columns per pass
         constexpr int kPasses = (kColsPerWarp + kPassCols - 1) / kPassCols;
-        constexpr int kVec = 16 / kEs;                                   // output elements per 16-byte chunk
         constexpr bool kGuardRows = F < 0 || (F & F_POS) != 0;           // compute8 may dereference per-row pointers
         constexpr uint32_t kBufs = Op::kStagingBufs;
         uint32_t region = staging_base + ((uint32_t)ew * kBufs + sbuf) * TC_STAGING_PER_WARP;
         uint32_t my_row = region + (uint32_t)lane * TC_STAGE_PITCH;
         const uint32_t sw = (uint32_t)(lane & 7);
-        const int srow0 = lane >> 3, cl = lane & 7;                      // staging copies: 4 rows x 128 B per instruction
         const int n_end = op.n_store();
         const bool has_res = (kEs == 2) && feat_on<F, F_RES>(op.has_res());
         const bool valid = row_ok && row.valid;
         // all 32 rows outside the live range, or the column slice beyond the last column: nothing to drain
         const bool warp_live = __any_sync(0xffffffffu, valid) && n_base < n_end;
-        const bool tma_st = (sc.io & 1) != 0, tma_ld = (sc.io & 2) != 0;
-        // TMA epilogue I/O: lanes 0..3 each own one 8-row x 128-byte group (1024 B) of the warp's staging rows
+        // epilogue I/O by TMA: lanes 0..3 each own one 8-row x 128-byte group (1024 B) of the warp's staging rows
         const int grow0 = m_tile0 + quad * 32 + 8 * lane;   // first GEMM row of this lane's group (lanes 0..3)
         const bool gissue = lane < 4 && grow0 < op.m_end(g);
-        // row starts as 16-byte units relative to the tensor base: ONE 32-bit shuffle per staged row (~0 = no row)
-        uint32_t out16 = 0xFFFFFFFFu;
-        if (!tma_st && valid) out16 = (uint32_t)(((const char*)row.out - (const char*)op.out_base()) >> 4);
-        // residual / addend block (bf16 outputs only), fetched BEFORE waiting for the accumulator so that its latency
-        // hides behind the MMA of this tile: by TMA straight into the staging rows, or 8 coalesced 16-byte loads per lane
-        uint4 res_pf[8];
+        auto staging_free = [&]() {   // the TMA store that last read this staging buffer has finished reading it
+          if (lane < 4) { if (kBufs == 2) ptx::bulk_wait_read1(); else ptx::bulk_wait_read(); }
+          __syncwarp();
+        };
+        // residual / addend block (bf16 outputs only): TMA load straight into the staging rows, issued BEFORE waiting
+        // for the accumulator so that its latency hides behind the MMA of this tile
         if (has_res && warp_live) {
-          if (tma_ld) {
-            if (tma_st && lane < 4) { if (kBufs == 2) ptx::bulk_wait_read1(); else ptx::bulk_wait_read(); }  // the buffer's last store has left it
-            __syncwarp();
-            if (lane == 0) ptx::mbar_expect_tx(res_bar(ew), 4 * 1024);
-            __syncwarp();
-            if (lane < 4) {
-              int c[5];
-              op.io_coords(g, grow0, n_base, c);
-              ptx::tma_load_5d(region + (uint32_t)lane * 1024u, &tma_res, res_bar(ew), c);
-            }
-          } else {
-            const uint32_t res16 = valid ? (uint32_t)(((const char*)row.res - (const char*)op.res_base()) >> 4) : 0xFFFFFFFFu;
-            const uint4* rb = reinterpret_cast<const uint4*>(op.res_base()) + (n_base >> 3) + cl;
-            int nv0 = n_end - n_base;
-            nv0 = nv0 < kColsPerWarp ? nv0 : kColsPerWarp;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint32_t o = __shfl_sync(0xffffffffu, res16, 4 * i + srow0);
-              res_pf[i] = (o != 0xFFFFFFFFu && cl * 8 < nv0) ? rb[o] : make_uint4(0, 0, 0, 0);
-            }
+          staging_free();
+          if (lane == 0) ptx::mbar_expect_tx(res_bar(ew), 4 * 1024);
+          __syncwarp();
+          if (lane < 4) {
+            int c[5];
+            op.res_coords(g, grow0, n_base, c);
+            ptx::tma_load_5d(region + (uint32_t)lane * 1024u, &tma_res, res_bar(ew), c);
           }
         }
         long long w0 = 0;
         if (first_half) {
-          w0 = ptx::mbar_wait(tfull_bar(acc), acc_phase);
+          w0 = ptx::mbar_wait(tfull_bar(acc), acc_phase, timed);
           w_tfull += w0;
           ptx::tc_fence_after();
         }
-        long long t_ph = clock64();
-        c_pro += t_ph - t_tile - w0;
+        long long t_ph = 0;
+        if (timed) { t_ph = clock64(); c_pro += t_ph - t_tile - w0; }
 #pragma unroll 1
         for (int pass = 0; pass < (warp_live ? kPasses : 0); ++pass) {
           const int pn0 = n_base + pass * kPassCols;
@@ -503,91 +499,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           nvalid = nvalid < pcols ? nvalid : pcols;
           if (nvalid <= 0) break;  // warp-uniform
           if (has_res) {           // (kPasses == 1 whenever has_res)
-            if (tma_ld) {
-              w_res += ptx::mbar_wait(res_bar(ew), res_phase);
-              res_phase ^= 1u;
-            } else {
-              if (tma_st && lane < 4) { if (kBufs == 2) ptx::bulk_wait_read1(); else ptx::bulk_wait_read(); }
-              __syncwarp();
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                sts128(region + (uint32_t)(4 * i + srow0) * TC_STAGE_PITCH + (((uint32_t)cl ^ (uint32_t)((4 * i + srow0) & 7)) << 4), res_pf[i]);
-              __syncwarp();
-            }
-          } else if (tma_st) {
-            if (lane < 4) { if (kBufs == 2) ptx::bulk_wait_read1(); else ptx::bulk_wait_read(); }  // this buffer is free again
-            __syncwarp();
+            w_res += ptx::mbar_wait(res_bar(ew), res_phase, timed);
+            res_phase ^= 1u;
           }
-          // 32 accumulator columns per iteration: four independent 8-column groups give the scheduler the
-          // instruction-level parallelism that the few resident warps (3-4 per sub-partition) cannot
+          // (without a residual the staging rows are first written by the drain loop: the wait for the previous
+          //  TMA store sits behind the first TMEM load so that their latencies overlap)
+          bool staging_checked = has_res;
+          // 32 accumulator columns per iteration as four independent 8-column groups.  On full passes the groups
+          // sit in ONE basic block, so ptxas interleaves their instruction streams: the instruction-level
+          // parallelism that the few resident warps (3-4 per sub-partition) cannot supply.
+          auto group8 = [&](const uint32_t (&r)[32], int q, int cofs) {
+            float accv[8], resv[8], outv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { accv[i] = __uint_as_float(r[8 * q + i]); resv[i] = 0.0f; }
+            if constexpr (kEs == 2) {
+              const uint32_t slot = my_row + ((((uint32_t)cofs >> 3) ^ sw) << 4);
+              if (has_res) unpack_bf16x8(lds128(slot), resv);
+              op.template compute8<F>(row, pn0 + cofs, accv, resv, outv);
+              sts128(slot, make_uint4(pack_bf16x2(outv[0], outv[1]), pack_bf16x2(outv[2], outv[3]),
+                                      pack_bf16x2(outv[4], outv[5]), pack_bf16x2(outv[6], outv[7])));
+            } else {
+              op.template compute8<F>(row, pn0 + cofs, accv, resv, outv);
+              const uint32_t c4 = (uint32_t)cofs >> 2;  // 16-byte chunk index (4 floats)
+              sts128(my_row + ((c4 ^ sw) << 4), make_uint4(__float_as_uint(outv[0]), __float_as_uint(outv[1]),
+                                                           __float_as_uint(outv[2]), __float_as_uint(outv[3])));
+              sts128(my_row + (((c4 + 1) ^ sw) << 4), make_uint4(__float_as_uint(outv[4]), __float_as_uint(outv[5]),
+                                                                 __float_as_uint(outv[6]), __float_as_uint(outv[7])));
+            }
+          };
           const int nchunks = (nvalid + 31) >> 5;
 #pragma unroll 1
           for (int ci = 0; ci < nchunks; ++ci) {
             uint32_t r[32];
-            if (!(sc.dbg & 32)) {
-              ptx::tmem_ld32(t_row + (uint32_t)(pass * kPassCols + 32 * ci), r);
-              ptx::tmem_ld_wait();
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) r[i] = 0x3f800000u + (uint32_t)ci;
+            ptx::tmem_ld32(t_row + (uint32_t)(pass * kPassCols + 32 * ci), r);
+            ptx::tmem_ld_wait();
+            if (!staging_checked) {
+              staging_free();
+              staging_checked = true;
             }
             if (!kGuardRows || valid) {
+              if (32 * ci + 32 <= nvalid) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int cofs = 32 * ci + 8 * q;  // column offset inside the pass
-                if (cofs < nvalid) {
-                  float accv[8], resv[8], outv[8];
+                for (int q = 0; q < 4; ++q) group8(r, q, 32 * ci + 8 * q);
+              } else {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) { accv[i] = __uint_as_float(r[8 * q + i]); resv[i] = 0.0f; }
-                  if constexpr (kEs == 2) {
-                    const uint32_t slot = my_row + ((((uint32_t)cofs >> 3) ^ sw) << 4);
-                    if (has_res) unpack_bf16x8(lds128(slot), resv);
-                    if (!(sc.dbg & 8)) op.template compute8<F>(row, pn0 + cofs, accv, resv, outv);
-                    else {
-#pragma unroll
-                      for (int i = 0; i < 8; ++i) outv[i] = accv[i] + resv[i];
-                    }
-                    sts128(slot, make_uint4(pack_bf16x2(outv[0], outv[1]), pack_bf16x2(outv[2], outv[3]),
-                                            pack_bf16x2(outv[4], outv[5]), pack_bf16x2(outv[6], outv[7])));
-                  } else {
-                    op.template compute8<F>(row, pn0 + cofs, accv, resv, outv);
-                    const uint32_t c4 = (uint32_t)cofs >> 2;  // 16-byte chunk index (4 floats)
-                    sts128(my_row + ((c4 ^ sw) << 4), make_uint4(__float_as_uint(outv[0]), __float_as_uint(outv[1]),
-                                                                 __float_as_uint(outv[2]), __float_as_uint(outv[3])));
-                    sts128(my_row + (((c4 + 1) ^ sw) << 4), make_uint4(__float_as_uint(outv[4]), __float_as_uint(outv[5]),
-                                                                       __float_as_uint(outv[6]), __float_as_uint(outv[7])));
-                  }
-                }
+                for (int q = 0; q < 4; ++q)
+                  if (32 * ci + 8 * q < nvalid) group8(r, q, 32 * ci + 8 * q);
               }
             }
           }
-          { const long long t = clock64(); c_loop += t - t_ph; t_ph = t; }
-          if (tma_st) {
-            // staged rows -> global: one TMA store per 8-row group; rows / columns outside the tensor are clipped
-            ptx::fence_proxy_async();
-            __syncwarp();
-            if (gissue && !(sc.dbg & 4)) {
-              int c[5];
-              op.io_coords(g, grow0, pn0, c);
-              ptx::tma_store_5d(&tma_out, region + (uint32_t)lane * 1024u, c);
-            }
-            if (lane < 4) ptx::bulk_commit();
-            sbuf = (kBufs == 2) ? (sbuf ^ 1u) : 0u;
-            region = staging_base + ((uint32_t)ew * kBufs + sbuf) * TC_STAGING_PER_WARP;
-            my_row = region + (uint32_t)lane * TC_STAGE_PITCH;
-          } else {
-            __syncwarp();
-            // staged rows -> global: 4 rows x 128 B per warp instruction
-            uint4* ob = reinterpret_cast<uint4*>(const_cast<void*>(op.out_base())) + ((pn0 * kEs) >> 4) + cl;
-#pragma unroll 2
-            for (int i = 0; i < 8; ++i) {
-              const int srow = 4 * i + srow0;
-              const uint32_t o = __shfl_sync(0xffffffffu, out16, srow);
-              const uint4 v = lds128(region + (uint32_t)srow * TC_STAGE_PITCH + (((uint32_t)cl ^ (uint32_t)(srow & 7)) << 4));
-              if (o != 0xFFFFFFFFu && cl * kVec < nvalid && !(sc.dbg & 4)) ob[o] = v;
-            }
-            __syncwarp();
+          if (timed) { const long long t = clock64(); c_loop += t - t_ph; t_ph = t; }
+          // staged rows -> global: one TMA store per 8-row group; rows / columns outside the tensor are clipped
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (gissue && !(sc.dbg & 4)) {
+            int c[5];
+            op.io_coords(g, grow0, pn0, c);
+            ptx::tma_store_5d(&tma_out, region + (uint32_t)lane * 1024u, c);
           }
+          if (lane < 4) ptx::bulk_commit();
+          sbuf = (kBufs == 2) ? (sbuf ^ 1u) : 0u;
+          region = staging_base + ((uint32_t)ew * kBufs + sbuf) * TC_STAGING_PER_WARP;
+          my_row = region + (uint32_t)lane * TC_STAGE_PITCH;
         }
         // the accumulator has been drained: hand the TMEM stage back to the MMA warp before any further work
         if (last_half) {
@@ -598,7 +571,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // fused InstanceNorm statistics: one partial per (row, N tile, column slice); no cross-warp synchronisation
         if (feat_on<F, F_STATS>(op.wants_stats()) && row_ok)
           op.finish(g, m, nt * (BN / TC_SLICE_COLS) + part, valid ? row.stat_s() : 0.0f, valid ? row.stat_q() : 0.0f);
-        c_tail += clock64() - t_ph;
+        if (timed) c_tail += clock64() - t_ph;
       };
       if constexpr (!Op::kGeneral && Op::kFast0 == Op::kFast1) {
         drain(std::integral_constant<int, Op::kFast0>{});
@@ -611,7 +584,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }  // halves
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
     }
-    if ((sc.io & 1) && lane < 4) ptx::bulk_wait_read();  // outstanding TMA stores still read this CTA's shared memory
+    if (lane < 4) ptx::bulk_wait_read();  // outstanding TMA stores still read this CTA's shared memory
     if (sc.prof && ew == 0 && lane == 0) {
       atomicAdd(sc.prof + 3, (unsigned long long)w_tfull);
       atomicAdd(sc.prof + 4, (unsigned long long)w_res);
@@ -716,13 +689,14 @@ int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what) {
   SFNO_TRY(encode_operand(b, Op::B_KCONTIG, BN, &mb, what));
   TmaIo io_out, io_res;
   Tr::io(op, io_out, io_res);
-  int io = 0;
-  if (!(g_tc_debug.load(std::memory_order_relaxed) & 64)) {  // tc_debug bit6: force the LDS/STG epilogue (A/B comparison)
-    if (tma_io_ok(io_out)) io |= 1;
-    if (tma_io_ok(io_res)) io |= 2;
+  if (!tma_io_ok(io_out)) return fail(SFNO_ERR_UNSUPPORTED, "%s: output tensor is not expressible as TMA boxes (eligibility not checked?)", what);
+  SFNO_TRY(encode_io(io_out, &mo, what));
+  if (Tr::has_residual(op)) {
+    if (!tma_io_ok(io_res)) return fail(SFNO_ERR_UNSUPPORTED, "%s: residual tensor is not expressible as TMA boxes", what);
+    SFNO_TRY(encode_io(io_res, &mr, what));
+  } else {
+    mr = mo;
   }
-  if (io & 1) SFNO_TRY(encode_io(io_out, &mo, what)); else mo = ma;
-  if (io & 2) SFNO_TRY(encode_io(io_res, &mr, what)); else mr = ma;
   TcSched sc;
   sc.m_tiles = ceil_div(op.M, kDual ? 2 * TC_BM : TC_BM);
   sc.n_tiles = ceil_div(op.N, BN);
@@ -738,7 +712,6 @@ int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what) {
   sc.a_glo = a.group_lo;
   sc.b_glo = b.group_lo;
   sc.dbg = g_tc_debug.load(std::memory_order_relaxed);
-  sc.io = io;
   sc.prof = (sc.dbg & 128) ? tc_prof_buffer() : nullptr;
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<Op, BN, kDual>;

@@ -12,7 +12,8 @@ struct TcTraitsBase {
   static constexpr bool kDualM = false;
   static bool use_dual(const Op&) { return true; }
   static bool extra_ok(const Op&) { return true; }  // vector-store alignment rules of the epilogue, if any
-  static void io(const Op&, TmaIo&, TmaIo&) {}       // TMA views of the output / residual tensors (default: none)
+  static void io(const Op&, TmaIo&, TmaIo&) {}       // TMA views of the output / residual tensors
+  static bool has_residual(const Op&) { return false; }
 };
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
@@ -21,7 +22,11 @@ struct TcEligible {
   static bool eligible(const Op& op) {
     TmaOperand a, b;
     Derived::operands(op, a, b);
-    return tma_operand_ok(a) && tma_operand_ok(b) && op.M > 0 && op.N > 0 && op.K > 0 && Derived::extra_ok(op);
+    if (!(tma_operand_ok(a) && tma_operand_ok(b) && op.M > 0 && op.N > 0 && op.K > 0 && Derived::extra_ok(op))) return false;
+    // the epilogue moves tiles by TMA only: the output (and the residual, if any) must be expressible as boxes
+    TmaIo o, r;
+    Derived::io(op, o, r);
+    return tma_io_ok(o) && (!Derived::has_residual(op) || tma_io_ok(r));
   }
 };
 
@@ -80,11 +85,9 @@ struct TcTraits<OpDhconv<bf16>> : TcTraitsBase<OpDhconv<bf16>>, TcEligible<TcTra
   }
   static bool extra_ok(const OpDhconv<bf16>& op) { return aligned16(op.y) && op.N % 8 == 0; }
   static void io(const OpDhconv<bf16>& op, TmaIo& o, TmaIo&) {
-    o.base = op.y; o.es = 2;
-    o.dims[0] = op.N; o.dims[1] = op.B; o.dims[2] = op.lmax; o.dims[3] = op.mmax;
-    o.strides[0] = (uint64_t)op.N * 2; o.strides[1] = (uint64_t)op.B * op.N * 2; o.strides[2] = (uint64_t)op.lmax * op.B * op.N * 2;
-    if (op.B % 8 == 0) { o.ok = true; }
-    else if (8 % op.B == 0) { o.ok = true; o.box_rows[0] = op.B; o.box_rows[2] = 8 / op.B; }
+    o.base = op.y; o.es = 2; o.ok = true;
+    o.dims[0] = op.N; o.dims[1] = op.M; o.dims[2] = op.G;
+    o.strides[0] = (uint64_t)op.N * 2; o.strides[1] = (uint64_t)op.M * op.N * 2;
   }
 };
 
@@ -120,6 +123,7 @@ struct TcTraits<OpIdft<bf16, TOut, ACT>> : TcTraitsBase<OpIdft<bf16, TOut, ACT>>
     return op.nlon % 8 == 0 && op.out_bstride % 8 == 0 && aligned16(op.out) &&
            (!op.add || (sizeof(TOut) == 2 && aligned16(op.add) && op.add_bstride % 8 == 0));
   }
+  static bool has_residual(const OpIdft<bf16, TOut, ACT>& op) { return op.add != nullptr; }
   static void io(const OpIdft<bf16, TOut, ACT>& op, TmaIo& o, TmaIo& r) {
     const uint64_t es = sizeof(TOut);
     const int B = op.M / (op.C * op.Kp);
@@ -148,6 +152,7 @@ struct TcTraits<OpConv<bf16, TOut, ACT, DROP>> : TcTraitsBase<OpConv<bf16, TOut,
     return op.N % 8 == 0 && op.out_bstride % 8 == 0 && aligned16(op.out) &&
            (!op.res || (sizeof(TOut) == 2 && aligned16(op.res) && op.res_bstride % 8 == 0)) && (!op.pos || aligned16(op.pos));
   }
+  static bool has_residual(const OpConv<bf16, TOut, ACT, DROP>& op) { return op.res != nullptr; }
   static void io(const OpConv<bf16, TOut, ACT, DROP>& op, TmaIo& o, TmaIo& r) {
     const uint64_t es = sizeof(TOut);
     o.base = op.out; o.es = (int)es; o.ok = true;
@@ -155,7 +160,9 @@ struct TcTraits<OpConv<bf16, TOut, ACT, DROP>> : TcTraitsBase<OpConv<bf16, TOut,
     o.strides[0] = (uint64_t)op.N * es; o.strides[1] = (uint64_t)op.out_bstride * es;
     if (op.res && es == 2) {
       r = o;
-      r.base = op.res; r.strides[1] = (uint64_t)op.res_bstride * 2;
+      r.base = op.res;
+      if (op.res_bstride != 0) r.strides[1] = (uint64_t)op.res_bstride * 2;
+      else r.dims[2] = 1;   // one plane shared by all samples (position embedding)
     }
   }
 };

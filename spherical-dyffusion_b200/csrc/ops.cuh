@@ -11,7 +11,7 @@
 // Internal tensor layouts (T = float or bf16; Kp = nlat rounded up to 8):
 //   grid   x  [B][C][nlat][nlon]                      (NCHW, as the reference)
 //   F, G      [mmax][B][2][C][Kp]   /  [mmax][2][B][C][Kp]     longitude-spectral, latitude contiguous
-//   X, Y      [lmax][mmax][B][2][C] /  [mmax][lmax][B][2][C]   spectral, channel contiguous
+//   X, Y      [lmax][mmax][B][2][C]                             spectral, channel contiguous
 #pragma once
 #include "common.cuh"
 
@@ -71,7 +71,7 @@ struct NoFeatures {
   static constexpr bool kGeneral = false;
   __device__ int feat() const { return 0; }
   __device__ bool has_res() const { return false; }
-  __device__ const void* res_base() const { return nullptr; }
+  __device__ void res_coords(int, int, int, int (&)[5]) const {}
   __device__ bool wants_stats() const { return false; }
   __device__ void finish(int, int, int, float, float) const {}
 };
@@ -133,7 +133,6 @@ struct OpDft : FullRanges, NoFeatures {
     return (int64_t)b * x_bstride + ((int64_t)c * nlat + n) * nlon;
   }
   __device__ int n_store() const { return Kp; }
-  __device__ const void* out_base() const { return f; }
   // TMA view of F: {k, c, ri, b, m}; eight GEMM rows (m,ri) = 4 wavenumbers x {re, im} of one (b, c) plane
   __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const {
     const int b = g / C;
@@ -185,7 +184,6 @@ struct OpLeg : NoFeatures {
   __device__ int64_t a_off(int g, int m) const { return ((int64_t)g * lmax + m) * Kp; }
   __device__ int64_t b_off(int g, int n) const { return ((int64_t)g * N + n) * Kp; }
   __device__ int n_store() const { return N; }
-  __device__ const void* out_base() const { return x; }
   // TMA view of X: {(b,ri,c), m, l}; eight GEMM rows = eight degrees of wavenumber g
   __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const { c[0] = col0; c[1] = g; c[2] = row0; c[3] = 0; c[4] = 0; }
   struct Row { T* out; const T* res; bool valid; __device__ float stat_s() const { return 0.0f; } __device__ float stat_q() const { return 0.0f; } };
@@ -201,7 +199,7 @@ struct OpLeg : NoFeatures {
 
 // ------------------------------------------------------------------------------------------------
 // dhconv channel contraction (K3) as a REAL GEMM on the packed complex weight, per degree l:
-//   D[(m,b), (ri',o)] = sum_(ri,c) X[l][m][b][(ri,c)] * Wp[l][(ri',o)][(ri,c)]  -> Y[m][l][b][ri'][o]
+//   D[(m,b), (ri',o)] = sum_(ri,c) X[l][m][b][(ri,c)] * Wp[l][(ri',o)][(ri,c)]  -> Y[l][m][b][ri'][o]
 //   Wp = [[wr, -wi], [wi, wr]] (rows = output re/im, cols = input re/im)
 // ------------------------------------------------------------------------------------------------
 template <class T>
@@ -227,18 +225,10 @@ struct OpDhconv : NoFeatures {
   __device__ int64_t a_off(int g, int m) const { return ((int64_t)g * M + m) * K; }
   __device__ int64_t b_off(int g, int n) const { return ((int64_t)g * N + n) * K; }
   __device__ int n_store() const { return N; }
-  __device__ const void* out_base() const { return y; }
-  // TMA view of Y: {(ri',o), b, l, m}; eight GEMM rows (m,b) = eight samples of one wavenumber (B % 8 == 0) or
-  // 8/B wavenumbers x B samples (B divides 8)
-  __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const {
-    const int mm = row0 / B;
-    c[0] = col0; c[1] = row0 - mm * B; c[2] = g; c[3] = mm; c[4] = 0;
-  }
+  // TMA view of Y: {(ri',o), (m,b), l}
+  __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const { c[0] = col0; c[1] = row0; c[2] = g; c[3] = 0; c[4] = 0; }
   struct Row { T* out; const T* res; bool valid; __device__ float stat_s() const { return 0.0f; } __device__ float stat_q() const { return 0.0f; } };
-  __device__ Row row(int g, int m) const {
-    const int mm = m / B, b = m - mm * B;
-    return Row{y + (((int64_t)mm * lmax + g) * B + b) * N, nullptr, true};
-  }
+  __device__ Row row(int g, int m) const { return Row{y + ((int64_t)g * M + m) * N, nullptr, true}; }
   template <int F> __device__ Row row_f(int g, int m) const { return row(g, m); }
   __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = from_f32<T>(acc); }
   template <int F>
@@ -251,7 +241,7 @@ struct OpDhconv : NoFeatures {
 // ------------------------------------------------------------------------------------------------
 // inverse Legendre (K4): per m, rows (b,ri,o), columns = latitude k (contiguous in G):
 //   D[(b,ri,o), k] = sum_l S[m][l][(b,ri,o)] * Pt[m][k][l]  -> G[m][ri][b][o][k]
-//   S is Y [m][l][rows] (a_goff = lmax*rows, a_sk = rows) or X [l][m][rows] (a_goff = rows, a_sk = mmax*rows)
+//   S is X or Y, [l][m][rows] (a_goff = rows, a_sk = mmax*rows); any (a_goff, a_sk) pair is accepted
 // ------------------------------------------------------------------------------------------------
 template <class T>
 struct OpIleg : NoFeatures {
@@ -272,7 +262,6 @@ struct OpIleg : NoFeatures {
   __device__ int64_t a_off(int g, int m) const { return (int64_t)g * a_goff + m; }   // + l * a_sk
   __device__ int64_t b_off(int g, int n) const { return ((int64_t)g * nlat + n) * Lq; }
   __device__ int n_store() const { return Kp; }  // columns [nlat, Kp) are exact zeros (zero-filled table rows)
-  __device__ const void* out_base() const { return g_out; }
   // TMA view of G: {k, o, b, ri, m}; eight GEMM rows (b,ri,o) = eight channels (C % 8 == 0)
   __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const {
     const int b = row0 / (2 * C), rem = row0 - b * 2 * C, ri = rem / C;
@@ -332,14 +321,13 @@ struct OpIdft : IdftArgs<T, TOut>, FullRanges {
   // wait for operands 8-20 % of the time, which outweighs the hidden store latency.
   static constexpr int kStagingBufs = 1;
   __device__ int feat() const { return (this->add ? F_RES : 0) | (this->stat_part ? F_STATS : 0); }
-  __device__ const void* out_base() const { return this->out; }
-  __device__ const void* res_base() const { return this->add; }
   // TMA view of the grid tensor: {j, k, o, b}; eight GEMM rows (b,o,kp) = eight latitudes of one plane (Kp % 8 == 0);
   // the pad latitudes kp >= nlat are clipped by the tensor extent
   __device__ void io_coords(int, int row0, int col0, int (&c)[5]) const {
     const int bo = row0 / this->Kp, b = bo / this->C;
     c[0] = col0; c[1] = row0 - bo * this->Kp; c[2] = bo - b * this->C; c[3] = b; c[4] = 0;
   }
+  __device__ void res_coords(int g, int row0, int col0, int (&c)[5]) const { io_coords(g, row0, col0, c); }
   struct Row {
     TOut* out; const T* res; bool valid; float bias; f2 s2, q2;   // s2 / q2: packed partial sum / sum of squares
     __device__ float stat_s() const { return f2_hsum(s2); }
@@ -430,10 +418,11 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
   __device__ int feat() const {
     return (this->res ? F_RES : 0) | (this->stat_part ? F_STATS : 0) | (this->pos ? F_POS : 0) | (this->branch_scale ? F_SCALE : 0);
   }
-  __device__ const void* out_base() const { return this->out; }
-  __device__ const void* res_base() const { return this->res; }
   // TMA view of the activation tensor: {pixel, channel, sample}
   __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const { c[0] = col0; c[1] = row0; c[2] = g; c[3] = 0; c[4] = 0; }
+  __device__ void res_coords(int g, int row0, int col0, int (&c)[5]) const {   // a residual shared by all samples has one plane
+    io_coords(this->res_bstride != 0 ? g : 0, row0, col0, c);
+  }
   struct Row {
     TOut* out; const T* res; bool valid; const T* pos; float bias, ra, rd, scale; uint64_t rng_base; f2 s2, q2;
     __device__ float stat_s() const { return f2_hsum(s2); }

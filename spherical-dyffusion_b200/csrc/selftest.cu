@@ -73,11 +73,11 @@ static int run_both(Op op, int64_t out_elems, SetOut set_out, Scratch& s, double
   unsigned int* stats = s.get<unsigned int>(2, true);
   unsigned long long* nbad = s.get<unsigned long long>(1, true);
   if (!o0 || !o1 || !stats || !nbad) return fail(SFNO_ERR_CUDA, "selftest: out of memory");
-  const bool tc_ok = TcTraits<Op>::eligible(op);
-  res[2] = tc_ok ? 1.0 : 0.0;
   set_out(op, o0);
   SFNO_TRY(launch_gemm_simt(op, 0, "selftest_simt"));
   set_out(op, o1);
+  const bool tc_ok = TcTraits<Op>::eligible(op);   // (needs the output pointer: the epilogue's tensor maps are part of it)
+  res[2] = tc_ok ? 1.0 : 0.0;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   float ms = 0.0f;

@@ -69,18 +69,14 @@ def _run_case(op, dims, tc_debug=0):
     return json.loads(line)
 
 
-# engine variants selected by the correct-result tc_debug bits: 64 = epilogue I/O by LDS/STG instead of TMA boxes,
-# 256 = single 128-row tiles where the op would use dual-M tiles, 128 = role-wait counters on
+# engine variants selected by the correct-result tc_debug bits: 256 = single 128-row tiles where the op would use
+# dual-M tiles, 128 = role-wait counters on
 VARIANTS = [
     ("leg", [8, 256, 180, 180, 181, 1], 256),
-    ("leg", [2, 64, 180, 180, 5, 1], 64),
-    ("dft", [2, 32, 180, 360, 181, 0], 64),
-    ("dhconv", [8, 256, 180, 181, 1, 0], 64),
-    ("ileg", [2, 64, 180, 180, 181, 3], 64),
-    ("idft", [2, 16, 180, 360, 181, 7], 64),
-    ("conv", [2, 256, 34, 64800, 0, 0], 64),
-    ("convb", [2, 512, 256, 64800, 0, 21], 64),
-    ("convb", [2, 256, 256, 64800, 1, 15], 64 + 128),
+    ("leg", [2, 64, 180, 180, 5, 1], 256),
+    ("dhconv", [5, 32, 20, 21, 1, 0], 128),       # batch 5: eight-row boxes straddle wavenumbers
+    ("convb", [2, 256, 256, 64800, 1, 15], 128),
+    ("idft", [2, 16, 180, 360, 181, 7], 128),
 ]
 
 
@@ -96,7 +92,7 @@ def test_tc_engine_variants_match_cuda_core_engine(op, dims, tc_debug):
     assert r["max_err"] <= tol * r["max_ref"], r
     if tc_debug & 128:
         c = r["counters"]
-        assert c["ctas"] > 0 and 0.0 < c["epi_busy"] <= 1.5 and c["cta_cycles"] > 0
+        assert c["ctas"] > 0 and c["epi_busy"] > 0.0 and c["cta_cycles"] > 0
 
 
 @pytest.mark.parametrize("op,dims,expect_tc", CASES, ids=[f"{c[0]}-{'x'.join(map(str, c[1]))}" for c in CASES])
