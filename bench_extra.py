@@ -5,6 +5,7 @@
     python bench_extra.py rollout  [--members 25 --steps 24]  # config 4: ensemble rollout with per-step statistics (torchrun for N GPUs)
     python bench_extra.py scaled   [--batch 1]             # config 5: embed 512, 12 blocks, 720x1440 forward
     python bench_extra.py sht                              # config 2: RealSHT -> InverseRealSHT round-trip sweep, both grids
+    python bench_extra.py graph                            # small-batch latency: eager launches vs CUDA-graph replay
 
 Each prints one JSON line per measurement.  Synthetic data, random-init weights, CUDA-event timing after warm-up.
 """
@@ -172,6 +173,32 @@ def run_scaled(args):
         "per_kernel_ms_and_launches": per_kernel}), flush=True)
 
 
+def run_graph(args):
+    """Latency of one ACE forecaster forward at small batch: eager launches vs replay of a captured CUDA graph."""
+    from oracle.sfno_oracle import ACE_FORECASTER, SFNOConfig, random_state_dict
+
+    dev = torch.device("cuda:0")
+    cfg = SFNOConfig(**ACE_FORECASTER)
+    m = _model(cfg, random_state_dict(cfg, seed=0), dev, args.precision)
+    for B in (1, 2, 8):
+        x = torch.randn(B, 34, 180, 360, device=dev)
+        c = torch.randn(B, 2, 180, 360, device=dev)
+        t = torch.full((B,), 3.0, device=dev)
+        with torch.inference_mode():
+            eager_ms = _timeit(lambda: m(x, time=t, condition=c), 20, 3)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                m(x, time=t, condition=c)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                y = m(x, time=t, condition=c)
+            graph_ms = _timeit(graph.replay, 20, 3)
+        print(json.dumps({"workload": f"ACE forecaster forward, batch {B}, {args.precision}: eager launches vs CUDA-graph replay",
+                          "batch": B, "eager_ms": eager_ms, "graph_ms": graph_ms, "finite": bool(torch.isfinite(y).all())}), flush=True)
+
+
 def run_sht(args):
     import spherical_dyffusion_b200 as sb
 
@@ -191,7 +218,7 @@ def run_sht(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("workload", choices=["window", "rollout", "scaled", "sht"])
+    ap.add_argument("workload", choices=["window", "rollout", "scaled", "sht", "graph"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--members", type=int, default=25)
     ap.add_argument("--steps", type=int, default=None)
@@ -209,6 +236,8 @@ def main():
         args.batch = args.batch or 1
         args.steps = args.steps or 3
         run_scaled(args)
+    elif args.workload == "graph":
+        run_graph(args)
     else:
         run_sht(args)
 

@@ -8,7 +8,9 @@ under the reference's names; the arithmetic of ``forward`` runs in ``sfno_net_fo
 hand-written sm_100a kernels).  There is no PyTorch fallback.
 
 Extra keywords (not in the reference): ``precision`` ("fp32" parity mode | "bf16" tcgen05 mode),
-``check_time_range`` (keep the reference's host-synchronising time assert, default True).
+``check_time_range`` (keep the reference's host-synchronising time assert, default True).  The forward only enqueues
+kernels, so it can be captured in a CUDA graph (``torch.cuda.graph``); the time assert is skipped during capture and the
+dropout stream offset is frozen into the graph.
 """
 from __future__ import annotations
 
@@ -463,7 +465,8 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
             time = time.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
             if time.numel() != B:
                 raise RuntimeError(f"time has {time.numel()} entries for a batch of {B}")
-            if self.check_time_range:  # sfnonet.py:780-782 (host sync, as in the reference)
+            # sfnonet.py:780-782 (host sync, as in the reference); impossible -- and skipped -- while a CUDA graph is captured
+            if self.check_time_range and not torch.cuda.is_current_stream_capturing():
                 assert bool(((self.min_time <= time) & (time <= self.max_time)).all()), \
                     f"time must be in [{self.min_time}, {self.max_time}], but time is {time}"
             t_ptr = time.data_ptr()
