@@ -54,7 +54,11 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.mark_idx = [], None, gpu_index, 0
+
+    def mark(self):
+        """The timed region starts here: only later samples count (earlier ones were taken under the warm-up load)."""
+        self.mark_idx = len(self.rows)
 
     def start(self):
         try:
@@ -77,17 +81,21 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        smax = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = self.rows[self.mark_idx:]
+        during = bool(rows)
+        if not rows:  # timed region shorter than the sampling period: fall back to the last sample under warm-up load
+            rows = self.rows[-1:]
+        sm = sorted(float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        smax = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for nm, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampled": "timed region" if during else "warm-up (timed region < 100 ms)"}
 
 
 def build_case(batch, seed=0):
@@ -185,15 +193,16 @@ def run_b200(args):
 
     with torch.inference_mode():
         # ---- device-resident throughput ---------------------------------------------------------------------
-        for _ in range(max(args.warmup, 3)):
-            model(xd, time=td, condition=cd)
-        barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+        for _ in range(max(args.warmup, 3)):
+            model(xd, time=td, condition=cd)
+        barrier()
         n0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        sampler.mark()
         e0.record()
         for _ in range(args.steps):
             model(xd, time=td, condition=cd)

@@ -1,7 +1,7 @@
 """``RealSHT`` / ``InverseRealSHT`` with the interface the reference consumes from ``torch_harmonics``
-(constructed at ``sfnonet.py:551-554``, attributes read at ``s2convolutions.py:76-83``), executed by
-``sfno_sht_forward`` / ``sfno_sht_inverse`` of the C ABI: longitude DFT and Legendre contraction as
-GEMMs on the GPU.  Tables are built in fp64 by the library (``sfno_sht_tables_host``).
+(constructed at ``sfnonet.py:551-554``, attributes read at ``s2convolutions.py:76-83``), executed by the custom ops
+``torch.ops.sfno_b200.sht_forward / sht_inverse`` (``ops.py``) over ``sfno_sht_forward`` / ``sfno_sht_inverse`` of the
+C ABI: longitude DFT and Legendre contraction as GEMMs on the GPU.  Tables are built in fp64 by the library (``sfno_sht_tables_host``).
 """
 from __future__ import annotations
 
@@ -11,7 +11,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._util import require_cuda_f32, stream_ptr, workspace
+from . import ops as _ops  # noqa: F401  (registers torch.ops.sfno_b200.*)
+from ._util import require_cuda_f32
 
 
 class _ShtBase(nn.Module):
@@ -70,17 +71,7 @@ class RealSHT(_ShtBase):
         assert x.shape[-2] == self.nlat
         assert x.shape[-1] == self.nlon
         xf = require_cuda_f32(x, "x")
-        lead = xf.shape[:-2]
-        fields = int(torch.Size(lead).numel()) if len(lead) else 1
-        out = torch.empty(*lead, self.lmax, self.mmax, 2, dtype=torch.float32, device=xf.device)
-        if fields == 0:
-            return torch.view_as_complex(out)
-        plan = self._plan(xf.device)
-        L = _lib.lib()
-        with torch.cuda.device(xf.device):
-            ws = workspace(xf.device, L.sfno_sht_workspace_bytes(plan, fields), "sht")
-            _lib.check(L.sfno_sht_forward(plan, xf.data_ptr(), out.data_ptr(), fields, ws.data_ptr(), ws.numel(),
-                                          stream_ptr(xf.device)), "sfno_sht_forward")
+        out = torch.ops.sfno_b200.sht_forward(self._plan(xf.device).value, xf, self.lmax, self.mmax)
         return torch.view_as_complex(out)
 
 
@@ -93,15 +84,4 @@ class InverseRealSHT(_ShtBase):
         if not x.is_cuda:
             raise RuntimeError("coefficients must be a CUDA tensor: the B200 path has no CPU fallback")
         xr = torch.view_as_real(x.to(torch.complex64).contiguous())
-        lead = xr.shape[:-3]
-        fields = int(torch.Size(lead).numel()) if len(lead) else 1
-        out = torch.empty(*lead, self.nlat, self.nlon, dtype=torch.float32, device=xr.device)
-        if fields == 0:
-            return out
-        plan = self._plan(xr.device)
-        L = _lib.lib()
-        with torch.cuda.device(xr.device):
-            ws = workspace(xr.device, L.sfno_sht_workspace_bytes(plan, fields), "sht")
-            _lib.check(L.sfno_sht_inverse(plan, xr.data_ptr(), out.data_ptr(), fields, ws.data_ptr(), ws.numel(),
-                                          stream_ptr(xr.device)), "sfno_sht_inverse")
-        return out
+        return torch.ops.sfno_b200.sht_inverse(self._plan(xr.device).value, xr, self.nlat, self.nlon)

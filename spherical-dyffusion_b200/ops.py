@@ -1,0 +1,183 @@
+"""PyTorch custom-op layer over the C ABI (``torch.ops.sfno_b200.*``).
+
+Every op enqueues hand-written sm_100a kernels of ``libsfno_b200.so`` on PyTorch's current CUDA stream and allocates
+nothing but its result; plan / network handles cross the dispatcher as plain integers (the address of the opaque C
+handle).  Each op has a fake (meta) implementation for shape inference, so modules built on them trace under
+``torch.compile`` / ``torch.export`` as opaque calls.  There is no CPU implementation: a CPU tensor raises.
+
+=====================================  ==================================================================================
+op                                     replaces (reference file:line)
+=====================================  ==================================================================================
+``sfno_b200::sht_forward``             ``torch_harmonics.RealSHT.forward`` called at ``s2convolutions.py:165``
+``sfno_b200::sht_inverse``             ``torch_harmonics.InverseRealSHT.forward`` called at ``s2convolutions.py:168,186``
+``sfno_b200::spectral_contract``       ``_contract_dhconv`` / ``_contract_diagonal`` ``contractions.py:147-169``
+``sfno_b200::instance_norm``           ``nn.InstanceNorm2d`` ``sfnonet.py:641-647`` + ``time_scale_shift`` ``:280-287``
+``sfno_b200::conv1x1``                 ``nn.Conv2d(.., 1)`` ``sfnonet.py:239,614-617,739-742``, ``layers.py:73-75``
+``sfno_b200::net_forward``             ``SphericalFourierNeuralOperatorNet.forward`` ``sfnonet.py:797-841``
+=====================================  ==================================================================================
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._util import require_cuda_f32, stream_ptr, workspace
+
+_ACT = {"none": 0, "gelu": 1}
+
+
+def _handle(h: int) -> ctypes.c_void_p:
+    return ctypes.c_void_p(int(h))
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+# ---- spherical harmonic transforms ------------------------------------------------------------------------------------
+@torch.library.custom_op("sfno_b200::sht_forward", mutates_args=())
+def sht_forward(plan: int, x: torch.Tensor, lmax: int, mmax: int) -> torch.Tensor:
+    """x fp32 [..., nlat, nlon] -> coefficients fp32 [..., lmax, mmax, 2] (view_as_complex gives the reference layout)."""
+    xf = require_cuda_f32(x, "x")
+    lead = xf.shape[:-2]
+    fields = int(torch.Size(lead).numel()) if len(lead) else 1
+    out = torch.empty(*lead, lmax, mmax, 2, dtype=torch.float32, device=xf.device)
+    if fields == 0:
+        return out
+    L = _lib.lib()
+    with torch.cuda.device(xf.device):
+        ws = workspace(xf.device, L.sfno_sht_workspace_bytes(_handle(plan), fields), "sht")
+        _lib.check(L.sfno_sht_forward(_handle(plan), xf.data_ptr(), out.data_ptr(), fields, ws.data_ptr(), ws.numel(),
+                                      stream_ptr(xf.device)), "sfno_sht_forward")
+    return out
+
+
+@sht_forward.register_fake
+def _(plan, x, lmax, mmax):
+    return x.new_empty(*x.shape[:-2], lmax, mmax, 2, dtype=torch.float32)
+
+
+@torch.library.custom_op("sfno_b200::sht_inverse", mutates_args=())
+def sht_inverse(plan: int, coeffs: torch.Tensor, nlat: int, nlon: int) -> torch.Tensor:
+    """coefficients fp32 [..., lmax, mmax, 2] -> x fp32 [..., nlat, nlon]."""
+    if not coeffs.is_cuda:
+        raise RuntimeError("coefficients must be a CUDA tensor: the B200 path has no CPU fallback")
+    xr = coeffs.to(torch.float32).contiguous()
+    lead = xr.shape[:-3]
+    fields = int(torch.Size(lead).numel()) if len(lead) else 1
+    out = torch.empty(*lead, nlat, nlon, dtype=torch.float32, device=xr.device)
+    if fields == 0:
+        return out
+    L = _lib.lib()
+    with torch.cuda.device(xr.device):
+        ws = workspace(xr.device, L.sfno_sht_workspace_bytes(_handle(plan), fields), "sht")
+        _lib.check(L.sfno_sht_inverse(_handle(plan), xr.data_ptr(), out.data_ptr(), fields, ws.data_ptr(), ws.numel(),
+                                      stream_ptr(xr.device)), "sfno_sht_inverse")
+    return out
+
+
+@sht_inverse.register_fake
+def _(plan, coeffs, nlat, nlon):
+    return coeffs.new_empty(*coeffs.shape[:-3], nlat, nlon, dtype=torch.float32)
+
+
+# ---- spectral channel contraction -------------------------------------------------------------------------------------
+@torch.library.custom_op("sfno_b200::spectral_contract", mutates_args=())
+def spectral_contract(operator_type: int, x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """x fp32 [B, Cin, L, M, 2]; weight fp32 [Cin, Cout, L, 2] (dhconv) or [Cin, Cout, L, M, 2] (diagonal) -> [B, Cout, L, M, 2]."""
+    xf = require_cuda_f32(x, "x")
+    w = require_cuda_f32(weight, "weight")
+    B, Ci, Lm, Mm = (int(v) for v in xf.shape[:4])
+    Co = int(w.shape[1])
+    out = torch.empty(B, Co, Lm, Mm, 2, dtype=torch.float32, device=xf.device)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(xf.device):
+        _lib.check(_lib.lib().sfno_spectral_contract(int(operator_type), xf.data_ptr(), w.data_ptr(), out.data_ptr(), B, Ci, Co, Lm, Mm,
+                                                     stream_ptr(xf.device)), "sfno_spectral_contract")
+    return out
+
+
+@spectral_contract.register_fake
+def _(operator_type, x, weight):
+    return x.new_empty(x.shape[0], weight.shape[1], x.shape[2], x.shape[3], 2, dtype=torch.float32)
+
+
+# ---- InstanceNorm (+ time scale / shift) ------------------------------------------------------------------------------
+@torch.library.custom_op("sfno_b200::instance_norm", mutates_args=())
+def instance_norm(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], scale: Optional[torch.Tensor],
+                  shift: Optional[torch.Tensor], eps: float) -> torch.Tensor:
+    """x fp32 [B, C, H, W]; gamma/beta [C]; scale/shift [B, C] (``x * (scale + 1) + shift`` after the norm) -> same shape."""
+    xf = require_cuda_f32(x, "x")
+    B, C = int(xf.shape[0]), int(xf.shape[1])
+    hw = int(xf.numel() // max(B * C, 1))
+    y = torch.empty_like(xf)
+    if xf.numel() == 0:
+        return y
+    opt = [None if t is None else require_cuda_f32(t, "parameter") for t in (gamma, beta, scale, shift)]
+    L = _lib.lib()
+    with torch.cuda.device(xf.device):
+        ws = workspace(xf.device, L.sfno_instance_norm_workspace_bytes(B, C), "norm")
+        _lib.check(L.sfno_instance_norm(xf.data_ptr(), y.data_ptr(), _ptr(opt[0]), _ptr(opt[1]), _ptr(opt[2]), _ptr(opt[3]), B, C, hw,
+                                        float(eps), ws.data_ptr(), ws.numel(), stream_ptr(xf.device)), "sfno_instance_norm")
+    return y
+
+
+@instance_norm.register_fake
+def _(x, gamma, beta, scale, shift, eps):
+    return torch.empty_like(x, dtype=torch.float32)
+
+
+# ---- 1x1 convolution ---------------------------------------------------------------------------------------------------
+@torch.library.custom_op("sfno_b200::conv1x1", mutates_args=())
+def conv1x1(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor], act: int) -> torch.Tensor:
+    """x fp32 [B, Cin, H, W]; weight [Cout, Cin(,1,1)]; bias [Cout]; residual [B, Cout, H, W]; act 0 none / 1 GELU."""
+    xf = require_cuda_f32(x, "x")
+    w = require_cuda_f32(weight, "weight").reshape(weight.shape[0], -1)
+    B, Ci = int(xf.shape[0]), int(xf.shape[1])
+    Co = int(w.shape[0])
+    hw = int(xf.numel() // max(B * Ci, 1))
+    y = torch.empty(B, Co, *xf.shape[2:], dtype=torch.float32, device=xf.device)
+    if y.numel() == 0:
+        return y
+    b = None if bias is None else require_cuda_f32(bias, "bias")
+    r = None if residual is None else require_cuda_f32(residual, "residual")
+    with torch.cuda.device(xf.device):
+        _lib.check(_lib.lib().sfno_conv1x1(xf.data_ptr(), w.data_ptr(), _ptr(b), _ptr(r), y.data_ptr(), B, Ci, Co, hw, int(act),
+                                           stream_ptr(xf.device)), "sfno_conv1x1")
+    return y
+
+
+@conv1x1.register_fake
+def _(x, weight, bias, residual, act):
+    return x.new_empty(x.shape[0], weight.shape[0], *x.shape[2:], dtype=torch.float32)
+
+
+# ---- whole network -----------------------------------------------------------------------------------------------------
+@torch.library.custom_op("sfno_b200::net_forward", mutates_args=())
+def net_forward(net: int, parts: Sequence[torch.Tensor], time: Optional[torch.Tensor], out_channels: int, dropout: bool, seed: int,
+                offset: int) -> torch.Tensor:
+    """parts: the tensors the reference concatenates on dim 1 (inputs, condition, static condition), fp32 [B, c_i, H, W];
+    time fp32 [B] or None -> [B, out_channels, H, W] fp32.  `net` must have its parameters set (``sfno_net_set_param``)."""
+    x = parts[0]
+    B = int(x.shape[0])
+    out = torch.empty(B, out_channels, *x.shape[2:], dtype=torch.float32, device=x.device)
+    if B == 0:
+        return out
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        ws = workspace(x.device, L.sfno_net_workspace_bytes(_handle(net), B), "net")
+        ptrs = (ctypes.c_void_p * len(parts))(*[t.data_ptr() for t in parts])
+        chans = (ctypes.c_int * len(parts))(*[int(t.shape[1]) for t in parts])
+        _lib.check(L.sfno_net_forward_parts(_handle(net), ptrs, chans, len(parts), _ptr(time), out.data_ptr(), B, int(dropout), int(seed),
+                                            int(offset), ws.data_ptr(), ws.numel(), stream_ptr(x.device)), "sfno_net_forward_parts")
+    return out
+
+
+@net_forward.register_fake
+def _(net, parts, time, out_channels, dropout, seed, offset):
+    x = parts[0]
+    return x.new_empty(x.shape[0], out_channels, *x.shape[2:], dtype=torch.float32)

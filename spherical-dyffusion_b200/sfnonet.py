@@ -23,6 +23,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._base_model import ALL_DROPOUT_LAYERS, BaseModel, DropPath
+from . import ops as _ops  # noqa: F401  (registers torch.ops.sfno_b200.*)
 from ._util import require_cuda_f32, stream_ptr, workspace
 from .harmonics import InverseRealSHT, RealSHT
 
@@ -84,15 +85,8 @@ class SpectralConvS2(nn.Module):
         X = self.forward_transform(xf)
         if self.scale_residual:
             residual = self.inverse_transform(X).to(dtype)
-        B, Cin = X.shape[0], X.shape[1]
-        Cout = self.weight.shape[1]
-        Xr = torch.view_as_real(X.contiguous())
-        Y = torch.empty(B, Cout, self.modes_lat, self.modes_lon, 2, dtype=torch.float32, device=xf.device)
-        w = require_cuda_f32(self.weight.detach(), "weight")
-        with torch.cuda.device(xf.device):
-            _lib.check(_lib.lib().sfno_spectral_contract(_lib.SFNO_OP[self.operator_type], Xr.data_ptr(), w.data_ptr(),
-                                                         Y.data_ptr(), B, Cin, Cout, self.modes_lat, self.modes_lon,
-                                                         stream_ptr(xf.device)), "sfno_spectral_contract")
+        Y = torch.ops.sfno_b200.spectral_contract(_lib.SFNO_OP[self.operator_type], torch.view_as_real(X.contiguous()),
+                                                  self.weight.detach())
         y = self.inverse_transform(torch.view_as_complex(Y))
         if hasattr(self, "bias"):
             y = y + self.bias
@@ -454,7 +448,6 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
         x = parts[0]
         B = x.shape[0]
         device = x.device
-        t_ptr = None
         if self.with_time_emb:
             assert self.min_time is not None and self.max_time is not None, \
                 "min_time and max_time must be set before using time embedding"
@@ -469,25 +462,22 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
             if self.check_time_range and not torch.cuda.is_current_stream_capturing():
                 assert bool(((self.min_time <= time) & (time <= self.max_time)).all()), \
                     f"time must be in [{self.min_time}, {self.max_time}], but time is {time}"
-            t_ptr = time.data_ptr()
-        out = torch.empty(B, self.out_chans, *self.img_shape, dtype=torch.float32, device=device)
         if B == 0:
+            out = torch.empty(B, self.out_chans, *self.img_shape, dtype=torch.float32, device=device)
             return (out, None) if return_time_emb else out
         L = _lib.lib()
         with torch.cuda.device(device):
             self._ensure_net(device)
             self.sync_parameters(device)
-            ws = workspace(device, L.sfno_net_workspace_bytes(self._net, B), "net")
             drop = self.dropout_active()
             self._calls += 1
-            ptrs = (ctypes.c_void_p * len(parts))(*[t.data_ptr() for t in parts])
-            chans = (ctypes.c_int * len(parts))(*[int(t.shape[1]) for t in parts])
-            _lib.check(L.sfno_net_forward_parts(self._net, ptrs, chans, len(parts), t_ptr, out.data_ptr(), B, int(drop),
-                                                int(self.dropout_seed), int(self._calls) * 4096, ws.data_ptr(), ws.numel(),
-                                                stream_ptr(device)), "sfno_net_forward_parts")
+            # custom-op layer (ops.py) -> sfno_net_forward_parts of the C ABI
+            out = torch.ops.sfno_b200.net_forward(self._net.value, parts, time if self.with_time_emb else None, self.out_chans,
+                                                  bool(drop), int(self.dropout_seed), int(self._calls) * 4096)
             t_repr = None
             if return_time_emb and self.with_time_emb:
                 t_repr = torch.empty(B, self.time_dim, dtype=torch.float32, device=device)
+                ws = workspace(device, L.sfno_net_workspace_bytes(self._net, B), "net")
                 _lib.check(L.sfno_net_debug_tap(self._net, b"t_repr", t_repr.data_ptr(), t_repr.numel(), ws.data_ptr(),
                                                 stream_ptr(device)), "sfno_net_debug_tap")
         out = out.to(in_dtype) if in_dtype != torch.float32 else out

@@ -134,6 +134,8 @@ def test_instance_norm_matches_oracle(dev, with_time):
                                     sd_.data_ptr() if with_time else None, sh_.data_ptr() if with_time else None,
                                     B, C, H * W, 1e-6, ws.data_ptr(), ws.numel(), stream_ptr(dev)))
     assert rel_l2(y, ref) < 1e-5
+    y_op = torch.ops.sfno_b200.instance_norm(xd, gd, bd, sd_, sh_, 1e-6)   # the same call through the custom-op layer
+    assert torch.equal(y_op, y)
 
 
 @pytest.mark.parametrize("cin,cout,hw,act", [(5, 16, 288, "gelu"), (36, 256, 1000, "none"), (130, 34, 64800, "gelu")])
@@ -153,6 +155,8 @@ def test_conv1x1_matches_torch(dev, cin, cout, hw, act):
     _lib.check(sb.lib().sfno_conv1x1(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), y.data_ptr(), B, cin, cout, hw,
                                      _lib.SFNO_ACT[act], stream_ptr(dev)))
     assert rel_l2(y, ref) < 2e-6
+    y_op = torch.ops.sfno_b200.conv1x1(xd.reshape(B, cin, 1, hw), wd, bd, rd.reshape(B, cout, 1, hw), _lib.SFNO_ACT[act])
+    assert torch.equal(y_op.reshape(B, cout, hw), y)   # the same call through the custom-op layer
 
 
 def test_abi_error_statuses(dev):

@@ -158,3 +158,29 @@ def test_op_decomposition_equals_reference_golden(case, load_golden):
     emu = NetEmulator(cfg, fx["state_dict"], _tables_fn(H, W, H, W // 2 + 1))
     out = emu.forward(fx["inputs"], time=fx["time"], condition=fx["condition"])
     assert rel_l2(out, fx["output"]) < 5e-6
+
+
+def test_custom_op_layer_is_registered_with_fake_implementations():
+    """torch.ops.sfno_b200.* (ops.py): every op of the layer exists and infers shapes on fake tensors without touching
+    the library (the real implementations need a GPU)."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    import spherical_dyffusion_b200  # noqa: F401
+
+    for name in ("sht_forward", "sht_inverse", "spectral_contract", "instance_norm", "conv1x1", "net_forward"):
+        assert hasattr(torch.ops.sfno_b200, name), name
+    with FakeTensorMode():
+        x = torch.empty(2, 3, 12, 24)
+        assert torch.ops.sfno_b200.sht_forward(0, x, 12, 13).shape == (2, 3, 12, 13, 2)
+        assert torch.ops.sfno_b200.sht_inverse(0, torch.empty(2, 3, 12, 13, 2), 12, 24).shape == (2, 3, 12, 24)
+        assert torch.ops.sfno_b200.spectral_contract(0, torch.empty(2, 3, 12, 13, 2), torch.empty(3, 5, 12, 2)).shape == (2, 5, 12, 13, 2)
+        assert torch.ops.sfno_b200.instance_norm(x, None, None, None, None, 1e-6).shape == x.shape
+        assert torch.ops.sfno_b200.conv1x1(x, torch.empty(7, 3, 1, 1), None, None, 1).shape == (2, 7, 12, 24)
+        assert torch.ops.sfno_b200.net_forward(0, [x, x[:, :1]], None, 5, False, 0, 0).shape == (2, 5, 12, 24)
+
+
+def test_custom_ops_refuse_cpu_tensors():
+    import spherical_dyffusion_b200  # noqa: F401
+
+    with pytest.raises(RuntimeError):
+        torch.ops.sfno_b200.conv1x1(torch.zeros(1, 2, 4, 8), torch.zeros(3, 2), None, None, 0)
