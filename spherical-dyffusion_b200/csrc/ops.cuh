@@ -103,6 +103,7 @@ __host__ __device__ inline int live_l0(int m, int lmax) {
 }
 struct FullRanges {
   static constexpr bool kRanged = false;  // every tile of the M x N x G grid is live
+  static constexpr bool kSimtRowsOnFastLanes = false;
   __device__ int n_begin(int) const { return 0; }
   __device__ int k_begin(int) const { return 0; }
   __device__ int m_begin(int) const { return 0; }
@@ -168,6 +169,7 @@ struct OpDft : FullRanges, NoFeatures {
 // ------------------------------------------------------------------------------------------------
 template <class T>
 struct OpLeg : NoFeatures {
+  static constexpr bool kSimtRowsOnFastLanes = false;
   static constexpr bool kRanged = true;
   static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = true, kNFastest = false;
   using OutT = T;
@@ -204,6 +206,7 @@ struct OpLeg : NoFeatures {
 // ------------------------------------------------------------------------------------------------
 template <class T>
 struct OpDhconv : NoFeatures {
+  static constexpr bool kSimtRowsOnFastLanes = false;
   static constexpr bool kRanged = true;
   static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = true, kNFastest = true;
   using OutT = T;
@@ -245,6 +248,7 @@ struct OpDhconv : NoFeatures {
 // ------------------------------------------------------------------------------------------------
 template <class T>
 struct OpIleg : NoFeatures {
+  static constexpr bool kSimtRowsOnFastLanes = false;
   static constexpr bool kRanged = true;
   static constexpr bool A_KCONTIG = false, B_KCONTIG = true, kColContig = true, kNFastest = true;
   using OutT = T;
@@ -398,6 +402,7 @@ struct ConvArgs {
 // ACT / DROP < 0: decided at run time (CUDA-core engine and rarely used combinations)
 template <class T, class TOut, int ACT = -1, int DROP = -1>
 struct OpConv : ConvArgs<T, TOut>, FullRanges {
+  static constexpr bool kSimtRowsOnFastLanes = true;
   static constexpr bool A_KCONTIG = true, B_KCONTIG = false, kColContig = true, kNFastest = false;
   __device__ int n_end(int) const { return this->N; }
   __device__ int m_end(int) const { return this->M; }
