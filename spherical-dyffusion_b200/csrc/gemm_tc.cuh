@@ -36,6 +36,7 @@ struct TmaOperand {
   uint64_t strides[3] = {0, 0, 0};   // byte strides of dims[1..3]
   bool batched = false;
   int group_lo = 0;                  // > 0: group g addresses {g % group_lo, g / group_lo} in dims[2], dims[3]
+  int replicas = 0;                  // > 1: a shared operand stored `replicas` times along dims[2]; CTA i reads copy i % replicas
 };
 
 // Epilogue I/O through TMA: the output (and the residual / addend block) as a 5-D tensor whose 128-byte x 8-row
@@ -55,6 +56,7 @@ struct TcSched {
   int m_tiles, n_tiles, groups, num_tiles, k_blocks, k16_last;  // k16_last: MMAs (K=16) in the last k block
   int a_batched, b_batched;
   int a_glo, b_glo;  // > 0: the operand's group index splits into {g % glo, g / glo} (4-D tensor map)
+  int a_rep, b_rep;  // > 1: shared operand replicated along dims[2]: this CTA reads copy blockIdx.x % rep
   // role-wait profile (tc_debug bit7) or nullptr: cycles summed over CTAs {producer waits for a free stage, MMA waits
   // for operands, MMA waits for a free accumulator, epilogue warp 0 waits for the accumulator, epilogue warp 0 waits
   // for the residual block, CTA lifetime, epilogue warp 0 busy, CTAs}
@@ -314,13 +316,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // consecutive tiles (= concurrently running CTAs) share the operand that is re-read: the N tiles of one M tile
-  // when the activations sit on the A side (kNFastest), the M tiles of one N tile when they sit on the B side
+  // Tile order.  Consecutive tiles run concurrently on different SMs:
+  //   default     : they share the operand that is re-read -- the N tiles of one M tile when the activations sit on
+  //                 the A side (kNFastest), the M tiles of one N tile when they sit on the B side -- (L2 reuse);
+  //   kGFastest   : they belong to different groups, so that no two CTAs pull the same per-group table / weight tile at
+  //                 the same time (a broadcast read of one small region serialises on a few L2 slices).
   TileIter it;
-  it.init(blockIdx.x, gridDim.x, Op::kNFastest ? sc.n_tiles : sc.m_tiles, Op::kNFastest ? sc.m_tiles : sc.n_tiles);
+  if (Op::kGFastest) it.init(blockIdx.x, gridDim.x, sc.groups, Op::kNFastest ? sc.n_tiles : sc.m_tiles);
+  else it.init(blockIdx.x, gridDim.x, Op::kNFastest ? sc.n_tiles : sc.m_tiles, Op::kNFastest ? sc.m_tiles : sc.n_tiles);
   auto decode = [&](int& g, int& mt, int& nt) {
-    g = it.c;
-    if (Op::kNFastest) { nt = it.a; mt = it.b; } else { mt = it.a; nt = it.b; }
+    if (Op::kGFastest) {
+      g = it.a;
+      if (Op::kNFastest) { nt = it.b; mt = it.c; } else { mt = it.b; nt = it.c; }
+    } else {
+      g = it.c;
+      if (Op::kNFastest) { nt = it.a; mt = it.b; } else { mt = it.a; nt = it.b; }
+    }
   };
 
   // tiles outside the group's live row / column ranges carry no information: all roles skip them
@@ -335,6 +346,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       long long w_empty = 0;
+      const int rep_a = sc.a_rep > 1 ? (int)(blockIdx.x % (unsigned)sc.a_rep) : 0;
+      const int rep_b = sc.b_rep > 1 ? (int)(blockIdx.x % (unsigned)sc.b_rep) : 0;
       const long long t_cta = timed ? clock64() : 0;
       for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, it.next()) {
         int g, mt, nt;
@@ -342,7 +355,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (tile_skipped(g, mt, nt)) continue;
         const int m0 = op.m_begin(g) + mt * kBMT, n0 = nt * BN;   // M tiles start at the group's first live row
         const int halves = (kDual && m0 + TC_BM < op.m_end(g)) ? 2 : 1;
-        int ga = sc.a_batched ? g : 0, gb = sc.b_batched ? g : 0, ga_hi = 0, gb_hi = 0;
+        int ga = sc.a_batched ? g : rep_a, gb = sc.b_batched ? g : rep_b, ga_hi = 0, gb_hi = 0;
         if (sc.a_glo) { ga_hi = ga / sc.a_glo; ga -= ga_hi * sc.a_glo; }
         if (sc.b_glo) { gb_hi = gb / sc.b_glo; gb -= gb_hi * sc.b_glo; }
         for (int kb = op.k_begin(g) / TC_BK; kb < sc.k_blocks; ++kb) {
@@ -711,6 +724,8 @@ int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what) {
   sc.b_batched = b.batched ? 1 : 0;
   sc.a_glo = a.group_lo;
   sc.b_glo = b.group_lo;
+  sc.a_rep = a.replicas;
+  sc.b_rep = b.replicas;
   sc.dbg = g_tc_debug.load(std::memory_order_relaxed);
   sc.prof = (sc.dbg & 128) ? tc_prof_buffer() : nullptr;
   static bool attr_set = false;

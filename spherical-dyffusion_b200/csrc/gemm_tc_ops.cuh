@@ -36,6 +36,7 @@ struct TcTraits<OpDft<bf16>> : TcTraitsBase<OpDft<bf16>>, TcEligible<TcTraits<Op
   static void operands(const OpDft<bf16>& op, TmaOperand& a, TmaOperand& b) {
     a.base = op.A; a.dims[0] = op.nlon; a.dims[1] = op.M;                 // basis rows (m,ri), K-contiguous, shared
     a.strides[0] = (uint64_t)op.Wp * 2; a.batched = false;
+    if (op.a_reps > 1) { a.dims[2] = op.a_reps; a.strides[1] = (uint64_t)op.M * op.Wp * 2; a.replicas = op.a_reps; }
     b.base = op.Bm; b.dims[0] = op.nlon; b.dims[1] = op.nlat; b.dims[2] = op.C; b.dims[3] = op.B;  // {j, k, c, b}
     b.strides[0] = (uint64_t)op.nlon * 2; b.strides[1] = (uint64_t)op.nlat * op.nlon * 2; b.strides[2] = (uint64_t)op.x_bstride * 2;
     b.batched = true; b.group_lo = op.C;
@@ -118,6 +119,7 @@ struct TcTraits<OpIdft<bf16, TOut, ACT>> : TcTraitsBase<OpIdft<bf16, TOut, ACT>>
     a.strides[0] = (uint64_t)op.a_sk * 2; a.batched = false;
     b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.N; b.dims[2] = 1;
     b.strides[0] = (uint64_t)op.Kq2 * 2; b.batched = false;
+    if (op.b_reps > 1) { b.dims[2] = op.b_reps; b.strides[1] = (uint64_t)op.N * op.Kq2 * 2; b.replicas = op.b_reps; }
   }
   static bool extra_ok(const OpIdft<bf16, TOut, ACT>& op) {
     return op.nlon % 8 == 0 && op.out_bstride % 8 == 0 && aligned16(op.out) &&

@@ -48,7 +48,7 @@ int fail(int status, const char* fmt, ...) {
 
 // ---- table upload -------------------------------------------------------------------------------------
 template <class T>
-static int upload_padded(const std::vector<double>& src, int64_t rows, int cols, int ld, void** dst, size_t* bytes) {
+static int upload_padded(const std::vector<double>& src, int64_t rows, int cols, int ld, void** dst, size_t* bytes, int replicas = 1) {
   std::vector<T> host((size_t)rows * ld);
   for (int64_t r = 0; r < rows; ++r)
     for (int c = 0; c < ld; ++c) {
@@ -56,10 +56,11 @@ static int upload_padded(const std::vector<double>& src, int64_t rows, int cols,
       if constexpr (std::is_same<T, float>::value) host[(size_t)r * ld + c] = v;
       else host[(size_t)r * ld + c] = __float2bfloat16_rn(v);
     }
-  size_t nbytes = host.size() * sizeof(T);
-  SFNO_CUDA(cudaMalloc(dst, nbytes));
-  SFNO_CUDA(cudaMemcpy(*dst, host.data(), nbytes, cudaMemcpyHostToDevice));
-  *bytes += nbytes;
+  const size_t nbytes = host.size() * sizeof(T);
+  SFNO_CUDA(cudaMalloc(dst, nbytes * replicas));
+  for (int r = 0; r < replicas; ++r)
+    SFNO_CUDA(cudaMemcpy((char*)*dst + (size_t)r * nbytes, host.data(), nbytes, cudaMemcpyHostToDevice));
+  *bytes += nbytes * replicas;
   return SFNO_OK;
 }
 
@@ -76,9 +77,11 @@ static int upload_all(const ShtTables& h, ShtDeviceTables& d) {
   SFNO_TRY(upload_padded<T>(pt, (int64_t)d.mmax * d.nlat, d.lmax, d.Lq, &d.pt, &d.bytes));
   std::vector<double> e;
   build_dft_forward(d.nlon, d.mmax, e);
-  SFNO_TRY(upload_padded<T>(e, 2 * d.mmax, d.nlon, d.Wp, &d.efwd, &d.bytes));
+  // the DFT bases are read by every CTA of a launch at about the same time: replicas at different addresses spread
+  // that broadcast over the L2 slices (each CTA reads replica blockIdx % basis_reps)
+  SFNO_TRY(upload_padded<T>(e, 2 * d.mmax, d.nlon, d.Wp, &d.efwd, &d.bytes, d.basis_reps));
   build_dft_inverse(d.nlon, d.mmax, e);
-  SFNO_TRY(upload_padded<T>(e, d.nlon, 2 * d.mmax, d.Kq2, &d.einv, &d.bytes));
+  SFNO_TRY(upload_padded<T>(e, d.nlon, 2 * d.mmax, d.Kq2, &d.einv, &d.bytes, d.basis_reps));
   return SFNO_OK;
 }
 
@@ -135,6 +138,7 @@ static int sht_forward_impl(const ShtDeviceTables& t, const float* x, float* coe
   dft.A = (const T*)t.efwd; dft.Bm = xin; dft.a_sk = 1; dft.b_sk = 1;
   dft.f = F; dft.aff_a = nullptr; dft.aff_d = nullptr;
   dft.B = 1; dft.C = C; dft.nlat = t.nlat; dft.nlon = t.nlon; dft.Kp = t.Kp; dft.Wp = t.Wp; dft.x_bstride = 0;
+  dft.a_reps = t.basis_reps;
   SFNO_TRY(launch_gemm(dft, st, "dft_fwd"));
   OpLeg<T> leg{};
   leg.G = t.mmax; leg.M = t.lmax; leg.N = 2 * C; leg.K = t.nlat;
@@ -166,7 +170,7 @@ static int sht_inverse_impl(const ShtDeviceTables& t, const float* coeffs, float
   id.G = 1; id.M = C * t.Kp; id.N = t.nlon; id.K = 2 * t.mmax;
   id.A = Gb; id.Bm = (const T*)t.einv; id.a_sk = id.M; id.b_sk = 1;
   id.out = x; id.out_bstride = 0; id.bias = nullptr; id.add = nullptr; id.add_bstride = 0; id.act = SFNO_ACT_NONE;
-  id.C = C; id.nlat = t.nlat; id.nlon = t.nlon; id.Kp = t.Kp; id.Kq2 = t.Kq2; id.stat_part = nullptr;
+  id.C = C; id.nlat = t.nlat; id.nlon = t.nlon; id.Kp = t.Kp; id.Kq2 = t.Kq2; id.b_reps = t.basis_reps; id.stat_part = nullptr;
   (void)xt;
   return launch_idft(id, st, "dft_inv");
 }

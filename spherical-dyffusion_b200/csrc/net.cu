@@ -224,6 +224,7 @@ static int run_dft(const sfno_net* n, const ShtDeviceTables& t, int B, const T* 
   op.A = (const T*)t.efwd; op.Bm = x; op.a_sk = 1; op.b_sk = 1;
   op.f = F; op.aff_a = a; op.aff_d = d;
   op.B = B; op.C = n->C; op.nlat = t.nlat; op.nlon = t.nlon; op.Kp = t.Kp; op.Wp = t.Wp; op.x_bstride = x_bs;
+  op.a_reps = t.basis_reps;
   return launch_gemm(op, st, "dft_fwd");
 }
 template <class T>
@@ -253,7 +254,7 @@ static int run_idft(const sfno_net* n, const ShtDeviceTables& t, int B, const T*
   op.G = 1; op.M = B * n->C * t.Kp; op.N = t.nlon; op.K = 2 * t.mmax;
   op.A = G; op.Bm = (const T*)t.einv; op.a_sk = op.M; op.b_sk = 1;
   op.out = out; op.out_bstride = out_bs; op.bias = bias; op.add = add; op.add_bstride = add_bs; op.act = act;
-  op.C = n->C; op.nlat = t.nlat; op.nlon = t.nlon; op.Kp = t.Kp; op.Kq2 = t.Kq2;
+  op.C = n->C; op.nlat = t.nlat; op.nlon = t.nlon; op.Kp = t.Kp; op.Kq2 = t.Kq2; op.b_reps = t.basis_reps;
   op.stat_part = nullptr;
   if (fused) *fused = false;
   if (stat_part && idft_uses_tc(op)) { op.stat_part = stat_part; *fused = true; }

@@ -161,7 +161,7 @@ extern "C" int sfno_b200_selftest_gemm(int op_kind, const int* d, int nd, double
       op.bias = (epi & 1) ? s.rndf(C, 13) : nullptr;
       op.add = (epi & 4) ? s.rnd((int64_t)B * C * nlat * nlon, 14) : nullptr; op.add_bstride = op.out_bstride;
       op.act = (epi & 2) ? SFNO_ACT_GELU : SFNO_ACT_NONE;
-      op.C = C; op.nlat = nlat; op.nlon = nlon; op.Kp = Kp; op.Kq2 = Kq2;
+      op.C = C; op.nlat = nlat; op.nlon = nlon; op.Kp = Kp; op.Kq2 = Kq2; op.b_reps = 0;
       auto tc = [](const OpIdft<bf16, bf16>& o) {  // same compile-time specialisation as launch_idft
         const IdftArgs<bf16, bf16>& a = o;
         if (a.act == SFNO_ACT_GELU) return launch_gemm_tc(OpIdft<bf16, bf16, SFNO_ACT_GELU>(a), 0, "selftest_tc");

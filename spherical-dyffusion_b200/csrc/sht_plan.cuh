@@ -15,8 +15,9 @@ struct ShtDeviceTables {
   int Kq2 = 0;  // 2*mmax rounded up to 8 (row length of einv rows)
   void* wq = nullptr;    // [mmax][lmax][Kp]   analysis  (Legendre x quadrature weight), B operand of OpLeg
   void* pt = nullptr;    // [mmax][nlat][Lq]   synthesis, transposed: A operand of OpIleg
-  void* efwd = nullptr;  // [2*mmax][Wp]       forward DFT basis, A operand of OpDft
-  void* einv = nullptr;  // [nlon][Kq2]        inverse DFT basis, A operand of OpIdft
+  int basis_reps = 16;   // replicas of the two DFT bases (L2 broadcast spreading)
+  void* efwd = nullptr;  // [basis_reps][2*mmax][Wp]  forward DFT basis, A operand of OpDft
+  void* einv = nullptr;  // [basis_reps][nlon][Kq2]   inverse DFT basis, B operand of OpIdft
   size_t bytes = 0;
 };
 
