@@ -63,7 +63,8 @@ struct TcSched {
   unsigned long long* prof;
   // experiment switch (sfno_b200_set_option("tc_debug")), WRONG results, timing only: bit0 skip A loads, bit1 skip B
   // loads, bit2 skip global stores, bit4 skip the MMAs (bits 3 and 5 -- epilogue math, TMEM loads -- were removed
-  // from the drain loop once measured: profiles/r01_j_tc_dbg_sweep.txt)
+  // from the drain loop once measured: profiles/r01_j_tc_dbg_sweep.txt); correct-result switches: bit7 role-wait
+  // counters, bit8 single-M tiles, bit9 every CTA walks K from block 0 (no rotation)
   int dbg;
 };
 
@@ -358,7 +359,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         int ga = sc.a_batched ? g : rep_a, gb = sc.b_batched ? g : rep_b, ga_hi = 0, gb_hi = 0;
         if (sc.a_glo) { ga_hi = ga / sc.a_glo; ga -= ga_hi * sc.a_glo; }
         if (sc.b_glo) { gb_hi = gb / sc.b_glo; gb -= gb_hi * sc.b_glo; }
-        for (int kb = op.k_begin(g) / TC_BK; kb < sc.k_blocks; ++kb) {
+        // every CTA walks the K blocks of its tile from its own starting block (and wraps): at any instant the CTAs
+        // that share an operand (basis, table, weights) read different K slices of it, which spreads the broadcast
+        // over more L2 slices.  fp32 accumulation order differs per CTA but is fixed by the static schedule.
+        const int kbeg = op.k_begin(g) / TC_BK, nkb = sc.k_blocks - kbeg;
+        const int rot = (Op::kRanged || (sc.dbg & 512)) ? 0 : (int)(blockIdx.x % (unsigned)nkb);   // (spectral ops: measured neutral / slower)
+        for (int ik = 0; ik < nkb; ++ik) {
+          const int kb = kbeg + (ik + rot < nkb ? ik + rot : ik + rot - nkb);
           w_empty += ptx::mbar_wait<true>(empty_bar(stage), phase ^ 1u, timed);
           const bool load_a = !(sc.dbg & 1), load_b = !(sc.dbg & 2);
           ptx::mbar_expect_tx(full_bar(stage), (load_a ? halves * S::kAHalfBytes : 0) + (load_b ? S::kBBytes : 0));
@@ -410,7 +417,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         w_tempty += ptx::mbar_wait<true>(tempty_bar(acc), acc_phase ^ 1u, timed);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(kDual ? 0 : acc * BN);
-        for (int kb = kb0; kb < sc.k_blocks; ++kb) {
+        const int nkb = sc.k_blocks - kb0;
+        const int rot = (Op::kRanged || (sc.dbg & 512)) ? 0 : (int)(blockIdx.x % (unsigned)nkb);   // same walk as the producer
+        for (int ik = 0; ik < nkb; ++ik) {
+          const int kb = kb0 + (ik + rot < nkb ? ik + rot : ik + rot - nkb);
           w_full += ptx::mbar_wait<true>(full_bar(stage), phase, timed);
           ptx::tc_fence_after();
           const int nk = (kb == sc.k_blocks - 1) ? sc.k16_last : TC_BK / 16;
@@ -418,7 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const uint64_t bd = make_smem_desc(b_smem(stage) + k * b_kstep, b_lbo, 1024u);
             for (int hf = 0; hf < halves; ++hf) {
               const uint64_t ad = make_smem_desc(a_smem(stage, hf) + k * a_kstep, a_lbo, 1024u);
-              if (!(sc.dbg & 16)) ptx::mma_bf16(d_tmem + (uint32_t)(hf * BN), ad, bd, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+              if (!(sc.dbg & 16)) ptx::mma_bf16(d_tmem + (uint32_t)(hf * BN), ad, bd, idesc, (ik != 0 || k != 0) ? 1u : 0u);
             }
           }
           ptx::mma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
