@@ -317,6 +317,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) may run while
+  // the previous kernel of the stream drains its last tiles; nothing below touches global memory before the
+  // prerequisite grid has completed and flushed.  The next kernel may start its own set-up as soon as SMs free up.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
   // Tile order.  Consecutive tiles run concurrently on different SMs:
   //   default     : they share the operand that is re-read -- the N tiles of one M tile when the activations sit on
   //                 the A side (kNFastest), the M tiles of one N tile when they sit on the B side -- (L2 reuse);
@@ -745,7 +751,17 @@ int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what) {
     attr_set = true;
   }
   const int grid = std::min(sc.num_tiles, tc_num_sms());
-  kern<<<grid, tc_threads(BN), S::kTotal, stream>>>(ma, mb, mo, mr, op, sc);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)tc_threads(BN));
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap this kernel's set-up with its predecessor's tail
+  attr[0].val.programmaticStreamSerializationAllowed = (sc.dbg & 1024) ? 0 : 1;   // tc_debug bit10: plain stream order
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SFNO_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, mr, op, sc));
   return post_launch(what);
 }
 
