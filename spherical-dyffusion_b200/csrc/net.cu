@@ -345,7 +345,7 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
     // norm0 (+ time scale/shift before the filter) as a per-(b,c) affine  (sfnonet.py:290-299)
     const bool time_before = cfg.with_time_emb && cfg.time_scale_shift_before_filter;
     if (cfg.instance_norm && x_stats_fused) {
-      norm_affine_partials_conv_kernel<<<ceil_div(BC, 32), 1024, 0, st>>>(stat_part, conv_slices, (int64_t)BC, (float)P, cfg.norm_eps,
+      norm_affine_partials_conv_kernel<<<ceil_div(BC, NAP_BC), 1024, 0, st>>>(stat_part, conv_slices, (int64_t)BC, (float)P, cfg.norm_eps,
                                                                         bp.norm0_g, bp.norm0_b, time_before ? ts_i : nullptr, ts_bs, B, C, a0, d0);
       SFNO_TRY(post_launch("norm_affine0"));
     } else {

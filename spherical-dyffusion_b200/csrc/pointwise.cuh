@@ -156,29 +156,30 @@ static __global__ void __launch_bounds__(256) norm_affine_partials_kernel(
   d_out[i] = d;
 }
 
-// rows_per_bc == 1 (convolution partials, layout [slice][{s,q}][B*C]): 32 consecutive (b,c) per CTA so that every
-// read is a coalesced 128-byte row; 32 warps stride over the slices, fixed-order smem reduction (deterministic)
+// rows_per_bc == 1 (convolution partials, layout [slice][{s,q}][B*C]): 8 consecutive (b,c) per CTA (256 CTAs at
+// B*C = 2048 -- every SM takes part), each read a 32-byte sector; 128 lane groups stride over the slices, fixed-order
+// shared-memory reduction (deterministic)
+constexpr int NAP_BC = 8, NAP_STREAMS = 1024 / NAP_BC;
 static __global__ void __launch_bounds__(1024) norm_affine_partials_conv_kernel(
     const float* __restrict__ part, int slices, int64_t rows, float count, float eps, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ ts, int64_t ts_bstride, int B, int C, float* __restrict__ a_out,
     float* __restrict__ d_out) {
-  __shared__ double sh_s[32][32], sh_q[32][32];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;  // 32 warps stride over the slices
-  const int i = blockIdx.x * 32 + lane;
+  __shared__ double sh_s[NAP_STREAMS][NAP_BC], sh_q[NAP_STREAMS][NAP_BC];
+  const int bcl = threadIdx.x % NAP_BC, stream = threadIdx.x / NAP_BC;
+  const int i = blockIdx.x * NAP_BC + bcl;
   double s = 0.0, q = 0.0;
   if (i < B * C) {
 #pragma unroll 4
-    for (int sl = w; sl < slices; sl += 32) {
+    for (int sl = stream; sl < slices; sl += NAP_STREAMS) {
       const float* ps = part + ((int64_t)sl * 2) * rows + i;
       s += (double)ps[0];
       q += (double)ps[rows];
     }
   }
-  sh_s[w][lane] = s; sh_q[w][lane] = q;
+  sh_s[stream][bcl] = s; sh_q[stream][bcl] = q;
   __syncthreads();
-  if (w != 0 || i >= B * C) return;
-#pragma unroll
-  for (int k = 1; k < 32; ++k) { s += sh_s[k][lane]; q += sh_q[k][lane]; }
+  if (stream != 0 || i >= B * C) return;
+  for (int k = 1; k < NAP_STREAMS; ++k) { s += sh_s[k][bcl]; q += sh_q[k][bcl]; }
   const int b = i / C, c = i - b * C;
   const double mean = s / (double)count;
   double var = q / (double)count - mean * mean;
