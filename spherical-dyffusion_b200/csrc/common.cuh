@@ -79,10 +79,11 @@ __device__ __forceinline__ float apply_act(int act, float x) {
 }
 
 // ---- Philox4x32-10 counter RNG (dropout masks; statistical parity only with torch's nn.Dropout) --------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+template <int kRounds = 10>
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < kRounds; ++r) {
     uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
     uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
     ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
@@ -94,7 +95,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 // uniform in [0,1) for element index `idx` of stream (seed, offset)
 __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t offset, uint64_t idx) {
   uint4 c = make_uint4((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), (uint32_t)offset, (uint32_t)(offset >> 32));
-  uint4 r = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  uint4 r = philox4x32<10>(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   uint32_t v = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
   return (v >> 8) * (1.0f / 16777216.0f);
 }
@@ -110,14 +111,15 @@ __device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %
 __device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
 __device__ __forceinline__ float f2_hsum(f2 a) { float lo, hi; f2_get(a, lo, hi); return lo + hi; }
 
-// Dropout decisions: one Philox4x32-10 block serves EIGHT consecutive elements (16 random bits each, idx8 % 8 == 0):
-// element idx8 + j is kept iff its 16-bit value >= thr16 = round(p * 65536).  Bit j of the result = keep.
+// Dropout decisions: one Philox4x32-7 block (the smallest round count of the family that passes BigCrush; masks need
+// no more, and the rounds are the cost of the dropout epilogues) serves EIGHT consecutive elements (16 random bits
+// each, idx8 % 8 == 0): element idx8 + j is kept iff its 16-bit value >= thr16 = round(p * 65536).  Bit j = keep.
 __device__ __forceinline__ uint32_t dropout_threshold16(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
 __device__ __forceinline__ float dropout_keep_scale(uint32_t thr16) { return 65536.0f / (float)(65536u - thr16); }
 __device__ __forceinline__ uint32_t dropout_keep_mask8(uint64_t seed, uint64_t offset, uint64_t idx8, uint32_t thr16) {
   const uint64_t blk = idx8 >> 3;
   const uint4 c = make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)offset, (uint32_t)(offset >> 32));
-  const uint4 r = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint4 r = philox4x32<7>(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   uint32_t m = 0;
   m |= ((r.x & 0xffffu) >= thr16) ? 1u : 0u;   m |= ((r.x >> 16) >= thr16) ? 2u : 0u;
   m |= ((r.y & 0xffffu) >= thr16) ? 4u : 0u;   m |= ((r.y >> 16) >= thr16) ? 8u : 0u;
