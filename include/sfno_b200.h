@@ -52,8 +52,9 @@ int64_t sfno_b200_launch_count(void);
 /* Library-wide switches for tests: "force_simt" = 1 routes bf16 ops to the CUDA-core engine.
  * "tc_debug" = bit mask of TIMING-ONLY experiment switches of the tensor-core engine (results are wrong while any of
  * bits 0-4 is set): 1 skip A-operand loads, 2 skip B-operand loads, 4 skip global stores, 16 skip the MMAs;
- * correct-result switches: 64 = epilogue I/O by LDS/STG instead of TMA, 128 = accumulate the role-wait counters read by
- * sfno_b200_tc_counters, 256 = single 128-row tiles where an op would use dual-M tiles. */
+ * correct-result switches: 128 = accumulate the role-wait counters read by sfno_b200_tc_counters, 256 = single 128-row
+ * tiles where an op would use dual-M tiles, 512 = every CTA walks the K blocks from block 0 (no per-CTA rotation),
+ * 1024 = plain stream order (no programmatic dependent launch). */
 int sfno_b200_set_option(const char* key, int64_t value);
 
 /* Measurement hook: cycles summed over the CTAs of all tensor-core launches since the last call (tc_debug bit 7):

@@ -13,8 +13,8 @@ struct ShtDeviceTables {
   int Lq = 0;   // lmax rounded up to 8  (row length of pt rows)
   int Wp = 0;   // nlon rounded up to 8  (row length of efwd rows)
   int Kq2 = 0;  // 2*mmax rounded up to 8 (row length of einv rows)
-  void* wq = nullptr;    // [mmax][lmax][Kp]   analysis  (Legendre x quadrature weight), B operand of OpLeg
-  void* pt = nullptr;    // [mmax][nlat][Lq]   synthesis, transposed: A operand of OpIleg
+  void* wq = nullptr;    // [mmax][lmax][Kp]   analysis  (Legendre x quadrature weight), A operand of OpLeg
+  void* pt = nullptr;    // [mmax][nlat][Lq]   synthesis, transposed: B operand of OpIleg
   int basis_reps = 16;   // replicas of the two DFT bases (L2 broadcast spreading)
   void* efwd = nullptr;  // [basis_reps][2*mmax][Wp]  forward DFT basis, A operand of OpDft
   void* einv = nullptr;  // [basis_reps][nlon][Kq2]   inverse DFT basis, B operand of OpIdft
