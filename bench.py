@@ -98,6 +98,32 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "sampled": "timed region" if during else "warm-up (timed region < 100 ms)"}
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Run this process (and therefore first-touch its pinned staging buffers) on the CPUs of the NUMA node the GPU hangs
+    off: host<->device copies from the far socket run at a fraction of the link rate.  Returns (node, previous affinity)
+    or (None, None) when the topology cannot be read."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        prev = os.sched_getaffinity(0)
+        allowed = cpus & prev
+        if not allowed:
+            return None, None
+        os.sched_setaffinity(0, allowed)
+        return node, prev
+    except Exception:
+        return None, None
+
+
 def build_case(batch, seed=0):
     from oracle.sfno_oracle import ACE_FORECASTER, SFNOConfig, random_state_dict
 
@@ -161,6 +187,7 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node, prev_affinity = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
@@ -270,6 +297,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": int(y_pin.numel() * 4)},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "host": {"numa_node_of_gpu": numa_node, "cpus": len(os.sched_getaffinity(0))},
         "derived": {
             "steps_per_s_per_member": value / world / B / FORWARDS_PER_STEP,
             "member_sypd": value / FORWARDS_PER_STEP * 86400.0 / STEPS_PER_YEAR,
@@ -286,6 +314,8 @@ def run_b200(args):
             line["roofline"] = {"error": str(exc)}
         # ---- CPU baseline: the oracle port on the host cores, bounded sample ---------------------------------------
         if world == 1 and not args.no_cpu_baseline:
+            if prev_affinity:
+                os.sched_setaffinity(0, prev_affinity)   # the CPU baseline may use every core the process was given
             torch.set_num_threads(os.cpu_count() or 1)
             cfg1, sd1, x1, c1, t1 = build_case(1)
             times = cpu_forward_time(cfg1, sd1, x1, c1, t1, steps=2, warmup=1)
