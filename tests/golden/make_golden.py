@@ -49,6 +49,17 @@ CASES = {
         cfg=dict(num_input_channels=2, num_output_channels=2, num_conditional_channels=0, spatial_shape=(12, 24),
                  embed_dim=16, num_layers=2, operator_type="dhconv", data_grid="equiangular", with_time_emb=False),
         batch=2, seed=3, times=None),
+    # interpolator-shaped call: two stacked snapshots + forcing as input, odd batch (dhconv rows (m,b) with B = 3),
+    # embed 40 (2C = 80: partial K block), 3 blocks; only the block outputs are kept as taps (fixture size)
+    "sfno_dhconv_24x48_interp": dict(
+        cfg=dict(num_input_channels=6, num_output_channels=3, num_conditional_channels=2, spatial_shape=(24, 48),
+                 embed_dim=40, num_layers=3, operator_type="dhconv", data_grid="equiangular"),
+        batch=3, seed=5, times=[0.0, 2.0, 5.0], taps="out"),
+    # batch 1, Gaussian data grid, embed 64, two blocks (both with the SHT round-trip residual)
+    "sfno_dhconv_24x48_lg_b1": dict(
+        cfg=dict(num_input_channels=4, num_output_channels=4, num_conditional_channels=1, spatial_shape=(24, 48),
+                 embed_dim=64, num_layers=2, operator_type="dhconv", data_grid="legendre-gauss"),
+        batch=1, seed=6, times=[3.0], taps="out"),
     # the 'diagonal' operator (ctor default of the reference)
     "sfno_diagonal_12x24": dict(
         cfg=dict(num_input_channels=3, num_output_channels=3, num_conditional_channels=2, spatial_shape=(12, 24),
@@ -98,6 +109,8 @@ def make_case(name, spec):
         out, t_repr = model(inputs, time=time, condition=condition, return_time_emb=True)
     for h in handles:
         h.remove()
+    if spec.get("taps") == "out":   # smaller fixture: what the parity tests read
+        taps = {k: v for k, v in taps.items() if k.endswith(".out") or k == "blocks.0.sht"}
 
     fixture = dict(
         cfg=spec["cfg"], state_dict={k: v.clone() for k, v in model.state_dict().items()},
@@ -111,8 +124,10 @@ def make_case(name, spec):
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])
     for name, spec in CASES.items():
-        make_case(name, spec)
+        if not only or name in only:
+            make_case(name, spec)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -200,7 +200,8 @@ def test_net_matches_reference_golden_fp32(dev, case, load_golden):
     assert e < FP32_TOL
 
 
-@pytest.mark.parametrize("case", ["sfno_dhconv_12x24", "sfno_dhconv_18x36_lg", "sfno_dhconv_16x32_variants"])
+@pytest.mark.parametrize("case", ["sfno_dhconv_12x24", "sfno_dhconv_18x36_lg", "sfno_dhconv_16x32_variants",
+                                  "sfno_dhconv_24x48_interp", "sfno_dhconv_24x48_lg_b1"])
 def test_net_golden_bf16_bound(dev, case, load_golden):
     fx = load_golden(case)
     cfg = SFNOConfig(**fx["cfg"])
