@@ -139,6 +139,11 @@ SAMPLER_CASES = {
                                       batch=2, seed=10, forward_conditioning="none", condition_kind="static"),
     "dyffusion_window_12x24_h3_dyn": dict(horizon=3, channels=2, forcing=1, spatial_shape=(12, 24), embed_dim=16, num_layers=2,
                                           batch=2, seed=11, forward_conditioning="data", condition_kind="dynamical"),
+    # naive sampling (x_{s+1} = interpolate(x0, x0_hat) without the cold-sampling correction) + refinement of the
+    # intermediate predictions at the end of the window (dyffusion.py:541-565)
+    "dyffusion_window_12x24_h4_naive_refine": dict(horizon=4, channels=2, forcing=2, spatial_shape=(12, 24), embed_dim=16, num_layers=2,
+                                                   batch=2, seed=12, forward_conditioning="none", condition_kind="static",
+                                                   sampling_type="naive", refine=True),
 }
 
 
@@ -187,7 +192,7 @@ def make_sampler_case(name, spec):
     perturb(interp, spec["seed"] + 100)
     dy = DYffusion(model=forecaster, timesteps=h, interpolator=_InterpolatorHandle(interp, h), interpolator_local_checkpoint_path=None,
                    forward_conditioning=spec["forward_conditioning"], time_encoding="dynamics", enable_interpolator_dropout=False,
-                   sampling_type="cold")
+                   sampling_type=spec.get("sampling_type", "cold"), refine_intermediate_predictions=spec.get("refine", False))
     g = torch.Generator().manual_seed(3000 + spec["seed"])
     B = spec["batch"]
     x0 = torch.randn(B, C, *shape, generator=g)
@@ -209,5 +214,7 @@ def make_sampler_case(name, spec):
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])
     for name, spec in SAMPLER_CASES.items():
-        make_sampler_case(name, spec)
+        if not only or name in only:
+            make_sampler_case(name, spec)

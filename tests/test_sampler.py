@@ -46,7 +46,8 @@ def test_sampler_loop_matches_reference_window_cpu(case):
     fore = OracleNet(_cfg(fx["forecaster_cfg"]), fx["forecaster_sd"])
     ipol = OracleNet(_cfg(fx["interpolator_cfg"]), fx["interpolator_sd"])
     dy = DYffusion(fore, ipol, timesteps=spec["horizon"], forward_conditioning=spec["forward_conditioning"],
-                   time_encoding="dynamics", enable_interpolator_dropout=False)
+                   time_encoding="dynamics", enable_interpolator_dropout=False, sampling_type=spec.get("sampling_type", "cold"),
+                   refine_intermediate_predictions=spec.get("refine", False))
     preds = dy.sample(fx["x0"], **fx["kwargs"])
     assert sorted(k for k in preds if k.endswith("_preds")) == sorted(fx["preds"])
     for k, ref in fx["preds"].items():
@@ -92,7 +93,8 @@ def test_sampler_window_on_b200_matches_reference(case, precision, tol):
     fore = _b200_module(_cfg(fx["forecaster_cfg"]), fx["forecaster_sd"], dev, precision)
     ipol = _b200_module(_cfg(fx["interpolator_cfg"]), fx["interpolator_sd"], dev, precision)
     dy = DYffusion(fore, ipol, timesteps=spec["horizon"], forward_conditioning=spec["forward_conditioning"],
-                   time_encoding="dynamics", enable_interpolator_dropout=False)
+                   time_encoding="dynamics", enable_interpolator_dropout=False, sampling_type=spec.get("sampling_type", "cold"),
+                   refine_intermediate_predictions=spec.get("refine", False))
     kwargs = {k: v.to(dev) for k, v in fx["kwargs"].items()}
     preds = dy.sample(fx["x0"].to(dev), **kwargs)
     errs = {k: rel_l2(preds[k], ref) for k, ref in fx["preds"].items()}
