@@ -432,3 +432,20 @@ def test_forward_is_cuda_graph_capturable(dev, precision):
             graph.replay()
             torch.cuda.synchronize(dev)
             assert rel_l2(sy, ref) < 1e-6
+
+
+def test_net_embed512_matches_oracle(dev):
+    """embed 512 / hidden 1024 (the scaled configuration's widths) on a small grid, both precisions."""
+    cfg = SFNOConfig(num_input_channels=4, num_output_channels=4, num_conditional_channels=2, spatial_shape=(16, 32),
+                     embed_dim=512, num_layers=2)
+    sd = perturb_affine_and_biases(random_state_dict(cfg, seed=7, spectral_gain=256.0))
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 4, 16, 32, generator=g)
+    c = torch.randn(2, 2, 16, 32, generator=g)
+    t = torch.tensor([1.0, 4.0])
+    ref = SFNOOracle(cfg, sd)(x, time=t, condition=c)
+    for precision, tol in (("fp32", FP32_TOL), ("bf16", BF16_BOUND)):
+        m = module_from_cfg(cfg, sd, dev, precision)
+        with torch.inference_mode():
+            y = m(x.to(dev), time=t.to(dev), condition=c.to(dev))
+        assert rel_l2(y, ref) < tol, precision

@@ -53,6 +53,8 @@ CASES = [
     ("convb", [8, 512, 256, 64800, 0, 5], True),  # fc2 at ACE size: bias + affine residual
     ("convb", [2, 512, 256, 64800, 0, 21], True), # fc2 with dropout (interpolator)
     ("convb", [2, 256, 256, 64800, 1, 15], True), # everything but dropout
+    ("convb", [2, 512, 512, 4096, 0, 5], True),   # embed-512 widths (scaled configuration): inner skip / encoder
+    ("convb", [1, 512, 1024, 2048, 1, 3], True),  # ... fc1 of the embed-512 model
     ("convb", [1, 16, 16, 300, 0, 0], False),     # hw not a multiple of 8 -> CUDA-core engine
 ]
 
