@@ -95,6 +95,9 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         fn.restype = restype
         fn.argtypes = argtypes
     _lib = cdll
+    dbg = os.environ.get("SFNO_TC_DEBUG")   # experiment switches of the tensor-core engine (include/sfno_b200.h), tests / A-B runs only
+    if dbg:
+        cdll.sfno_b200_set_option(b"tc_debug", int(dbg))
     return cdll
 
 
