@@ -3,17 +3,20 @@
 //   persistent CTAs (one per SM), 128 x BN output tile, K in blocks of 64 bf16 (one 128-byte swizzle span)
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, 4-D maps {inner, outer, batch, batch_hi})
 //   warp 1      : MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM, 2 stages)
-//   warps 2..   : epilogue       (tcgen05.ld 32x32b.x16 -> fused op epilogue; BN/64 warps per TMEM sub-partition, each
-//                                 a 64-column slice = one 128-byte staging row of bf16; compact rolled loops so the
-//                                 code stays inside the instruction cache)
-//   (BN = 256: 576 threads cap the kernel at 96 registers per thread; moving registers between roles with
-//    setmaxnreg was tried -- 640 threads, 56/104 -- and lost: ptxas spilled the residual prefetch block)
+//   warps 2..   : epilogue       BN/64 warps per TMEM sub-partition, each draining a 64-column slice:
+//                                 tcgen05.ld 32x32b.x32 -> fused op epilogue on packed fp32 pairs -> the warp's private
+//                                 32 x 128-byte swizzled staging rows -> TMA store (8-row x 128-byte boxes of a <= 5-D
+//                                 view of the output); residual / addend blocks arrive by TMA load the same way.
+//                                 No LDG / STG in the epilogue.
+//   (BN = 256: 576 threads cap the kernel at 96 registers per thread, BN = 192: 448 threads / 128 registers; moving
+//    registers between roles with setmaxnreg was tried -- 640 threads, 56/104 -- and lost)
 //   smem ring of kStages {A tile, B tile}, mbarrier full/empty; TMEM full/empty barriers decouple the MMA of
 //   tile i+1 from the epilogue of tile i.
 //
 // Operands are consumed directly in the layout they have in HBM: K-contiguous operands as K-major
 // SWIZZLE_128B tiles, M/N-contiguous operands as MN-major SWIZZLE_128B tiles (64-element atoms), so no
 // transposition pass exists anywhere on the path.  Out-of-bounds rows / K are zero-filled by TMA.
+// Launched with programmatic stream serialisation: the set-up of kernel n+1 overlaps the tail of kernel n.
 #pragma once
 #include <cuda.h>
 
