@@ -515,6 +515,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             ptx::tma_load_5d(region + (uint32_t)lane * 1024u, &tma_res, res_bar(ew), c);
           }
         }
+        bool released = false;
         long long w0 = 0;
         if (first_half) {
           w0 = ptx::mbar_wait(tfull_bar(acc), acc_phase, timed);
@@ -565,6 +566,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             uint32_t r[32];
             ptx::tmem_ld32(t_row + (uint32_t)(pass * kPassCols + 32 * ci), r);
             ptx::tmem_ld_wait();
+            // that was this warp's last read of the accumulator: hand the TMEM stage back to the MMA warp now, the
+            // math / staging / store of the last columns need it no more
+            if (last_half && !released && ci == nchunks - 1 && (pass == kPasses - 1 || n_end - (pn0 + kPassCols) <= 0)) {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+              released = true;
+            }
             if (!staging_checked) {
               staging_free();
               staging_checked = true;
@@ -595,7 +604,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           my_row = region + (uint32_t)lane * TC_STAGE_PITCH;
         }
         // the accumulator has been drained: hand the TMEM stage back to the MMA warp before any further work
-        if (last_half) {
+        if (last_half && !released) {   // (warps without live rows / columns never entered the drain loop)
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
