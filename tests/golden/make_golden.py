@@ -144,6 +144,11 @@ SAMPLER_CASES = {
     "dyffusion_window_12x24_h4_naive_refine": dict(horizon=4, channels=2, forcing=2, spatial_shape=(12, 24), embed_dim=16, num_layers=2,
                                                    batch=2, seed=12, forward_conditioning="none", condition_kind="static",
                                                    sampling_type="naive", refine=True),
+    # two artificial interpolation steps before t1 (schedule "before_t1_only", dyffusion.py:63-97,128-184): the
+    # interpolator is called at fractional times in (0, 1), the forecaster at the matching "dynamics" time encodings
+    "dyffusion_window_12x24_h3_addsteps": dict(horizon=3, channels=2, forcing=1, spatial_shape=(12, 24), embed_dim=16, num_layers=2,
+                                               batch=2, seed=13, forward_conditioning="none", condition_kind="static",
+                                               additional_interpolation_steps=2),
 }
 
 
@@ -186,13 +191,17 @@ def make_sampler_case(name, spec):
                       max_time=float(h - 1), **common)
     forecaster = ref_shim.build_reference_sfno(num_input_channels=C, num_output_channels=C, num_conditional_channels=fc_cond,
                                                spatial_shape=shape, seed=spec["seed"], min_max_time=(0, h - 1), **fcfg.model_kwargs())
+    add = spec.get("additional_interpolation_steps", 0)
+    imin = 0 if add else 1   # fractional interpolation times in (0, 1) when artificial steps exist (dyffusion.py:632-640)
+    icfg.min_time = float(imin)
     interp = ref_shim.build_reference_sfno(num_input_channels=2 * C, num_output_channels=C, num_conditional_channels=F,
-                                           spatial_shape=shape, seed=spec["seed"] + 100, min_max_time=(1, h - 1), **icfg.model_kwargs())
+                                           spatial_shape=shape, seed=spec["seed"] + 100, min_max_time=(imin, h - 1), **icfg.model_kwargs())
     perturb(forecaster, spec["seed"])
     perturb(interp, spec["seed"] + 100)
     dy = DYffusion(model=forecaster, timesteps=h, interpolator=_InterpolatorHandle(interp, h), interpolator_local_checkpoint_path=None,
                    forward_conditioning=spec["forward_conditioning"], time_encoding="dynamics", enable_interpolator_dropout=False,
-                   sampling_type=spec.get("sampling_type", "cold"), refine_intermediate_predictions=spec.get("refine", False))
+                   sampling_type=spec.get("sampling_type", "cold"), refine_intermediate_predictions=spec.get("refine", False),
+                   schedule="before_t1_only", additional_interpolation_steps=add)
     g = torch.Generator().manual_seed(3000 + spec["seed"])
     B = spec["batch"]
     x0 = torch.randn(B, C, *shape, generator=g)
