@@ -149,6 +149,12 @@ SAMPLER_CASES = {
     "dyffusion_window_12x24_h3_addsteps": dict(horizon=3, channels=2, forcing=1, spatial_shape=(12, 24), embed_dim=16, num_layers=2,
                                                batch=2, seed=13, forward_conditioning="none", condition_kind="static",
                                                additional_interpolation_steps=2),
+    # "linear" schedule with one artificial step between every pair of dynamical steps, discrete time encoding, and no
+    # cold-sampling correction on the last step
+    "dyffusion_window_12x24_h3_linear": dict(horizon=3, channels=2, forcing=1, spatial_shape=(12, 24), embed_dim=16, num_layers=2,
+                                             batch=2, seed=14, forward_conditioning="none", condition_kind="static",
+                                             schedule="linear", additional_interpolation_steps_factor=1, time_encoding="discrete",
+                                             use_cold_sampling_for_last_step=False),
 }
 
 
@@ -189,19 +195,26 @@ def make_sampler_case(name, spec):
                       max_time=float(h - 1), **common)
     icfg = SFNOConfig(num_input_channels=2 * C, num_output_channels=C, num_conditional_channels=F, min_time=1.0,
                       max_time=float(h - 1), **common)
+    n_diff = h + spec.get("additional_interpolation_steps", 0) + spec.get("additional_interpolation_steps_factor", 0) * (h - 1)
+    fmax = (n_diff - 1) if spec.get("time_encoding", "dynamics") == "discrete" else (h - 1)
+    fcfg.max_time = float(fmax)
     forecaster = ref_shim.build_reference_sfno(num_input_channels=C, num_output_channels=C, num_conditional_channels=fc_cond,
-                                               spatial_shape=shape, seed=spec["seed"], min_max_time=(0, h - 1), **fcfg.model_kwargs())
+                                               spatial_shape=shape, seed=spec["seed"], min_max_time=(0, fmax), **fcfg.model_kwargs())
     add = spec.get("additional_interpolation_steps", 0)
-    imin = 0 if add else 1   # fractional interpolation times in (0, 1) when artificial steps exist (dyffusion.py:632-640)
+    fac = spec.get("additional_interpolation_steps_factor", 0)
+    tenc = spec.get("time_encoding", "dynamics")
+    imin = 0 if (add or fac) else 1   # fractional interpolation times in (0, 1) when artificial steps exist (dyffusion.py:632-640)
     icfg.min_time = float(imin)
     interp = ref_shim.build_reference_sfno(num_input_channels=2 * C, num_output_channels=C, num_conditional_channels=F,
                                            spatial_shape=shape, seed=spec["seed"] + 100, min_max_time=(imin, h - 1), **icfg.model_kwargs())
     perturb(forecaster, spec["seed"])
     perturb(interp, spec["seed"] + 100)
     dy = DYffusion(model=forecaster, timesteps=h, interpolator=_InterpolatorHandle(interp, h), interpolator_local_checkpoint_path=None,
-                   forward_conditioning=spec["forward_conditioning"], time_encoding="dynamics", enable_interpolator_dropout=False,
+                   forward_conditioning=spec["forward_conditioning"], time_encoding=tenc, enable_interpolator_dropout=False,
                    sampling_type=spec.get("sampling_type", "cold"), refine_intermediate_predictions=spec.get("refine", False),
-                   schedule="before_t1_only", additional_interpolation_steps=add)
+                   schedule=spec.get("schedule", "before_t1_only"), additional_interpolation_steps=add,
+                   additional_interpolation_steps_factor=fac,
+                   use_cold_sampling_for_last_step=spec.get("use_cold_sampling_for_last_step", True))
     g = torch.Generator().manual_seed(3000 + spec["seed"])
     B = spec["batch"]
     x0 = torch.randn(B, C, *shape, generator=g)
