@@ -60,6 +60,13 @@ CASES = {
         cfg=dict(num_input_channels=4, num_output_channels=4, num_conditional_channels=1, spatial_shape=(24, 48),
                  embed_dim=64, num_layers=2, operator_type="dhconv", data_grid="legendre-gauss"),
         batch=1, seed=6, times=[3.0], taps="out"),
+    # interpolator-style module in eval mode: dropout layers exist (state-dict key mlp.fwd.3, layers.py:76-80) but are
+    # inactive, DropPath modules likewise; mlp_ratio 1
+    "sfno_dhconv_16x32_dropout_eval": dict(
+        cfg=dict(num_input_channels=4, num_output_channels=2, num_conditional_channels=1, spatial_shape=(16, 32),
+                 embed_dim=24, num_layers=3, operator_type="dhconv", data_grid="equiangular", mlp_ratio=1.0,
+                 dropout_mlp=0.1, drop_path_rate=0.1),
+        batch=2, seed=7, times=[1.0, 2.0], taps="out"),
     # the 'diagonal' operator (ctor default of the reference)
     "sfno_diagonal_12x24": dict(
         cfg=dict(num_input_channels=3, num_output_channels=3, num_conditional_channels=2, spatial_shape=(12, 24),
