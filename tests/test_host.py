@@ -184,3 +184,20 @@ def test_custom_ops_refuse_cpu_tensors():
 
     with pytest.raises(RuntimeError):
         torch.ops.sfno_b200.conv1x1(torch.zeros(1, 2, 4, 8), torch.zeros(3, 2), None, None, 0)
+
+
+def test_custom_ops_trace_with_fake_tensors():
+    """The custom ops are opaque, shape-inferring nodes for tracers (make_fx in fake mode never runs a kernel)."""
+    from torch.fx.experimental.proxy_tensor import make_fx
+
+    import spherical_dyffusion_b200  # noqa: F401
+
+    def fn(x, w, b):
+        y = torch.ops.sfno_b200.conv1x1(x, w, b, None, 1)
+        return torch.ops.sfno_b200.instance_norm(y, None, None, None, None, 1e-6)
+
+    gm = make_fx(fn, tracing_mode="fake")(torch.empty(2, 3, 8, 16), torch.empty(5, 3), torch.empty(5))
+    targets = [str(n.target) for n in gm.graph.nodes if n.op == "call_function"]
+    assert any("sfno_b200.conv1x1" in t for t in targets) and any("sfno_b200.instance_norm" in t for t in targets)
+    out = [n for n in gm.graph.nodes if n.op == "output"][0]
+    assert tuple(out.args[0].meta["val"].shape) == (2, 5, 8, 16)
