@@ -289,6 +289,9 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
   const int BC = B * C;
   // ---- input: fp32 -> T, and into the tail channels of the big-skip concat buffer (sfnonet.py:804-805,832)
   {
+    // under the per-launch profile: the event gap since profile_begin is host time (wrapper, argument checks), not
+    // part of the first kernel -- give it its own entry
+    if (g_profile_on.load(std::memory_order_relaxed)) profile_mark("host_before_first_launch");
     dim3 grid(1184 / std::max(1, std::min(B, 8)) + 1, B);
     concat_convert_kernel<T><<<grid, 256, 0, st>>>(parts, (int64_t)P, xin, (int64_t)n->Cin * P);
     SFNO_TRY(post_launch("convert_input"));

@@ -80,12 +80,16 @@ def _ncu_traffic(kernel_name):
 
 
 def roofline_from_profile(recs, pk, model=None, batch=None):
+    recs = OrderedDict(recs)
+    host_gap = recs.pop("host_before_first_launch", None)   # host time between profile_begin and the first launch
     total = sum(r["ms_total"] for r in recs.values())
     top_name, top = max(recs.items(), key=lambda kv: kv[1]["ms_total"])
     out = {"kernel": top_name, "share_of_step": top["ms_total"] / total if total else None,
            "launches_per_step": top["launches"], "ms_per_launch": top["ms_total"] / max(top["launches"], 1),
            "step_ms_profiled": total,
            "per_kernel_ms": {k: round(v["ms_total"], 4) for k, v in sorted(recs.items(), key=lambda kv: -kv[1]["ms_total"])}}
+    if host_gap is not None:
+        out["host_before_first_launch_ms"] = round(host_gap["ms_total"], 4)
     if model is not None and batch is not None:
         work = algorithmic_work(model, batch).get(top_name)
         if work is not None:
