@@ -92,3 +92,67 @@ def test_statistics_single_process_matches_metrics():
     ref = _reference_metrics(members, truth, weights)
     for k in ref:
         assert torch.allclose(out[k], ref[k], rtol=1e-4, atol=1e-5), k
+
+
+# ---- pinned against the reference's own metric functions (tests/golden/make_golden_metrics.py) -------------------------
+METRIC_CASES = ["e2", "e5_ties", "e8", "e25"]
+
+
+def _metrics_fixture():
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ensemble_metrics.pt")
+    return torch.load(path, map_location="cpu", weights_only=False)
+
+
+class SortedFormOps(TorchOps):
+    """The arithmetic of ``ensemble_crps_kernel`` (csrc/ensemble.cu) restated with torch: the pairwise term through the
+    order statistics, sum_{i<j} |x_i - x_j| = sum_k (2k - E + 1) x_(k)."""
+
+    def crps(self, members, truth):
+        E = members.shape[0]
+        skill = (members - truth).abs().sum(0) / E
+        xs = members.sort(dim=0).values
+        coef = (2 * torch.arange(E, dtype=members.dtype) - E + 1).reshape(E, *([1] * (members.dim() - 1)))
+        return skill - (coef * xs).sum(0) / (E * (E - 1))
+
+
+@pytest.mark.parametrize("case", METRIC_CASES)
+@pytest.mark.parametrize("ops", [TorchOps, SortedFormOps])
+def test_statistics_match_reference_metric_functions(case, ops):
+    fx = _metrics_fixture()[case]
+    E = fx["spec"]["E"]
+    ref = fx["ref"]
+    weights = area_weights(fx["lats"], fx["members"].shape[-1])
+    assert torch.equal(weights, ref["weights"])
+    out = EnsembleStatistics(E, ops=ops()).step(fx["members"], truth=fx["truth"], weights=weights)
+    for k in ("mean", "spread", "rmse", "ssr", "crps"):
+        assert torch.allclose(out[k], ref[k], rtol=2e-5, atol=1e-6), (k, out[k], ref[k])
+    unweighted = EnsembleStatistics(E, ops=ops()).step(fx["members"], truth=fx["truth"], weights=None)
+    assert torch.allclose(unweighted["crps"], ref["crps_unweighted"], rtol=2e-5, atol=1e-6)
+    flat = fx["members"].reshape(E, -1)
+    pointwise = ops().crps(flat, fx["truth"].reshape(-1)).reshape(fx["truth"].shape)
+    assert torch.allclose(pointwise, ref["crps_pointwise"], rtol=1e-4, atol=2e-6)
+
+
+def _fixture_worker(rank, world, port, case, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fx = _metrics_fixture()[case]
+        stats = EnsembleStatistics(fx["spec"]["E"], ops=SortedFormOps())
+        out = stats.step(fx["members"][stats.local_ids], truth=fx["truth"], weights=fx["ref"]["weights"])
+        results[rank] = all(bool(torch.allclose(out[k], fx["ref"][k], rtol=2e-5, atol=1e-6))
+                            for k in ("mean", "spread", "rmse", "ssr", "crps"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_statistics_match_reference_metric_functions_two_ranks():
+    """25 members over two ranks (13 + 12, uneven shards) reproduce the reference's numbers."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_fixture_worker, args=(2, port, "e25", results), nprocs=2, join=True)
+    assert dict(results) == {0: True, 1: True}

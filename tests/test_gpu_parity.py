@@ -342,6 +342,28 @@ def test_ensemble_statistics(dev, E):
     assert rel_l2(crps, skill - 0.5 * spread) < 1e-5
 
 
+@pytest.mark.parametrize("case", ["e2", "e5_ties", "e8", "e25"])
+def test_ensemble_statistics_match_reference_metric_functions(dev, case):
+    """The CUDA statistics kernels against numbers produced by the reference's own metrics.py
+    (tests/golden/make_golden_metrics.py): mean, spread, RMSE, spread-skill ratio, fair CRPS (reduced and per point)."""
+    import os
+
+    from spherical_dyffusion_b200.ensemble import CudaEnsembleOps, EnsembleStatistics, area_weights
+
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ensemble_metrics.pt"),
+                    map_location="cpu", weights_only=False)[case]
+    E, ref = fx["spec"]["E"], fx["ref"]
+    members, truth = fx["members"].to(dev), fx["truth"].to(dev)
+    weights = area_weights(fx["lats"], members.shape[-1])
+    assert torch.equal(weights, ref["weights"])
+    out = EnsembleStatistics(E).step(members, truth=truth, weights=weights.to(dev))
+    assert rel_l2(out["mean"], ref["mean"]) < 1e-6
+    for k in ("spread", "rmse", "ssr", "crps"):
+        assert rel_l2(out[k], ref[k]) < 2e-5, k
+    pointwise = CudaEnsembleOps().crps(members.reshape(E, -1).contiguous(), truth.reshape(-1).contiguous())
+    assert rel_l2(pointwise.reshape(truth.shape), ref["crps_pointwise"]) < 1e-5
+
+
 def test_ensemble_statistics_module_and_rollout(dev):
     """EnsembleStatistics with the CUDA kernels (single rank) against the metric definitions, and a tiny rollout."""
     from spherical_dyffusion_b200.dyffusion import DYffusion
