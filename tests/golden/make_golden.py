@@ -162,6 +162,16 @@ SAMPLER_CASES = {
                                              batch=2, seed=14, forward_conditioning="none", condition_kind="static",
                                              schedule="linear", additional_interpolation_steps_factor=1, time_encoding="discrete",
                                              use_cold_sampling_for_last_step=False),
+    # the released-checkpoint set-up: one input-only channel travels in front of the state
+    # (hack_for_imprecise_interpolation, dyffusion.py:41-44,501-502,655-661)
+    "dyffusion_window_12x24_h3_hack": dict(horizon=3, channels=2, forcing=1, spatial_shape=(12, 24), embed_dim=16, num_layers=2,
+                                           batch=2, seed=15, forward_conditioning="none", condition_kind="static", hack=True),
+    # no cold correction on the last step, but a cold-corrected initial state for the next autoregressive window
+    # (preds_autoregressive_init, dyffusion.py:505-512); the reference cannot combine this with the hack above
+    # (x_s and xhat_th differ by the extra channel at :508)
+    "dyffusion_window_12x24_h3_arinit": dict(horizon=3, channels=2, forcing=1, spatial_shape=(12, 24), embed_dim=16, num_layers=2,
+                                             batch=2, seed=16, forward_conditioning="none", condition_kind="static",
+                                             use_cold_sampling_for_last_step=False, use_cold_sampling_for_init_of_ar_step=True),
 }
 
 
@@ -198,21 +208,22 @@ def make_sampler_case(name, spec):
     fc_cond = F + (C if spec["forward_conditioning"] == "data" else 0)
     common = dict(spatial_shape=shape, embed_dim=spec["embed_dim"], num_layers=spec["num_layers"], operator_type="dhconv",
                   data_grid="equiangular")
-    fcfg = SFNOConfig(num_input_channels=C, num_output_channels=C, num_conditional_channels=fc_cond, min_time=0.0,
+    Cx = C + (1 if spec.get("hack") else 0)   # state channels the sampler carries (input-only channel in front)
+    fcfg = SFNOConfig(num_input_channels=Cx, num_output_channels=C, num_conditional_channels=fc_cond, min_time=0.0,
                       max_time=float(h - 1), **common)
-    icfg = SFNOConfig(num_input_channels=2 * C, num_output_channels=C, num_conditional_channels=F, min_time=1.0,
+    icfg = SFNOConfig(num_input_channels=2 * Cx, num_output_channels=C, num_conditional_channels=F, min_time=1.0,
                       max_time=float(h - 1), **common)
     n_diff = h + spec.get("additional_interpolation_steps", 0) + spec.get("additional_interpolation_steps_factor", 0) * (h - 1)
     fmax = (n_diff - 1) if spec.get("time_encoding", "dynamics") == "discrete" else (h - 1)
     fcfg.max_time = float(fmax)
-    forecaster = ref_shim.build_reference_sfno(num_input_channels=C, num_output_channels=C, num_conditional_channels=fc_cond,
+    forecaster = ref_shim.build_reference_sfno(num_input_channels=Cx, num_output_channels=C, num_conditional_channels=fc_cond,
                                                spatial_shape=shape, seed=spec["seed"], min_max_time=(0, fmax), **fcfg.model_kwargs())
     add = spec.get("additional_interpolation_steps", 0)
     fac = spec.get("additional_interpolation_steps_factor", 0)
     tenc = spec.get("time_encoding", "dynamics")
     imin = 0 if (add or fac) else 1   # fractional interpolation times in (0, 1) when artificial steps exist (dyffusion.py:632-640)
     icfg.min_time = float(imin)
-    interp = ref_shim.build_reference_sfno(num_input_channels=2 * C, num_output_channels=C, num_conditional_channels=F,
+    interp = ref_shim.build_reference_sfno(num_input_channels=2 * Cx, num_output_channels=C, num_conditional_channels=F,
                                            spatial_shape=shape, seed=spec["seed"] + 100, min_max_time=(imin, h - 1), **icfg.model_kwargs())
     perturb(forecaster, spec["seed"])
     perturb(interp, spec["seed"] + 100)
@@ -221,10 +232,12 @@ def make_sampler_case(name, spec):
                    sampling_type=spec.get("sampling_type", "cold"), refine_intermediate_predictions=spec.get("refine", False),
                    schedule=spec.get("schedule", "before_t1_only"), additional_interpolation_steps=add,
                    additional_interpolation_steps_factor=fac,
-                   use_cold_sampling_for_last_step=spec.get("use_cold_sampling_for_last_step", True))
+                   use_cold_sampling_for_last_step=spec.get("use_cold_sampling_for_last_step", True),
+                   use_cold_sampling_for_init_of_ar_step=spec.get("use_cold_sampling_for_init_of_ar_step"),
+                   hack_for_imprecise_interpolation=spec.get("hack", False))
     g = torch.Generator().manual_seed(3000 + spec["seed"])
     B = spec["batch"]
-    x0 = torch.randn(B, C, *shape, generator=g)
+    x0 = torch.randn(B, Cx, *shape, generator=g)
     kwargs = {}
     if spec["condition_kind"] == "static":
         kwargs["static_condition"] = torch.randn(B, F, *shape, generator=g)
@@ -235,7 +248,7 @@ def make_sampler_case(name, spec):
     fixture = dict(spec=spec, forecaster_cfg={k: v for k, v in fcfg.__dict__.items()}, interpolator_cfg={k: v for k, v in icfg.__dict__.items()},
                    forecaster_sd={k: v.clone() for k, v in forecaster.state_dict().items()},
                    interpolator_sd={k: v.clone() for k, v in interp.state_dict().items()},
-                   x0=x0, kwargs=kwargs, preds={k: v.clone() for k, v in preds.items() if k.endswith("_preds")},
+                   x0=x0, kwargs=kwargs, preds={k: v.clone() for k, v in preds.items() if k.endswith("_preds") or k == "preds_autoregressive_init"},
                    torch_version=torch.__version__)
     path = os.path.join(OUT, f"{name}.pt")
     torch.save(fixture, path)
