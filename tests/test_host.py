@@ -201,3 +201,27 @@ def test_custom_ops_trace_with_fake_tensors():
     assert any("sfno_b200.conv1x1" in t for t in targets) and any("sfno_b200.instance_norm" in t for t in targets)
     out = [n for n in gm.graph.nodes if n.op == "output"][0]
     assert tuple(out.args[0].meta["val"].shape) == (2, 5, 8, 16)
+
+
+def test_library_sass_carries_the_blackwell_instructions():
+    """The shipped library is sm_100a code whose tensor-core engine really is tcgen05 + TMA + TMEM (not an mma.sync /
+    LDG recompilation): the SASS of libsfno_b200.so must contain the 5th-generation MMA, TMA tensor loads and stores,
+    TMEM loads and the packed fp32 pair math of the epilogues (mnemonics: /opt/skills/guides/B200_PROFILING.md)."""
+    import collections
+    import re
+    import shutil
+    import subprocess
+
+    import spherical_dyffusion_b200 as sb
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    path = sb._lib.LIB_PATH
+    elf = subprocess.run([cuobjdump, "-lelf", path], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in elf, elf
+    sass = subprocess.run([cuobjdump, "-sass", path], capture_output=True, text=True, check=True).stdout
+    counts = collections.Counter(re.findall(r"\b(UTCHMMA|UTMALDG|UTMASTG|LDTM|UTCBAR|FFMA2|HMMA|IMMA)\b", sass))
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR", "FFMA2"):
+        assert counts[mnemonic] > 0, (mnemonic, dict(counts))
+    assert counts["HMMA"] == 0 and counts["IMMA"] == 0, dict(counts)   # no warp-level mma.sync path in the library
