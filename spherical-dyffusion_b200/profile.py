@@ -118,6 +118,19 @@ def roofline_from_profile(recs, pk, model=None, batch=None):
                                "TFLOPs": round(flops / sec / 1e12, 1),
                                "frac_tensor": round(flops / sec / 1e12 / pk["bf16_tflops_sustained"], 3)}
         out["per_kernel_roofline"] = table
+        # BASELINE.json's "SHT tensor-pipe % of peak": the transform pair (longitude DFT + Legendre, both directions) and
+        # the spectral contraction as one aggregate -- dense algorithmic flops of all their launches / their summed time
+        work = algorithmic_work(model, batch)
+        for key, names in (("sht", ("dft_fwd", "legendre_fwd", "legendre_inv", "dft_inv")),
+                           ("sht_and_spectral_conv", ("dft_fwd", "legendre_fwd", "dhconv", "legendre_inv", "dft_inv"))):
+            live = [n for n in names if n in recs and recs[n]["ms_total"] > 0]
+            if len(live) == len(names):
+                flops = sum(work[n][0] * recs[n]["launches"] for n in live)
+                sec = sum(recs[n]["ms_total"] for n in live) * 1e-3
+                out.setdefault("tensor_pipe", {})[key] = {
+                    "TFLOPs_dense": round(flops / sec / 1e12, 1), "ms_per_forward": round(sec * 1e3, 4),
+                    "frac_of_bf16_sustained": round(flops / sec / 1e12 / pk["bf16_tflops_sustained"], 3),
+                    "frac_of_bf16_burst": round(flops / sec / 1e12 / pk["bf16_tflops"], 3)}
         out["per_kernel_roofline_note"] = ("DENSE algorithmic bytes / flops per launch (SURVEY 8d); the Legendre and dhconv "
                                            "kernels execute only the l >= m half, so their fractions are upper bounds on the traffic actually moved")
     return out

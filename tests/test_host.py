@@ -225,3 +225,32 @@ def test_library_sass_carries_the_blackwell_instructions():
     for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR", "FFMA2"):
         assert counts[mnemonic] > 0, (mnemonic, dict(counts))
     assert counts["HMMA"] == 0 and counts["IMMA"] == 0, dict(counts)   # no warp-level mma.sync path in the library
+
+
+def test_roofline_arithmetic_from_a_per_launch_profile():
+    """bench.py's `roofline` object from a per-launch profile: the host time in front of the first launch is not a
+    kernel, the dominant kernel is rated against the measured HBM peak with SURVEY 8d's algorithmic bytes, and the
+    transform pair / spectral contraction are aggregated into the tensor-pipe fraction BASELINE.json's metric names."""
+    from collections import OrderedDict
+    from types import SimpleNamespace
+
+    from spherical_dyffusion_b200.profile import algorithmic_work, roofline_from_profile
+
+    model = SimpleNamespace(precision="bf16", embed_dim=256, in_chans=36, out_chans=34, img_shape=(180, 360), modes_lat=180,
+                            modes_lon=181, mlp_ratio=2.0, big_skip=True)
+    pk = dict(bf16_tflops=1654.5, hbm_gbs=6554.6, bf16_tflops_sustained=1377.3, source="measured")
+    ms = {"host_before_first_launch": (0.32, 1), "dft_inv": (2.0, 10), "dft_fwd": (1.7, 10), "legendre_fwd": (0.95, 10),
+          "legendre_inv": (1.0, 10), "dhconv": (1.0, 8), "mlp_fc1": (1.8, 8), "convert_input": (0.03, 1)}
+    recs = OrderedDict((k, dict(ms_total=t, launches=n)) for k, (t, n) in ms.items())
+    out = roofline_from_profile(recs, pk, model=model, batch=8)
+    assert out["kernel"] == "dft_inv" and out["bound"] == "hbm" and out["unit"] == "GB/s"
+    assert out["host_before_first_launch_ms"] == 0.32 and "host_before_first_launch" not in out["per_kernel_ms"]
+    assert abs(out["step_ms_profiled"] - (sum(t for t, _ in ms.values()) - 0.32)) < 1e-9
+    flops, nbytes = algorithmic_work(model, 8)["dft_inv"]
+    # inverse DFT: read the longitude-spectral tensor, read the inner-skip block, write the activation tensor (bf16)
+    assert nbytes == 8 * 256 * 180 * 181 * 2 * 2 + 2 * 8 * 256 * 180 * 360 * 2
+    assert abs(out["achieved"] - nbytes / 0.2e-3 / 1e9) < 1e-6 and abs(out["frac"] - out["achieved"] / 6554.6) < 1e-12
+    sht = out["tensor_pipe"]["sht"]
+    dense = sum(algorithmic_work(model, 8)[k][0] * 10 for k in ("dft_fwd", "legendre_fwd", "legendre_inv", "dft_inv"))
+    assert abs(sht["TFLOPs_dense"] - dense / 5.65e-3 / 1e12) < 0.06
+    assert out["tensor_pipe"]["sht_and_spectral_conv"]["ms_per_forward"] == 6.65
