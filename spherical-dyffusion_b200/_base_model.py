@@ -50,109 +50,90 @@ def disable_inference_dropout(model: nn.Module):
             m.eval()
 
 
+_CTOR_FIELDS = ("num_input_channels", "num_output_channels", "num_output_channels_raw", "num_conditional_channels",
+                "spatial_shape_in", "spatial_shape_out", "loss_function", "loss_function_weights", "datamodule_config",
+                "debug_mode", "name")
+
+
 class BaseModel(nn.Module):
-    def __init__(
-        self,
-        num_input_channels: int = None,
-        num_output_channels: int = None,
-        num_output_channels_raw: int = None,
-        num_conditional_channels: int = 0,
-        spatial_shape_in: Union[Sequence[int], int] = None,
-        spatial_shape_out: Union[Sequence[int], int] = None,
-        loss_function: Optional[str] = None,
-        loss_function_weights: Optional[dict] = None,
-        datamodule_config: Any = None,
-        debug_mode: bool = False,
-        name: str = "",
-        verbose: bool = True,
-    ):
+    """Keyword surface of the reference constructor (``_base_model.py:46-60``); everything is recorded in ``hparams`` and
+    the channel / shape bookkeeping the diffusion wrapper reads (``_base_diffusion.py:31-35``) is exposed as attributes."""
+
+    def __init__(self, num_input_channels: int = None, num_output_channels: int = None, num_output_channels_raw: int = None,
+                 num_conditional_channels: int = 0, spatial_shape_in: Union[Sequence[int], int] = None,
+                 spatial_shape_out: Union[Sequence[int], int] = None, loss_function: Optional[str] = None,
+                 loss_function_weights: Optional[dict] = None, datamodule_config: Any = None, debug_mode: bool = False,
+                 name: str = "", verbose: bool = True):
         super().__init__()
-        self.hparams = AttrDict(
-            num_input_channels=num_input_channels, num_output_channels=num_output_channels,
-            num_output_channels_raw=num_output_channels_raw, num_conditional_channels=num_conditional_channels,
-            spatial_shape_in=spatial_shape_in, spatial_shape_out=spatial_shape_out, loss_function=loss_function,
-            loss_function_weights=loss_function_weights, datamodule_config=datamodule_config, debug_mode=debug_mode,
-            name=name)
-        self.log_text = logging.getLogger(self.__class__.__name__ if name == "" else name)
-        self.name = name
+        given = locals()
+        self.hparams = AttrDict({k: given[k] for k in _CTOR_FIELDS})
+        for k in _CTOR_FIELDS[:6] + ("datamodule_config", "name"):   # channels, shapes, datamodule config, name
+            setattr(self, k, given[k])
         self.verbose = verbose
+        self.log_text = logging.getLogger(name or type(self).__name__)
         if not verbose:
             self.log_text.setLevel(logging.WARN)
-        self.num_input_channels = num_input_channels
-        self.num_output_channels = num_output_channels
-        self.num_output_channels_raw = num_output_channels_raw
-        self.num_conditional_channels = num_conditional_channels
-        self.spatial_shape_in = spatial_shape_in
-        self.spatial_shape_out = spatial_shape_out
-        self.datamodule_config = datamodule_config
-        self.criterion = None
-        self._channel_dim = None
-        self.ema_scope = None  # may be set by the experiment module (_base_experiment.py:386-401)
+        self.criterion = None      # no loss on the inference path
+        self.ema_scope = None      # may be set by the experiment module (_base_experiment.py:386-401)
+        self._channel_dim = 1      # NCHW
 
-    @property
-    def short_description(self) -> str:
-        return self.name if self.name else self.__class__.__name__
+    # ---- small read-only surface ------------------------------------------------------------------------------------
+    short_description = property(lambda self: self.name or type(self).__name__)
+    channel_dim = property(lambda self: self._channel_dim)
+    num_params = property(lambda self: sum(p.numel() for p in self.get_parameters() if p.requires_grad))
 
     def get_parameters(self) -> list:
-        return list(self.parameters())
-
-    @property
-    def num_params(self):
-        return sum(p.numel() for p in self.get_parameters() if p.requires_grad)
-
-    @property
-    def channel_dim(self):
-        if self._channel_dim is None:
-            self._channel_dim = 1
-        return self._channel_dim
+        return [*self.parameters()]
 
     @property
     def device(self):
-        try:
-            return next(self.parameters()).device
-        except StopIteration:
-            return torch.device("cpu")
+        first = next(self.parameters(), None)
+        return first.device if first is not None else torch.device("cpu")
 
-    def concat_condition_if_needed(self, inputs: Tensor, condition: Tensor = None, static_condition: Tensor = None):
-        """``_base_model.py:166-192`` (same branches, same error types)."""
-        if self.num_conditional_channels > 0:
-            if condition is None and static_condition is None:
-                raise ValueError(
-                    f"condition and static_condition are both None but num_conditional_channels is {self.num_conditional_channels}")
-            elif condition is not None and static_condition is not None:
-                condition = torch.cat((condition, static_condition), dim=1)
-            elif condition is None:
-                condition = static_condition
-            if hasattr(self, "upsample_condition"):
-                condition = self.upsample_condition(condition)
-            try:
-                x = torch.cat((inputs, condition), dim=1)
-            except RuntimeError as e:
-                raise RuntimeError(f"inputs.shape: {inputs.shape}, condition.shape: {condition.shape}") from e
-        else:
-            x = inputs
+    # ---- conditioning (``_base_model.py:166-192``: same outcomes, same exception classes) ---------------------------------
+    def merged_condition(self, condition: Optional[Tensor], static_condition: Optional[Tensor]) -> Optional[Tensor]:
+        """The tensor appended to the inputs on the channel axis, or None for an unconditional model."""
+        if self.num_conditional_channels <= 0:
             assert condition is None, "condition is not None but num_conditional_channels is 0"
             assert static_condition is None, "static_condition is not None but num_conditional_channels is 0"
-        return x
+            return None
+        present = [c for c in (condition, static_condition) if c is not None]
+        if not present:
+            raise ValueError(
+                f"condition and static_condition are both None but num_conditional_channels is {self.num_conditional_channels}")
+        merged = present[0] if len(present) == 1 else torch.cat(present, dim=1)
+        upsample = getattr(self, "upsample_condition", None)
+        return upsample(merged) if upsample is not None else merged
 
+    def concat_condition_if_needed(self, inputs: Tensor, condition: Tensor = None, static_condition: Tensor = None):
+        extra = self.merged_condition(condition, static_condition)
+        if extra is None:
+            return inputs
+        try:
+            return torch.cat((inputs, extra), dim=1)
+        except RuntimeError as e:
+            raise RuntimeError(f"inputs.shape: {inputs.shape}, condition.shape: {extra.shape}") from e
+
+    # ---- entry points the experiment / diffusion wrappers call -------------------------------------------------------------
     def get_loss(self, *args, **kwargs):
         raise NotImplementedError("training (get_loss / backward) is out of scope of the B200 inference path (SURVEY 8f-4)")
 
     def predict_forward(self, *inputs: Tensor, metadata: Any = None, **kwargs):
-        """``_base_model.py:265-270``."""
+        """``_base_model.py:265-270``: plain call; ``metadata`` is accepted and unused, as in the reference."""
         return self(*inputs, **kwargs)
 
     @contextmanager
     def inference_dropout_scope(self, condition: bool, context=None):
-        """``_base_model.py:273-286``."""
+        """``_base_model.py:273-286``: dropout layers (and DropPath) sample inside the scope when ``condition`` is True."""
         assert isinstance(condition, bool), f"Condition must be a boolean, got {condition}"
-        if condition:
-            enable_inference_dropout(self)
+        if not condition:
+            yield None
+            return
+        self.enable_inference_dropout()
         try:
             yield None
         finally:
-            if condition:
-                disable_inference_dropout(self)
+            self.disable_inference_dropout()
 
     def enable_inference_dropout(self):
         enable_inference_dropout(self)
