@@ -125,6 +125,7 @@ def bind_to_gpu_numa_node(device_index: int):
 
 
 def build_case(batch, seed=0):
+    """Configuration, weights and inputs of the CPU legs (reference arm / cpu_baseline) -- the only users of oracle/."""
     from oracle.sfno_oracle import ACE_FORECASTER, SFNOConfig, random_state_dict
 
     cfg = SFNOConfig(**ACE_FORECASTER)
@@ -174,6 +175,20 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def build_b200_case(batch, precision, seed, dev):
+    """The B200 arm's workload: random-init ACE forecaster (the reference's initialisers, spherical_dyffusion_b200.configs)
+    on `dev`, synthetic N(0,1) host inputs [batch,34,180,360] + forcings [batch,2,180,360], time 3.  Nothing of oracle/."""
+    from spherical_dyffusion_b200 import configs
+
+    model = configs.build(configs.ACE_FORECASTER, precision=precision, seed=seed, min_max_time=(0, 5), check_time_range=False)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, 34, 180, 360, generator=g)
+    c = torch.randn(batch, 2, 180, 360, generator=g)
+    t = torch.full((batch,), 3.0)
+    return model, x, c, t
+
+
 def run_b200(args):
     import torch.distributed as dist
 
@@ -194,14 +209,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch
-    cfg, sd, x, c, t = build_case(B, seed=rank)
-    model = sb.SphericalFourierNeuralOperatorNet(
-        num_input_channels=34, num_output_channels=34, num_output_channels_raw=34, num_conditional_channels=2,
-        spatial_shape_in=(180, 360), spatial_shape_out=(180, 360), precision=args.precision, check_time_range=False,
-        **cfg.model_kwargs())
-    model.load_state_dict(sd)
-    model.set_min_max_time(0, 5)
-    model = model.to(dev).eval()
+    model, x, c, t = build_b200_case(B, args.precision, rank, dev)
     xd, cd, td = x.to(dev), c.to(dev), t.to(dev)
     x_pin, c_pin = x.pin_memory(), c.pin_memory()
     y_pin = torch.empty(B, 34, 180, 360).pin_memory()

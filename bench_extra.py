@@ -25,17 +25,11 @@ import torch  # noqa: E402
 STEPS_PER_YEAR = 1460.0
 
 
-def _model(cfg, sd, dev, precision):
-    import spherical_dyffusion_b200 as sb
+def _model(config, dev, precision, seed=0, min_max_time=(0.0, 5.0)):
+    """Random-init module of a spherical_dyffusion_b200.configs entry on `dev` (eval mode)."""
+    from spherical_dyffusion_b200 import configs
 
-    m = sb.SphericalFourierNeuralOperatorNet(
-        num_input_channels=cfg.num_input_channels, num_output_channels=cfg.num_output_channels,
-        num_output_channels_raw=cfg.num_output_channels, num_conditional_channels=cfg.num_conditional_channels,
-        spatial_shape_in=cfg.spatial_shape, spatial_shape_out=cfg.spatial_shape, precision=precision, check_time_range=False,
-        **cfg.model_kwargs())
-    m.load_state_dict(sd)
-    m.set_min_max_time(cfg.min_time, cfg.max_time)
-    return m.to(dev).eval()
+    return configs.build(config, precision=precision, seed=seed, min_max_time=min_max_time, check_time_range=False).to(dev).eval()
 
 
 def _timeit(fn, steps, warmup):
@@ -52,12 +46,10 @@ def _timeit(fn, steps, warmup):
 
 
 def _ace_pair(dev, precision, seed=0):
-    from oracle.sfno_oracle import ACE_FORECASTER, ACE_INTERPOLATOR, SFNOConfig, random_state_dict
+    from spherical_dyffusion_b200 import configs
 
-    fcfg = SFNOConfig(**ACE_FORECASTER)
-    icfg = SFNOConfig(**ACE_INTERPOLATOR)
-    fore = _model(fcfg, random_state_dict(fcfg, seed=seed), dev, precision)
-    ipol = _model(icfg, random_state_dict(icfg, seed=seed + 1), dev, precision)
+    fore = _model(configs.ACE_FORECASTER, dev, precision, seed=seed, min_max_time=(0.0, 5.0))
+    ipol = _model(configs.ACE_INTERPOLATOR, dev, precision, seed=seed + 1, min_max_time=(1.0, 5.0))
     return fore, ipol
 
 
@@ -140,19 +132,14 @@ def run_rollout(args):
 
 
 def run_scaled(args):
-    from oracle.sfno_oracle import SFNOConfig, random_state_dict
+    from spherical_dyffusion_b200 import configs
 
     dev = torch.device("cuda:0")
-    cfg = SFNOConfig(num_input_channels=34, num_output_channels=34, num_conditional_channels=2, spatial_shape=(720, 1440),
-                     embed_dim=512, num_layers=12)
     # random weights generated on the GPU to avoid a 20 GB host state dict
     import spherical_dyffusion_b200 as sb
 
     with torch.device(dev):
-        m = sb.SphericalFourierNeuralOperatorNet(
-            num_input_channels=34, num_output_channels=34, num_output_channels_raw=34, num_conditional_channels=2,
-            spatial_shape_in=(720, 1440), spatial_shape_out=(720, 1440), precision=args.precision, check_time_range=False,
-            **cfg.model_kwargs())
+        m = sb.SphericalFourierNeuralOperatorNet(**configs.SCALED_FORECASTER, precision=args.precision, check_time_range=False)
     m.set_min_max_time(0, 5)
     m = m.to(dev).eval()
     B = args.batch
@@ -175,11 +162,10 @@ def run_scaled(args):
 
 def run_graph(args):
     """Latency of one ACE forecaster forward at small batch: eager launches vs replay of a captured CUDA graph."""
-    from oracle.sfno_oracle import ACE_FORECASTER, SFNOConfig, random_state_dict
+    from spherical_dyffusion_b200 import configs
 
     dev = torch.device("cuda:0")
-    cfg = SFNOConfig(**ACE_FORECASTER)
-    m = _model(cfg, random_state_dict(cfg, seed=0), dev, args.precision)
+    m = _model(configs.ACE_FORECASTER, dev, args.precision)
     for B in (1, 2, 8):
         x = torch.randn(B, 34, 180, 360, device=dev)
         c = torch.randn(B, 2, 180, 360, device=dev)

@@ -39,3 +39,32 @@ def test_b200_arm_has_no_cpu_fallback():
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert p.returncode != 0
     assert not any(ln.startswith("{") for ln in p.stdout.splitlines())
+
+
+def test_b200_arm_workload_is_built_without_the_oracle():
+    """The B200 arm's model and inputs come from the product package alone (oracle/ is the checker, never part of the
+    measured path), and they are the configuration the oracle-timed CPU legs use: same state_dict layout, same
+    library configuration struct, same input shapes."""
+    import ast
+    import importlib.util
+
+    import torch
+
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for fn in (n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("run_b200", "build_b200_case", "model_roofline")):
+        for node in ast.walk(fn):
+            if isinstance(node, (ast.Import, ast.ImportFrom)):
+                names = [a.name for a in node.names] + [getattr(node, "module", None) or ""]
+                assert not any(n.split(".")[0] == "oracle" for n in names), (fn.name, names)
+
+    model, x, c, t = bench.build_b200_case(2, "bf16", 0, torch.device("cpu"))
+    assert not model.training and model.precision == "bf16" and model.num_params == 210626560
+    assert tuple(x.shape) == (2, 34, 180, 360) and tuple(c.shape) == (2, 2, 180, 360) and t.tolist() == [3.0, 3.0]
+    cfg, sd, x1, c1, t1 = bench.build_case(1)
+    mine = model.state_dict()
+    assert list(mine) == list(sd) and all(mine[k].shape == sd[k].shape for k in sd)
+    assert x1.shape[1:] == x.shape[1:] and c1.shape[1:] == c.shape[1:] and float(t1[0]) == 3.0
+    assert (model.min_time, model.max_time) == (0, 5)
