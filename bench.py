@@ -44,6 +44,8 @@ def peaks():
 def workload_config(args):
     return {"workload": f"ACE SFNO forecaster forward 36->34ch embed256 x8 blocks dhconv 180x360, batch {args.batch}/GPU",
             "batch_per_gpu": args.batch, "precision": args.precision,
+            "baseline_config": "BASELINE.json configs[0] (ACE-sized SFNO, 180x360) at configs[2]'s batch 8 / bf16; configs[1,3,4] = "
+                               "bench_extra.py sht / rollout / scaled",
             "l2": "per-step working set (>= 2.5 GB of activations) exceeds the 126 MB L2; no explicit flush"}
 
 
