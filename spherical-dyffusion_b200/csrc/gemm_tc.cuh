@@ -26,6 +26,10 @@
 
 namespace sfno {
 
+#ifndef SFNO_TC_LDTM_PAIR
+#define SFNO_TC_LDTM_PAIR 0   // 1: paired TMEM loads in the bf16 drain loop (experiment, see the drain loop)
+#endif
+
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_SLICE_COLS = 64;  // accumulator columns drained by one epilogue warp
@@ -88,6 +92,10 @@ struct TileIter {
     c += dc + carry;
   }
 };
+
+// ops that take the paired TMEM loads of the SFNO_TC_LDTM_PAIR experiment (specialised in gemm_tc_ops.cuh)
+template <class Op>
+struct TcLdtmPair { static constexpr bool value = false; };
 
 template <class Op>
 struct TcTraits {
@@ -561,8 +569,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           };
           const int nchunks = (nvalid + 31) >> 5;
+          // Experiment (compile with -DSFNO_TC_LDTM_PAIR=1; NOT yet run on a GPU, off in the shipped library): both
+          // 32-column TMEM loads of a bf16 pass are issued back to back and waited for once, so their latency is paid
+          // once per pass instead of once per chunk and the accumulator stage goes back to the MMA warp before any
+          // epilogue math of the tile.  Only for the ops whose drain loop keeps 64 accumulator registers without
+          // spilling under the launch bound (TcLdtmPair<Op>: DFT, inverse Legendre, inverse DFT; the conv epilogues
+          // spill 300-550 bytes with it, the BN = 256 kernels are capped at 96 registers).
+          bool pair_done = false;
+          if constexpr (SFNO_TC_LDTM_PAIR != 0 && TcLdtmPair<Op>::value) {
+            if (nchunks == 2) {
+              uint32_t r0[32], r1[32];
+              ptx::tmem_ld32(t_row + (uint32_t)(pass * kPassCols), r0);
+              ptx::tmem_ld32(t_row + (uint32_t)(pass * kPassCols + 32), r1);
+              ptx::tmem_ld_wait();
+              if (last_half && !released && (pass == kPasses - 1 || n_end - (pn0 + kPassCols) <= 0)) {
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+                released = true;
+              }
+              if (!staging_checked) {
+                staging_free();
+                staging_checked = true;
+              }
+              if (!kGuardRows || valid) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) group8(r0, q, 8 * q);
+                if (nvalid == 64) {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) group8(r1, q, 32 + 8 * q);
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q)
+                    if (32 + 8 * q < nvalid) group8(r1, q, 32 + 8 * q);
+                }
+              }
+              pair_done = true;
+            }
+          }
 #pragma unroll 1
-          for (int ci = 0; ci < nchunks; ++ci) {
+          for (int ci = 0; ci < (pair_done ? 0 : nchunks); ++ci) {
             uint32_t r[32];
             ptx::tmem_ld32(t_row + (uint32_t)(pass * kPassCols + 32 * ci), r);
             ptx::tmem_ld_wait();

@@ -169,4 +169,9 @@ struct TcTraits<OpConv<bf16, TOut, ACT, DROP>> : TcTraitsBase<OpConv<bf16, TOut,
   }
 };
 
+// SFNO_TC_LDTM_PAIR experiment: the ops whose epilogue holds two 32-column accumulator chunks without spilling
+template <> struct TcLdtmPair<OpDft<bf16>> { static constexpr bool value = true; };
+template <> struct TcLdtmPair<OpIleg<bf16>> { static constexpr bool value = true; };
+template <int ACT> struct TcLdtmPair<OpIdft<bf16, bf16, ACT>> { static constexpr bool value = true; };
+
 }  // namespace sfno
