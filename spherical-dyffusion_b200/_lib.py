@@ -10,7 +10,9 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libsfno_b200.so")
+# SFNO_B200_LIB: load another build of the same library (A/B runs of engine experiments, scripts/build_variant.sh);
+# unset in normal use
+LIB_PATH = os.environ.get("SFNO_B200_LIB") or os.path.join(PKG_DIR, "libsfno_b200.so")
 
 SFNO_GRID = {"legendre-gauss": 0, "equiangular": 1}
 SFNO_PREC = {"fp32": 0, "float32": 0, "bf16": 1, "bfloat16": 1}
