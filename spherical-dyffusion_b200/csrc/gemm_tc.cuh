@@ -26,6 +26,9 @@
 
 namespace sfno {
 
+#ifndef SFNO_TC_BACKOFF_NS
+#define SFNO_TC_BACKOFF_NS 64   // sleep of the single-thread roles (TMA producer, MMA issuer) between barrier polls
+#endif
 #ifndef SFNO_TC_LDTM_PAIR
 #define SFNO_TC_LDTM_PAIR 0   // 1: paired TMEM loads in the bf16 drain loop (experiment, see the drain loop)
 #endif
@@ -134,7 +137,7 @@ __device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity, bo
     if (mbar_try_wait(bar, parity)) return 0;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-      if (kBackoff) __nanosleep(64);  // single-thread roles with slack: do not compete with the epilogue warps for issue slots
+      if (kBackoff) __nanosleep(SFNO_TC_BACKOFF_NS);  // single-thread roles with slack: do not compete with the epilogue warps for issue slots
       if (clock64() - t0 > 4000000000LL) __trap();
     }
     return 0;
@@ -142,7 +145,7 @@ __device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity, bo
   // role-wait profile (tc_debug bit7): try_wait itself may block for a while, so it sits inside the timed region
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (kBackoff) __nanosleep(64);
+    if (kBackoff) __nanosleep(SFNO_TC_BACKOFF_NS);
     if (clock64() - t0 > 4000000000LL) __trap();
   }
   return clock64() - t0;
