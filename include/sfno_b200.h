@@ -176,6 +176,14 @@ int sfno_net_forward(sfno_net* net, const float* x_dev, const float* time_dev, f
 int sfno_net_forward_parts(sfno_net* net, const float* const* parts_dev, const int* part_channels, int nparts,
                            const float* time_dev, float* y_dev, int batch, int dropout_enabled, uint64_t seed, uint64_t offset,
                            void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Same forward with a DEVICE-RESIDENT Philox state instead of host seed / offset integers: rng_state_dev[2] =
+ * {seed, offset} (uint64).  Masks are keyed on the values found there when the kernels run, and the call enqueues
+ * offset += 4096 after its last kernel, so a CUDA graph that captured this call draws fresh masks on every replay
+ * (what torch's graph-safe generator does for nn.Dropout, dyffusion.py:226-235).  rng_state_dev may be NULL iff
+ * dropout_enabled == 0. */
+int sfno_net_forward_parts_rng(sfno_net* net, const float* const* parts_dev, const int* part_channels, int nparts,
+                               const float* time_dev, float* y_dev, int batch, int dropout_enabled, uint64_t* rng_state_dev,
+                               void* workspace_dev, size_t workspace_bytes, void* stream);
 /* Per-net test switch: "stop_after_block" = -2 run everything (default), -1 stop after encoder + pos-embed,
  * i stop after block i (the output tensor is then left untouched; read the state with sfno_net_debug_tap). */
 int sfno_net_set_option(sfno_net* net, const char* key, int64_t value);
@@ -185,16 +193,39 @@ int64_t sfno_net_debug_tap(sfno_net* net, const char* name, float* dst_dev, int6
                            void* workspace_dev, void* stream);
 
 /* ---- ensemble statistics (new; spec = src/evaluation/metrics.py:166-175,199-246) -------------------
- * members_dev [members][n] fp32 on this rank.  Accumulates sum and sum of squares into sums_dev[2][n]
- * (fp32, caller zero-initialises, all-reduces across ranks with NCCL, then calls _finalize). */
-int sfno_ensemble_accumulate(const float* members_dev, int members, int64_t n, float* sums_dev, void* stream);
-/* mean_dev[n], var_dev[n] (unbiased over `total_members`, as torch.var) from all-reduced sums. */
-int sfno_ensemble_finalize(const float* sums_dev, int total_members, int64_t n, float* mean_dev, float* var_dev,
-                           void* stream);
-/* Fair CRPS per grid point (metrics.py:199-246): members_dev [members][n] (all members, after all-gather),
- * truth_dev [n] -> crps_dev [n] = mean_i|x_i - y| - sum_{i<j}|x_i-x_j| / (E*(E-1)) . members <= 64. */
+ * Variance is the reference's two-pass `predicted.var(dim=0)` (metrics.py:166-175), never sum(x^2) - E*mean^2:
+ *   1. every rank:  sfno_ensemble_local_sum        -> sum_r[n] over ITS members (members may be 0 on a rank)
+ *   2. all-reduce(SUM) of sum_r (NCCL, host side)   -> sum[n]; pivot p = sum / E, bit-identical on every rank
+ *   3. every rank:  sfno_ensemble_shifted_moments  -> moments_r[2][n] = { sum_e (x - p), sum_e (x - p)^2 }
+ *   4. all-reduce(SUM) of moments_r                  -> moments[2][n]
+ *   5. sfno_ensemble_finalize -> mean = p + S1 / E, var = (S2 - S1^2 / E) / (E - 1)   (unbiased, as torch.var)
+ * members_dev [members][n] fp32 on this rank. */
+int sfno_ensemble_local_sum(const float* members_dev, int members, int64_t n, float* sum_dev, void* stream);
+int sfno_ensemble_shifted_moments(const float* members_dev, int members, int64_t n, const float* sum_global_dev,
+                                  int total_members, float* moments_dev, void* stream);
+int sfno_ensemble_finalize(const float* sum_global_dev, const float* moments_dev, int total_members, int64_t n,
+                           float* mean_dev, float* var_dev, void* stream);
+/* One pass over ALL members (after the all-gather): mean_dev[n], var_dev[n] (two-pass, unbiased) and the fair CRPS per
+ * grid point (metrics.py:199-246): crps = mean_i|x_i - y| - sum_{i<j}|x_i-x_j| / (E*(E-1)), sorted form, no [E,E,..]
+ * tensor.  Any output may be NULL; truth_dev may be NULL iff crps_dev is.  members <= 64. */
+int sfno_ensemble_stats(const float* members_dev, const float* truth_dev, int members, int64_t n, float* mean_dev,
+                        float* var_dev, float* crps_dev, void* stream);
 int sfno_ensemble_crps(const float* members_dev, const float* truth_dev, int members, int64_t n,
                        float* crps_dev, void* stream);
+
+/* ---- sampler glue (caller of the hot path) ---------------------------------------------
+ * Cold-sampling update of BaseDYffusion.sample_loop (src/diffusion/dyffusion.py:519):
+ *   x_out = x_s + (x_next - x_cur)   in one pass (x_out may alias x_s); fp32, n elements. */
+int sfno_cold_update(const float* x_s_dev, const float* x_next_dev, const float* x_cur_dev, float* x_out_dev,
+                     int64_t n, void* stream);
+
+/* ---- parameter fingerprints ---------------------------------------------------------------------------
+ * out_dev[i] = position-weighted 64-bit checksum of the bit patterns of tensor i (ptrs_dev[i], numel_dev[i] fp32
+ * elements), one launch for all tensors.  The host wrapper compares it with the value recorded at the last
+ * sfno_net_set_param to detect in-place updates that bypass autograd's version counter (`p.data.copy_`, used by the
+ * reference's EMA swap src/models/modules/ema.py:54-91).  out_dev is overwritten. */
+int sfno_param_fingerprint(const float* const* ptrs_dev, const int64_t* numel_dev, int count, uint64_t* out_dev,
+                           void* stream);
 
 #ifdef __cplusplus
 }

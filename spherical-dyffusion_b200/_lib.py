@@ -71,9 +71,15 @@ _SIGNATURES = {
                                        c_uint64, c_uint64, c_void_p, c_size_t, c_void_p]),
     "sfno_net_set_option": (c_int, [c_void_p, c_char_p, c_int64]),
     "sfno_net_debug_tap": (c_int64, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p, c_void_p]),
-    "sfno_ensemble_accumulate": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
-    "sfno_ensemble_finalize": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "sfno_net_forward_parts_rng": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int), c_int, c_void_p, c_void_p, c_int, c_int,
+                                           c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sfno_param_fingerprint": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "sfno_ensemble_local_sum": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "sfno_ensemble_shifted_moments": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
+    "sfno_ensemble_finalize": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "sfno_ensemble_stats": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfno_ensemble_crps": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "sfno_cold_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

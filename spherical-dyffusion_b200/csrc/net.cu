@@ -211,7 +211,7 @@ static ConvArgs<T, TOut> make_conv(int B, int P, int cin, int cout, const T* in,
   op.A = w; op.Bm = in; op.a_sk = 1; op.b_sk = P;
   op.in_bstride = in_bs; op.w_bstride = w_bs; op.ldw = ldw;
   op.bias = bias; op.bias_bstride = bias_bs; op.act = act;
-  op.drop_p = 0.0f; op.seed = 0; op.offset = 0; op.branch_scale = nullptr;
+  op.drop_p = 0.0f; op.seed = 0; op.offset = 0; op.rng_dev = nullptr; op.branch_scale = nullptr;
   op.res = nullptr; op.res_bstride = 0; op.res_a = nullptr; op.res_d = nullptr; op.pos = nullptr;
   op.out = out; op.out_bstride = out_bs; op.stat_part = nullptr;
   return op;
@@ -263,7 +263,7 @@ static int run_idft(const sfno_net* n, const ShtDeviceTables& t, int B, const T*
 
 template <class T>
 static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time, float* y, int B, int dropout, uint64_t seed,
-                        uint64_t offset, char* ws, cudaStream_t st) {
+                        uint64_t offset, uint64_t* rng_dev, char* ws, cudaStream_t st) {
   const sfno_net_config& cfg = n->cfg;
   const WsLayout w = ws_layout(n, B);
   const int C = n->C, P = n->P, hid = n->hid, nl = n->nl, tdim = n->tdim;
@@ -419,7 +419,7 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
     const float dp = nl > 1 ? cfg.drop_path_rate * (float)i / (float)(nl - 1) : 0.0f;
     const bool use_dp = dropout && dp > 0.0f;
     if (use_dp) {
-      drop_path_scale_kernel<<<ceil_div(B, 128), 128, 0, st>>>(dscale, B, dp, seed, offset + (uint64_t)i * 4 + 2);
+      drop_path_scale_kernel<<<ceil_div(B, 128), 128, 0, st>>>(dscale, B, dp, seed, offset + (uint64_t)i * 4 + 2, rng_dev);
       SFNO_TRY(post_launch("drop_path_scale"));
     }
     const float pdrop = dropout ? cfg.dropout_mlp : 0.0f;
@@ -428,10 +428,10 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
     fold_affine_weight_kernel<T><<<B * hid, 128, 0, st>>>(bp.fc1_w32, bp.fc1_b, a1, d1, hid, C, C, fc1_wb, fc1_bb);
     SFNO_TRY(post_launch("fold_fc1"));
     auto f1 = make_conv<T, T>(B, P, C, hid, t1, CP, fc1_wb, (int64_t)hid * C, C, fc1_bb, hid, cfg.activation, hd, (int64_t)hid * P);
-    f1.drop_p = pdrop; f1.seed = seed; f1.offset = offset + (uint64_t)i * 4 + 0;
+    f1.drop_p = pdrop; f1.seed = seed; f1.offset = offset + (uint64_t)i * 4 + 0; f1.rng_dev = rng_dev;
     SFNO_TRY(launch_conv(f1, st, "mlp_fc1"));
     auto f2 = make_conv<T, T>(B, P, hid, C, hd, (int64_t)hid * P, (const T*)bp.fc2_wT, 0, hid, bp.fc2_b, 0, SFNO_ACT_NONE, nxt, nxt_bs);
-    f2.drop_p = pdrop; f2.seed = seed; f2.offset = offset + (uint64_t)i * 4 + 1;
+    f2.drop_p = pdrop; f2.seed = seed; f2.offset = offset + (uint64_t)i * 4 + 1; f2.rng_dev = rng_dev;
     f2.branch_scale = use_dp ? dscale : nullptr;
     if (scale_residual) { f2.res = res; f2.res_bstride = CP; }
     else { f2.res = cur; f2.res_bstride = cur_bs; f2.res_a = a0; f2.res_d = d0; }
@@ -451,6 +451,11 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
     SFNO_TRY(launch_conv(d0c, st, "decoder0"));
     auto d1c = make_conv<T, float>(B, P, C, n->Cout, t1, CP, (const T*)n->dec1_w, 0, C, nullptr, 0, SFNO_ACT_NONE, y, (int64_t)n->Cout * P);
     SFNO_TRY(launch_conv(d1c, st, "decoder1"));
+  }
+  // device-resident Philox state: the next forward (or the next replay of a captured graph) draws from a fresh stream
+  if (rng_dev && dropout) {
+    rng_advance_kernel<<<1, 1, 0, st>>>(rng_dev, (uint64_t)SFNO_RNG_OFFSETS_PER_FORWARD);
+    SFNO_TRY(post_launch("rng_advance"));
   }
   return SFNO_OK;
 }
@@ -569,7 +574,7 @@ size_t sfno_net_workspace_bytes(const sfno_net* n, int batch) {
 }
 
 static int forward_dispatch(sfno_net* n, const ConcatParts& parts, const float* time_dev, float* y_dev, int batch, int dropout_enabled,
-                            uint64_t seed, uint64_t offset, void* workspace_dev, size_t workspace_bytes, void* stream) {
+                            uint64_t seed, uint64_t offset, uint64_t* rng_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
   SFNO_CHECK_ARG(n && y_dev && workspace_dev, "NULL argument");
   SFNO_CHECK_ARG(batch > 0 && batch <= n->cfg.max_batch, "batch %d outside (0, max_batch=%d]", batch, n->cfg.max_batch);
   SFNO_CHECK_ARG((time_dev != nullptr) == (n->cfg.with_time_emb != 0), "time must be given iff with_time_emb");
@@ -583,8 +588,8 @@ static int forward_dispatch(sfno_net* n, const ConcatParts& parts, const float* 
   if (workspace_bytes < ws_layout(n, batch).total) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small: %zu < %zu", workspace_bytes, ws_layout(n, batch).total);
   cudaStream_t st = (cudaStream_t)stream;
   return n->cfg.precision == SFNO_PREC_BF16
-             ? forward_impl<bf16>(n, parts, time_dev, y_dev, batch, dropout_enabled, seed, offset, (char*)workspace_dev, st)
-             : forward_impl<float>(n, parts, time_dev, y_dev, batch, dropout_enabled, seed, offset, (char*)workspace_dev, st);
+             ? forward_impl<bf16>(n, parts, time_dev, y_dev, batch, dropout_enabled, seed, offset, rng_dev, (char*)workspace_dev, st)
+             : forward_impl<float>(n, parts, time_dev, y_dev, batch, dropout_enabled, seed, offset, rng_dev, (char*)workspace_dev, st);
 }
 
 int sfno_net_forward(sfno_net* n, const float* x_dev, const float* time_dev, float* y_dev, int batch, int dropout_enabled,
@@ -592,7 +597,7 @@ int sfno_net_forward(sfno_net* n, const float* x_dev, const float* time_dev, flo
   SFNO_CHECK_ARG(n && x_dev, "NULL argument");
   ConcatParts parts{};
   parts.src[0] = x_dev; parts.channels[0] = n->Cin; parts.nparts = 1;
-  return forward_dispatch(n, parts, time_dev, y_dev, batch, dropout_enabled, seed, offset, workspace_dev, workspace_bytes, stream);
+  return forward_dispatch(n, parts, time_dev, y_dev, batch, dropout_enabled, seed, offset, nullptr, workspace_dev, workspace_bytes, stream);
 }
 
 int sfno_net_forward_parts(sfno_net* n, const float* const* parts_dev, const int* part_channels, int nparts, const float* time_dev,
@@ -603,7 +608,27 @@ int sfno_net_forward_parts(sfno_net* n, const float* const* parts_dev, const int
   ConcatParts parts{};
   parts.nparts = nparts;
   for (int k = 0; k < nparts; ++k) { parts.src[k] = parts_dev[k]; parts.channels[k] = part_channels[k]; }
-  return forward_dispatch(n, parts, time_dev, y_dev, batch, dropout_enabled, seed, offset, workspace_dev, workspace_bytes, stream);
+  return forward_dispatch(n, parts, time_dev, y_dev, batch, dropout_enabled, seed, offset, nullptr, workspace_dev, workspace_bytes, stream);
+}
+
+int sfno_net_forward_parts_rng(sfno_net* n, const float* const* parts_dev, const int* part_channels, int nparts, const float* time_dev,
+                               float* y_dev, int batch, int dropout_enabled, uint64_t* rng_state_dev, void* workspace_dev,
+                               size_t workspace_bytes, void* stream) {
+  SFNO_CHECK_ARG(n && parts_dev && part_channels, "NULL argument");
+  SFNO_CHECK_ARG(nparts >= 1 && nparts <= 3, "between 1 and 3 input parts, got %d", nparts);
+  SFNO_CHECK_ARG(rng_state_dev != nullptr || !dropout_enabled, "dropout needs the device RNG state");
+  ConcatParts parts{};
+  parts.nparts = nparts;
+  for (int k = 0; k < nparts; ++k) { parts.src[k] = parts_dev[k]; parts.channels[k] = part_channels[k]; }
+  return forward_dispatch(n, parts, time_dev, y_dev, batch, dropout_enabled, 0, 0, rng_state_dev, workspace_dev, workspace_bytes, stream);
+}
+
+int sfno_param_fingerprint(const float* const* ptrs_dev, const int64_t* numel_dev, int count, uint64_t* out_dev, void* stream) {
+  SFNO_CHECK_ARG(ptrs_dev && numel_dev && out_dev && count > 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  SFNO_CUDA(cudaMemsetAsync(out_dev, 0, (size_t)count * sizeof(uint64_t), st));
+  param_fingerprint_kernel<<<dim3(96, (unsigned)count), 512, 0, st>>>(ptrs_dev, numel_dev, (unsigned long long*)out_dev);
+  return post_launch("param_fingerprint");
 }
 
 int64_t sfno_net_debug_tap(sfno_net* n, const char* name, float* dst_dev, int64_t capacity, void* workspace_dev, void* stream) {

@@ -397,6 +397,9 @@ struct ConvArgs {
   const float* bias; int64_t bias_bstride;
   int act;
   float drop_p; uint64_t seed, offset;    // dropout (after act), drop_p = 0 -> off
+  // graph-safe Philox state: when set, the stream key is {rng_dev[0], rng_dev[1] + offset} read on the device, so a
+  // captured CUDA graph draws fresh masks on every replay (the forward advances rng_dev[1] after its last kernel)
+  const uint64_t* rng_dev;
   const float* branch_scale;              // [batch] DropPath factor (0 or 1/keep) or nullptr
   const T* res; int64_t res_bstride;      // residual [b][cout][hw] or nullptr
   const float* res_a; const float* res_d; // [batch*cout] affine on the residual or nullptr
@@ -435,7 +438,7 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
     io_coords(this->res_bstride != 0 ? g : 0, row0, col0, c);
   }
   struct Row {
-    TOut* out; const T* res; bool valid; const T* pos; float bias, ra, rd, scale; uint64_t rng_base; f2 s2, q2;
+    TOut* out; const T* res; bool valid; const T* pos; float bias, ra, rd, scale; uint64_t rng_base, seed, offset; f2 s2, q2;
     __device__ float stat_s() const { return f2_hsum(s2); }
     __device__ float stat_q() const { return f2_hsum(q2); }
   };
@@ -447,7 +450,7 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
     r.s2 = f2_splat(0.0f); r.q2 = f2_splat(0.0f);
     r.out = this->out + (int64_t)g * this->out_bstride + off;
     r.bias = this->bias ? this->bias[(int64_t)g * this->bias_bstride + m] : 0.0f;
-    r.res = nullptr; r.ra = 1.0f; r.rd = 0.0f; r.pos = nullptr; r.scale = 1.0f; r.rng_base = 0;
+    r.res = nullptr; r.ra = 1.0f; r.rd = 0.0f; r.pos = nullptr; r.scale = 1.0f; r.rng_base = 0; r.seed = 0; r.offset = 0;
     if (feat_on<F, F_RES>(this->res != nullptr)) {
       r.res = this->res + (int64_t)g * this->res_bstride + off;
       if (this->res_a) r.ra = this->res_a[g * this->M + m];
@@ -458,6 +461,8 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
     if (dropping()) {   // the 1/keep factor of the dropout rides on the DropPath scale
       r.rng_base = ((uint64_t)g * this->M + m) * (uint64_t)this->N;
       r.scale *= dropout_keep_scale(dropout_threshold16(this->drop_p));
+      r.seed = this->rng_dev ? this->rng_dev[0] : this->seed;
+      r.offset = this->offset + (this->rng_dev ? this->rng_dev[1] : 0ull);
     }
     return r;
   }
@@ -468,7 +473,7 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
   }
   __device__ void store(const Row& r, int, int, int n, float acc) const {
     float v = act_ct<T, ACT>(this->act, acc + r.bias) * r.scale;
-    if (dropping() && !dropout_keep(this->seed, this->offset, r.rng_base + n, dropout_threshold16(this->drop_p))) v = 0.0f;
+    if (dropping() && !dropout_keep(r.seed, r.offset, r.rng_base + n, dropout_threshold16(this->drop_p))) v = 0.0f;
     if (r.res) v += fmaf(r.ra, to_f32(r.res[n]), r.rd);
     if (r.pos) v += to_f32(r.pos[n]);
     r.out[n] = from_f32<TOut>(v);
@@ -476,7 +481,7 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
   template <int F>
   __device__ void compute8(Row& r, int n, const float (&acc)[8], const float (&res)[8], float (&o)[8]) const {
     uint32_t keep = 0xffu;
-    if (dropping()) keep = dropout_keep_mask8(this->seed, this->offset, r.rng_base + n, dropout_threshold16(this->drop_p));
+    if (dropping()) keep = dropout_keep_mask8(r.seed, r.offset, r.rng_base + n, dropout_threshold16(this->drop_p));
     const f2 b2 = f2_splat(r.bias), sc2 = f2_splat(r.scale), ra2 = f2_splat(r.ra), rd2 = f2_splat(r.rd);
     float t[8];
     if (feat_on<F, F_POS>(r.pos != nullptr)) load_vec8(r.pos + n, t);

@@ -263,12 +263,31 @@ static __global__ void sinusoidal_kernel(const float* __restrict__ time, float s
 }
 
 // DropPath factor per sample (drop_path.py:5-22): floor(keep + U) / keep
-static __global__ void drop_path_scale_kernel(float* __restrict__ out, int B, float drop_prob, uint64_t seed, uint64_t offset) {
+static __global__ void drop_path_scale_kernel(float* __restrict__ out, int B, float drop_prob, uint64_t seed, uint64_t offset,
+                                              const uint64_t* __restrict__ rng_dev) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  if (rng_dev) { seed = rng_dev[0]; offset += rng_dev[1]; }   // device-resident Philox state (graph-safe)
   const float keep = 1.0f - drop_prob;
   const float u = philox_uniform(seed, offset, (uint64_t)b);
   out[b] = floorf(keep + u) / keep;
+}
+
+// device-resident Philox state {seed, offset}: one forward owns SFNO_RNG_OFFSETS_PER_FORWARD consecutive offsets
+constexpr unsigned SFNO_RNG_OFFSETS_PER_FORWARD = 4096;
+static __global__ void rng_advance_kernel(uint64_t* state, uint64_t by) { state[1] += by; }
+
+// position-weighted checksum of the bit patterns of `count` fp32 tensors, out[t] pre-zeroed (grid.y = tensor)
+static __global__ void param_fingerprint_kernel(const float* const* __restrict__ ptrs, const int64_t* __restrict__ numel,
+                                                unsigned long long* __restrict__ out) {
+  const int t = blockIdx.y;
+  const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(ptrs[t]);
+  const int64_t n = numel[t];
+  unsigned long long acc = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc += (unsigned long long)p[i] * (0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1) | 1ull);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc != 0) atomicAdd(out + t, acc);
 }
 
 // ---- conversions -----------------------------------------------------------------------------------------

@@ -3,10 +3,11 @@
 Members never interact inside the SFNO or the sampler, so rank r simply owns members {r, r+G, ...} and keeps their
 state resident on its GPU.  The only exchange is for the statistics of ``src/evaluation/metrics.py``:
 
-* mean / variance (``ensemble_spread`` :166-175, ``spread_skill_ratio`` :178-196): ``all_reduce(SUM)`` of
-  [sum x, sum x^2] accumulated locally by ``sfno_ensemble_accumulate``;
-* fair CRPS (``crps_ensemble`` :199-246): ``all_gather`` of the members, then the sorted-form kernel
-  ``sfno_ensemble_crps`` (no [E, E, ...] tensor is ever materialised).
+* mean / variance (``ensemble_spread`` :166-175, ``spread_skill_ratio`` :178-196) without a truth field:
+  ``all_reduce(SUM)`` of the local sums (a common pivot), then of the moments shifted by it
+  (``sfno_ensemble_local_sum`` / ``_shifted_moments``) -- the reference's two-pass ``var``, never sum(x^2) - E mean^2;
+* with a truth field (fair CRPS, ``crps_ensemble`` :199-246): ``all_gather`` of the members, then ONE fused kernel
+  (``sfno_ensemble_stats``: mean, two-pass variance, sorted-form CRPS; no [E, E, ...] tensor is ever materialised).
 
 Collectives are plain ``torch.distributed`` (NCCL over NVLink on the GPU box, Gloo in the CPU tests).  The local
 arithmetic runs through the C ABI on the GPU; ``ops`` exists so the CPU tests can exercise the sharding / collective
@@ -35,26 +36,46 @@ def max_local_members(n_members: int, world_size: int) -> int:
 class CudaEnsembleOps:
     """Local statistics kernels of libsfno_b200 (fp32, flattened [members, n])."""
 
-    def accumulate(self, members: torch.Tensor, sums: torch.Tensor) -> None:
+    def local_sum(self, members: torch.Tensor) -> torch.Tensor:
+        """Sum over this rank's members [n]; members may be empty."""
         assert members.is_cuda and members.dtype == torch.float32 and members.is_contiguous()
         E, n = members.shape
-        _lib.check(_lib.lib().sfno_ensemble_accumulate(members.data_ptr(), E, n, sums.data_ptr(), stream_ptr(members.device)),
-                   "sfno_ensemble_accumulate")
+        s = torch.empty(n, dtype=torch.float32, device=members.device)
+        _lib.check(_lib.lib().sfno_ensemble_local_sum(members.data_ptr() if E else None, E, n, s.data_ptr(),
+                                                      stream_ptr(members.device)), "sfno_ensemble_local_sum")
+        return s
 
-    def finalize(self, sums: torch.Tensor, total_members: int):
-        n = sums.shape[1]
-        mean = torch.empty(n, dtype=torch.float32, device=sums.device)
-        var = torch.empty(n, dtype=torch.float32, device=sums.device)
-        _lib.check(_lib.lib().sfno_ensemble_finalize(sums.data_ptr(), total_members, n, mean.data_ptr(), var.data_ptr(),
-                                                     stream_ptr(sums.device)), "sfno_ensemble_finalize")
+    def shifted_moments(self, members: torch.Tensor, sum_global: torch.Tensor, total_members: int) -> torch.Tensor:
+        """[2, n]: sum (x - p), sum (x - p)^2 of this rank's members about the common pivot p = sum_global / E."""
+        E, n = members.shape
+        mom = torch.empty(2, n, dtype=torch.float32, device=members.device)
+        _lib.check(_lib.lib().sfno_ensemble_shifted_moments(members.data_ptr() if E else None, E, n, sum_global.data_ptr(),
+                                                            total_members, mom.data_ptr(), stream_ptr(members.device)),
+                   "sfno_ensemble_shifted_moments")
+        return mom
+
+    def finalize(self, sum_global, moments, total_members: int):
+        n = sum_global.numel()
+        mean = torch.empty(n, dtype=torch.float32, device=sum_global.device)
+        var = torch.empty(n, dtype=torch.float32, device=sum_global.device)
+        _lib.check(_lib.lib().sfno_ensemble_finalize(sum_global.data_ptr(), moments.data_ptr(), total_members, n, mean.data_ptr(),
+                                                     var.data_ptr(), stream_ptr(sum_global.device)), "sfno_ensemble_finalize")
         return mean, var
 
-    def crps(self, members: torch.Tensor, truth: torch.Tensor) -> torch.Tensor:
+    def stats(self, members: torch.Tensor, truth: Optional[torch.Tensor]):
+        """All members [E, n] (after the gather) -> (mean, var, crps or None) in ONE pass over the members."""
+        assert members.is_cuda and members.dtype == torch.float32 and members.is_contiguous()
         E, n = members.shape
-        out = torch.empty(n, dtype=torch.float32, device=members.device)
-        _lib.check(_lib.lib().sfno_ensemble_crps(members.data_ptr(), truth.data_ptr(), E, n, out.data_ptr(),
-                                                 stream_ptr(members.device)), "sfno_ensemble_crps")
-        return out
+        mean = torch.empty(n, dtype=torch.float32, device=members.device)
+        var = torch.empty(n, dtype=torch.float32, device=members.device)
+        crps = torch.empty(n, dtype=torch.float32, device=members.device) if truth is not None else None
+        _lib.check(_lib.lib().sfno_ensemble_stats(members.data_ptr(), truth.data_ptr() if truth is not None else None, E, n,
+                                                  mean.data_ptr(), var.data_ptr(), crps.data_ptr() if crps is not None else None,
+                                                  stream_ptr(members.device)), "sfno_ensemble_stats")
+        return mean, var, crps
+
+    def crps(self, members: torch.Tensor, truth: torch.Tensor) -> torch.Tensor:
+        return self.stats(members, truth)[2]
 
 
 def weighted_mean(x: torch.Tensor, weights: Optional[torch.Tensor]) -> torch.Tensor:
@@ -82,16 +103,17 @@ class EnsembleStatistics:
         self.local_ids = member_shard(n_members, self.world, self.rank)
 
     def mean_var(self, local_members: torch.Tensor):
-        """local_members [E_local, ...] fp32 -> (mean [...], unbiased variance [...]) over ALL members."""
+        """local_members [E_local, ...] fp32 -> (mean [...], unbiased variance [...]) over ALL members, without gathering
+        them: all-reduce of the sums (-> common pivot), then of the shifted first / second moments about it."""
         shape = local_members.shape[1:]
         flat = local_members.reshape(local_members.shape[0], -1).contiguous()
-        n = flat.shape[1]
-        sums = torch.zeros(2, n, dtype=torch.float32, device=flat.device)
-        if flat.shape[0] > 0:
-            self.ops.accumulate(flat, sums)
+        s_glob = self.ops.local_sum(flat)
         if self.world > 1:
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
-        mean, var = self.ops.finalize(sums, self.n_members)
+            dist.all_reduce(s_glob, op=dist.ReduceOp.SUM, group=self.group)   # -> the common pivot p = sum / E
+        mom = self.ops.shifted_moments(flat, s_glob, self.n_members)
+        if self.world > 1:
+            dist.all_reduce(mom, op=dist.ReduceOp.SUM, group=self.group)
+        mean, var = self.ops.finalize(s_glob, mom, self.n_members)
         return mean.reshape(shape), var.reshape(shape)
 
     def gather_members(self, local_members: torch.Tensor) -> torch.Tensor:
@@ -116,15 +138,19 @@ class EnsembleStatistics:
         """Statistics the reference records per time step (``aggregators/timestepwise.py:131-177``):
         ensemble mean, spread = sqrt(weighted mean variance), and with a truth field: RMSE of the mean, spread-skill
         ratio (with the sqrt((E+1)/E) correction) and the fair CRPS.  Spatial dims are the last two."""
-        mean, var = self.mean_var(local_members)
+        E = self.n_members
+        if truth is None:
+            mean, var = self.mean_var(local_members)
+            return {"mean": mean, "var": var, "spread": torch.sqrt(weighted_mean(var, weights))}
+        # with a verification field the fair CRPS needs every member of a grid point on one rank: gather once, then ONE
+        # pass over the gathered members gives mean, two-pass variance and CRPS (no all-reduce, no [E, E, ...] tensor)
+        members = self.gather_members(local_members)
+        flat = members.reshape(E, -1).contiguous()
+        mean, var, crps = self.ops.stats(flat, truth.reshape(-1).contiguous())
+        mean, var, crps = mean.reshape(truth.shape), var.reshape(truth.shape), crps.reshape(truth.shape)
         out = {"mean": mean, "var": var, "spread": torch.sqrt(weighted_mean(var, weights))}
-        if truth is not None:
-            E = self.n_members
-            rmse = torch.sqrt(weighted_mean((mean - truth) ** 2, weights))
-            out["rmse"] = rmse
-            out["ssr"] = out["spread"] * ((E + 1) / E) ** 0.5 / rmse
-            members = self.gather_members(local_members)
-            flat = members.reshape(E, -1).contiguous()
-            crps = self.ops.crps(flat, truth.reshape(-1).contiguous()).reshape(truth.shape)
-            out["crps"] = weighted_mean(crps, weights)
+        rmse = torch.sqrt(weighted_mean((mean - truth) ** 2, weights))
+        out["rmse"] = rmse
+        out["ssr"] = out["spread"] * ((E + 1) / E) ** 0.5 / rmse
+        out["crps"] = weighted_mean(crps, weights)
         return out

@@ -14,6 +14,7 @@ op                                     replaces (reference file:line)
 ``sfno_b200::instance_norm``           ``nn.InstanceNorm2d`` ``sfnonet.py:641-647`` + ``time_scale_shift`` ``:280-287``
 ``sfno_b200::conv1x1``                 ``nn.Conv2d(.., 1)`` ``sfnonet.py:239,614-617,739-742``, ``layers.py:73-75``
 ``sfno_b200::net_forward``             ``SphericalFourierNeuralOperatorNet.forward`` ``sfnonet.py:797-841``
+``sfno_b200::cold_update``             ``x_s + (x_interpolated_s_next - x_interpolated_s)`` ``src/diffusion/dyffusion.py:519``
 =====================================  ==================================================================================
 """
 from __future__ import annotations
@@ -157,27 +158,52 @@ def _(x, weight, bias, residual, act):
 
 
 # ---- whole network -----------------------------------------------------------------------------------------------------
-@torch.library.custom_op("sfno_b200::net_forward", mutates_args=())
-def net_forward(net: int, parts: Sequence[torch.Tensor], time: Optional[torch.Tensor], out_channels: int, dropout: bool, seed: int,
-                offset: int) -> torch.Tensor:
+@torch.library.custom_op("sfno_b200::net_forward", mutates_args=("rng_state",))
+def net_forward(net: int, parts: Sequence[torch.Tensor], time: Optional[torch.Tensor], out_channels: int, dropout: bool,
+                rng_state: Optional[torch.Tensor]) -> torch.Tensor:
     """parts: the tensors the reference concatenates on dim 1 (inputs, condition, static condition), fp32 [B, c_i, H, W];
-    time fp32 [B] or None -> [B, out_channels, H, W] fp32.  `net` must have its parameters set (``sfno_net_set_param``)."""
+    time fp32 [B] or None -> [B, out_channels, H, W] fp32.  `net` must have its parameters set (``sfno_net_set_param``).
+    rng_state: int64 [2] = {seed, offset} on the device (the Philox key of the dropout masks; advanced by the call, so a
+    captured CUDA graph draws fresh masks on every replay); required iff ``dropout``."""
     x = parts[0]
     B = int(x.shape[0])
     out = torch.empty(B, out_channels, *x.shape[2:], dtype=torch.float32, device=x.device)
     if B == 0:
         return out
+    if dropout and (rng_state is None or rng_state.dtype != torch.int64 or rng_state.numel() != 2 or rng_state.device != x.device):
+        raise RuntimeError("net_forward with dropout needs rng_state: an int64 [2] tensor on the input's device")
     L = _lib.lib()
     with torch.cuda.device(x.device):
-        ws = workspace(x.device, L.sfno_net_workspace_bytes(_handle(net), B), "net")
+        ws = workspace(x.device, L.sfno_net_workspace_bytes(_handle(net), B), f"net{int(net)}")
         ptrs = (ctypes.c_void_p * len(parts))(*[t.data_ptr() for t in parts])
         chans = (ctypes.c_int * len(parts))(*[int(t.shape[1]) for t in parts])
-        _lib.check(L.sfno_net_forward_parts(_handle(net), ptrs, chans, len(parts), _ptr(time), out.data_ptr(), B, int(dropout), int(seed),
-                                            int(offset), ws.data_ptr(), ws.numel(), stream_ptr(x.device)), "sfno_net_forward_parts")
+        _lib.check(L.sfno_net_forward_parts_rng(_handle(net), ptrs, chans, len(parts), _ptr(time), out.data_ptr(), B, int(dropout),
+                                                _ptr(rng_state), ws.data_ptr(), ws.numel(), stream_ptr(x.device)),
+                   "sfno_net_forward_parts_rng")
     return out
 
 
 @net_forward.register_fake
-def _(net, parts, time, out_channels, dropout, seed, offset):
+def _(net, parts, time, out_channels, dropout, rng_state):
     x = parts[0]
     return x.new_empty(x.shape[0], out_channels, *x.shape[2:], dtype=torch.float32)
+
+
+# ---- sampler glue ---------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("sfno_b200::cold_update", mutates_args=())
+def cold_update(x_s: torch.Tensor, x_next: torch.Tensor, x_cur: torch.Tensor) -> torch.Tensor:
+    """``x_s + (x_next - x_cur)`` in one pass: the cold-sampling update of ``dyffusion.py:519``."""
+    a, b, c = (require_cuda_f32(t, "x") for t in (x_s, x_next, x_cur))
+    if not (a.shape == b.shape == c.shape):
+        raise RuntimeError(f"cold_update: shapes differ: {tuple(a.shape)}, {tuple(b.shape)}, {tuple(c.shape)}")
+    out = torch.empty_like(a)
+    if a.numel():
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.lib().sfno_cold_update(a.data_ptr(), b.data_ptr(), c.data_ptr(), out.data_ptr(), a.numel(),
+                                                   stream_ptr(a.device)), "sfno_cold_update")
+    return out
+
+
+@cold_update.register_fake
+def _(x_s, x_next, x_cur):
+    return torch.empty_like(x_s, dtype=torch.float32)

@@ -29,12 +29,12 @@ class EnsembleRollout:
         Returns per-recorded-step lists of the scalar statistics (per channel)."""
         dev = initial_condition.device
         n_local = len(self.stats.local_ids)
-        h = self.sampler.num_timesteps
+        h = self.sampler.horizon   # dynamical steps per window (num_timesteps also counts artificial diffusion steps)
         state = initial_condition.unsqueeze(0).expand(n_local, *initial_condition.shape).contiguous()
         # give every member its own dropout stream
         for net in (self.sampler.model, self.sampler.interpolator):
-            if hasattr(net, "dropout_seed"):
-                net.dropout_seed = 1 + self.stats.rank
+            if hasattr(net, "seed_dropout"):
+                net.seed_dropout(1 + self.stats.rank)
         history: Dict[str, List[torch.Tensor]] = {}
         step = 0
         while step < n_steps:
@@ -51,6 +51,8 @@ class EnsembleRollout:
                         if name in ("mean", "var"):
                             continue
                         history.setdefault(name, []).append(v)
-            state = preds[f"t{h}_preds"]
+            # the next window starts from the sampler's autoregressive initial state when it produces one
+            # (stepper_multistep.py:412-416, forecasting_multi_horizon.py:281), else from the last prediction
+            state = preds.get("preds_autoregressive_init", preds[f"t{h}_preds"])
             step += h
         return history

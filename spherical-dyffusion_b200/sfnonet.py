@@ -8,9 +8,13 @@ under the reference's names; the arithmetic of ``forward`` runs in ``sfno_net_fo
 hand-written sm_100a kernels).  There is no PyTorch fallback.
 
 Extra keywords (not in the reference): ``precision`` ("fp32" parity mode | "bf16" tcgen05 mode),
-``check_time_range`` (keep the reference's host-synchronising time assert, default True).  The forward only enqueues
-kernels, so it can be captured in a CUDA graph (``torch.cuda.graph``); the time assert is skipped during capture and the
-dropout stream offset is frozen into the graph.
+``check_time_range`` (keep the reference's host-synchronising time assert, default True), ``param_check`` (how in-place
+parameter updates are detected before a forward: "checksum" (default) fingerprints every parameter on the device and
+reads 8 bytes per tensor back -- catches ``p.data.copy_`` as used by the reference's EMA swap ``ema.py:54-91``;
+"version" trusts ``(data_ptr, _version)`` and ``invalidate_parameters()``, costs nothing and never synchronises).
+The forward only enqueues kernels, so it can be captured in a CUDA graph (``torch.cuda.graph``); the time assert and the
+checksum are skipped during capture, and the dropout masks are keyed on a device-resident Philox state that the forward
+itself advances, so every replay of a captured graph draws fresh masks.
 """
 from __future__ import annotations
 
@@ -24,7 +28,7 @@ import torch.nn as nn
 from . import _lib
 from ._base_model import ALL_DROPOUT_LAYERS, BaseModel, DropPath
 from . import ops as _ops  # noqa: F401  (registers torch.ops.sfno_b200.*)
-from ._util import require_cuda_f32, stream_ptr, workspace
+from ._util import release_workspace, require_cuda_f32, stream_ptr, workspace
 from .harmonics import InverseRealSHT, RealSHT
 
 
@@ -188,6 +192,7 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
         data_grid: Literal["legendre-gauss", "equiangular"] = "equiangular",
         precision: str = "fp32",
         check_time_range: bool = True,
+        param_check: str = "checksum",
         **kwargs,
     ):
         super().__init__(**kwargs)
@@ -222,6 +227,8 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
             raise NotImplementedError("encoder_layers!=1 / use_mlp=False / filter or pos-emb dropout / checkpointing are not built")
         if precision not in _lib.SFNO_PREC:
             raise ValueError(f"Unknown precision {precision}")
+        if param_check not in ("checksum", "version"):
+            raise ValueError(f"Unknown param_check {param_check}")
 
         self.params = params or {}
         self.spectral_transform, self.filter_type, self.operator_type = spectral_transform, filter_type, operator_type
@@ -239,6 +246,7 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
         self.big_skip = big_skip
         self.precision = precision
         self.check_time_range = check_time_range
+        self.param_check = param_check
         self.mlp_ratio = mlp_ratio
         self.dropout_mlp = dropout_mlp
         self.drop_path_rate = drop_path_rate
@@ -308,8 +316,12 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
         self._net = None          # sfno_net handle (created on first CUDA forward)
         self._net_device = None
         self._param_versions: dict = {}
-        self._calls = 0           # forward counter -> Philox offset, so successive calls draw fresh masks
-        self.dropout_seed = 0
+        self._fp_table = None     # device tables of the fingerprint kernel (pointers, sizes), rebuilt when storage moves
+        self._fp_values = None    # fingerprints recorded at the last upload (host tensor)
+        self._rng_state = None    # int64 [2] on the device: {seed, offset} of the dropout Philox stream
+        self._rng_key = None      # (seed, offset) the state was last initialised from
+        self.dropout_seed = 0     # assigning it (or dropout_offset) re-keys the stream at the next forward
+        self.dropout_offset = 0
 
     # ---- reference helpers -------------------------------------------------------------------------------------
     def _init_weights(self, m):
@@ -338,11 +350,33 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
     def _destroy_net(self):
         if self.__dict__.get("_net") is not None:
             try:
+                release_workspace(self._net_device, f"net{int(self._net.value)}")
                 _lib.lib().sfno_net_destroy(self._net)
             except Exception:
                 pass
         self._net, self._net_device = None, None
         self._param_versions = {}
+        self._fp_table, self._fp_values = None, None
+
+    def invalidate_parameters(self):
+        """Force a re-upload of every parameter at the next forward.  Call it after writing parameters through a path
+        autograd's version counter does not see (``p.data.copy_``: the reference's EMA ``copy_to`` / ``restore``,
+        ``ema.py:54-91``) when the module runs with ``param_check="version"``; ``load_state_dict`` and ``_apply``
+        (``.to()``, ``.float()``) call it themselves."""
+        self._param_versions = {}
+        self._fp_values = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_parameters()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if "_param_versions" in self.__dict__:
+            self.invalidate_parameters()
+            self._rng_state, self._rng_key = None, None
+        return out
 
     def __del__(self):
         try:
@@ -387,26 +421,75 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
         self._net, self._net_device = handle, device
         self._expected = _lib.lib().sfno_net_param_names(handle).decode().split("\n")
 
+    def _fingerprints(self, device, params):
+        """One launch over all parameters -> host int64 tensor of position-weighted checksums (synchronises)."""
+        ptrs = [p.data_ptr() for p in params]
+        if self._fp_table is None or self._fp_table[0] != ptrs:
+            tp = torch.tensor(ptrs, dtype=torch.int64).to(device)
+            tn = torch.tensor([p.numel() for p in params], dtype=torch.int64).to(device)
+            self._fp_table = (ptrs, tp, tn, torch.empty(len(params), dtype=torch.int64, device=device))
+        _, tp, tn, out = self._fp_table
+        _lib.check(_lib.lib().sfno_param_fingerprint(tp.data_ptr(), tn.data_ptr(), len(params), out.data_ptr(), stream_ptr(device)),
+                   "sfno_param_fingerprint")
+        return out.cpu()
+
     def sync_parameters(self, device, force: bool = False):
-        """(Re)pack every parameter whose storage or version changed since the last upload.  EMA swaps and
-        ``load_state_dict`` mutate parameters in place (``ema.py:54-91``), which bumps ``_version``."""
+        """(Re)pack every parameter that changed since the last upload.  ``load_state_dict``, optimiser steps and in-place
+        tensor methods bump ``_version``; writes through ``p.data`` (the reference's EMA swap, ``ema.py:54-91``) do not --
+        ``param_check="checksum"`` compares a device-side fingerprint of the values instead (skipped while a CUDA graph
+        is being captured: nothing may synchronise there, and a replay re-runs the captured kernels on the packed copies
+        anyway)."""
         L = _lib.lib()
         sd = dict(self.named_parameters())
         st = stream_ptr(device)
+        params = []
         for name in self._expected:
             p = sd.get(name)
             if p is None:
                 raise KeyError(f"the native net expects parameter {name!r} which this module does not hold")
             if p.device != device:
                 raise RuntimeError(f"parameter {name} lives on {p.device}, inputs on {device}: move the model with .to()/.cuda()")
+            params.append(p)
+        fp = None
+        plain = all(p.dtype == torch.float32 and p.is_contiguous() for p in params)
+        if self.param_check == "checksum" and plain and not torch.cuda.is_current_stream_capturing():
+            fp = self._fingerprints(device, params)
+        for i, (name, p) in enumerate(zip(self._expected, params)):
             key = (p.data_ptr(), p._version)
-            if not force and self._param_versions.get(name) == key:
+            same = self._param_versions.get(name) == key
+            if same and fp is not None and (self._fp_values is None or int(self._fp_values[i]) != int(fp[i])):
+                same = False
+            if not force and same:
                 continue
             v = p.detach()
             if v.dtype != torch.float32 or not v.is_contiguous():
                 v = v.float().contiguous()
             _lib.check(L.sfno_net_set_param(self._net, name.encode(), v.data_ptr(), v.numel(), st), f"sfno_net_set_param({name})")
             self._param_versions[name] = key
+        if fp is not None:
+            self._fp_values = fp
+
+    def refresh_parameters(self):
+        """Eagerly bring the packed device copies up to date (a captured CUDA graph replays kernels that read them)."""
+        if self._net is not None:
+            with torch.cuda.device(self._net_device):
+                self.sync_parameters(self._net_device)
+
+    def seed_dropout(self, seed: int, offset: int = 0):
+        """Re-key the dropout Philox stream: the next forward with live dropout draws from (seed, offset), every later
+        one from the following sub-stream (ensemble members differ only by this key)."""
+        self.dropout_seed, self.dropout_offset = int(seed), int(offset)
+        self._rng_key = None
+
+    def _rng(self, device):
+        """Device-resident Philox state {seed, offset}; (re)initialised when ``dropout_seed`` / ``dropout_offset`` change."""
+        key = (int(self.dropout_seed), int(self.dropout_offset))
+        if self._rng_state is None or self._rng_state.device != device or self._rng_key != key:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("the dropout RNG state must exist before a CUDA-graph capture: run one eager forward first")
+            self._rng_state = torch.tensor(list(key), dtype=torch.int64).to(device)
+            self._rng_key = key
+        return self._rng_state
 
     def dropout_active(self) -> bool:
         """True when any dropout layer is in training state (``dyffusion.py:226-235`` inference dropout)."""
@@ -470,14 +553,13 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
             self._ensure_net(device)
             self.sync_parameters(device)
             drop = self.dropout_active()
-            self._calls += 1
-            # custom-op layer (ops.py) -> sfno_net_forward_parts of the C ABI
+            # custom-op layer (ops.py) -> sfno_net_forward_parts_rng of the C ABI
             out = torch.ops.sfno_b200.net_forward(self._net.value, parts, time if self.with_time_emb else None, self.out_chans,
-                                                  bool(drop), int(self.dropout_seed), int(self._calls) * 4096)
+                                                  bool(drop), self._rng(device) if drop else None)
             t_repr = None
             if return_time_emb and self.with_time_emb:
                 t_repr = torch.empty(B, self.time_dim, dtype=torch.float32, device=device)
-                ws = workspace(device, L.sfno_net_workspace_bytes(self._net, B), "net")
+                ws = workspace(device, L.sfno_net_workspace_bytes(self._net, B), f"net{int(self._net.value)}")
                 _lib.check(L.sfno_net_debug_tap(self._net, b"t_repr", t_repr.data_ptr(), t_repr.numel(), ws.data_ptr(),
                                                 stream_ptr(device)), "sfno_net_debug_tap")
         out = out.to(in_dtype) if in_dtype != torch.float32 else out
@@ -496,7 +578,7 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
             try:
                 self.forward(inputs, time=time, condition=condition, static_condition=static_condition)
                 B = x.shape[0]
-                ws = workspace(device, L.sfno_net_workspace_bytes(self._net, B), "net")
+                ws = workspace(device, L.sfno_net_workspace_bytes(self._net, B), f"net{int(self._net.value)}")
                 act = torch.empty(B, self.embed_dim, *self.img_shape, dtype=torch.float32, device=device)
                 _lib.check(L.sfno_net_debug_tap(self._net, b"x", act.data_ptr(), act.numel(), ws.data_ptr(), stream_ptr(device)))
             finally:

@@ -13,20 +13,26 @@ from spherical_dyffusion_b200.ensemble import EnsembleStatistics, area_weights, 
 
 
 class TorchOps:
-    def accumulate(self, members, sums):
-        sums[0] += members.sum(0)
-        sums[1] += (members * members).sum(0)
+    """torch stand-in with the interface of CudaEnsembleOps (two-pass / Chan moments, pairwise CRPS)."""
 
-    def finalize(self, sums, total):
-        mean = sums[0] / total
-        var = (sums[1] - total * mean * mean) / (total - 1)
-        return mean, var.clamp_min(0)
+    def local_sum(self, members):
+        return members.sum(0)
+
+    def shifted_moments(self, members, sum_global, total_members):
+        d = members - sum_global / total_members
+        return torch.stack([d.sum(0), (d * d).sum(0)])
+
+    def finalize(self, sum_global, mom, total):
+        return sum_global / total + mom[0] / total, (mom[1] - mom[0] ** 2 / total) / (total - 1)
 
     def crps(self, members, truth):
         E = members.shape[0]
         skill = (members - truth).abs().mean(0)
         spread = (members[None] - members[:, None]).abs().sum((0, 1)) / (E * (E - 1))
         return skill - 0.5 * spread
+
+    def stats(self, members, truth):
+        return members.mean(0), members.var(dim=0), (self.crps(members, truth) if truth is not None else None)
 
 
 def test_member_shard_partition():
@@ -65,6 +71,11 @@ def _worker(rank, world, port, E, results):
         out = stats.step(local, truth=truth, weights=weights)
         ref = _reference_metrics(members, truth, weights)
         ok = all(torch.allclose(out[k], ref[k], rtol=1e-4, atol=1e-5) for k in ref)
+        # without a truth field: no gather, two all-reduces (sums -> pivot, shifted moments); a large offset must not hurt
+        big = local + 1.0e5
+        nt = stats.step(big, weights=weights)
+        ok = ok and torch.allclose(nt["var"], (members + 1.0e5).var(dim=0), rtol=2e-3, atol=1e-4)
+        ok = ok and torch.allclose(nt["mean"], (members + 1.0e5).mean(0), rtol=1e-6)
         gathered = stats.gather_members(local)
         ok = ok and torch.equal(gathered, members)
         results[rank] = bool(ok)

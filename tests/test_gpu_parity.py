@@ -235,6 +235,22 @@ def test_net_parameter_resync_after_inplace_update(dev, load_golden):
     m.load_state_dict(fx["state_dict"])
     with torch.inference_mode():
         assert rel_l2(m(x, time=t, condition=c), fx["output"]) < FP32_TOL
+    # the reference's EMA swap writes through .data (ema.py:54-91 copy_to / restore): autograd's version counter does
+    # not move, the device-side fingerprint (param_check="checksum", the default) must catch it
+    versions = [p._version for p in m.parameters()]
+    for p in m.parameters():
+        p.data.copy_(p.data * 1.5)
+    assert versions == [p._version for p in m.parameters()]
+    with torch.inference_mode():
+        assert rel_l2(m(x, time=t, condition=c), ref) < FP32_TOL
+    # param_check="version" trusts the counter: stale until invalidate_parameters() is called
+    m.param_check = "version"
+    for p in m.parameters():
+        p.data.copy_(p.data / 1.5)
+    with torch.inference_mode():
+        assert rel_l2(m(x, time=t, condition=c), ref) < FP32_TOL          # still the x1.5 weights
+        m.invalidate_parameters()
+        assert rel_l2(m(x, time=t, condition=c), fx["output"]) < FP32_TOL
 
 
 def test_net_time_assert_and_static_condition(dev, load_golden):
@@ -260,10 +276,10 @@ def test_net_inference_dropout_statistics(dev):
     with torch.inference_mode():
         y_det = m(x)
         with m.inference_dropout_scope(condition=True):
-            m._calls = 100
+            m.seed_dropout(0, 100 * 4096)
             y1 = m(x)
             y2 = m(x)
-            m._calls = 100
+            m.seed_dropout(0, 100 * 4096)
             y1b = m(x)
         y_det2 = m(x)
     assert torch.equal(y_det, y_det2)
@@ -321,25 +337,46 @@ def test_ace_forward_bf16_bound(dev, ace_case):
 # ensemble statistics kernels (metrics.py:166-175,199-246)
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("E", [2, 7, 25])
-def test_ensemble_statistics(dev, E):
+@pytest.mark.parametrize("n", [34 * 60 * 12, 1003])
+def test_ensemble_statistics(dev, E, n):
+    """Shifted moments of two member shards about the common pivot (the two-rank path on one GPU), the fused one-pass
+    statistics kernel, and both at a large offset (|mean| >> spread: surface pressure) and an n % 4 != 0 tail."""
+    from spherical_dyffusion_b200.ensemble import CudaEnsembleOps
+
     g = torch.Generator().manual_seed(E)
-    n = 34 * 60 * 12
-    mem = torch.randn(E, n, generator=g) * 2 + 1
-    truth = torch.randn(n, generator=g)
-    L = sb.lib()
-    md, td = mem.to(dev), truth.to(dev)
-    sums = torch.zeros(2, n, device=dev)
-    _lib.check(L.sfno_ensemble_accumulate(md[: E // 2].data_ptr(), E // 2, n, sums.data_ptr(), stream_ptr(dev)))
-    _lib.check(L.sfno_ensemble_accumulate(md[E // 2:].data_ptr(), E - E // 2, n, sums.data_ptr(), stream_ptr(dev)))
-    mean, var = torch.empty(n, device=dev), torch.empty(n, device=dev)
-    _lib.check(L.sfno_ensemble_finalize(sums.data_ptr(), E, n, mean.data_ptr(), var.data_ptr(), stream_ptr(dev)))
-    assert rel_l2(mean, mem.mean(0)) < 1e-6
-    assert rel_l2(var, mem.var(0)) < 1e-4
-    crps = torch.empty(n, device=dev)
-    _lib.check(L.sfno_ensemble_crps(md.data_ptr(), td.data_ptr(), E, n, crps.data_ptr(), stream_ptr(dev)))
-    skill = (mem - truth).abs().mean(0)
-    spread = (mem[None] - mem[:, None]).abs().sum((0, 1)) / (E * (E - 1))
-    assert rel_l2(crps, skill - 0.5 * spread) < 1e-5
+    ops = CudaEnsembleOps()
+    for offset, var_tol in ((1.0, 1e-5), (1.0e5, 2e-3)):
+        mem = torch.randn(E, n, generator=g) * 2 + offset
+        truth = torch.randn(n, generator=g) + offset
+        md, td = mem.to(dev), truth.to(dev)
+        ref_var = mem.double().var(0).float()
+        a, b = md[: E // 2].contiguous(), md[E // 2:].contiguous()
+        s_glob = ops.local_sum(a) + ops.local_sum(b)
+        mom = ops.shifted_moments(a, s_glob, E) + ops.shifted_moments(b, s_glob, E)
+        mean, var = ops.finalize(s_glob, mom, E)
+        assert rel_l2(mean, mem.double().mean(0).float()) < 1e-6
+        assert rel_l2(var, ref_var) < var_tol
+        mean2, var2, crps = ops.stats(md, td)
+        assert rel_l2(mean2, mem.double().mean(0).float()) < 1e-6
+        assert rel_l2(var2, ref_var) < var_tol
+        skill = (mem - truth).abs().mean(0)
+        spread = (mem[None] - mem[:, None]).abs().sum((0, 1)) / (E * (E - 1))
+        assert rel_l2(crps, skill - 0.5 * spread) < (1e-5 if offset == 1.0 else 2e-2)
+        # the raw-moment form this replaces loses everything at the large offset
+        raw = ((mem * mem).sum(0) - E * mem.mean(0) ** 2) / (E - 1)
+        if offset > 1.0:
+            assert rel_l2(raw, ref_var) > 10 * rel_l2(var, ref_var)
+
+
+def test_cold_update_kernel(dev):
+    """x_s + (x_next - x_cur) of dyffusion.py:519 in one launch (vector path, scalar tail, unaligned views)."""
+    g = torch.Generator().manual_seed(3)
+    for shape in ((2, 34, 12, 24), (1, 3, 5, 7)):
+        a, b, c = (torch.randn(*shape, generator=g).to(dev) for _ in range(3))
+        out = torch.ops.sfno_b200.cold_update(a, b, c)
+        assert torch.equal(out, a + (b - c))
+    a, b, c = (torch.randn(1001, generator=g).to(dev)[1:] for _ in range(3))
+    assert torch.equal(torch.ops.sfno_b200.cold_update(a, b, c), a + (b - c))
 
 
 @pytest.mark.parametrize("case", ["e2", "e5_ties", "e8", "e25"])
