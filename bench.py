@@ -44,6 +44,8 @@ def peaks():
 def workload_config(args):
     return {"workload": f"ACE SFNO forecaster forward 36->34ch embed256 x8 blocks dhconv 180x360, batch {args.batch}/GPU",
             "batch_per_gpu": args.batch, "precision": args.precision,
+            "check_time_range": False,   # the drop-in default (True) adds the reference's per-forward host sync (sfnonet.py:777-782)
+            "param_check": "version",    # the drop-in default ("checksum") fingerprints the parameters every forward (+0.15 ms, one sync)
             "baseline_config": "BASELINE.json configs[0] (ACE-sized SFNO, 180x360) at configs[2]'s batch 8 / bf16; configs[1,3,4] = "
                                "bench_extra.py sht / rollout / scaled",
             "l2": "per-step working set (>= 2.5 GB of activations) exceeds the 126 MB L2; no explicit flush"}
@@ -182,7 +184,8 @@ def build_b200_case(batch, precision, seed, dev):
     on `dev`, synthetic N(0,1) host inputs [batch,34,180,360] + forcings [batch,2,180,360], time 3.  Nothing of oracle/."""
     from spherical_dyffusion_b200 import configs
 
-    model = configs.build(configs.ACE_FORECASTER, precision=precision, seed=seed, min_max_time=(0, 5), check_time_range=False)
+    model = configs.build(configs.ACE_FORECASTER, precision=precision, seed=seed, min_max_time=(0, 5), check_time_range=False,
+                          param_check="version")
     model = model.to(dev).eval()
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(batch, 34, 180, 360, generator=g)
@@ -302,7 +305,7 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": workload_config(args),
+        "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic", "config": workload_config(args),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x.numel() * 4 + c.numel() * 4),
                 "d2h_bytes_per_step": int(y_pin.numel() * 4)},
         "gpu_launches": int(launches),
@@ -315,6 +318,15 @@ def run_b200(args):
             "model_flops_frac_of_bf16_peak": value / world * FLOP_PER_SAMPLE / 1e12 / pk["bf16_tflops_sustained"],
         },
     }
+
+    # ---- BASELINE.json configs[3]: sharded 25-member ensemble rollout with the NCCL statistics gather (all ranks) ----
+    if not args.no_rollout:
+        del x_buf, c_buf
+        torch.cuda.empty_cache()
+        try:
+            line["ensemble_rollout"] = run_rollout(args, dev, world, rank)
+        except Exception as exc:
+            line["ensemble_rollout"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         # ---- roofline of the dominant kernel, timed live by the library with CUDA events on the launch stream ----
@@ -336,6 +348,74 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_rollout(args, dev, world, rank):
+    """BASELINE.json configs[3]: a 25-member ensemble rollout sharded member-major over the ranks (1/2/4/8 GPUs), every
+    rank advancing its members as one batch through DYffusion sampling windows (6 forecaster + 10 interpolator forwards
+    per window, interpolator dropout live, one captured CUDA graph per window), with the per-step ensemble statistics of
+    src/evaluation/metrics.py:166-246 (mean, spread, RMSE, spread-skill ratio, fair CRPS) INSIDE the timed region:
+    NCCL all-gather of the members + one fused statistics kernel per 6-hour step.  The reference loops over the members
+    sequentially at batch 1 (src/ace_inference/inference/loop.py:199-208)."""
+    import torch.distributed as dist
+
+    from spherical_dyffusion_b200 import configs
+    from spherical_dyffusion_b200.dyffusion import DYffusion
+    from spherical_dyffusion_b200.ensemble import EnsembleStatistics, area_weights, max_local_members
+    from spherical_dyffusion_b200.rollout import EnsembleRollout
+
+    members, windows, h = args.rollout_members, args.rollout_windows, 6
+    kw = dict(precision=args.precision, check_time_range=False, param_check="version")
+    fore = configs.build(configs.ACE_FORECASTER, seed=0, min_max_time=(0.0, 5.0), **kw).to(dev).eval()
+    ipol = configs.build(configs.ACE_INTERPOLATOR, seed=1, min_max_time=(1.0, 5.0), **kw).to(dev).eval()
+    dy = DYffusion(fore, ipol, timesteps=h, forward_conditioning="none", time_encoding="dynamics",
+                   capture_graph=not args.no_graph, graph_outputs="view")
+    stats = EnsembleStatistics(members)
+    weights = area_weights(torch.linspace(-89.5, 89.5, 180), 360).to(dev)
+    g = torch.Generator().manual_seed(0)   # the same initial condition, forcing and verification field on every rank
+    ic = torch.randn(34, 180, 360, generator=g).to(dev)
+    base_forcing = torch.randn(2, 180, 360, generator=g).to(dev)
+    truth = torch.randn(34, 180, 360, generator=g).to(dev)
+
+    def forcing_fn(step, n, d):
+        return (base_forcing * (1.0 + 0.01 * step)).unsqueeze(0).expand(n, -1, -1, -1).contiguous()
+
+    ro = EnsembleRollout(dy, stats, forcing_fn, truth_fn=lambda s, d: truth, weights=weights)
+    ro.run(ic, n_steps=h)    # warm-up window (creates the nets, captures the window graph)
+    ro.run(ic, n_steps=h)
+    ro.time_stats = True
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    hist = ro.run(ic, n_steps=windows * h)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1), ro.stats_ms()], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_stats = float(t[0]), float(t[1])
+    steps = windows * h
+    steps_per_s = steps / (ms * 1e-3)
+    local = max_local_members(members, world)
+    out = {
+        "workload": f"{members}-member ensemble rollout, {windows} windows = {steps} x 6-h steps, member-major over {world} GPU(s), "
+                    f"interpolator dropout on, per-step mean/spread/rmse/ssr/fair-CRPS (all-gather + fused kernel) inside the timed region",
+        "members": members, "windows": windows, "steps": steps, "max_local_members": local,
+        "ideal_speedup_vs_1gpu": members / local, "ms_total": ms, "ensemble_steps_per_s": steps_per_s,
+        "ensemble_sypd": steps_per_s * 86400.0 / STEPS_PER_YEAR, "member_steps_per_s_aggregate": steps_per_s * members,
+        "statistics_ms_total": ms_stats, "statistics_share": ms_stats / ms,
+        "statistics_bytes_gathered_per_step": int(members * 34 * 180 * 360 * 4) if world > 1 else 0,
+        "window_graph": bool(not args.no_graph), "forwards_per_window": dy.forwards_per_window(),
+        "last_crps_mean": float(hist["crps"][-1].mean()), "last_spread_mean": float(hist["spread"][-1].mean()),
+    }
+    dy.release_graphs()
+    del ro, dy, fore, ipol
+    torch.cuda.empty_cache()
+    return out
+
+
 def model_roofline(model, xd, td, cd, pk):
     """Per-kernel device times of one forward (CUDA events inside the library) -> roofline of the dominant kernel."""
     from spherical_dyffusion_b200.profile import profile_forward, roofline_from_profile
@@ -351,8 +431,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rollout", action="store_true", help="skip the ensemble-rollout leg (configs[3])")
+    ap.add_argument("--no-graph", action="store_true", help="ensemble rollout: eager windows instead of one CUDA graph per window")
+    ap.add_argument("--rollout-members", type=int, default=25)
+    ap.add_argument("--rollout-windows", type=int, default=10)
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 3
@@ -361,8 +445,8 @@ def main():
         args.warmup = min(args.warmup, 2)
         run_reference(args)
     else:
-        args.steps = args.steps if args.steps is not None else 20
-        args.warmup = args.warmup if args.warmup is not None else 3
+        args.steps = args.steps if args.steps is not None else 100   # ~1.2 s timed region: >= 10 clock samples
+        args.warmup = args.warmup if args.warmup is not None else 5
         run_b200(args)
 
 

@@ -13,7 +13,10 @@
  *   - handles are re-entrant per handle (one in-flight call per handle and stream)
  *   - `precision`: SFNO_PREC_F32 = fp32 storage, fp32 CUDA-core FMA accumulate (parity mode,
  *                  <= 1e-4 rel-L2 vs the fp32 reference); SFNO_PREC_BF16 = bf16 storage, tcgen05
- *                  tensor-core MMA with fp32 TMEM accumulators (throughput mode, stated bf16 bound)
+ *                  tensor-core MMA with fp32 TMEM accumulators (throughput mode, stated bf16 bound);
+ *                  SFNO_PREC_TF32 = fp32 storage, tcgen05 kind::tf32 MMA (operands rounded to TF32 by
+ *                  their producers, fp32 accumulation): what the reference computes under
+ *                  torch.set_float32_matmul_precision("high") (src/utilities/config_utils.py:310-313)
  */
 #ifndef SFNO_B200_H_
 #define SFNO_B200_H_
@@ -37,7 +40,7 @@ typedef enum sfno_status {
 } sfno_status;
 
 enum { SFNO_GRID_LEGENDRE_GAUSS = 0, SFNO_GRID_EQUIANGULAR = 1 };
-enum { SFNO_PREC_F32 = 0, SFNO_PREC_BF16 = 1 };
+enum { SFNO_PREC_F32 = 0, SFNO_PREC_BF16 = 1, SFNO_PREC_TF32 = 2 };
 enum { SFNO_OP_DHCONV = 0, SFNO_OP_DIAGONAL = 1 };
 enum { SFNO_ACT_NONE = 0, SFNO_ACT_GELU = 1, SFNO_ACT_RELU = 2, SFNO_ACT_SILU = 3 };
 
@@ -218,6 +221,27 @@ int sfno_ensemble_crps(const float* members_dev, const float* truth_dev, int mem
  *   x_out = x_s + (x_next - x_cur)   in one pass (x_out may alias x_s); fp32, n elements. */
 int sfno_cold_update(const float* x_s_dev, const float* x_next_dev, const float* x_cur_dev, float* x_out_dev,
                      int64_t n, void* stream);
+
+/* ---- rollout step glue -----------------------------------------------------------------
+ * The state of an autoregressive rollout stays packed [batch][channels][hw] on the device; each side of the sampler is
+ * one launch.
+ * sfno_normalize_pack: StandardNormalizer.normalize (src/ace_inference/core/normalizer.py:96-112) + Packer.pack
+ *   (packer.py:71-77): out[b][c][p] = (fields[c][b][p] - mean[c]) / std[c]; fields_dev is a DEVICE array of `channels`
+ *   device pointers to independent [batch][hw] fp32 tensors (the reference's dict of named fields); mean_dev / std_dev
+ *   [channels] or NULL (0 / 1). */
+int sfno_normalize_pack(const float* const* fields_dev, int channels, int batch, int64_t hw, const float* mean_dev,
+                        const float* std_dev, float* out_dev, void* stream);
+/* sfno_prescribe_denormalize: Prescriber.__call__ (src/ace_inference/core/prescriber.py:68-95) on the packed normalised
+ *   prediction, in place (the result seeds the next window, stepper_multistep.py:402-421), fused with
+ *   StandardNormalizer.denormalize (normalizer.py:105-112) into gen_denorm_dev (may be NULL):
+ *     channel == prescribed_channel:  interpolate ? mask * target + (1 - mask) * gen
+ *                                                 : (int(round(mask)) == mask_value ? target : gen)
+ *   target_norm_dev / mask_dev: [batch][hw] with the given sample strides (0 = one field shared by all samples);
+ *   prescribed_channel < 0: no prescriber (denormalise only). */
+int sfno_prescribe_denormalize(float* gen_norm_dev, const float* target_norm_dev, int64_t target_bstride,
+                               const float* mask_dev, int64_t mask_bstride, int prescribed_channel, int mask_value,
+                               int interpolate, const float* mean_dev, const float* std_dev, float* gen_denorm_dev,
+                               int channels, int batch, int64_t hw, void* stream);
 
 /* ---- parameter fingerprints ---------------------------------------------------------------------------
  * out_dev[i] = position-weighted 64-bit checksum of the bit patterns of tensor i (ptrs_dev[i], numel_dev[i] fp32

@@ -93,6 +93,16 @@ def sht_tables(nlat: int, nlon: int, lmax: int | None, mmax: int | None, grid: s
     return weights, pct, lmax, mmax
 
 
+def round_tf32(t: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest TF32 value (10-bit mantissa), kept in fp32: the operand rounding of a TF32 matmul.  Used only to
+    EMULATE what the reference computes under ``torch.set_float32_matmul_precision("high")``
+    (``src/utilities/config_utils.py:310-313``) next to the B200 library's tf32 mode; the parity oracle is fp32."""
+    if t.dtype != torch.float32:
+        return t
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 # ----------------------------------------------------------------------------------------------
 # modules with the attributes the reference reads (.nlat .nlon .lmax .mmax .grid, .float())
 # ----------------------------------------------------------------------------------------------
@@ -113,6 +123,8 @@ class RealSHT(nn.Module):
         xf = 2.0 * torch.pi * torch.fft.rfft(x, dim=-1, norm="forward")
         xf = torch.view_as_real(xf)
         w = self.weights.to(xf.dtype)
+        if getattr(self, "tf32_matmul", False):
+            xf, w = round_tf32(xf), round_tf32(w)
         re = torch.einsum("...km,mlk->...lm", xf[..., : self.mmax, 0], w)
         im = torch.einsum("...km,mlk->...lm", xf[..., : self.mmax, 1], w)
         return torch.view_as_complex(torch.stack((re, im), dim=-1).contiguous())
@@ -134,6 +146,8 @@ class InverseRealSHT(nn.Module):
         assert x.shape[-1] == self.mmax
         xr = torch.view_as_real(x)
         p = self.pct.to(xr.dtype)
+        if getattr(self, "tf32_matmul", False):
+            xr, p = round_tf32(xr), round_tf32(p)
         re = torch.einsum("...lm,mlk->...km", xr[..., 0], p)
         im = torch.einsum("...lm,mlk->...km", xr[..., 1], p)
         xs = torch.view_as_complex(torch.stack((re, im), dim=-1).contiguous())

@@ -155,7 +155,12 @@ def _act(name):
     return {"gelu": F.gelu, "relu": F.relu, "silu": F.silu}[name]
 
 
+_TF32_MATMUL = False   # set by SFNOOracle(tf32_matmul=True) around its forward: emulation of TF32 matmuls, see harmonics.round_tf32
+
+
 def _conv1x1(x, w, b=None):
+    if _TF32_MATMUL:
+        x, w = harmonics.round_tf32(x), harmonics.round_tf32(w)
     return F.conv2d(x, w, b)
 
 
@@ -192,6 +197,9 @@ def time_scale_shift(x, t_repr, w, b):
 
 def dhconv_contract(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """contractions.py:159-169: ``einsum('bixy,iox->boxy')`` on complex views; w is real [i,o,l,2]."""
+    if _TF32_MATMUL:
+        x = torch.view_as_complex(harmonics.round_tf32(torch.view_as_real(x)))
+        w = harmonics.round_tf32(w)
     return torch.einsum("bixy,iox->boxy", x, torch.view_as_complex(w.contiguous()))
 
 
@@ -203,8 +211,13 @@ def diagonal_contract(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
 class SFNOOracle:
     """Functional restatement of ``SphericalFourierNeuralOperatorNet.forward`` (sfnonet.py:797-841)."""
 
-    def __init__(self, cfg: SFNOConfig, state_dict: Dict[str, torch.Tensor], dtype=torch.float32):
+    def __init__(self, cfg: SFNOConfig, state_dict: Dict[str, torch.Tensor], dtype=torch.float32, tf32_matmul: bool = False):
+        """``tf32_matmul=True`` rounds the operands of every 1x1 convolution, Legendre contraction and spectral channel
+        contraction to TF32 -- an emulation of the reference under ``torch_matmul_precision: high``
+        (``config_utils.py:310-313``) used to put the tf32 mode's error next to the reference's own; parity is always
+        judged against the plain fp32 oracle."""
         assert cfg.normalization_layer in ("instance_norm", "none")
+        self.tf32_matmul = tf32_matmul
         assert cfg.encoder_layers == 1
         self.cfg = cfg
         self.dtype = dtype
@@ -218,6 +231,8 @@ class SFNOOracle:
         self.itrans_up = harmonics.InverseRealSHT(H, W, lmax=L, mmax=M, grid=cfg.data_grid).to(dtype)
         self.trans = harmonics.RealSHT(h, w, lmax=L, mmax=M, grid="legendre-gauss").to(dtype)
         self.itrans = harmonics.InverseRealSHT(h, w, lmax=L, mmax=M, grid="legendre-gauss").to(dtype)
+        for t in (self.trans_down, self.itrans_up, self.trans, self.itrans):
+            t.tf32_matmul = tf32_matmul
         # sfnonet.py:622 -- stochastic depth schedule
         self.dpr = [x.item() for x in torch.linspace(0, cfg.drop_path_rate, cfg.num_layers)]
         self.inference_dropout = False  # dyffusion.py:226-235 turns dropout layers on at sampling time
@@ -299,6 +314,14 @@ class SFNOOracle:
 
     @torch.inference_mode()
     def forward(self, inputs, time=None, condition=None, static_condition=None, return_time_emb=False):
+        global _TF32_MATMUL
+        prev, _TF32_MATMUL = _TF32_MATMUL, self.tf32_matmul
+        try:
+            return self._forward(inputs, time, condition, static_condition, return_time_emb)
+        finally:
+            _TF32_MATMUL = prev
+
+    def _forward(self, inputs, time=None, condition=None, static_condition=None, return_time_emb=False):
         cfg, sd = self.cfg, self.sd
         dt = self.dtype
         # _base_model.py:166-192

@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SFNO_B200_LIB") or os.path.join(PKG_DIR, "libsfno_b200.so")
 
 SFNO_GRID = {"legendre-gauss": 0, "equiangular": 1}
-SFNO_PREC = {"fp32": 0, "float32": 0, "bf16": 1, "bfloat16": 1}
+SFNO_PREC = {"fp32": 0, "float32": 0, "bf16": 1, "bfloat16": 1, "tf32": 2}
 SFNO_OP = {"dhconv": 0, "diagonal": 1}
 SFNO_ACT = {"none": 0, "gelu": 1, "relu": 2, "silu": 3}
 
@@ -79,6 +79,9 @@ _SIGNATURES = {
     "sfno_ensemble_finalize": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "sfno_ensemble_stats": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfno_ensemble_crps": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "sfno_normalize_pack": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sfno_prescribe_denormalize": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+                                           c_void_p, c_int, c_int, c_int64, c_void_p]),
     "sfno_cold_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 

@@ -34,8 +34,24 @@ namespace sfno {
 #endif
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;
+constexpr int TC_BK = 64;          // K block of the bf16 engine in elements (= one 128-byte swizzle span)
 constexpr int TC_SLICE_COLS = 64;  // accumulator columns drained by one epilogue warp
+
+// Operand element of the engine: bf16 (kind::f16) or fp32 storage consumed as TF32 (kind::tf32: the tensor core reads
+// the upper 19 bits; producers round to TF32 so that nothing is truncated).  One K block is always one 128-byte swizzle
+// span and one MMA always covers 32 bytes of K, so shared-memory stage sizes and MMA counts per block do not depend on
+// the element; only the element counts do.
+template <class TIn> struct TcElem;
+template <> struct TcElem<bf16> {
+  static constexpr int kBytes = 2, kBK = 64, kUmmaK = 16, kAtom = 64;   // kAtom: elements of one 128-byte MN-major atom row
+  static constexpr uint32_t kFormat = 1;                                 // UMMA F16F32Format::BF16
+  static constexpr CUtensorMapDataType kTmaType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+};
+template <> struct TcElem<float> {
+  static constexpr int kBytes = 4, kBK = 32, kUmmaK = 8, kAtom = 32;
+  static constexpr uint32_t kFormat = 2;                                 // UMMA F16F32Format::TF32
+  static constexpr CUtensorMapDataType kTmaType = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+};
 constexpr int tc_epi_warps(int bn) { return 4 * (bn / TC_SLICE_COLS); }   // 4 TMEM sub-partitions x column slices
 constexpr int tc_threads(int bn) { return 64 + 32 * tc_epi_warps(bn); }
 constexpr int TC_WARP_TMA = 0, TC_WARP_MMA = 1;
@@ -49,10 +65,13 @@ struct TmaOperand {
   int replicas = 0;                  // > 1: a shared operand stored `replicas` times along dims[2]; CTA i reads copy i % replicas
 };
 
-// Epilogue I/O through TMA: the output (and the residual / addend block) as a 5-D tensor whose 128-byte x 8-row
-// boxes are exactly the 1024-byte groups of a warp's swizzled staging rows.  Eight consecutive GEMM rows must map to
-// a box of the tensor (box_rows = extents of dims[1..4], product 8); shapes that cannot guarantee it are not eligible
-// for this engine.
+// Epilogue I/O through TMA: the output (and the residual / addend block) as a 5-D tensor whose 128-byte-wide boxes
+// are the swizzled staging rows of an epilogue warp: either ONE box of all 32 rows (one TMA instruction per warp and
+// pass) or four boxes of 8 rows.  A warp-divergent TMA instruction is executed as a serial loop over the issuing
+// lanes whose iterations wait for the previous one to release its uniform registers (measured: 14-26 % of the stall
+// samples of the conv / DFT kernels, profiles/r02_d_source_stalls.md), so the 32-row form is used whenever 32
+// consecutive GEMM rows map to a box of the tensor (box_rows = extents of dims[1..4], product 32 or 8); shapes that
+// cannot guarantee even 8 are not eligible for this engine.
 struct TmaIo {
   const void* base = nullptr;
   int es = 2;                               // element size: 2 (bf16) or 4 (fp32)
@@ -63,10 +82,11 @@ struct TmaIo {
 };
 
 struct TcSched {
-  int m_tiles, n_tiles, groups, num_tiles, k_blocks, k16_last;  // k16_last: MMAs (K=16) in the last k block
+  int m_tiles, n_tiles, groups, num_tiles, k_blocks, k16_last;  // k16_last: MMAs (32 bytes of K each) in the last k block
   int a_batched, b_batched;
   int a_glo, b_glo;  // > 0: the operand's group index splits into {g % glo, g / glo} (4-D tensor map)
   int a_rep, b_rep;  // > 1: shared operand replicated along dims[2]: this CTA reads copy blockIdx.x % rep
+  int out_box32, res_box32;   // the output / residual tensor map has 32-row boxes (one TMA instruction per warp and pass)
   // role-wait profile (tc_debug bit7) or nullptr: cycles summed over CTAs {producer waits for a free stage, MMA waits
   // for operands, MMA waits for a free accumulator, epilogue warp 0 waits for the accumulator, epilogue warp 0 waits
   // for the residual block, CTA lifetime, epilogue warp 0 busy, CTAs}
@@ -192,6 +212,19 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <class TIn>
+__device__ __forceinline__ void mma_elem(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (sizeof(TIn) == 2) mma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+  else mma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
 // mbarrier arrive when all previously issued MMAs of this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -228,19 +261,20 @@ __device__ __forceinline__ bool elect_one() {
 }  // namespace ptx
 
 // ---- descriptors -----------------------------------------------------------------------------------------
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1, SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1); layout 2 = SWIZZLE_128B (16-byte chunks),
+// 1 = SWIZZLE_128B_BASE32B (32-byte chunks, 4-row period): the only layout the hardware accepts for MN-major tf32 operands
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  d |= (uint64_t)layout << 61;
   return d;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> fp32, M = 128
-__host__ __device__ constexpr uint32_t make_idesc(bool a_mn_major, bool b_mn_major, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+// instruction descriptor (cute::UMMA::InstrDescriptor): fmt x fmt -> fp32, M = 128; fmt 1 = bf16, 2 = tf32
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn_major, bool b_mn_major, int n, uint32_t fmt = 1) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
@@ -249,7 +283,7 @@ constexpr int TC_STAGING_PER_WARP = 32 * TC_STAGE_PITCH;  // 32 rows
 
 template <int BN, bool kStaging, bool kDual = false, int kBufs = 1>
 struct TcSmem {
-  static constexpr int kAHalfBytes = TC_BM * TC_BK * 2;
+  static constexpr int kAHalfBytes = TC_BM * TC_BK * 2;          // rows x 128 bytes: the same for bf16 (BK 64) and tf32 (BK 32)
   static constexpr int kABytes = (kDual ? 2 : 1) * kAHalfBytes;   // dual-M: two 128-row A tiles share one B tile
   static constexpr int kBBytes = BN * TC_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -290,6 +324,8 @@ __global__ void __launch_bounds__(tc_threads(BN), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res, const Op op, const TcSched sc) {
   using S = TcSmem<BN, Op::kColContig, kDual, Op::kStagingBufs>;
+  using E = TcElem<typename Op::InT>;
+  constexpr int kBK = E::kBK;              // K block in elements (one 128-byte swizzle span)
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = 512;  // two accumulator stages of up to 256 fp32 columns, or (dual-M) one stage of two
   constexpr int kBMT = kDual ? 2 * TC_BM : TC_BM;   // rows per tile
@@ -382,22 +418,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // every CTA walks the K blocks of its tile from its own starting block (and wraps): at any instant the CTAs
         // that share an operand (basis, table, weights) read different K slices of it, which spreads the broadcast
         // over more L2 slices.  fp32 accumulation order differs per CTA but is fixed by the static schedule.
-        const int kbeg = op.k_begin(g) / TC_BK, nkb = sc.k_blocks - kbeg;
+        const int kbeg = op.k_begin(g) / kBK, nkb = sc.k_blocks - kbeg;
         const int rot = (Op::kRanged || (sc.dbg & 512)) ? 0 : (int)(blockIdx.x % (unsigned)nkb);   // (spectral ops: measured neutral / slower)
         for (int ik = 0; ik < nkb; ++ik) {
           const int kb = kbeg + (ik + rot < nkb ? ik + rot : ik + rot - nkb);
           w_empty += ptx::mbar_wait<true>(empty_bar(stage), phase ^ 1u, timed);
           const bool load_a = !(sc.dbg & 1), load_b = !(sc.dbg & 2);
           ptx::mbar_expect_tx(full_bar(stage), (load_a ? halves * S::kAHalfBytes : 0) + (load_b ? S::kBBytes : 0));
-          const int k0 = kb * TC_BK;
+          const int k0 = kb * kBK;
+          // MN-major operands arrive as atoms of E::kAtom elements (128 bytes) x kBK k-rows
           for (int hf = 0; hf < (load_a ? halves : 0); ++hf) {
             const int mh = m0 + hf * TC_BM;
             if (Op::A_KCONTIG) {
               ptx::tma_load_4d(a_smem(stage, hf), &tma_a, full_bar(stage), k0, mh, ga, ga_hi);
             } else {
 #pragma unroll
-              for (int h = 0; h < TC_BM / 64; ++h)
-                ptx::tma_load_4d(a_smem(stage, hf) + h * (64 * TC_BK * 2), &tma_a, full_bar(stage), mh + 64 * h, k0, ga, ga_hi);
+              for (int h = 0; h < TC_BM / E::kAtom; ++h)
+                ptx::tma_load_4d(a_smem(stage, hf) + h * (kBK * 128), &tma_a, full_bar(stage), mh + E::kAtom * h, k0, ga, ga_hi);
             }
           }
           if (!load_b) {
@@ -405,8 +442,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             ptx::tma_load_4d(b_smem(stage), &tma_b, full_bar(stage), k0, n0, gb, gb_hi);
           } else {
 #pragma unroll
-            for (int h = 0; h < BN / 64; ++h)
-              ptx::tma_load_4d(b_smem(stage) + h * (64 * TC_BK * 2), &tma_b, full_bar(stage), n0 + 64 * h, k0, gb, gb_hi);
+            for (int h = 0; h < BN / E::kAtom; ++h)
+              ptx::tma_load_4d(b_smem(stage) + h * (kBK * 128), &tma_b, full_bar(stage), n0 + E::kAtom * h, k0, gb, gb_hi);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -420,11 +457,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else if (warp == TC_WARP_MMA) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(!Op::A_KCONTIG, !Op::B_KCONTIG, BN);
-      // K-major: 8-row atoms of 1024 B (SBO), K advance 32 B per MMA.  MN-major: 64-element atoms, next atom along
-      // M/N after BK rows of 128 B (LBO = 8192), next 8 k-rows after 1024 B (SBO), K advance 2048 B per MMA.
-      constexpr uint32_t a_lbo = Op::A_KCONTIG ? 16u : (uint32_t)(TC_BK * 128), a_kstep = Op::A_KCONTIG ? 32u : 2048u;
-      constexpr uint32_t b_lbo = Op::B_KCONTIG ? 16u : (uint32_t)(TC_BK * 128), b_kstep = Op::B_KCONTIG ? 32u : 2048u;
+      constexpr uint32_t idesc = make_idesc(!Op::A_KCONTIG, !Op::B_KCONTIG, BN, E::kFormat);
+      // K-major: 8-row atoms of 1024 B (SBO), K advance 32 B per MMA.  MN-major: 128-byte atoms, next atom along
+      // M/N after BK k-rows of 128 B (LBO), next 8 k-rows after 1024 B (SBO), K advance = kUmmaK k-rows of 128 B per MMA
+      // (bf16: LBO 8192, 2048 B per MMA; tf32: LBO 4096, 1024 B per MMA).
+      // MN-major tf32 operands use the 32-byte-chunk swizzle (TMA: SWIZZLE_128B_ATOM_32B): atoms of 4 k-rows (SBO 512).
+      constexpr uint32_t kMnStep = (uint32_t)(E::kUmmaK * 128);
+      constexpr bool kMn32 = sizeof(typename Op::InT) == 4;
+      constexpr uint32_t a_lbo = Op::A_KCONTIG ? 16u : (uint32_t)(kBK * 128), a_kstep = Op::A_KCONTIG ? 32u : kMnStep;
+      constexpr uint32_t b_lbo = Op::B_KCONTIG ? 16u : (uint32_t)(kBK * 128), b_kstep = Op::B_KCONTIG ? 32u : kMnStep;
+      constexpr uint32_t a_sbo = (!Op::A_KCONTIG && kMn32) ? 512u : 1024u, a_layout = (!Op::A_KCONTIG && kMn32) ? 1u : 2u;
+      constexpr uint32_t b_sbo = (!Op::B_KCONTIG && kMn32) ? 512u : 1024u, b_layout = (!Op::B_KCONTIG && kMn32) ? 1u : 2u;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       long long w_full = 0, w_tempty = 0;
@@ -432,7 +475,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         int g, mt, nt;
         decode(g, mt, nt);
         if (tile_skipped(g, mt, nt)) continue;
-        const int kb0 = op.k_begin(g) / TC_BK;
+        const int kb0 = op.k_begin(g) / kBK;
         const int halves = (kDual && op.m_begin(g) + mt * kBMT + TC_BM < op.m_end(g)) ? 2 : 1;
         w_tempty += ptx::mbar_wait<true>(tempty_bar(acc), acc_phase ^ 1u, timed);
         ptx::tc_fence_after();
@@ -443,12 +486,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const int kb = kb0 + (ik + rot < nkb ? ik + rot : ik + rot - nkb);
           w_full += ptx::mbar_wait<true>(full_bar(stage), phase, timed);
           ptx::tc_fence_after();
-          const int nk = (kb == sc.k_blocks - 1) ? sc.k16_last : TC_BK / 16;
+          const int nk = (kb == sc.k_blocks - 1) ? sc.k16_last : kBK / E::kUmmaK;
           for (int k = 0; k < nk; ++k) {
-            const uint64_t bd = make_smem_desc(b_smem(stage) + k * b_kstep, b_lbo, 1024u);
+            const uint64_t bd = make_smem_desc(b_smem(stage) + k * b_kstep, b_lbo, b_sbo, b_layout);
             for (int hf = 0; hf < halves; ++hf) {
-              const uint64_t ad = make_smem_desc(a_smem(stage, hf) + k * a_kstep, a_lbo, 1024u);
-              if (!(sc.dbg & 16)) ptx::mma_bf16(d_tmem + (uint32_t)(hf * BN), ad, bd, idesc, (ik != 0 || k != 0) ? 1u : 0u);
+              const uint64_t ad = make_smem_desc(a_smem(stage, hf) + k * a_kstep, a_lbo, a_sbo, a_layout);
+              if (!(sc.dbg & 16)) ptx::mma_elem<typename Op::InT>(d_tmem + (uint32_t)(hf * BN), ad, bd, idesc, (ik != 0 || k != 0) ? 1u : 0u);
             }
           }
           ptx::mma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
@@ -503,27 +546,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         uint32_t my_row = region + (uint32_t)lane * TC_STAGE_PITCH;
         const uint32_t sw = (uint32_t)(lane & 7);
         const int n_end = op.n_store();
-        const bool has_res = (kEs == 2) && feat_on<F, F_RES>(op.has_res());
+        // residual / addend blocks are staged by TMA: bf16 outputs cover the warp's 64-column slice with one staging
+        // buffer; fp32 outputs need two 32-column passes, i.e. both buffers of a double-buffered staging area
+        static_assert(kEs == 2 || kEs == 4, "outputs are bf16 or fp32");
+        constexpr bool kResOk = (kEs == 2) || (kBufs == 2 && kPasses == 2);
+        const bool has_res = kResOk && feat_on<F, F_RES>(op.has_res());
         const bool valid = row_ok && row.valid;
         // all 32 rows outside the live range, or the column slice beyond the last column: nothing to drain
         const bool warp_live = __any_sync(0xffffffffu, valid) && n_base < n_end;
-        // epilogue I/O by TMA: lanes 0..3 each own one 8-row x 128-byte group (1024 B) of the warp's staging rows
-        const int grow0 = m_tile0 + quad * 32 + 8 * lane;   // first GEMM row of this lane's group (lanes 0..3)
-        const bool gissue = lane < 4 && grow0 < op.m_end(g);
+        // epilogue I/O by TMA: lane 0 moves the warp's 32 staging rows as one box, or lanes 0..3 each move one 8-row x
+        // 128-byte group (1024 B) of them
+        const bool out32 = sc.out_box32 != 0, res32 = sc.res_box32 != 0;
+        const int wrow0 = m_tile0 + quad * 32;               // first GEMM row of the warp
+        const int grow0 = wrow0 + 8 * lane;                  // first GEMM row of this lane's 8-row group (lanes 0..3)
+        const bool gissue = out32 ? (lane == 0 && wrow0 < op.m_end(g)) : (lane < 4 && grow0 < op.m_end(g));
         auto staging_free = [&]() {   // the TMA store that last read this staging buffer has finished reading it
           if (lane < 4) { if (kBufs == 2) ptx::bulk_wait_read1(); else ptx::bulk_wait_read(); }
           __syncwarp();
         };
-        // residual / addend block (bf16 outputs only): TMA load straight into the staging rows, issued BEFORE waiting
-        // for the accumulator so that its latency hides behind the MMA of this tile
+        // residual / addend block: TMA load straight into the staging rows, issued BEFORE waiting for the accumulator
+        // so that its latency hides behind the MMA of this tile
         if (has_res && warp_live) {
-          staging_free();
-          if (lane == 0) ptx::mbar_expect_tx(res_bar(ew), 4 * 1024);
+          if (kEs == 2) staging_free();
+          else { if (lane < 4) ptx::bulk_wait_read(); __syncwarp(); }   // fp32: both buffers are about to be refilled
+          const int res_passes = (kEs == 2 || n_end - (n_base + kPassCols) <= 0) ? 1 : 2;
+          if (lane == 0) ptx::mbar_expect_tx(res_bar(ew), (uint32_t)res_passes * 4 * 1024);
           __syncwarp();
-          if (lane < 4) {
-            int c[5];
-            op.res_coords(g, grow0, n_base, c);
-            ptx::tma_load_5d(region + (uint32_t)lane * 1024u, &tma_res, res_bar(ew), c);
+          if (res32 ? lane == 0 : lane < 4) {   // (rows outside the tensor are zero-filled and still count as bytes)
+            for (int rp = 0; rp < res_passes; ++rp) {
+              int c[5];
+              op.res_coords(g, res32 ? wrow0 : grow0, n_base + rp * kPassCols, c);
+              const uint32_t buf = staging_base + ((uint32_t)ew * kBufs + (kBufs == 2 ? (sbuf ^ (uint32_t)rp) : 0u)) * TC_STAGING_PER_WARP;
+              ptx::tma_load_5d(buf + (res32 ? 0u : (uint32_t)lane * 1024u), &tma_res, res_bar(ew), c);
+            }
           }
         }
         bool released = false;
@@ -542,7 +597,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           int nvalid = n_end - pn0;
           nvalid = nvalid < pcols ? nvalid : pcols;
           if (nvalid <= 0) break;  // warp-uniform
-          if (has_res) {           // (kPasses == 1 whenever has_res)
+          if (has_res && pass == 0) {   // one barrier phase covers every staged pass of the tile
             w_res += ptx::mbar_wait(res_bar(ew), res_phase, timed);
             res_phase ^= 1u;
           }
@@ -563,12 +618,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               sts128(slot, make_uint4(pack_bf16x2(outv[0], outv[1]), pack_bf16x2(outv[2], outv[3]),
                                       pack_bf16x2(outv[4], outv[5]), pack_bf16x2(outv[6], outv[7])));
             } else {
-              op.template compute8<F>(row, pn0 + cofs, accv, resv, outv);
               const uint32_t c4 = (uint32_t)cofs >> 2;  // 16-byte chunk index (4 floats)
-              sts128(my_row + ((c4 ^ sw) << 4), make_uint4(__float_as_uint(outv[0]), __float_as_uint(outv[1]),
-                                                           __float_as_uint(outv[2]), __float_as_uint(outv[3])));
-              sts128(my_row + (((c4 + 1) ^ sw) << 4), make_uint4(__float_as_uint(outv[4]), __float_as_uint(outv[5]),
-                                                                 __float_as_uint(outv[6]), __float_as_uint(outv[7])));
+              const uint32_t slot0 = my_row + ((c4 ^ sw) << 4), slot1 = my_row + (((c4 + 1) ^ sw) << 4);
+              if (has_res) {
+                const uint4 u0 = lds128(slot0), u1 = lds128(slot1);
+                resv[0] = __uint_as_float(u0.x); resv[1] = __uint_as_float(u0.y); resv[2] = __uint_as_float(u0.z); resv[3] = __uint_as_float(u0.w);
+                resv[4] = __uint_as_float(u1.x); resv[5] = __uint_as_float(u1.y); resv[6] = __uint_as_float(u1.z); resv[7] = __uint_as_float(u1.w);
+              }
+              op.template compute8<F>(row, pn0 + cofs, accv, resv, outv);
+              if (op.out_tf32()) {   // the tensor is an operand of a later tf32 MMA: round here, the MMA would truncate
+#pragma unroll
+                for (int i = 0; i < 8; ++i) outv[i] = tf32_rna(outv[i]);
+              }
+              sts128(slot0, make_uint4(__float_as_uint(outv[0]), __float_as_uint(outv[1]), __float_as_uint(outv[2]), __float_as_uint(outv[3])));
+              sts128(slot1, make_uint4(__float_as_uint(outv[4]), __float_as_uint(outv[5]), __float_as_uint(outv[6]), __float_as_uint(outv[7])));
             }
           };
           const int nchunks = (nvalid + 31) >> 5;
@@ -644,8 +707,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           __syncwarp();
           if (gissue && !(sc.dbg & 4)) {
             int c[5];
-            op.io_coords(g, grow0, pn0, c);
-            ptx::tma_store_5d(&tma_out, region + (uint32_t)lane * 1024u, c);
+            op.io_coords(g, out32 ? wrow0 : grow0, pn0, c);
+            ptx::tma_store_5d(&tma_out, region + (out32 ? 0u : (uint32_t)lane * 1024u), c);
+            if constexpr (Op::kSplitBox) {   // 32 rows that straddle two planes of the output: a second, clipped box
+              if (out32 && op.io_coords_second(g, wrow0, pn0, c)) ptx::tma_store_5d(&tma_out, region, c);
+            }
           }
           if (lane < 4) ptx::bulk_commit();
           sbuf = (kBufs == 2) ? (sbuf ^ 1u) : 0u;
@@ -700,7 +766,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled get_encode_tiled();
 int tc_num_sms();
 
+template <class TIn>
 inline int encode_operand(const TmaOperand& o, bool k_contig, int rows_box, CUtensorMap* map, const char* what) {
+  using E = TcElem<TIn>;
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return fail(SFNO_ERR_CUDA, "%s: cuTensorMapEncodeTiled unavailable", what);
   cuuint64_t dims[4] = {o.dims[0], o.dims[1], o.dims[2], o.dims[3]};
@@ -708,11 +776,13 @@ inline int encode_operand(const TmaOperand& o, bool k_contig, int rows_box, CUte
   for (int i = 1; i < 3; ++i)
     if (dims[i + 1] == 1) strides[i] = strides[i - 1] * dims[i];  // extent-1 dimension: any valid multiple of 16
   cuuint32_t box[4] = {1, 1, 1, 1};
-  if (k_contig) { box[0] = TC_BK; box[1] = (cuuint32_t)rows_box; }
-  else { box[0] = 64; box[1] = TC_BK; }
+  if (k_contig) { box[0] = E::kBK; box[1] = (cuuint32_t)rows_box; }
+  else { box[0] = E::kAtom; box[1] = E::kBK; }
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(o.base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  // MN-major tf32 tiles must sit in shared memory with the 32-byte-chunk variant of the 128-byte swizzle
+  const CUtensorMapSwizzle swz = (!k_contig && E::kBytes == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = enc(map, E::kTmaType, 4, const_cast<void*>(o.base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(SFNO_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d): base=%p dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) box=(%u,%u)",
@@ -752,8 +822,9 @@ inline bool tma_io_ok(const TmaIo& o) {
   }
   for (int i = 0; i < 5; ++i)
     if (o.dims[i] == 0 || o.dims[i] > (1ull << 31)) return false;
-  return rows == 8;
+  return rows == 8 || rows == 32;
 }
+inline int tma_io_rows(const TmaIo& o) { return (int)(o.box_rows[0] * o.box_rows[1] * o.box_rows[2] * o.box_rows[3]); }
 
 inline bool tma_operand_ok(const TmaOperand& o) {
   if (((uintptr_t)o.base & 15) != 0) return false;
@@ -775,8 +846,9 @@ int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what) {
   TmaOperand a, b;
   Tr::operands(op, a, b);
   CUtensorMap ma, mb, mo, mr;
-  SFNO_TRY(encode_operand(a, Op::A_KCONTIG, TC_BM, &ma, what));
-  SFNO_TRY(encode_operand(b, Op::B_KCONTIG, BN, &mb, what));
+  using E = TcElem<typename Op::InT>;
+  SFNO_TRY(encode_operand<typename Op::InT>(a, Op::A_KCONTIG, TC_BM, &ma, what));
+  SFNO_TRY(encode_operand<typename Op::InT>(b, Op::B_KCONTIG, BN, &mb, what));
   TmaIo io_out, io_res;
   Tr::io(op, io_out, io_res);
   if (!tma_io_ok(io_out)) return fail(SFNO_ERR_UNSUPPORTED, "%s: output tensor is not expressible as TMA boxes (eligibility not checked?)", what);
@@ -794,15 +866,17 @@ int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what) {
   const int64_t tiles = (int64_t)sc.m_tiles * sc.n_tiles * sc.groups;
   if (tiles > (1ll << 30)) return fail(SFNO_ERR_UNSUPPORTED, "%s: too many tiles", what);
   sc.num_tiles = (int)tiles;
-  sc.k_blocks = ceil_div(op.K, TC_BK);
-  const int k_rem = op.K - (sc.k_blocks - 1) * TC_BK;
-  sc.k16_last = ceil_div(k_rem, 16);
+  sc.k_blocks = ceil_div(op.K, E::kBK);
+  const int k_rem = op.K - (sc.k_blocks - 1) * E::kBK;
+  sc.k16_last = ceil_div(k_rem, E::kUmmaK);
   sc.a_batched = a.batched ? 1 : 0;
   sc.b_batched = b.batched ? 1 : 0;
   sc.a_glo = a.group_lo;
   sc.b_glo = b.group_lo;
   sc.a_rep = a.replicas;
   sc.b_rep = b.replicas;
+  sc.out_box32 = tma_io_rows(io_out) == 32;
+  sc.res_box32 = Tr::has_residual(op) && tma_io_rows(io_res) == 32;
   sc.dbg = g_tc_debug.load(std::memory_order_relaxed);
   sc.prof = (sc.dbg & 128) ? tc_prof_buffer() : nullptr;
   static bool attr_set = false;

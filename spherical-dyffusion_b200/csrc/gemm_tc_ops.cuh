@@ -1,4 +1,5 @@
-// TMA operand descriptions of the bf16 ops for the tcgen05 engine (which tensor, which extents, which strides).
+// TMA operand descriptions of the ops for the tcgen05 engine (which tensor, which extents, which strides), for bf16
+// storage (kind::f16) and fp32 storage consumed as TF32 (kind::tf32).
 // Extents are the exact logical sizes: TMA zero-fills everything outside, so K / row tails need no padding.
 #pragma once
 #include "gemm_tc.cuh"
@@ -30,140 +31,152 @@ struct TcEligible {
   }
 };
 
-template <>
-struct TcTraits<OpDft<bf16>> : TcTraitsBase<OpDft<bf16>>, TcEligible<TcTraits<OpDft<bf16>>, OpDft<bf16>> {
+template <class T>
+struct TcTraits<OpDft<T>> : TcTraitsBase<OpDft<T>>, TcEligible<TcTraits<OpDft<T>>, OpDft<T>> {
   static constexpr int BN = 192;
-  static void operands(const OpDft<bf16>& op, TmaOperand& a, TmaOperand& b) {
+  static constexpr uint64_t es = sizeof(T);
+  static void operands(const OpDft<T>& op, TmaOperand& a, TmaOperand& b) {
     a.base = op.A; a.dims[0] = op.nlon; a.dims[1] = op.M;                 // basis rows (m,ri), K-contiguous, shared
-    a.strides[0] = (uint64_t)op.Wp * 2; a.batched = false;
-    if (op.a_reps > 1) { a.dims[2] = op.a_reps; a.strides[1] = (uint64_t)op.M * op.Wp * 2; a.replicas = op.a_reps; }
+    a.strides[0] = (uint64_t)op.Wp * es; a.batched = false;
+    if (op.a_reps > 1) { a.dims[2] = op.a_reps; a.strides[1] = (uint64_t)op.M * op.Wp * es; a.replicas = op.a_reps; }
     b.base = op.Bm; b.dims[0] = op.nlon; b.dims[1] = op.nlat; b.dims[2] = op.C; b.dims[3] = op.B;  // {j, k, c, b}
-    b.strides[0] = (uint64_t)op.nlon * 2; b.strides[1] = (uint64_t)op.nlat * op.nlon * 2; b.strides[2] = (uint64_t)op.x_bstride * 2;
+    b.strides[0] = (uint64_t)op.nlon * es; b.strides[1] = (uint64_t)op.nlat * op.nlon * es; b.strides[2] = (uint64_t)op.x_bstride * es;
     b.batched = true; b.group_lo = op.C;
   }
-  static bool extra_ok(const OpDft<bf16>& op) { return aligned16(op.f) && op.Kp % 8 == 0; }
-  static void io(const OpDft<bf16>& op, TmaIo& o, TmaIo&) {
-    const uint64_t kp = (uint64_t)op.Kp * 2;
-    o.base = op.f; o.es = 2; o.ok = true;
+  static bool extra_ok(const OpDft<T>& op) { return aligned16(op.f) && op.Kp % 8 == 0; }
+  static void io(const OpDft<T>& op, TmaIo& o, TmaIo&) {
+    const uint64_t kp = (uint64_t)op.Kp * es;
+    o.base = op.f; o.es = (int)es; o.ok = true;
     o.dims[0] = op.Kp; o.dims[1] = op.C; o.dims[2] = 2; o.dims[3] = op.B; o.dims[4] = op.M / 2;
     o.strides[0] = kp; o.strides[1] = kp * op.C; o.strides[2] = kp * op.C * 2; o.strides[3] = kp * op.C * 2 * op.B;
-    o.box_rows[0] = 1; o.box_rows[1] = 2; o.box_rows[2] = 1; o.box_rows[3] = 4;
+    o.box_rows[0] = 1; o.box_rows[1] = 2; o.box_rows[2] = 1; o.box_rows[3] = 16;   // 32 GEMM rows = 16 wavenumbers x {re, im}
   }
 };
 
-template <>
-struct TcTraits<OpLeg<bf16>> : TcTraitsBase<OpLeg<bf16>>, TcEligible<TcTraits<OpLeg<bf16>>, OpLeg<bf16>> {
+template <class T>
+struct TcTraits<OpLeg<T>> : TcTraitsBase<OpLeg<T>>, TcEligible<TcTraits<OpLeg<T>>, OpLeg<T>> {
+  static constexpr uint64_t es = sizeof(T);
   // dual-M (two 128-row A tiles per B tile, single-buffered accumulators): the 180 degrees of a wavenumber fit ONE
   // 256-row tile, which halves the F traffic.  Measured (profiles/r01_j_tc_dual_ab.txt): -8 % for the triangular
   // Legendre; +30 % / +9 % / +28 % for DFT / dhconv / inverse Legendre (losing the second accumulator stage costs
   // more than the saved L2 traffic), so only this op uses it, and only with the triangular ranges.
   static constexpr bool kDualM = true;
-  static bool use_dual(const OpLeg<bf16>& op) { return op.triangular != 0; }
+  static bool use_dual(const OpLeg<T>& op) { return op.triangular != 0; }
   static constexpr int BN = 256;
-  static void operands(const OpLeg<bf16>& op, TmaOperand& a, TmaOperand& b) {
+  static void operands(const OpLeg<T>& op, TmaOperand& a, TmaOperand& b) {
     a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.lmax; a.dims[2] = op.G;   // table rows l of wavenumber m
-    a.strides[0] = (uint64_t)op.Kp * 2; a.strides[1] = (uint64_t)op.lmax * op.Kp * 2; a.batched = true;
+    a.strides[0] = (uint64_t)op.Kp * es; a.strides[1] = (uint64_t)op.lmax * op.Kp * es; a.batched = true;
     b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.N; b.dims[2] = op.G;      // F rows (b,ri,c) of wavenumber m
-    b.strides[0] = (uint64_t)op.Kp * 2; b.strides[1] = (uint64_t)op.N * op.Kp * 2; b.batched = true;
+    b.strides[0] = (uint64_t)op.Kp * es; b.strides[1] = (uint64_t)op.N * op.Kp * es; b.batched = true;
   }
-  static bool extra_ok(const OpLeg<bf16>& op) { return aligned16(op.x) && op.N % 8 == 0; }
-  static void io(const OpLeg<bf16>& op, TmaIo& o, TmaIo&) {
-    o.base = op.x; o.es = 2; o.ok = true;
+  static bool extra_ok(const OpLeg<T>& op) { return aligned16(op.x) && op.N % 8 == 0; }
+  static void io(const OpLeg<T>& op, TmaIo& o, TmaIo&) {
+    o.base = op.x; o.es = (int)es; o.ok = true;
     o.dims[0] = op.N; o.dims[1] = op.mmax; o.dims[2] = op.lmax;
-    o.strides[0] = (uint64_t)op.N * 2; o.strides[1] = (uint64_t)op.mmax * op.N * 2;
-    o.box_rows[0] = 1; o.box_rows[1] = 8;
+    o.strides[0] = (uint64_t)op.N * es; o.strides[1] = (uint64_t)op.mmax * op.N * es;
+    o.box_rows[0] = 1; o.box_rows[1] = 32;   // 32 GEMM rows = 32 degrees of one wavenumber
   }
 };
 
-template <>
-struct TcTraits<OpDhconv<bf16>> : TcTraitsBase<OpDhconv<bf16>>, TcEligible<TcTraits<OpDhconv<bf16>>, OpDhconv<bf16>> {
+template <class T>
+struct TcTraits<OpDhconv<T>> : TcTraitsBase<OpDhconv<T>>, TcEligible<TcTraits<OpDhconv<T>>, OpDhconv<T>> {
   static constexpr int BN = 256;
-  static void operands(const OpDhconv<bf16>& op, TmaOperand& a, TmaOperand& b) {
+  static constexpr uint64_t es = sizeof(T);
+  static void operands(const OpDhconv<T>& op, TmaOperand& a, TmaOperand& b) {
     a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.M; a.dims[2] = op.G;       // X rows (m,b) of degree l
-    a.strides[0] = (uint64_t)op.K * 2; a.strides[1] = (uint64_t)op.M * op.K * 2; a.batched = true;
+    a.strides[0] = (uint64_t)op.K * es; a.strides[1] = (uint64_t)op.M * op.K * es; a.batched = true;
     b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.N; b.dims[2] = op.G;       // packed weight rows (ri',o) of degree l
-    b.strides[0] = (uint64_t)op.K * 2; b.strides[1] = (uint64_t)op.N * op.K * 2; b.batched = true;
+    b.strides[0] = (uint64_t)op.K * es; b.strides[1] = (uint64_t)op.N * op.K * es; b.batched = true;
   }
-  static bool extra_ok(const OpDhconv<bf16>& op) { return aligned16(op.y) && op.N % 8 == 0; }
-  static void io(const OpDhconv<bf16>& op, TmaIo& o, TmaIo&) {
-    o.base = op.y; o.es = 2; o.ok = true;
+  static bool extra_ok(const OpDhconv<T>& op) { return aligned16(op.y) && op.N % 8 == 0; }
+  static void io(const OpDhconv<T>& op, TmaIo& o, TmaIo&) {
+    o.base = op.y; o.es = (int)es; o.ok = true;
     o.dims[0] = op.N; o.dims[1] = op.M; o.dims[2] = op.G;
-    o.strides[0] = (uint64_t)op.N * 2; o.strides[1] = (uint64_t)op.M * op.N * 2;
+    o.strides[0] = (uint64_t)op.N * es; o.strides[1] = (uint64_t)op.M * op.N * es;
+    o.box_rows[0] = 32;   // rows (m,b) of one degree; the live range of a degree ends on a multiple of 64 * B
   }
 };
 
-template <>
-struct TcTraits<OpIleg<bf16>> : TcTraitsBase<OpIleg<bf16>>, TcEligible<TcTraits<OpIleg<bf16>>, OpIleg<bf16>> {
+template <class T>
+struct TcTraits<OpIleg<T>> : TcTraitsBase<OpIleg<T>>, TcEligible<TcTraits<OpIleg<T>>, OpIleg<T>> {
   static constexpr int BN = 192;
-  static void operands(const OpIleg<bf16>& op, TmaOperand& a, TmaOperand& b) {
+  static constexpr uint64_t es = sizeof(T);
+  static void operands(const OpIleg<T>& op, TmaOperand& a, TmaOperand& b) {
     a.base = op.A; a.dims[0] = op.M; a.dims[1] = op.K; a.dims[2] = op.G;  // M-contiguous: {(b,ri,o), l, m}
-    a.strides[0] = (uint64_t)op.a_sk * 2; a.strides[1] = (uint64_t)op.a_goff * 2; a.batched = true;
+    a.strides[0] = (uint64_t)op.a_sk * es; a.strides[1] = (uint64_t)op.a_goff * es; a.batched = true;
     b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.nlat; b.dims[2] = op.G;
-    b.strides[0] = (uint64_t)op.Lq * 2; b.strides[1] = (uint64_t)op.nlat * op.Lq * 2; b.batched = true;
+    b.strides[0] = (uint64_t)op.Lq * es; b.strides[1] = (uint64_t)op.nlat * op.Lq * es; b.batched = true;
   }
-  static bool extra_ok(const OpIleg<bf16>& op) { return aligned16(op.g_out) && op.Kp % 8 == 0; }
-  static void io(const OpIleg<bf16>& op, TmaIo& o, TmaIo&) {
-    const uint64_t kp = (uint64_t)op.Kp * 2;
-    o.base = op.g_out; o.es = 2; o.ok = op.C % 8 == 0;
+  static bool extra_ok(const OpIleg<T>& op) { return aligned16(op.g_out) && op.Kp % 8 == 0; }
+  static void io(const OpIleg<T>& op, TmaIo& o, TmaIo&) {
+    const uint64_t kp = (uint64_t)op.Kp * es;
+    o.base = op.g_out; o.es = (int)es; o.ok = op.C % 8 == 0;
     o.dims[0] = op.Kp; o.dims[1] = op.C; o.dims[2] = op.B; o.dims[3] = 2; o.dims[4] = op.G;
     o.strides[0] = kp; o.strides[1] = kp * op.C; o.strides[2] = kp * op.C * op.B; o.strides[3] = kp * op.C * op.B * 2;
+    if (op.C % 32 == 0) o.box_rows[0] = 32;   // 32 GEMM rows (b,ri,o) = 32 channels of one (b, ri)
   }
 };
 
-template <class TOut, int ACT>
-struct TcTraits<OpIdft<bf16, TOut, ACT>> : TcTraitsBase<OpIdft<bf16, TOut, ACT>>,
-                                             TcEligible<TcTraits<OpIdft<bf16, TOut, ACT>>, OpIdft<bf16, TOut, ACT>> {
+template <class T, class TOut, int ACT>
+struct TcTraits<OpIdft<T, TOut, ACT>> : TcTraitsBase<OpIdft<T, TOut, ACT>>,
+                                          TcEligible<TcTraits<OpIdft<T, TOut, ACT>>, OpIdft<T, TOut, ACT>> {
   static constexpr int BN = 192;
-  static void operands(const OpIdft<bf16, TOut, ACT>& op, TmaOperand& a, TmaOperand& b) {
+  static constexpr uint64_t ei = sizeof(T);
+  static void operands(const OpIdft<T, TOut, ACT>& op, TmaOperand& a, TmaOperand& b) {
     a.base = op.A; a.dims[0] = op.M; a.dims[1] = op.K; a.dims[2] = 1;  // M-contiguous: {(b,o,kp), (m,ri)}
-    a.strides[0] = (uint64_t)op.a_sk * 2; a.batched = false;
+    a.strides[0] = (uint64_t)op.a_sk * ei; a.batched = false;
     b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.N; b.dims[2] = 1;
-    b.strides[0] = (uint64_t)op.Kq2 * 2; b.batched = false;
-    if (op.b_reps > 1) { b.dims[2] = op.b_reps; b.strides[1] = (uint64_t)op.N * op.Kq2 * 2; b.replicas = op.b_reps; }
+    b.strides[0] = (uint64_t)op.Kq2 * ei; b.batched = false;
+    if (op.b_reps > 1) { b.dims[2] = op.b_reps; b.strides[1] = (uint64_t)op.N * op.Kq2 * ei; b.replicas = op.b_reps; }
   }
-  static bool extra_ok(const OpIdft<bf16, TOut, ACT>& op) {
+  // the addend has the element type of the operands (T) and is staged through the output's staging rows: same size
+  static bool extra_ok(const OpIdft<T, TOut, ACT>& op) {
     return op.nlon % 8 == 0 && op.out_bstride % 8 == 0 && aligned16(op.out) &&
-           (!op.add || (sizeof(TOut) == 2 && aligned16(op.add) && op.add_bstride % 8 == 0));
+           (!op.add || (sizeof(TOut) == sizeof(T) && aligned16(op.add) && op.add_bstride % 8 == 0));
   }
-  static bool has_residual(const OpIdft<bf16, TOut, ACT>& op) { return op.add != nullptr; }
-  static void io(const OpIdft<bf16, TOut, ACT>& op, TmaIo& o, TmaIo& r) {
+  static bool has_residual(const OpIdft<T, TOut, ACT>& op) { return op.add != nullptr; }
+  static void io(const OpIdft<T, TOut, ACT>& op, TmaIo& o, TmaIo& r) {
     const uint64_t es = sizeof(TOut);
     const int B = op.M / (op.C * op.Kp);
     o.base = op.out; o.es = (int)es; o.ok = op.Kp % 8 == 0;
     o.dims[0] = op.nlon; o.dims[1] = op.nlat; o.dims[2] = op.C; o.dims[3] = B;
     o.strides[0] = (uint64_t)op.nlon * es; o.strides[1] = (uint64_t)op.nlat * op.nlon * es; o.strides[2] = (uint64_t)op.out_bstride * es;
-    if (op.add && es == 2) {
+    if (op.add && es == sizeof(T)) {   // loaded in 8-row boxes: a clipped 32-row LOAD would zero-fill rows of the other plane
       r = o;
-      r.base = op.add; r.strides[2] = (uint64_t)op.add_bstride * 2;
+      r.base = op.add; r.strides[2] = (uint64_t)op.add_bstride * es;
     }
+    o.box_rows[0] = 32;   // stores: one 32-latitude box, plus a second clipped one where the rows straddle two planes
   }
 };
 
-template <class TOut, int ACT, int DROP>
-struct TcTraits<OpConv<bf16, TOut, ACT, DROP>> : TcTraitsBase<OpConv<bf16, TOut, ACT, DROP>>,
-                                                   TcEligible<TcTraits<OpConv<bf16, TOut, ACT, DROP>>, OpConv<bf16, TOut, ACT, DROP>> {
+template <class T, class TOut, int ACT, int DROP>
+struct TcTraits<OpConv<T, TOut, ACT, DROP>> : TcTraitsBase<OpConv<T, TOut, ACT, DROP>>,
+                                                TcEligible<TcTraits<OpConv<T, TOut, ACT, DROP>>, OpConv<T, TOut, ACT, DROP>> {
   static constexpr int BN = 192;
-  static void operands(const OpConv<bf16, TOut, ACT, DROP>& op, TmaOperand& a, TmaOperand& b) {
+  static constexpr uint64_t ei = sizeof(T);
+  static void operands(const OpConv<T, TOut, ACT, DROP>& op, TmaOperand& a, TmaOperand& b) {
     const bool wb = op.w_bstride != 0;
     a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.M; a.dims[2] = wb ? op.G : 1;  // weights [o][c], K-contiguous
-    a.strides[0] = (uint64_t)op.ldw * 2; a.strides[1] = (uint64_t)op.w_bstride * 2; a.batched = wb;
+    a.strides[0] = (uint64_t)op.ldw * ei; a.strides[1] = (uint64_t)op.w_bstride * ei; a.batched = wb;
     b.base = op.Bm; b.dims[0] = op.N; b.dims[1] = op.K; b.dims[2] = op.G;  // N-contiguous: {pixel, channel, sample}
-    b.strides[0] = (uint64_t)op.N * 2; b.strides[1] = (uint64_t)op.in_bstride * 2; b.batched = true;
+    b.strides[0] = (uint64_t)op.N * ei; b.strides[1] = (uint64_t)op.in_bstride * ei; b.batched = true;
   }
-  static bool extra_ok(const OpConv<bf16, TOut, ACT, DROP>& op) {
-    return op.N % 8 == 0 && op.out_bstride % 8 == 0 && aligned16(op.out) &&
-           (!op.res || (sizeof(TOut) == 2 && aligned16(op.res) && op.res_bstride % 8 == 0)) && (!op.pos || aligned16(op.pos));
+  // the residual has the element type of the operands (T) and is staged through the output's staging rows: same size
+  static bool extra_ok(const OpConv<T, TOut, ACT, DROP>& op) {
+    return op.N % 8 == 0 && op.out_bstride % 8 == 0 && aligned16(op.out) && (op.ldw * ei) % 16 == 0 &&
+           (!op.res || (sizeof(TOut) == sizeof(T) && aligned16(op.res) && op.res_bstride % 8 == 0)) && (!op.pos || aligned16(op.pos));
   }
-  static bool has_residual(const OpConv<bf16, TOut, ACT, DROP>& op) { return op.res != nullptr; }
-  static void io(const OpConv<bf16, TOut, ACT, DROP>& op, TmaIo& o, TmaIo& r) {
+  static bool has_residual(const OpConv<T, TOut, ACT, DROP>& op) { return op.res != nullptr; }
+  static void io(const OpConv<T, TOut, ACT, DROP>& op, TmaIo& o, TmaIo& r) {
     const uint64_t es = sizeof(TOut);
     o.base = op.out; o.es = (int)es; o.ok = true;
     o.dims[0] = op.N; o.dims[1] = op.M; o.dims[2] = op.G;
     o.strides[0] = (uint64_t)op.N * es; o.strides[1] = (uint64_t)op.out_bstride * es;
-    if (op.res && es == 2) {
+    o.box_rows[0] = 32;   // 32 output channels of one sample (rows past the last channel are clipped / zero-filled)
+    if (op.res && es == sizeof(T)) {
       r = o;
       r.base = op.res;
-      if (op.res_bstride != 0) r.strides[1] = (uint64_t)op.res_bstride * 2;
+      if (op.res_bstride != 0) r.strides[1] = (uint64_t)op.res_bstride * es;
       else r.dims[2] = 1;   // one plane shared by all samples (position embedding)
     }
   }

@@ -47,12 +47,23 @@ int fail(int status, const char* fmt, ...) {
 }
 
 // ---- table upload -------------------------------------------------------------------------------------
+// round-to-nearest (ties away, as cvt.rna.tf32.f32) of an fp32 value to the 10-bit TF32 mantissa
+static float round_tf32_host(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  memcpy(&v, &u, 4);
+  return v;
+}
+static thread_local bool g_upload_tf32 = false;   // tables of a SFNO_PREC_TF32 plan are stored TF32-exact
+
 template <class T>
 static int upload_padded(const std::vector<double>& src, int64_t rows, int cols, int ld, void** dst, size_t* bytes, int replicas = 1) {
   std::vector<T> host((size_t)rows * ld);
   for (int64_t r = 0; r < rows; ++r)
     for (int c = 0; c < ld; ++c) {
       float v = c < cols ? (float)src[(size_t)r * cols + c] : 0.0f;
+      if (g_upload_tf32) v = round_tf32_host(v);
       if constexpr (std::is_same<T, float>::value) host[(size_t)r * ld + c] = v;
       else host[(size_t)r * ld + c] = __float2bfloat16_rn(v);
     }
@@ -93,7 +104,9 @@ int sht_tables_upload(int nlat, int nlon, int lmax, int mmax, int grid, int prec
   d = ShtDeviceTables{};
   d.nlat = nlat; d.nlon = nlon; d.lmax = lmax; d.mmax = mmax; d.grid = grid; d.precision = precision;
   d.Kp = round_up(nlat, 8); d.Lq = round_up(lmax, 8); d.Wp = round_up(nlon, 8); d.Kq2 = round_up(2 * mmax, 8);
+  g_upload_tf32 = precision == SFNO_PREC_TF32;
   int st = precision == SFNO_PREC_BF16 ? upload_all<bf16>(h, d) : upload_all<float>(h, d);
+  g_upload_tf32 = false;
   if (st != SFNO_OK) sht_tables_free(d);
   return st;
 }
@@ -139,6 +152,7 @@ static int sht_forward_impl(const ShtDeviceTables& t, const float* x, float* coe
   dft.f = F; dft.aff_a = nullptr; dft.aff_d = nullptr;
   dft.B = 1; dft.C = C; dft.nlat = t.nlat; dft.nlon = t.nlon; dft.Kp = t.Kp; dft.Wp = t.Wp; dft.x_bstride = 0;
   dft.a_reps = t.basis_reps;
+  dft.round_out = 1;   // F feeds the Legendre MMA
   SFNO_TRY(launch_gemm(dft, st, "dft_fwd"));
   OpLeg<T> leg{};
   leg.G = t.mmax; leg.M = t.lmax; leg.N = 2 * C; leg.K = t.nlat;
@@ -165,6 +179,7 @@ static int sht_inverse_impl(const ShtDeviceTables& t, const float* coeffs, float
   il.A = X; il.Bm = (const T*)t.pt; il.b_sk = 1;
   il.a_goff = il.M; il.a_sk = (int64_t)t.mmax * il.M;  // X layout [l][m][rows]
   il.g_out = Gb; il.B = 1; il.C = C; il.Kp = t.Kp; il.Lq = t.Lq; il.nlat = t.nlat; il.triangular = 0;
+  il.round_out = 1;    // G feeds the inverse-DFT MMA
   SFNO_TRY(launch_gemm(il, st, "legendre_inv"));
   IdftArgs<T, float> id{};
   id.G = 1; id.M = C * t.Kp; id.N = t.nlon; id.K = 2 * t.mmax;
@@ -270,7 +285,7 @@ int sfno_sht_tables_host(int nlat, int nlon, int lmax, int mmax, int grid, doubl
 
 int sfno_sht_plan_create(sfno_sht_plan** plan, int nlat, int nlon, int lmax, int mmax, int grid, int precision) {
   SFNO_CHECK_ARG(plan != nullptr, "plan is NULL");
-  SFNO_CHECK_ARG(precision == SFNO_PREC_F32 || precision == SFNO_PREC_BF16, "bad precision %d", precision);
+  SFNO_CHECK_ARG(precision == SFNO_PREC_F32 || precision == SFNO_PREC_BF16 || precision == SFNO_PREC_TF32, "bad precision %d", precision);
   auto* p = new sfno_sht_plan();
   int st = sht_tables_upload(nlat, nlon, lmax, mmax, grid, precision, p->t);
   if (st != SFNO_OK) { delete p; return st; }
@@ -296,6 +311,7 @@ int sfno_sht_forward(const sfno_sht_plan* plan, const float* x_dev, float* coeff
   SFNO_CHECK_ARG(fields > 0 && fields < (1 << 24), "bad field count %lld", (long long)fields);
   if (workspace_bytes < sht_ws_layout(plan->t, fields).total) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  Tf32Scope tf32(plan->t.precision == SFNO_PREC_TF32);
   return plan->t.precision == SFNO_PREC_BF16 ? sht_forward_impl<bf16>(plan->t, x_dev, coeffs_dev, fields, (char*)workspace_dev, st)
                                              : sht_forward_impl<float>(plan->t, x_dev, coeffs_dev, fields, (char*)workspace_dev, st);
 }
@@ -306,6 +322,7 @@ int sfno_sht_inverse(const sfno_sht_plan* plan, const float* coeffs_dev, float* 
   SFNO_CHECK_ARG(fields > 0 && fields < (1 << 24), "bad field count %lld", (long long)fields);
   if (workspace_bytes < sht_ws_layout(plan->t, fields).total) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  Tf32Scope tf32(plan->t.precision == SFNO_PREC_TF32);
   return plan->t.precision == SFNO_PREC_BF16 ? sht_inverse_impl<bf16>(plan->t, coeffs_dev, x_dev, fields, (char*)workspace_dev, st)
                                              : sht_inverse_impl<float>(plan->t, coeffs_dev, x_dev, fields, (char*)workspace_dev, st);
 }

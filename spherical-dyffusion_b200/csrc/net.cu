@@ -135,11 +135,23 @@ __global__ void diag_contract_internal_kernel(const T* __restrict__ X, const flo
   }
 }
 
+static thread_local bool g_pack_tf32 = false;
+
+// operands of a tf32 MMA are stored TF32-exact (round to nearest here; the tensor core would truncate)
+static int round_tf32_inplace(float* p, int64_t n, cudaStream_t st) {
+  round_tf32_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n, 256), 148 * 16), 256, 0, st>>>(p, n);
+  return post_launch("round_tf32");
+}
+
 template <class T>
 static int pack_rows(const float* src, int rows, int cols, int ld, void* dst, cudaStream_t st) {
   const int64_t total = (int64_t)rows * ld;
   pack_rows_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(src, rows, cols, ld, (T*)dst);
-  return post_launch("pack_rows");
+  SFNO_TRY(post_launch("pack_rows"));
+  if constexpr (std::is_same<T, float>::value) {
+    if (g_pack_tf32) return round_tf32_inplace((float*)dst, total, st);
+  }
+  return SFNO_OK;
 }
 
 static int copy_f32(float* dst, const float* src, int64_t n, cudaStream_t st) {
@@ -182,7 +194,11 @@ static int set_param_impl(sfno_net* n, const std::string& name, const float* v, 
       if (n->cfg.operator_type == SFNO_OP_DHCONV) {
         SFNO_TRY(expect((int64_t)C * C * L * 2));
         pack_dhconv_weight_kernel<T><<<4096, 256, 0, st>>>(v, C, C, L, (T*)b.wpack);
-        return post_launch("pack_dhconv_weight");
+        SFNO_TRY(post_launch("pack_dhconv_weight"));
+        if constexpr (std::is_same<T, float>::value) {
+          if (g_pack_tf32) return round_tf32_inplace((float*)b.wpack, (int64_t)L * 4 * C * C, st);
+        }
+        return SFNO_OK;
       }
       SFNO_TRY(expect((int64_t)C * C * L * M * 2));
       return copy_f32(b.wdiag, v, numel, st);
@@ -214,6 +230,7 @@ static ConvArgs<T, TOut> make_conv(int B, int P, int cin, int cout, const T* in,
   op.drop_p = 0.0f; op.seed = 0; op.offset = 0; op.rng_dev = nullptr; op.branch_scale = nullptr;
   op.res = nullptr; op.res_bstride = 0; op.res_a = nullptr; op.res_d = nullptr; op.pos = nullptr;
   op.out = out; op.out_bstride = out_bs; op.stat_part = nullptr;
+  op.round_out = 1;   // activations stay inside the net (only the decoder output leaves it, see forward_impl)
   return op;
 }
 
@@ -224,7 +241,7 @@ static int run_dft(const sfno_net* n, const ShtDeviceTables& t, int B, const T* 
   op.A = (const T*)t.efwd; op.Bm = x; op.a_sk = 1; op.b_sk = 1;
   op.f = F; op.aff_a = a; op.aff_d = d;
   op.B = B; op.C = n->C; op.nlat = t.nlat; op.nlon = t.nlon; op.Kp = t.Kp; op.Wp = t.Wp; op.x_bstride = x_bs;
-  op.a_reps = t.basis_reps;
+  op.a_reps = t.basis_reps; op.round_out = 1;
   return launch_gemm(op, st, "dft_fwd");
 }
 template <class T>
@@ -233,7 +250,7 @@ static int run_leg(const sfno_net* n, const ShtDeviceTables& t, int B, const T* 
   op.G = t.mmax; op.M = t.lmax; op.N = B * 2 * n->C; op.K = t.nlat;
   op.A = (const T*)t.wq; op.Bm = F; op.a_sk = 1; op.b_sk = 1;
   op.x = X; op.Kp = t.Kp; op.lmax = t.lmax; op.mmax = t.mmax;
-  op.triangular = n->cfg.operator_type == SFNO_OP_DHCONV;
+  op.triangular = n->cfg.operator_type == SFNO_OP_DHCONV; op.round_out = 1;
   return launch_gemm(op, st, "legendre_fwd");
 }
 template <class T>
@@ -243,7 +260,7 @@ static int run_ileg(const sfno_net* n, const ShtDeviceTables& t, int B, const T*
   op.A = S; op.Bm = (const T*)t.pt; op.b_sk = 1;
   op.a_goff = op.M; op.a_sk = (int64_t)t.mmax * op.M;   // X and Y share the layout [l][m][(b,ri,c)]
   op.g_out = G; op.B = B; op.C = n->C; op.Kp = t.Kp; op.Lq = t.Lq; op.nlat = t.nlat;
-  op.triangular = n->cfg.operator_type == SFNO_OP_DHCONV;
+  op.triangular = n->cfg.operator_type == SFNO_OP_DHCONV; op.round_out = 1;
   return launch_gemm(op, st, "legendre_inv");
 }
 // stat_part != nullptr: ask for fused output statistics; *fused reports whether the engine could provide them
@@ -255,7 +272,7 @@ static int run_idft(const sfno_net* n, const ShtDeviceTables& t, int B, const T*
   op.A = G; op.Bm = (const T*)t.einv; op.a_sk = op.M; op.b_sk = 1;
   op.out = out; op.out_bstride = out_bs; op.bias = bias; op.add = add; op.add_bstride = add_bs; op.act = act;
   op.C = n->C; op.nlat = t.nlat; op.nlon = t.nlon; op.Kp = t.Kp; op.Kq2 = t.Kq2; op.b_reps = t.basis_reps;
-  op.stat_part = nullptr;
+  op.stat_part = nullptr; op.round_out = 1;
   if (fused) *fused = false;
   if (stat_part && idft_uses_tc(op)) { op.stat_part = stat_part; *fused = true; }
   return launch_idft(op, st, "dft_inv");
@@ -265,6 +282,8 @@ template <class T>
 static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time, float* y, int B, int dropout, uint64_t seed,
                         uint64_t offset, uint64_t* rng_dev, char* ws, cudaStream_t st) {
   const sfno_net_config& cfg = n->cfg;
+  const bool tf32 = std::is_same<T, float>::value && cfg.precision == SFNO_PREC_TF32;
+  Tf32Scope tf32_scope(tf32);   // fp32-storage GEMMs of this forward run as kind::tf32 on the tensor cores
   const WsLayout w = ws_layout(n, B);
   const int C = n->C, P = n->P, hid = n->hid, nl = n->nl, tdim = n->tdim;
   const int64_t CP = (int64_t)C * P;
@@ -293,10 +312,10 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
     // part of the first kernel -- give it its own entry
     if (g_profile_on.load(std::memory_order_relaxed)) profile_mark("host_before_first_launch");
     dim3 grid(1184 / std::max(1, std::min(B, 8)) + 1, B);
-    concat_convert_kernel<T><<<grid, 256, 0, st>>>(parts, (int64_t)P, xin, (int64_t)n->Cin * P);
+    concat_convert_kernel<T><<<grid, 256, 0, st>>>(parts, (int64_t)P, xin, (int64_t)n->Cin * P, tf32 ? 1 : 0);
     SFNO_TRY(post_launch("convert_input"));
     if (cfg.big_skip) {
-      concat_convert_kernel<T><<<grid, 256, 0, st>>>(parts, (int64_t)P, xcat + CP, xcat_bs);
+      concat_convert_kernel<T><<<grid, 256, 0, st>>>(parts, (int64_t)P, xcat + CP, xcat_bs, tf32 ? 1 : 0);
       SFNO_TRY(post_launch("convert_input_skip"));
     }
   }
@@ -372,7 +391,7 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
       OpDhconv<T> op{};
       op.G = n->L; op.M = n->M * B; op.N = 2 * C; op.K = 2 * C;
       op.A = X; op.Bm = (const T*)bp.wpack; op.a_sk = 1; op.b_sk = 1;
-      op.y = Y; op.B = B; op.lmax = n->L; op.mmax = n->M; op.triangular = 1;
+      op.y = Y; op.B = B; op.lmax = n->L; op.mmax = n->M; op.triangular = 1; op.round_out = 1;
       SFNO_TRY(launch_gemm(op, st, "dhconv"));
     } else {
       const int64_t total = (int64_t)n->L * n->M * B * C;
@@ -388,7 +407,7 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
       auto sk = make_conv<T, T>(B, P, C, C, res, CP, (const T*)bp.skip_wT, 0, C, bp.skip_b, 0, SFNO_ACT_NONE, t1, CP);
       SFNO_TRY(launch_conv(sk, st, "inner_skip"));
     } else {
-      fold_affine_weight_kernel<T><<<B * C, 128, 0, st>>>(bp.skip_w32, bp.skip_b, a0, d0, C, C, C, skip_wb, skip_bb);
+      fold_affine_weight_kernel<T><<<B * C, 128, 0, st>>>(bp.skip_w32, bp.skip_b, a0, d0, C, C, C, skip_wb, skip_bb, tf32 ? 1 : 0);
       SFNO_TRY(post_launch("fold_skip"));
       auto sk = make_conv<T, T>(B, P, C, C, cur, cur_bs, skip_wb, (int64_t)C * C, C, skip_bb, C, SFNO_ACT_NONE, t1, CP);
       SFNO_TRY(launch_conv(sk, st, "inner_skip"));
@@ -425,7 +444,7 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
     const float pdrop = dropout ? cfg.dropout_mlp : 0.0f;
 
     // MLP (layers.py:73-80) + DropPath + outer skip (sfnonet.py:326-335)
-    fold_affine_weight_kernel<T><<<B * hid, 128, 0, st>>>(bp.fc1_w32, bp.fc1_b, a1, d1, hid, C, C, fc1_wb, fc1_bb);
+    fold_affine_weight_kernel<T><<<B * hid, 128, 0, st>>>(bp.fc1_w32, bp.fc1_b, a1, d1, hid, C, C, fc1_wb, fc1_bb, tf32 ? 1 : 0);
     SFNO_TRY(post_launch("fold_fc1"));
     auto f1 = make_conv<T, T>(B, P, C, hid, t1, CP, fc1_wb, (int64_t)hid * C, C, fc1_bb, hid, cfg.activation, hd, (int64_t)hid * P);
     f1.drop_p = pdrop; f1.seed = seed; f1.offset = offset + (uint64_t)i * 4 + 0; f1.rng_dev = rng_dev;
@@ -450,6 +469,7 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
     auto d0c = make_conv<T, T>(B, P, kin, C, cur, cur_bs, (const T*)n->dec0_w, 0, n->Ccat_p, n->dec0_b, 0, cfg.activation, t1, CP);
     SFNO_TRY(launch_conv(d0c, st, "decoder0"));
     auto d1c = make_conv<T, float>(B, P, C, n->Cout, t1, CP, (const T*)n->dec1_w, 0, C, nullptr, 0, SFNO_ACT_NONE, y, (int64_t)n->Cout * P);
+    d1c.round_out = 0;   // the result leaves the library in full fp32
     SFNO_TRY(launch_conv(d1c, st, "decoder1"));
   }
   // device-resident Philox state: the next forward (or the next replay of a captured graph) draws from a fresh stream
@@ -474,7 +494,7 @@ int sfno_b200_set_option(const char* key, int64_t value) {
 int sfno_net_create(const sfno_net_config* c, sfno_net** out) {
   SFNO_CHECK_ARG(c && out, "NULL argument");
   SFNO_CHECK_ARG(c->struct_size == (int32_t)sizeof(sfno_net_config), "sfno_net_config size mismatch (%d vs %zu)", c->struct_size, sizeof(sfno_net_config));
-  SFNO_CHECK_ARG(c->precision == SFNO_PREC_F32 || c->precision == SFNO_PREC_BF16, "bad precision");
+  SFNO_CHECK_ARG(c->precision == SFNO_PREC_F32 || c->precision == SFNO_PREC_BF16 || c->precision == SFNO_PREC_TF32, "bad precision");
   SFNO_CHECK_ARG(c->nlat >= 2 && c->nlon >= 4 && c->in_chans > 0 && c->out_chans > 0 && c->embed_dim > 0 && c->num_layers > 0, "bad sizes");
   SFNO_CHECK_ARG(c->embed_dim % 2 == 0, "embed_dim must be even");
   SFNO_CHECK_ARG(c->lmax > 0 && c->mmax > 0 && c->mmax <= c->nlon / 2 + 1, "bad lmax/mmax");
@@ -558,8 +578,11 @@ const char* sfno_net_param_names(const sfno_net* n) { return n ? n->names.c_str(
 
 int sfno_net_set_param(sfno_net* n, const char* name, const float* value_dev, int64_t numel, void* stream) {
   SFNO_CHECK_ARG(n && name && value_dev, "NULL argument");
-  return n->cfg.precision == SFNO_PREC_BF16 ? set_param_impl<bf16>(n, name, value_dev, numel, (cudaStream_t)stream)
-                                            : set_param_impl<float>(n, name, value_dev, numel, (cudaStream_t)stream);
+  g_pack_tf32 = n->cfg.precision == SFNO_PREC_TF32;   // packed MMA operands are stored TF32-exact
+  const int st = n->cfg.precision == SFNO_PREC_BF16 ? set_param_impl<bf16>(n, name, value_dev, numel, (cudaStream_t)stream)
+                                                    : set_param_impl<float>(n, name, value_dev, numel, (cudaStream_t)stream);
+  g_pack_tf32 = false;
+  return st;
 }
 
 int sfno_net_set_option(sfno_net* n, const char* key, int64_t value) {

@@ -65,7 +65,11 @@ __device__ __forceinline__ f2 act_ct2(int act_rt, f2 v) {
   }
 }
 
-struct NoFeatures {
+struct NoSplitBox {   // 32 consecutive GEMM rows never straddle two planes of the output tensor
+  static constexpr bool kSplitBox = false;
+  __device__ bool io_coords_second(int, int, int, int (&)[5]) const { return false; }
+};
+struct NoFeatures : NoSplitBox {
   static constexpr int kStagingBufs = 1;   // load-bound ops: shared memory goes to the operand ring
   static constexpr int kFast0 = 0, kFast1 = 0;
   static constexpr bool kGeneral = false;
@@ -75,6 +79,9 @@ struct NoFeatures {
   __device__ bool wants_stats() const { return false; }
   __device__ void finish(int, int, int, float, float) const {}
 };
+// fp32 outputs that a later tf32 MMA consumes are rounded to TF32 (round-to-nearest) by the tensor-core epilogue: the
+// MMA itself truncates, which biases every product towards zero.  Ops carry `round_out` (0 for tensors that leave the
+// library: final outputs keep full fp32).  bf16 storage ignores it.
 
 __device__ __forceinline__ void load_vec8(const bf16* p, float (&v)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
@@ -120,6 +127,9 @@ template <class T>
 struct OpDft : FullRanges, NoFeatures {
   static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = true, kNFastest = false;
   using OutT = T;
+  using InT = T;
+  int round_out;
+  __device__ bool out_tf32() const { return round_out != 0; }
   __device__ int n_end(int) const { return N; }
   __device__ int m_end(int) const { return M; }
   int G, M, N, K;  // G = B*C, M = 2*mmax, N = nlat, K = nlon
@@ -176,6 +186,9 @@ struct OpLeg : NoFeatures {
   static constexpr bool kRanged = true;
   static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = true, kNFastest = false;
   using OutT = T;
+  using InT = T;
+  int round_out;
+  __device__ bool out_tf32() const { return round_out != 0; }
   int triangular;  // 1: store only the live degrees l >= live_l0(m)
   __device__ int m_begin(int g) const { return triangular ? live_l0(g, M) : 0; }
   __device__ int m_end(int) const { return M; }
@@ -214,6 +227,9 @@ struct OpDhconv : NoFeatures {
   static constexpr bool kRanged = true;
   static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = true, kNFastest = true;
   using OutT = T;
+  using InT = T;
+  int round_out;
+  __device__ bool out_tf32() const { return round_out != 0; }
   int triangular;  // 1: only the live wavenumbers of degree l
   __device__ int m_begin(int) const { return 0; }
   __device__ int m_end(int g) const {
@@ -257,6 +273,9 @@ struct OpIleg : NoFeatures {
   static constexpr bool kRanged = true;
   static constexpr bool A_KCONTIG = false, B_KCONTIG = true, kColContig = true, kNFastest = true;
   using OutT = T;
+  using InT = T;
+  int round_out;
+  __device__ bool out_tf32() const { return round_out != 0; }
   int triangular;  // 1: contract only over the live degrees l >= (m & ~63)
   __device__ int n_begin(int) const { return 0; }
   __device__ int n_end(int) const { return N; }
@@ -307,6 +326,7 @@ struct IdftArgs {
   int act;
   int C, nlat, nlon, Kp, Kq2;
   int b_reps;   // replicas of the basis, [b_reps][nlon][Kq2] (0 / 1: a single copy)
+  int round_out;  // fp32 output feeds a tf32 MMA: round to TF32 in the tensor-core epilogue
   // optional fused InstanceNorm statistics of the OUTPUT: per (column slice, row) partial sum / sum of squares,
   // stat_part[(slice*2 + {0,1}) * M + row]; reduced in a fixed order by norm_affine_partials_kernel (deterministic)
   float* stat_part;
@@ -317,6 +337,8 @@ struct OpIdft : IdftArgs<T, TOut>, FullRanges {
   __device__ int n_end(int) const { return this->N; }
   __device__ int m_end(int) const { return this->M; }
   using OutT = TOut;
+  using InT = T;
+  __device__ bool out_tf32() const { return this->round_out != 0; }
   using Args = IdftArgs<T, TOut>;
   OpIdft() = default;
   __host__ __device__ explicit OpIdft(const Args& a) : Args(a) {}
@@ -329,7 +351,9 @@ struct OpIdft : IdftArgs<T, TOut>, FullRanges {
   // 2 = the TMA store of one tile reads staging buffer b while the next tile fills b^1.  Measured slower (fc1 0.22 ->
   // 0.255 ms, inverse DFT 0.20 -> 0.246 ms): the second buffer costs one operand stage (4 -> 3) and these kernels do
   // wait for operands 8-20 % of the time, which outweighs the hidden store latency.
-  static constexpr int kStagingBufs = 1;
+  // fp32 in / fp32 out (tf32 mode): two buffers, one per 32-column pass, so that a residual / addend block of the whole
+  // 64-column slice can be staged by TMA before the accumulator is ready.
+  static constexpr int kStagingBufs = (sizeof(T) == 4 && sizeof(TOut) == 4) ? 2 : 1;
   __device__ int feat() const { return (this->add ? F_RES : 0) | (this->stat_part ? F_STATS : 0); }
   // TMA view of the grid tensor: {j, k, o, b}; eight GEMM rows (b,o,kp) = eight latitudes of one plane (Kp % 8 == 0);
   // the pad latitudes kp >= nlat are clipped by the tensor extent
@@ -338,6 +362,18 @@ struct OpIdft : IdftArgs<T, TOut>, FullRanges {
     c[0] = col0; c[1] = row0 - bo * this->Kp; c[2] = bo - b * this->C; c[3] = b; c[4] = 0;
   }
   __device__ void res_coords(int g, int row0, int col0, int (&c)[5]) const { io_coords(g, row0, col0, c); }
+  // One 32-row box covers the rows [row0, row0 + 32) of plane bo; when they run past the plane (Kp rows, the pad rows
+  // kp >= nlat have no destination and are clipped) the rest belongs to plane bo + 1: the SAME staging rows are stored
+  // once more with the box origin at the negative latitude k0 - Kp of that plane -- staged row r lands on latitude
+  // k0 - Kp + r, rows above the plane (negative latitude) are clipped.  Stores only: a load would zero-fill.
+  static constexpr bool kSplitBox = true;
+  __device__ bool io_coords_second(int, int row0, int col0, int (&c)[5]) const {
+    const int bo = row0 / this->Kp, k0 = row0 - bo * this->Kp;
+    if (k0 + 32 <= this->Kp) return false;
+    const int bo2 = bo + 1, b = bo2 / this->C;
+    c[0] = col0; c[1] = k0 - this->Kp; c[2] = bo2 - b * this->C; c[3] = b; c[4] = 0;
+    return true;
+  }
   struct Row {
     TOut* out; const T* res; bool valid; float bias; f2 s2, q2;   // s2 / q2: packed partial sum / sum of squares
     __device__ float stat_s() const { return f2_hsum(s2); }
@@ -405,17 +441,20 @@ struct ConvArgs {
   const float* res_a; const float* res_d; // [batch*cout] affine on the residual or nullptr
   const T* pos;                           // [cout][hw] or nullptr
   TOut* out; int64_t out_bstride;
+  int round_out;  // fp32 output feeds a tf32 MMA: round to TF32 in the tensor-core epilogue
   // optional fused InstanceNorm statistics of the OUTPUT: stat_part[(slice*2 + {0,1}) * (G*M) + g*M + m]
   float* stat_part;
 };
 // ACT / DROP < 0: decided at run time (CUDA-core engine and rarely used combinations)
 template <class T, class TOut, int ACT = -1, int DROP = -1>
-struct OpConv : ConvArgs<T, TOut>, FullRanges {
+struct OpConv : ConvArgs<T, TOut>, FullRanges, NoSplitBox {
   static constexpr bool kSimtRowsOnFastLanes = true;
   static constexpr bool A_KCONTIG = true, B_KCONTIG = false, kColContig = true, kNFastest = false;
   __device__ int n_end(int) const { return this->N; }
   __device__ int m_end(int) const { return this->M; }
   using OutT = TOut;
+  using InT = T;
+  __device__ bool out_tf32() const { return this->round_out != 0; }
   using Args = ConvArgs<T, TOut>;
   OpConv() = default;
   __host__ __device__ explicit OpConv(const Args& a) : Args(a) {}
@@ -428,7 +467,9 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges {
   // 2 = the TMA store of one tile reads staging buffer b while the next tile fills b^1.  Measured slower (fc1 0.22 ->
   // 0.255 ms, inverse DFT 0.20 -> 0.246 ms): the second buffer costs one operand stage (4 -> 3) and these kernels do
   // wait for operands 8-20 % of the time, which outweighs the hidden store latency.
-  static constexpr int kStagingBufs = 1;
+  // fp32 in / fp32 out (tf32 mode): two buffers, one per 32-column pass, so that a residual / addend block of the whole
+  // 64-column slice can be staged by TMA before the accumulator is ready.
+  static constexpr int kStagingBufs = (sizeof(T) == 4 && sizeof(TOut) == 4) ? 2 : 1;
   __device__ int feat() const {
     return (this->res ? F_RES : 0) | (this->stat_part ? F_STATS : 0) | (this->pos ? F_POS : 0) | (this->branch_scale ? F_SCALE : 0);
   }

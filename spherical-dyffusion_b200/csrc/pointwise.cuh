@@ -213,7 +213,7 @@ template <class T>
 static __global__ void __launch_bounds__(128) fold_affine_weight_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                                                  const float* __restrict__ a, const float* __restrict__ d,
                                                                  int cout, int cin, int ldw, T* __restrict__ wb,
-                                                                 float* __restrict__ bb) {
+                                                                 float* __restrict__ bb, int round_tf32 = 0) {
   __shared__ float sh[33];
   const int b = blockIdx.x / cout, o = blockIdx.x - b * cout;
   const float* wr = w + (int64_t)o * cin;
@@ -225,6 +225,7 @@ static __global__ void __launch_bounds__(128) fold_affine_weight_kernel(const fl
       v = wr[c] * a[b * cin + c];
       s = fmaf(wr[c], d[b * cin + c], s);
     }
+    if (round_tf32) v = tf32_rna(v);   // operand of a tf32 MMA
     dst[c] = from_f32<T>(v);
   }
   s = block_sum(s, sh);
@@ -271,6 +272,10 @@ static __global__ void drop_path_scale_kernel(float* __restrict__ out, int B, fl
   const float keep = 1.0f - drop_prob;
   const float u = philox_uniform(seed, offset, (uint64_t)b);
   out[b] = floorf(keep + u) / keep;
+}
+
+static __global__ void round_tf32_kernel(float* __restrict__ p, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = tf32_rna(p[i]);
 }
 
 // device-resident Philox state {seed, offset}: one forward owns SFNO_RNG_OFFSETS_PER_FORWARD consecutive offsets
@@ -326,7 +331,7 @@ struct ConcatParts {
   int nparts;
 };
 template <class T>
-static __global__ void concat_convert_kernel(ConcatParts parts, int64_t hw, T* __restrict__ dst, int64_t dst_bstride) {
+static __global__ void concat_convert_kernel(ConcatParts parts, int64_t hw, T* __restrict__ dst, int64_t dst_bstride, int round_tf32 = 0) {
   const int b = blockIdx.y;
   int coff = 0;
   for (int k = 0; k < parts.nparts; ++k) {
@@ -347,7 +352,7 @@ static __global__ void concat_convert_kernel(ConcatParts parts, int64_t hw, T* _
       }
     } else {
       for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x)
-        d[i] = from_f32<T>(s[i]);
+        d[i] = from_f32<T>(round_tf32 ? tf32_rna(s[i]) : s[i]);
     }
     coff += parts.channels[k];
   }

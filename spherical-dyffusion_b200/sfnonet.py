@@ -474,6 +474,8 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
         if self._net is not None:
             with torch.cuda.device(self._net_device):
                 self.sync_parameters(self._net_device)
+                if self._rng_state is not None:
+                    self._rng(self._net_device)   # a pending seed_dropout() re-keys the state the graph reads
 
     def seed_dropout(self, seed: int, offset: int = 0):
         """Re-key the dropout Philox stream: the next forward with live dropout draws from (seed, offset), every later
@@ -487,7 +489,11 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
         if self._rng_state is None or self._rng_state.device != device or self._rng_key != key:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("the dropout RNG state must exist before a CUDA-graph capture: run one eager forward first")
-            self._rng_state = torch.tensor(list(key), dtype=torch.int64).to(device)
+            fresh = torch.tensor(list(key), dtype=torch.int64)
+            if self._rng_state is not None and self._rng_state.device == device:
+                self._rng_state.copy_(fresh)   # in place: captured graphs have this tensor's address baked in
+            else:
+                self._rng_state = fresh.to(device)
             self._rng_key = key
         return self._rng_state
 

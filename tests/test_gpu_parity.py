@@ -18,8 +18,10 @@ from spherical_dyffusion_b200._util import stream_ptr, workspace
 pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-4      # north_star: <= 1e-4 relative L2 in fp32
-BF16_BOUND = 3e-2    # stated bf16 bound on the end-to-end forward (measured values are logged by the tests)
-BF16_OP_BOUND = 1e-2  # single transform / op in bf16
+BF16_BOUND = 1.35e-2  # stated bf16 bound on the end-to-end forward: 1.5 x the largest measured value (8.93e-3, profiles/r02_b_pytest_gpu.log)
+BF16_OP_BOUND = 5.7e-3  # single transform / op in bf16: 1.5 x measured (3.75e-3)
+TF32_BOUND = 3e-3     # tf32 mode (fp32 storage, kind::tf32 tensor-core MMA), end-to-end forward
+TF32_OP_BOUND = 1e-3  # single transform in tf32
 
 
 @pytest.fixture(scope="module")
@@ -508,3 +510,83 @@ def test_net_embed512_matches_oracle(dev):
         with torch.inference_mode():
             y = m(x.to(dev), time=t.to(dev), condition=c.to(dev))
         assert rel_l2(y, ref) < tol, precision
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tf32 mode: fp32 storage, tcgen05 kind::tf32 (VERDICT r1 "missing" 1: an fp32-grade tensor-core mode)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("grid", ["legendre-gauss", "equiangular"])
+def test_sht_tf32_bound(dev, grid):
+    nlat, nlon = 180, 360
+    x = torch.randn(1, 16, nlat, nlon, generator=torch.Generator().manual_seed(3))
+    X_ref = oh.RealSHT(nlat, nlon, lmax=180, mmax=181, grid=grid).float()(x)
+    X = sb.RealSHT(nlat, nlon, lmax=180, mmax=181, grid=grid, precision="tf32")(x.to(dev))
+    e_fwd = rel_l2(X, X_ref)
+    xr_ref = oh.InverseRealSHT(nlat, nlon, lmax=180, mmax=181, grid=grid).float()(X_ref)
+    xr = sb.InverseRealSHT(nlat, nlon, lmax=180, mmax=181, grid=grid, precision="tf32")(X_ref.to(dev))
+    e_inv = rel_l2(xr, xr_ref)
+    print(f"tf32 SHT rel-L2: forward {e_fwd:.3e} inverse {e_inv:.3e} ({grid})")
+    assert e_fwd < TF32_OP_BOUND and e_inv < TF32_OP_BOUND
+
+
+@pytest.mark.parametrize("case", ["sfno_dhconv_12x24", "sfno_dhconv_18x36_lg", "sfno_dhconv_16x32_variants", "sfno_dhconv_24x48_interp"])
+def test_net_forward_tf32_matches_golden(dev, load_golden, case):
+    fx = load_golden(case)
+    cfg = SFNOConfig(**fx["cfg"])
+    m = module_from_cfg(cfg, fx["state_dict"], dev, "tf32")
+    cond = fx["condition"].to(dev) if fx["condition"] is not None else None
+    time = fx["time"].to(dev) if fx["time"] is not None else None
+    with torch.inference_mode():
+        y = m(fx["inputs"].to(dev), time=time, condition=cond)
+    e = rel_l2(y, fx["output"])
+    print(f"{case}: tf32 out rel-L2 {e:.3e}")
+    assert e < TF32_BOUND
+
+
+def test_ace_forward_tf32(dev, ace_case):
+    """ACE-sized forward in tf32 mode against the fp32 oracle, next to an EMULATION of what the reference computes under
+    torch_matmul_precision "high" (config_utils.py:310-313): the oracle with matmul operands rounded to TF32."""
+    cfg, sd, x, c, t, ref = ace_case
+    m = module_from_cfg(cfg, sd, dev, "tf32")
+    with torch.inference_mode():
+        y = m(x.to(dev), time=t.to(dev), condition=c.to(dev))
+    e = rel_l2(y, ref)
+    emu = rel_l2(SFNOOracle(cfg, sd, tf32_matmul=True)(x, time=t, condition=c), ref)
+    print(f"ACE-sized forward tf32 rel-L2 vs fp32 oracle: {e:.3e}; oracle with TF32-rounded matmul operands: {emu:.3e}")
+    assert e < TF32_BOUND
+
+
+# ---------------------------------------------------------------------------------------------------------
+# rollout step glue (SURVEY 8f-3): normalise + pack / prescribe + denormalise against the reference's own classes
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["mask_int", "interp", "mask_zero"])
+def test_step_glue_matches_reference_classes(dev, case):
+    """tests/golden/rollout_glue.pt was produced by the reference's StandardNormalizer / Packer / Prescriber
+    (tests/golden/make_golden_rollout.py); the two fused kernels reproduce it."""
+    import os
+
+    from spherical_dyffusion_b200.rollout import StepGlue
+
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rollout_glue.pt"), map_location="cpu",
+                    weights_only=False)[case]
+    c = fx["spec"]
+    glue = StepGlue(c["names"], c["out"], fx["means"], fx["stds"], prescribed_name=c["prescribed"], mask_name=c["mask"],
+                    mask_value=c["mask_value"], interpolate=c["interpolate"])
+    packed = glue.normalize_pack({k: v.to(dev) for k, v in fx["data"].items()})
+    assert packed.shape == fx["packed_norm"].shape
+    assert torch.allclose(packed.cpu(), fx["packed_norm"], rtol=1e-6, atol=1e-6)
+    p = c["prescribed"]
+    target_norm = ((fx["target"][p] - fx["means"][p]) / fx["stds"][p]).to(dev)
+    gen = fx["gen"].to(dev).clone()
+    out, den = glue.finish(gen, target_norm, fx["target"][c["mask"]].to(dev))
+    assert out.data_ptr() == gen.data_ptr()                       # in place: it seeds the next window
+    assert torch.allclose(out.cpu(), fx["gen_prescribed"], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(den.cpu(), fx["gen_denorm"], rtol=1e-6, atol=1e-4)
+    # without a prescriber: denormalise only
+    plain = StepGlue(c["names"], c["out"], fx["means"], fx["stds"])
+    g2 = fx["gen"].to(dev).clone()
+    _, den2 = plain.finish(g2)
+    mean = torch.tensor([fx["means"][n] for n in c["out"]]).view(1, -1, 1, 1)
+    std = torch.tensor([fx["stds"][n] for n in c["out"]]).view(1, -1, 1, 1)
+    assert torch.equal(g2.cpu(), fx["gen"])
+    assert torch.allclose(den2.cpu(), fx["gen"] * std + mean, rtol=1e-6, atol=1e-4)

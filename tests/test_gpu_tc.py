@@ -59,8 +59,38 @@ CASES = [
 ]
 
 
-def _run_case(op, dims, tc_debug=0):
-    cmd = [sys.executable, os.path.join(ROOT, "tests", "tc_selftest_cli.py"), str(OPS[op])] + [str(d) for d in dims]
+# fp32 storage through the tensor cores as TF32 (kind::tf32) vs the CUDA-core FMA engine on TF32-exact operands: both
+# compute the same products, only the fp32 summation order differs.  Same op kinds (+100 in the C entry point).
+TF32_CASES = [
+    ("leg", [1, 8, 16, 16, 9, 0], True),
+    ("leg", [2, 64, 180, 180, 181, 1], True),      # triangular, dual-M tiles
+    ("leg", [2, 64, 180, 180, 5, 0], True),
+    ("dft", [1, 8, 16, 32, 17, 0], True),
+    ("dft", [2, 32, 180, 360, 181, 0], True),       # K = 360: 11 full K blocks of 32 + one of 8
+    ("dft", [1, 8, 18, 36, 19, 0], True),           # nlon * 4 bytes IS 16-byte aligned in fp32
+    ("dhconv", [2, 64, 20, 21, 0, 0], True),
+    ("dhconv", [3, 32, 20, 21, 1, 0], True),
+    ("dhconv", [2, 256, 180, 181, 1, 0], True),
+    ("ileg", [1, 8, 16, 16, 9, 1], True),           # MN-major A operand in 32-element atoms, X layout
+    ("ileg", [2, 64, 180, 180, 181, 2], True),
+    ("ileg", [2, 64, 180, 180, 181, 3], True),
+    ("idft", [1, 8, 16, 32, 17, 0], True),
+    ("idft", [2, 16, 180, 360, 181, 7], True),      # + bias + fp32 addend staged by TMA (two 32-column passes) -> GELU
+    ("idft", [2, 64, 180, 360, 181, 0], True),
+    ("convb", [2, 36, 256, 64800, 0, 3], True),     # MN-major B operand (pixels), K = 36 tail
+    ("convb", [2, 256, 256, 64800, 0, 8], True),    # + pos-embed
+    ("convb", [2, 256, 512, 64800, 1, 3], True),    # fc1: folded weights, bias, GELU (exact erf in this mode)
+    ("convb", [2, 512, 256, 64800, 0, 5], True),    # fc2: bias + affine fp32 residual staged by TMA
+    ("convb", [2, 512, 256, 64800, 0, 21], True),   # ... with dropout
+    ("convb", [2, 256, 256, 64800, 1, 15], True),
+    ("convb", [2, 256, 34, 64800, 0, 0], True),     # decoder1: 34 rows
+    ("convb", [1, 16, 16, 300, 0, 0], True),        # hw * 4 bytes is 16-byte aligned in fp32
+    ("convb", [1, 16, 16, 301, 0, 0], False),       # hw not a multiple of 8 -> CUDA-core engine
+]
+
+
+def _run_case(op, dims, tc_debug=0, tf32=False):
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "tc_selftest_cli.py"), str(OPS[op] + (100 if tf32 else 0))] + [str(d) for d in dims]
     env = dict(os.environ)
     env.pop("SFNO_TC_DEBUG", None)
     if tc_debug:
@@ -111,3 +141,17 @@ def test_tc_engine_matches_cuda_core_engine(op, dims, expect_tc):
     tol = 2e-5 if op == "conv" else 1.2e-2
 
     assert r["max_err"] <= tol * r["max_ref"], r
+
+
+@pytest.mark.parametrize("op,dims,expect_tc", TF32_CASES, ids=[f"tf32-{c[0]}-{'x'.join(map(str, c[1]))}" for c in TF32_CASES])
+def test_tf32_engine_matches_cuda_core_engine(op, dims, expect_tc):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    r = _run_case(op, dims, tf32=True)
+    print(json.dumps(r))
+    assert r["status"] == 0, r["error"]
+    assert bool(r["tc_used"]) == expect_tc
+    assert r["nonfinite"] == 0
+    assert r["max_ref"] > 0
+    # identical products (TF32-exact operands), fp32 accumulation in both engines, fp32 outputs (not rounded here)
+    assert r["max_err"] <= 3e-5 * r["max_ref"], r
