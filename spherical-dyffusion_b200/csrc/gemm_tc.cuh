@@ -69,7 +69,7 @@ struct TmaOperand {
 // are the swizzled staging rows of an epilogue warp: either ONE box of all 32 rows (one TMA instruction per warp and
 // pass) or four boxes of 8 rows.  A warp-divergent TMA instruction is executed as a serial loop over the issuing
 // lanes whose iterations wait for the previous one to release its uniform registers (measured: 14-26 % of the stall
-// samples of the conv / DFT kernels, profiles/r02_d_source_stalls.md), so the 32-row form is used whenever 32
+// samples of the conv / DFT kernels, profiles/r02_c_source_stalls.md), so the 32-row form is used whenever 32
 // consecutive GEMM rows map to a box of the tensor (box_rows = extents of dims[1..4], product 32 or 8); shapes that
 // cannot guarantee even 8 are not eligible for this engine.
 struct TmaIo {
@@ -322,7 +322,8 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&v)[8]) {
 template <class Op, int BN, bool kDual>
 __global__ void __launch_bounds__(tc_threads(BN), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res, const Op op, const TcSched sc) {
+               const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
+               const __grid_constant__ CUtensorMap tma_out8, const Op op, const TcSched sc) {
   using S = TcSmem<BN, Op::kColContig, kDual, Op::kStagingBufs>;
   using E = TcElem<typename Op::InT>;
   constexpr int kBK = E::kBK;              // K block in elements (one 128-byte swizzle span)
@@ -705,12 +706,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           // staged rows -> global: one TMA store per 8-row group; rows / columns outside the tensor are clipped
           ptx::fence_proxy_async();
           __syncwarp();
-          if (gissue && !(sc.dbg & 4)) {
-            int c[5];
-            op.io_coords(g, out32 ? wrow0 : grow0, pn0, c);
-            ptx::tma_store_5d(&tma_out, region + (out32 ? 0u : (uint32_t)lane * 1024u), c);
-            if constexpr (Op::kSplitBox) {   // 32 rows that straddle two planes of the output: a second, clipped box
-              if (out32 && op.io_coords_second(g, wrow0, pn0, c)) ptx::tma_store_5d(&tma_out, region, c);
+          if (!(sc.dbg & 4)) {
+            // a warp whose 32 rows straddle two planes of the output (Op::kSplitBox: the inverse DFT, whose planes hold
+            // Kp = nlat rounded to 8 GEMM rows) falls back to four 8-row boxes through the second tensor map (TMA
+            // stores do not take negative box origins, so a clipped second 32-row box is not an option)
+            const bool split = Op::kSplitBox && out32 && op.box_straddles(wrow0);   // warp-uniform
+            if (out32 && !split) {
+              if (gissue) {
+                int c[5];
+                op.io_coords(g, wrow0, pn0, c);
+                ptx::tma_store_5d(&tma_out, region, c);
+              }
+            } else if (lane < 4 && grow0 < op.m_end(g)) {
+              int c[5];
+              op.io_coords(g, grow0, pn0, c);
+              ptx::tma_store_5d(out32 ? &tma_out8 : &tma_out, region + (uint32_t)lane * 1024u, c);
             }
           }
           if (lane < 4) ptx::bulk_commit();
@@ -845,7 +855,7 @@ int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what) {
   if (op.M <= 0 || op.N <= 0 || op.G <= 0) return SFNO_OK;
   TmaOperand a, b;
   Tr::operands(op, a, b);
-  CUtensorMap ma, mb, mo, mr;
+  CUtensorMap ma, mb, mo, mr, mo8;
   using E = TcElem<typename Op::InT>;
   SFNO_TRY(encode_operand<typename Op::InT>(a, Op::A_KCONTIG, TC_BM, &ma, what));
   SFNO_TRY(encode_operand<typename Op::InT>(b, Op::B_KCONTIG, BN, &mb, what));
@@ -853,6 +863,12 @@ int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what) {
   Tr::io(op, io_out, io_res);
   if (!tma_io_ok(io_out)) return fail(SFNO_ERR_UNSUPPORTED, "%s: output tensor is not expressible as TMA boxes (eligibility not checked?)", what);
   SFNO_TRY(encode_io(io_out, &mo, what));
+  mo8 = mo;
+  if (Op::kSplitBox && tma_io_rows(io_out) == 32) {   // 8-row boxes for the warps whose 32 rows straddle two planes
+    TmaIo io8 = io_out;
+    io8.box_rows[0] = 8;
+    SFNO_TRY(encode_io(io8, &mo8, what));
+  }
   if (Tr::has_residual(op)) {
     if (!tma_io_ok(io_res)) return fail(SFNO_ERR_UNSUPPORTED, "%s: residual tensor is not expressible as TMA boxes", what);
     SFNO_TRY(encode_io(io_res, &mr, what));
@@ -896,7 +912,7 @@ int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what) {
   attr[0].val.programmaticStreamSerializationAllowed = (sc.dbg & 1024) ? 0 : 1;   // tc_debug bit10: plain stream order
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SFNO_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, mr, op, sc));
+  SFNO_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, mr, mo8, op, sc));
   return post_launch(what);
 }
 

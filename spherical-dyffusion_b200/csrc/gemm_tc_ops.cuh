@@ -145,7 +145,7 @@ struct TcTraits<OpIdft<T, TOut, ACT>> : TcTraitsBase<OpIdft<T, TOut, ACT>>,
       r = o;
       r.base = op.add; r.strides[2] = (uint64_t)op.add_bstride * es;
     }
-    o.box_rows[0] = 32;   // stores: one 32-latitude box, plus a second clipped one where the rows straddle two planes
+    o.box_rows[0] = 32;   // stores: one 32-latitude box per warp; warps whose rows straddle two planes use 8-row boxes
   }
 };
 

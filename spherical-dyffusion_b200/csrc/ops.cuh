@@ -67,7 +67,7 @@ __device__ __forceinline__ f2 act_ct2(int act_rt, f2 v) {
 
 struct NoSplitBox {   // 32 consecutive GEMM rows never straddle two planes of the output tensor
   static constexpr bool kSplitBox = false;
-  __device__ bool io_coords_second(int, int, int, int (&)[5]) const { return false; }
+  __device__ bool box_straddles(int) const { return false; }
 };
 struct NoFeatures : NoSplitBox {
   static constexpr int kStagingBufs = 1;   // load-bound ops: shared memory goes to the operand ring
@@ -362,18 +362,10 @@ struct OpIdft : IdftArgs<T, TOut>, FullRanges {
     c[0] = col0; c[1] = row0 - bo * this->Kp; c[2] = bo - b * this->C; c[3] = b; c[4] = 0;
   }
   __device__ void res_coords(int g, int row0, int col0, int (&c)[5]) const { io_coords(g, row0, col0, c); }
-  // One 32-row box covers the rows [row0, row0 + 32) of plane bo; when they run past the plane (Kp rows, the pad rows
-  // kp >= nlat have no destination and are clipped) the rest belongs to plane bo + 1: the SAME staging rows are stored
-  // once more with the box origin at the negative latitude k0 - Kp of that plane -- staged row r lands on latitude
-  // k0 - Kp + r, rows above the plane (negative latitude) are clipped.  Stores only: a load would zero-fill.
+  // A plane (b, o) holds Kp GEMM rows (nlat rounded up to 8: the pad rows have no destination and are clipped by the
+  // tensor extent).  The 32 rows of a warp may run past the plane; those warps store in 8-row boxes, which never do.
   static constexpr bool kSplitBox = true;
-  __device__ bool io_coords_second(int, int row0, int col0, int (&c)[5]) const {
-    const int bo = row0 / this->Kp, k0 = row0 - bo * this->Kp;
-    if (k0 + 32 <= this->Kp) return false;
-    const int bo2 = bo + 1, b = bo2 / this->C;
-    c[0] = col0; c[1] = k0 - this->Kp; c[2] = bo2 - b * this->C; c[3] = b; c[4] = 0;
-    return true;
-  }
+  __device__ bool box_straddles(int row0) const { return row0 % this->Kp + 32 > this->Kp; }
   struct Row {
     TOut* out; const T* res; bool valid; float bias; f2 s2, q2;   // s2 / q2: packed partial sum / sum of squares
     __device__ float stat_s() const { return f2_hsum(s2); }

@@ -20,8 +20,8 @@ pytestmark = pytest.mark.gpu
 FP32_TOL = 1e-4      # north_star: <= 1e-4 relative L2 in fp32
 BF16_BOUND = 1.35e-2  # stated bf16 bound on the end-to-end forward: 1.5 x the largest measured value (8.93e-3, profiles/r02_b_pytest_gpu.log)
 BF16_OP_BOUND = 5.7e-3  # single transform / op in bf16: 1.5 x measured (3.75e-3)
-TF32_BOUND = 3e-3     # tf32 mode (fp32 storage, kind::tf32 tensor-core MMA), end-to-end forward
-TF32_OP_BOUND = 1e-3  # single transform in tf32
+TF32_BOUND = 1.8e-3   # tf32 mode (fp32 storage, kind::tf32 tensor-core MMA), end-to-end forward: 1.5 x measured (1.21e-3; ACE 1.09e-3)
+TF32_OP_BOUND = 8e-4  # single transform in tf32: 1.5 x measured (5.25e-4)
 
 
 @pytest.fixture(scope="module")
