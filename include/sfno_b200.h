@@ -110,9 +110,38 @@ int sfno_sht_inverse(const sfno_sht_plan* plan, const float* coeffs_dev, float* 
  *   x_dev      complex64 [batch][cin][lmax][mmax]
  *   weight_dev fp32 real view [cin][cout][lmax][2] (dhconv) or [cin][cout][lmax][mmax][2] (diagonal)
  *   out_dev    complex64 [batch][cout][lmax][mmax]
- * fp32 CUDA-core arithmetic (the packed tensor-core form lives inside sfno_net_forward). */
+ * fp32 CUDA-core arithmetic; the packed tensor-core form is sfno_spectral_conv (and lives inside sfno_net_forward). */
 int sfno_spectral_contract(int operator_type, const float* x_dev, const float* weight_dev, float* out_dev,
                            int batch, int cin, int cout, int lmax, int mmax, void* stream);
+
+/* ---- fused spectral convolution and precision-selectable pieces (SURVEY 8b "must export") -----------
+ * sfno_spectral_conv replaces SpectralConvS2.forward (src/models/sfno/s2convolutions.py:158-193) as ONE call:
+ *   X = RealSHT(x);  residual = InverseRealSHT(X) if the two transforms differ (:166-169), else the caller keeps x;
+ *   Y = contract(X, weight) (:172-179);  y = InverseRealSHT(Y) + bias (:186-189)
+ * on the tensor-core ops of the plans' precision (SFNO_PREC_BF16: kind::f16, SFNO_PREC_TF32: kind::tf32, SFNO_PREC_F32:
+ * CUDA-core parity engine).  The weight handle owns the packed form of filter.weight ([cin][cout][lmax][2] dhconv,
+ * [cin][cout][lmax][mmax][2] diagonal; fp32, reference layout) and filter.bias ([cout] or NULL); call _set again after an
+ * in-place update.  x_dev [batch][cin][nlat][nlon] fp32 (forward plan's grid), y_dev [batch][cout][nlat'][nlon'] fp32
+ * (inverse plan's grid), residual_dev NULL or [batch][cin][nlat'][nlon']. */
+typedef struct sfno_spectral_weight sfno_spectral_weight;
+int sfno_spectral_weight_create(sfno_spectral_weight** weight, int operator_type, int cin, int cout, int lmax, int mmax,
+                                int precision);
+int sfno_spectral_weight_set(sfno_spectral_weight* weight, const float* weight_dev, const float* bias_dev, void* stream);
+int sfno_spectral_weight_destroy(sfno_spectral_weight* weight);
+size_t sfno_spectral_conv_workspace_bytes(const sfno_sht_plan* fwd, const sfno_sht_plan* inv,
+                                          const sfno_spectral_weight* weight, int batch);
+int sfno_spectral_conv(const sfno_sht_plan* fwd, const sfno_sht_plan* inv, const sfno_spectral_weight* weight,
+                       const float* x_dev, float* y_dev, float* residual_dev, int batch, void* workspace_dev,
+                       size_t workspace_bytes, void* stream);
+/* nn.Conv2d(cin, cout, 1) with the fused epilogue of the hot path -- + bias -> activation -> dropout(p; Philox stream
+ * (seed, offset); layers.py:76-80, live at inference: dyffusion.py:226-235) + residual -- and a selectable engine:
+ * SFNO_PREC_BF16 / SFNO_PREC_TF32 stage the operands in the workspace and run the tensor-core op, SFNO_PREC_F32 is
+ * sfno_conv1x1 (no workspace needed).  Tensors as sfno_conv1x1. */
+size_t sfno_conv1x1_ex_workspace_bytes(int batch, int cin, int cout, int64_t hw, int precision);
+int sfno_conv1x1_ex(const float* x_dev, const float* weight_dev, const float* bias_dev, const float* residual_dev,
+                    float* y_dev, int batch, int cin, int cout, int64_t hw, int activation, float dropout_p,
+                    uint64_t seed, uint64_t offset, int precision, void* workspace_dev, size_t workspace_bytes,
+                    void* stream);
 
 /* ---- pointwise pieces (fp32, NCHW) -- exported so each can be parity-tested on its own ------------- */
 /* nn.InstanceNorm2d(C, eps, affine=True, track_running_stats=False) (sfnonet.py:641-647), optionally
@@ -215,6 +244,11 @@ int sfno_ensemble_stats(const float* members_dev, const float* truth_dev, int me
                         float* var_dev, float* crps_dev, void* stream);
 int sfno_ensemble_crps(const float* members_dev, const float* truth_dev, int members, int64_t n,
                        float* crps_dev, void* stream);
+/* Same on a subset of the rows of members_dev: rows_dev[members] (int32, device) are the row indices of the live members
+ * in the all-gathered buffer of UNEVEN shards (25 members over 8 ranks: 4+3+...: every rank contributes max-local rows,
+ * the surplus rows are padding).  The statistics are invariant under member order, so nothing is re-ordered or compacted. */
+int sfno_ensemble_stats_rows(const float* members_dev, const int* rows_dev, const float* truth_dev, int members, int64_t n,
+                             float* mean_dev, float* var_dev, float* crps_dev, void* stream);
 
 /* ---- sampler glue (caller of the hot path) ---------------------------------------------
  * Cold-sampling update of BaseDYffusion.sample_loop (src/diffusion/dyffusion.py:519):

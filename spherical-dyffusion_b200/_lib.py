@@ -78,6 +78,15 @@ _SIGNATURES = {
     "sfno_ensemble_shifted_moments": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "sfno_ensemble_finalize": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "sfno_ensemble_stats": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sfno_ensemble_stats_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sfno_spectral_weight_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int]),
+    "sfno_spectral_weight_set": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sfno_spectral_weight_destroy": (c_int, [c_void_p]),
+    "sfno_spectral_conv_workspace_bytes": (c_size_t, [c_void_p, c_void_p, c_void_p, c_int]),
+    "sfno_spectral_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "sfno_conv1x1_ex_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int64, c_int]),
+    "sfno_conv1x1_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_float,
+                                c_uint64, c_uint64, c_int, c_void_p, c_size_t, c_void_p]),
     "sfno_ensemble_crps": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "sfno_normalize_pack": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfno_prescribe_denormalize": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,

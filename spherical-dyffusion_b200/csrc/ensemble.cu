@@ -68,16 +68,20 @@ __global__ void ensemble_finalize_kernel(const float* __restrict__ sum_global, c
 
 // One pass over ALL members of a grid point held in registers: ensemble mean, unbiased two-pass variance and the fair
 // CRPS via the sorted form  sum_{i<j}|x_i-x_j| = sum_k (2k - E + 1) x_(k).  truth / crps may be NULL (moments only).
+// rows: optional [E] row indices into x (the all-gathered, padded member buffer of uneven shards); nullptr = 0 .. E-1
 template <int MAXE>
-__global__ void ensemble_stats_kernel(const float* __restrict__ x, const float* __restrict__ truth, int E, int64_t n,
-                                      float* __restrict__ mean, float* __restrict__ var, float* __restrict__ crps) {
+__global__ void ensemble_stats_kernel(const float* __restrict__ x, const int* __restrict__ rows, const float* __restrict__ truth, int E,
+                                      int64_t n, float* __restrict__ mean, float* __restrict__ var, float* __restrict__ crps) {
+  __shared__ int srow[MAXE];
+  for (int e = threadIdx.x; e < MAXE; e += blockDim.x) srow[e] = (e < E) ? (rows ? rows[e] : e) : 0;
+  __syncthreads();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v[MAXE];
     const float y = truth ? truth[i] : 0.0f;
     float skill = 0.0f, s = 0.0f;
 #pragma unroll
     for (int e = 0; e < MAXE; ++e) {
-      v[e] = e < E ? x[(int64_t)e * n + i] : 3.0e38f;
+      v[e] = e < E ? x[(int64_t)srow[e] * n + i] : 3.0e38f;
       if (e < E) { skill += fabsf(v[e] - y); s += v[e]; }
     }
     const float mu = s / (float)E;
@@ -156,17 +160,25 @@ int sfno_ensemble_finalize(const float* sum_global_dev, const float* moments_dev
   return post_launch("ensemble_finalize");
 }
 
+int sfno_ensemble_stats_rows(const float* members_dev, const int* rows_dev, const float* truth_dev, int members, int64_t n, float* mean_dev,
+                             float* var_dev, float* crps_dev, void* stream);
+
 int sfno_ensemble_stats(const float* members_dev, const float* truth_dev, int members, int64_t n, float* mean_dev, float* var_dev,
                         float* crps_dev, void* stream) {
+  return sfno_ensemble_stats_rows(members_dev, nullptr, truth_dev, members, n, mean_dev, var_dev, crps_dev, stream);
+}
+
+int sfno_ensemble_stats_rows(const float* members_dev, const int* rows_dev, const float* truth_dev, int members, int64_t n, float* mean_dev,
+                             float* var_dev, float* crps_dev, void* stream) {
   SFNO_CHECK_ARG(members_dev && members > 0 && n > 0, "bad arguments");
   SFNO_CHECK_ARG(crps_dev == nullptr || truth_dev != nullptr, "the CRPS needs a truth field");
   if (members > 64) return fail(SFNO_ERR_UNSUPPORTED, "at most 64 members, got %d", members);
   const unsigned grid = stream_grid(n, 128) * 2;
   cudaStream_t st = (cudaStream_t)stream;
-  if (members <= 8) ensemble_stats_kernel<8><<<grid, 128, 0, st>>>(members_dev, truth_dev, members, n, mean_dev, var_dev, crps_dev);
-  else if (members <= 16) ensemble_stats_kernel<16><<<grid, 128, 0, st>>>(members_dev, truth_dev, members, n, mean_dev, var_dev, crps_dev);
-  else if (members <= 32) ensemble_stats_kernel<32><<<grid, 128, 0, st>>>(members_dev, truth_dev, members, n, mean_dev, var_dev, crps_dev);
-  else ensemble_stats_kernel<64><<<grid, 128, 0, st>>>(members_dev, truth_dev, members, n, mean_dev, var_dev, crps_dev);
+  if (members <= 8) ensemble_stats_kernel<8><<<grid, 128, 0, st>>>(members_dev, rows_dev, truth_dev, members, n, mean_dev, var_dev, crps_dev);
+  else if (members <= 16) ensemble_stats_kernel<16><<<grid, 128, 0, st>>>(members_dev, rows_dev, truth_dev, members, n, mean_dev, var_dev, crps_dev);
+  else if (members <= 32) ensemble_stats_kernel<32><<<grid, 128, 0, st>>>(members_dev, rows_dev, truth_dev, members, n, mean_dev, var_dev, crps_dev);
+  else ensemble_stats_kernel<64><<<grid, 128, 0, st>>>(members_dev, rows_dev, truth_dev, members, n, mean_dev, var_dev, crps_dev);
   return post_launch("ensemble_stats");
 }
 

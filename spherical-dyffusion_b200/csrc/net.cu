@@ -110,31 +110,6 @@ static WsLayout ws_layout(const sfno_net* n, int B) {
   return w;
 }
 
-// diagonal operator on the internal layouts: X[l][m][b][ri][c] -> Y[l][m][b][ri][o], w[i][o][l][m][2]
-template <class T>
-__global__ void diag_contract_internal_kernel(const T* __restrict__ X, const float2* __restrict__ w, T* __restrict__ Y,
-                                              int B, int C, int L, int M) {
-  const int64_t total = (int64_t)L * M * B * C;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int o = (int)(idx % C);
-    int64_t r = idx / C;
-    const int b = (int)(r % B); r /= B;
-    const int m = (int)(r % M);
-    const int l = (int)(r / M);
-    const T* xr = X + (((int64_t)l * M + m) * B + b) * 2 * C;
-    float re = 0.0f, im = 0.0f;
-    for (int i = 0; i < C; ++i) {
-      const float xa = to_f32(xr[i]), xb = to_f32(xr[C + i]);
-      const float2 wv = w[(((int64_t)i * C + o) * L + l) * M + m];
-      re = fmaf(xa, wv.x, re); re = fmaf(-xb, wv.y, re);
-      im = fmaf(xa, wv.y, im); im = fmaf(xb, wv.x, im);
-    }
-    T* yr = Y + (((int64_t)l * M + m) * B + b) * 2 * C;
-    yr[o] = from_f32<T>(re);
-    yr[C + o] = from_f32<T>(im);
-  }
-}
-
 static thread_local bool g_pack_tf32 = false;
 
 // operands of a tf32 MMA are stored TF32-exact (round to nearest here; the tensor core would truncate)

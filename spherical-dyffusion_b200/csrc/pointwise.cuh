@@ -441,4 +441,30 @@ static __global__ void internal_to_coeffs_kernel(const T* __restrict__ x, float*
   }
 }
 
+// diagonal operator on the internal layouts: X[l][m][b][ri][c] -> Y[l][m][b][ri][o], w[i][o][l][m][2]
+template <class T>
+static __global__ void diag_contract_internal_kernel(const T* __restrict__ X, const float2* __restrict__ w, T* __restrict__ Y,
+                                              int B, int C, int L, int M) {
+  const int64_t total = (int64_t)L * M * B * C;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(idx % C);
+    int64_t r = idx / C;
+    const int b = (int)(r % B); r /= B;
+    const int m = (int)(r % M);
+    const int l = (int)(r / M);
+    const T* xr = X + (((int64_t)l * M + m) * B + b) * 2 * C;
+    float re = 0.0f, im = 0.0f;
+    for (int i = 0; i < C; ++i) {
+      const float xa = to_f32(xr[i]), xb = to_f32(xr[C + i]);
+      const float2 wv = w[(((int64_t)i * C + o) * L + l) * M + m];
+      re = fmaf(xa, wv.x, re); re = fmaf(-xb, wv.y, re);
+      im = fmaf(xa, wv.y, im); im = fmaf(xb, wv.x, im);
+    }
+    T* yr = Y + (((int64_t)l * M + m) * B + b) * 2 * C;
+    yr[o] = from_f32<T>(re);
+    yr[C + o] = from_f32<T>(im);
+  }
+}
+
+
 }  // namespace sfno

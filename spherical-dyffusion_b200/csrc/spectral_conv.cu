@@ -1,0 +1,272 @@
+// Op-level B200-native entry points of the spectral branch (SURVEY 8b "must export"): the fused SpectralConvS2.forward
+// (s2convolutions.py:158-193) and precision-selectable pieces, on the SAME tensor-core ops the whole-network executor
+// uses (bf16: kind::f16, tf32: kind::tf32, fp32: CUDA-core parity engine) -- so a maintainer who swaps only the
+// SpectralConvS2 / Conv2d sub-modules of the reference model gets the B200 path, not an fp32 side door.
+#include <cstring>
+
+#include "common.cuh"
+#include "engine.cuh"
+#include "ops.cuh"
+#include "pointwise.cuh"
+#include "sht_plan.cuh"
+
+struct sfno_spectral_weight {
+  int operator_type = 0, cin = 0, cout = 0, lmax = 0, mmax = 0, precision = 0;
+  void* wpack = nullptr;   // dhconv: T [lmax][2*cout][2*cin] (packed real form of the complex weight)
+  float* wdiag = nullptr;  // diagonal: fp32 [cin][cout][lmax][mmax][2] (reference layout)
+  float* bias = nullptr;   // [cout]
+  bool has_bias = false;
+};
+
+namespace sfno {
+
+struct SpecWs { size_t xt, fg, X, Y, total; };
+static SpecWs spec_ws_layout(const ShtDeviceTables& f, const ShtDeviceTables& i, int B, int cin, int cout) {
+  const size_t e = f.precision == SFNO_PREC_BF16 ? 2 : 4;
+  const int cmax = std::max(cin, cout);
+  SpecWs w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  w.xt = take((size_t)B * cin * f.nlat * f.nlon * e);
+  w.fg = take((size_t)f.mmax * B * 2 * cmax * std::max(f.Kp, i.Kp) * e);
+  w.X = take((size_t)f.lmax * f.mmax * B * 2 * cin * e);
+  w.Y = take((size_t)f.lmax * f.mmax * B * 2 * cout * e);
+  w.total = off;
+  return w;
+}
+
+template <class T>
+static int spec_forward(const ShtDeviceTables& t, int B, int C, const T* x, T* F, T* X, int triangular, cudaStream_t st) {
+  OpDft<T> dft{};
+  dft.G = B * C; dft.M = 2 * t.mmax; dft.N = t.nlat; dft.K = t.nlon;
+  dft.A = (const T*)t.efwd; dft.Bm = x; dft.a_sk = 1; dft.b_sk = 1;
+  dft.f = F; dft.aff_a = nullptr; dft.aff_d = nullptr;
+  dft.B = B; dft.C = C; dft.nlat = t.nlat; dft.nlon = t.nlon; dft.Kp = t.Kp; dft.Wp = t.Wp; dft.x_bstride = (int64_t)C * t.nlat * t.nlon;
+  dft.a_reps = t.basis_reps; dft.round_out = 1;
+  SFNO_TRY(launch_gemm(dft, st, "dft_fwd"));
+  OpLeg<T> leg{};
+  leg.G = t.mmax; leg.M = t.lmax; leg.N = B * 2 * C; leg.K = t.nlat;
+  leg.A = (const T*)t.wq; leg.Bm = F; leg.a_sk = 1; leg.b_sk = 1;
+  leg.x = X; leg.Kp = t.Kp; leg.lmax = t.lmax; leg.mmax = t.mmax; leg.triangular = triangular; leg.round_out = 1;
+  return launch_gemm(leg, st, "legendre_fwd");
+}
+
+template <class T>
+static int spec_inverse(const ShtDeviceTables& t, int B, int C, const T* S, T* G, const float* bias, float* out, int triangular, cudaStream_t st) {
+  OpIleg<T> il{};
+  il.G = t.mmax; il.M = B * 2 * C; il.N = t.nlat; il.K = t.lmax;
+  il.A = S; il.Bm = (const T*)t.pt; il.b_sk = 1;
+  il.a_goff = il.M; il.a_sk = (int64_t)t.mmax * il.M;
+  il.g_out = G; il.B = B; il.C = C; il.Kp = t.Kp; il.Lq = t.Lq; il.nlat = t.nlat; il.triangular = triangular; il.round_out = 1;
+  SFNO_TRY(launch_gemm(il, st, "legendre_inv"));
+  IdftArgs<T, float> id{};
+  id.G = 1; id.M = B * C * t.Kp; id.N = t.nlon; id.K = 2 * t.mmax;
+  id.A = G; id.Bm = (const T*)t.einv; id.a_sk = id.M; id.b_sk = 1;
+  id.out = out; id.out_bstride = (int64_t)C * t.nlat * t.nlon; id.bias = bias; id.add = nullptr; id.add_bstride = 0; id.act = SFNO_ACT_NONE;
+  id.C = C; id.nlat = t.nlat; id.nlon = t.nlon; id.Kp = t.Kp; id.Kq2 = t.Kq2; id.b_reps = t.basis_reps; id.stat_part = nullptr;
+  id.round_out = 0;   // leaves the library in full fp32
+  return launch_idft(id, st, "dft_inv");
+}
+
+template <class T>
+static int spectral_conv_impl(const ShtDeviceTables& f, const ShtDeviceTables& i, const sfno_spectral_weight* w, const float* x, float* y,
+                              float* residual, int B, char* ws, cudaStream_t st) {
+  const SpecWs L = spec_ws_layout(f, i, B, w->cin, w->cout);
+  T* xt = (T*)(ws + L.xt);
+  T* FG = (T*)(ws + L.fg);
+  T* X = (T*)(ws + L.X);
+  T* Y = (T*)(ws + L.Y);
+  const bool tf32 = f.precision == SFNO_PREC_TF32;
+  Tf32Scope scope(tf32);
+  const int64_t per = (int64_t)w->cin * f.nlat * f.nlon;
+  const T* xin;
+  if constexpr (std::is_same<T, float>::value) {
+    if (tf32) {   // operands of a tf32 MMA are stored TF32-exact
+      ConcatParts parts{};
+      parts.src[0] = x; parts.channels[0] = w->cin; parts.nparts = 1;
+      concat_convert_kernel<float><<<dim3(256, B), 256, 0, st>>>(parts, (int64_t)f.nlat * f.nlon, xt, per, 1);
+      SFNO_TRY(post_launch("convert_input"));
+      xin = xt;
+    } else {
+      xin = x;
+    }
+  } else {
+    ConcatParts parts{};
+    parts.src[0] = x; parts.channels[0] = w->cin; parts.nparts = 1;
+    concat_convert_kernel<T><<<dim3(256, B), 256, 0, st>>>(parts, (int64_t)f.nlat * f.nlon, xt, per, 0);
+    SFNO_TRY(post_launch("convert_input"));
+    xin = xt;
+  }
+  const int tri = w->operator_type == SFNO_OP_DHCONV;   // dhconv never mixes wavenumbers: only degrees l >= m carry information
+  SFNO_TRY(spec_forward<T>(f, B, w->cin, xin, FG, X, tri, st));
+  if (residual) SFNO_TRY(spec_inverse<T>(i, B, w->cin, X, FG, nullptr, residual, tri, st));   // s2convolutions.py:166-169
+  if (w->operator_type == SFNO_OP_DHCONV) {
+    OpDhconv<T> op{};
+    op.G = f.lmax; op.M = f.mmax * B; op.N = 2 * w->cout; op.K = 2 * w->cin;
+    op.A = X; op.Bm = (const T*)w->wpack; op.a_sk = 1; op.b_sk = 1;
+    op.y = Y; op.B = B; op.lmax = f.lmax; op.mmax = f.mmax; op.triangular = 1; op.round_out = 1;
+    SFNO_TRY(launch_gemm(op, st, "dhconv"));
+  } else {
+    const int64_t total = (int64_t)f.lmax * f.mmax * B * w->cout;
+    diag_contract_internal_kernel<T><<<(unsigned)std::min<int64_t>(ceil_div64(total, 128), 1 << 20), 128, 0, st>>>(
+        X, (const float2*)w->wdiag, Y, B, w->cout, f.lmax, f.mmax);
+    SFNO_TRY(post_launch("diag_contract"));
+  }
+  return spec_inverse<T>(i, B, w->cout, Y, FG, w->has_bias ? w->bias : nullptr, y, tri, st);
+}
+
+}  // namespace sfno
+
+using namespace sfno;
+
+template <class T>
+static int conv1x1_ex_impl(const float* x, const float* wgt, const float* bias, const float* residual, float* y, int B, int cin, int cout,
+                           int64_t hw, int act, float drop_p, uint64_t seed, uint64_t offset, bool tf32, char* ws, cudaStream_t st) {
+  const int ldw = round_up(cin, 8);
+  T* xt = (T*)ws;
+  T* wt = (T*)(ws + align_up((size_t)B * cin * hw * sizeof(T), 1024));
+  T* rt = (T*)((char*)wt + align_up((size_t)cout * ldw * sizeof(T), 1024));
+  Tf32Scope scope(tf32);
+  ConcatParts parts{};
+  parts.src[0] = x; parts.channels[0] = cin; parts.nparts = 1;
+  concat_convert_kernel<T><<<dim3(256, B), 256, 0, st>>>(parts, hw, xt, (int64_t)cin * hw, tf32 ? 1 : 0);
+  SFNO_TRY(post_launch("convert_input"));
+  pack_rows_kernel<T><<<(unsigned)ceil_div64((int64_t)cout * ldw, 256), 256, 0, st>>>(wgt, cout, cin, ldw, wt);
+  SFNO_TRY(post_launch("pack_rows"));
+  if constexpr (std::is_same<T, float>::value) {
+    if (tf32) {
+      round_tf32_kernel<<<(unsigned)ceil_div64((int64_t)cout * ldw, 256), 256, 0, st>>>((float*)wt, (int64_t)cout * ldw);
+      SFNO_TRY(post_launch("round_tf32"));
+    }
+  }
+  ConvArgs<T, float> op{};
+  op.G = B; op.M = cout; op.N = (int)hw; op.K = cin;
+  op.A = wt; op.Bm = xt; op.a_sk = 1; op.b_sk = hw;
+  op.in_bstride = (int64_t)cin * hw; op.w_bstride = 0; op.ldw = ldw;
+  op.bias = bias; op.bias_bstride = 0; op.act = act;
+  op.drop_p = drop_p; op.seed = seed; op.offset = offset; op.rng_dev = nullptr; op.branch_scale = nullptr;
+  op.res = nullptr; op.res_bstride = 0; op.res_a = nullptr; op.res_d = nullptr; op.pos = nullptr;
+  op.out = y; op.out_bstride = (int64_t)cout * hw; op.stat_part = nullptr; op.round_out = 0;
+  if (residual) {   // the residual is an operand-typed tensor of the op: stage it in T next to the input
+    ConcatParts rp{};
+    rp.src[0] = residual; rp.channels[0] = cout; rp.nparts = 1;
+    concat_convert_kernel<T><<<dim3(256, B), 256, 0, st>>>(rp, hw, rt, (int64_t)cout * hw, 0);
+    SFNO_TRY(post_launch("convert_residual"));
+    op.res = rt; op.res_bstride = (int64_t)cout * hw;
+  }
+  return launch_conv(op, st, "conv1x1");
+}
+
+extern "C" {
+
+int sfno_spectral_weight_create(sfno_spectral_weight** out, int operator_type, int cin, int cout, int lmax, int mmax, int precision) {
+  SFNO_CHECK_ARG(out != nullptr, "NULL argument");
+  SFNO_CHECK_ARG(operator_type == SFNO_OP_DHCONV || operator_type == SFNO_OP_DIAGONAL, "bad operator_type %d", operator_type);
+  SFNO_CHECK_ARG(cin > 0 && cout > 0 && lmax > 0 && mmax > 0, "bad sizes");
+  SFNO_CHECK_ARG(precision == SFNO_PREC_F32 || precision == SFNO_PREC_BF16 || precision == SFNO_PREC_TF32, "bad precision %d", precision);
+  if (operator_type == SFNO_OP_DIAGONAL && cin != cout) return fail(SFNO_ERR_UNSUPPORTED, "the diagonal operator needs cin == cout");
+  auto* w = new sfno_spectral_weight();
+  w->operator_type = operator_type; w->cin = cin; w->cout = cout; w->lmax = lmax; w->mmax = mmax; w->precision = precision;
+  const size_t e = precision == SFNO_PREC_BF16 ? 2 : 4;
+  cudaError_t err = cudaSuccess;
+  if (operator_type == SFNO_OP_DHCONV) err = cudaMalloc(&w->wpack, (size_t)lmax * 4 * cin * cout * e);
+  else err = cudaMalloc((void**)&w->wdiag, (size_t)cin * cout * lmax * mmax * 2 * sizeof(float));
+  if (err == cudaSuccess) err = cudaMalloc((void**)&w->bias, (size_t)cout * sizeof(float));
+  if (err != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(w->wpack); cudaFree(w->wdiag); cudaFree(w->bias);
+    delete w;
+    return fail(SFNO_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(err));
+  }
+  *out = w;
+  return SFNO_OK;
+}
+
+int sfno_spectral_weight_destroy(sfno_spectral_weight* w) {
+  if (!w) return SFNO_OK;
+  cudaFree(w->wpack); cudaFree(w->wdiag); cudaFree(w->bias);
+  delete w;
+  return SFNO_OK;
+}
+
+int sfno_spectral_weight_set(sfno_spectral_weight* w, const float* weight_dev, const float* bias_dev, void* stream) {
+  SFNO_CHECK_ARG(w && weight_dev, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (w->operator_type == SFNO_OP_DHCONV) {
+    const int64_t n = (int64_t)w->lmax * 4 * w->cin * w->cout;
+    if (w->precision == SFNO_PREC_BF16) pack_dhconv_weight_kernel<bf16><<<4096, 256, 0, st>>>(weight_dev, w->cin, w->cout, w->lmax, (bf16*)w->wpack);
+    else pack_dhconv_weight_kernel<float><<<4096, 256, 0, st>>>(weight_dev, w->cin, w->cout, w->lmax, (float*)w->wpack);
+    SFNO_TRY(post_launch("pack_dhconv_weight"));
+    if (w->precision == SFNO_PREC_TF32) {
+      round_tf32_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n, 256), 148 * 16), 256, 0, st>>>((float*)w->wpack, n);
+      SFNO_TRY(post_launch("round_tf32"));
+    }
+  } else {
+    SFNO_CUDA(cudaMemcpyAsync(w->wdiag, weight_dev, (size_t)w->cin * w->cout * w->lmax * w->mmax * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  w->has_bias = bias_dev != nullptr;
+  if (bias_dev) SFNO_CUDA(cudaMemcpyAsync(w->bias, bias_dev, (size_t)w->cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return SFNO_OK;
+}
+
+size_t sfno_spectral_conv_workspace_bytes(const sfno_sht_plan* fwd, const sfno_sht_plan* inv, const sfno_spectral_weight* w, int batch) {
+  if (!fwd || !inv || !w || batch <= 0) return 0;
+  return spec_ws_layout(fwd->t, inv->t, batch, w->cin, w->cout).total;
+}
+
+int sfno_spectral_conv(const sfno_sht_plan* fwd, const sfno_sht_plan* inv, const sfno_spectral_weight* w, const float* x_dev, float* y_dev,
+                       float* residual_dev, int batch, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  SFNO_CHECK_ARG(fwd && inv && w && x_dev && y_dev && workspace_dev, "NULL argument");
+  SFNO_CHECK_ARG(batch > 0, "bad batch %d", batch);
+  const ShtDeviceTables& f = fwd->t;
+  const ShtDeviceTables& i = inv->t;
+  if (f.precision != i.precision || f.precision != w->precision) return fail(SFNO_ERR_INVALID_ARGUMENT, "plans and weight must share one precision");
+  if (f.lmax != i.lmax || f.mmax != i.mmax || f.lmax != w->lmax || f.mmax != w->mmax)
+    return fail(SFNO_ERR_SHAPE_MISMATCH, "forward plan (%d,%d), inverse plan (%d,%d) and weight (%d,%d) disagree on (lmax, mmax)", f.lmax, f.mmax,
+                i.lmax, i.mmax, w->lmax, w->mmax);
+  SFNO_CHECK_ARG(((uintptr_t)workspace_dev & 1023) == 0, "workspace must be 1024-byte aligned");
+  if (workspace_bytes < spec_ws_layout(f, i, batch, w->cin, w->cout).total) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  return f.precision == SFNO_PREC_BF16 ? spectral_conv_impl<bf16>(f, i, w, x_dev, y_dev, residual_dev, batch, (char*)workspace_dev, st)
+                                       : spectral_conv_impl<float>(f, i, w, x_dev, y_dev, residual_dev, batch, (char*)workspace_dev, st);
+}
+
+// nn.Conv2d(cin, cout, 1) with the whole fused epilogue and a selectable engine: precision bf16 / tf32 convert the
+// operands into the workspace and run the tensor-core op (fp32 result); fp32 is the CUDA-core parity engine.
+size_t sfno_conv1x1_ex_workspace_bytes(int batch, int cin, int cout, int64_t hw, int precision) {
+  if (batch <= 0 || cin <= 0 || cout <= 0 || hw <= 0) return 0;
+  if (precision == SFNO_PREC_F32) return 1024;
+  const size_t e = precision == SFNO_PREC_BF16 ? 2 : 4;
+  return align_up((size_t)batch * cin * hw * e, 1024) + align_up((size_t)cout * round_up(cin, 8) * e, 1024) +
+         align_up((size_t)batch * cout * hw * e, 1024) + 1024;
+}
+
+int sfno_conv1x1_ex(const float* x_dev, const float* weight_dev, const float* bias_dev, const float* residual_dev, float* y_dev, int batch,
+                    int cin, int cout, int64_t hw, int activation, float dropout_p, uint64_t seed, uint64_t offset, int precision,
+                    void* workspace_dev, size_t workspace_bytes, void* stream) {
+  SFNO_CHECK_ARG(x_dev && weight_dev && y_dev, "NULL argument");
+  SFNO_CHECK_ARG(batch > 0 && cin > 0 && cout > 0 && hw > 0 && hw < (1ll << 31), "bad sizes");
+  SFNO_CHECK_ARG(dropout_p >= 0.0f && dropout_p < 1.0f, "dropout probability %f outside [0, 1)", (double)dropout_p);
+  SFNO_CHECK_ARG(precision == SFNO_PREC_F32 || precision == SFNO_PREC_BF16 || precision == SFNO_PREC_TF32, "bad precision %d", precision);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == SFNO_PREC_F32) {
+    ConvArgs<float, float> op{};
+    op.G = batch; op.M = cout; op.N = (int)hw; op.K = cin;
+    op.A = weight_dev; op.Bm = x_dev; op.a_sk = 1; op.b_sk = hw;
+    op.in_bstride = (int64_t)cin * hw; op.w_bstride = 0; op.ldw = cin;
+    op.bias = bias_dev; op.bias_bstride = 0; op.act = activation;
+    op.drop_p = dropout_p; op.seed = seed; op.offset = offset; op.rng_dev = nullptr; op.branch_scale = nullptr;
+    op.res = residual_dev; op.res_bstride = (int64_t)cout * hw; op.res_a = nullptr; op.res_d = nullptr; op.pos = nullptr;
+    op.out = y_dev; op.out_bstride = (int64_t)cout * hw; op.stat_part = nullptr; op.round_out = 0;
+    return launch_conv(op, st, "conv1x1");
+  }
+  SFNO_CHECK_ARG(workspace_dev && ((uintptr_t)workspace_dev & 1023) == 0, "workspace must be 1024-byte aligned");
+  if (workspace_bytes < sfno_conv1x1_ex_workspace_bytes(batch, cin, cout, hw, precision)) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
+  if (precision == SFNO_PREC_BF16)
+    return conv1x1_ex_impl<bf16>(x_dev, weight_dev, bias_dev, residual_dev, y_dev, batch, cin, cout, hw, activation, dropout_p, seed, offset, false,
+                                 (char*)workspace_dev, st);
+  return conv1x1_ex_impl<float>(x_dev, weight_dev, bias_dev, residual_dev, y_dev, batch, cin, cout, hw, activation, dropout_p, seed, offset, true,
+                                (char*)workspace_dev, st);
+}
+
+}  // extern "C"

@@ -62,16 +62,20 @@ class CudaEnsembleOps:
                                                      var.data_ptr(), stream_ptr(sum_global.device)), "sfno_ensemble_finalize")
         return mean, var
 
-    def stats(self, members: torch.Tensor, truth: Optional[torch.Tensor]):
-        """All members [E, n] (after the gather) -> (mean, var, crps or None) in ONE pass over the members."""
+    def stats(self, members: torch.Tensor, truth: Optional[torch.Tensor], rows: Optional[torch.Tensor] = None):
+        """All members [E, n] (after the gather) -> (mean, var, crps or None) in ONE pass over the members.  ``rows``
+        (int32 [E], device): the live rows of a padded gather buffer [>= E, n]; the statistics do not depend on the member
+        order, so the buffer is used as it arrives."""
         assert members.is_cuda and members.dtype == torch.float32 and members.is_contiguous()
-        E, n = members.shape
+        n = members.shape[1]
+        E = members.shape[0] if rows is None else int(rows.numel())
         mean = torch.empty(n, dtype=torch.float32, device=members.device)
         var = torch.empty(n, dtype=torch.float32, device=members.device)
         crps = torch.empty(n, dtype=torch.float32, device=members.device) if truth is not None else None
-        _lib.check(_lib.lib().sfno_ensemble_stats(members.data_ptr(), truth.data_ptr() if truth is not None else None, E, n,
-                                                  mean.data_ptr(), var.data_ptr(), crps.data_ptr() if crps is not None else None,
-                                                  stream_ptr(members.device)), "sfno_ensemble_stats")
+        _lib.check(_lib.lib().sfno_ensemble_stats_rows(members.data_ptr(), rows.data_ptr() if rows is not None else None,
+                                                       truth.data_ptr() if truth is not None else None, E, n, mean.data_ptr(),
+                                                       var.data_ptr(), crps.data_ptr() if crps is not None else None,
+                                                       stream_ptr(members.device)), "sfno_ensemble_stats_rows")
         return mean, var, crps
 
     def crps(self, members: torch.Tensor, truth: torch.Tensor) -> torch.Tensor:
@@ -101,6 +105,8 @@ class EnsembleStatistics:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.local_ids = member_shard(n_members, self.world, self.rank)
+        self._rows: Dict[str, torch.Tensor] = {}     # live rows of the padded gather buffer, per device
+        self._sendbuf: Dict[tuple, torch.Tensor] = {}
 
     def mean_var(self, local_members: torch.Tensor):
         """local_members [E_local, ...] fp32 -> (mean [...], unbiased variance [...]) over ALL members, without gathering
@@ -133,6 +139,27 @@ class EnsembleStatistics:
                 members[ids] = out[r, : len(ids)]
         return members
 
+    def gather_padded(self, local_members: torch.Tensor):
+        """All-gather WITHOUT compaction or re-ordering: returns (buffer [world * k, ...] with k = max local members, int32
+        row indices of the live members).  Uneven shards leave padding rows at the end of a rank's block; they are
+        never read.  One copy of the local members into the send slot, one collective."""
+        if self.world == 1:
+            return local_members, None
+        k = max_local_members(self.n_members, self.world)
+        dev = local_members.device
+        key = (str(dev), tuple(local_members.shape[1:]))
+        send = self._sendbuf.get(key)
+        if send is None:
+            send = self._sendbuf[key] = torch.zeros(k, *local_members.shape[1:], dtype=local_members.dtype, device=dev)
+        send[: local_members.shape[0]].copy_(local_members)
+        out = torch.empty(self.world * k, *local_members.shape[1:], dtype=local_members.dtype, device=dev)
+        dist.all_gather_into_tensor(out, send, group=self.group)
+        rows = self._rows.get(str(dev))
+        if rows is None:
+            live = [r * k + j for r in range(self.world) for j in range(len(member_shard(self.n_members, self.world, r)))]
+            rows = self._rows[str(dev)] = torch.tensor(live, dtype=torch.int32).to(dev)
+        return out, rows
+
     def step(self, local_members: torch.Tensor, truth: Optional[torch.Tensor] = None,
              weights: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """Statistics the reference records per time step (``aggregators/timestepwise.py:131-177``):
@@ -144,9 +171,9 @@ class EnsembleStatistics:
             return {"mean": mean, "var": var, "spread": torch.sqrt(weighted_mean(var, weights))}
         # with a verification field the fair CRPS needs every member of a grid point on one rank: gather once, then ONE
         # pass over the gathered members gives mean, two-pass variance and CRPS (no all-reduce, no [E, E, ...] tensor)
-        members = self.gather_members(local_members)
-        flat = members.reshape(E, -1).contiguous()
-        mean, var, crps = self.ops.stats(flat, truth.reshape(-1).contiguous())
+        members, rows = self.gather_padded(local_members)
+        flat = members.reshape(members.shape[0], -1).contiguous()
+        mean, var, crps = self.ops.stats(flat, truth.reshape(-1).contiguous(), rows)
         mean, var, crps = mean.reshape(truth.shape), var.reshape(truth.shape), crps.reshape(truth.shape)
         out = {"mean": mean, "var": var, "spread": torch.sqrt(weighted_mean(var, weights))}
         rmse = torch.sqrt(weighted_mean((mean - truth) ** 2, weights))

@@ -13,6 +13,8 @@ op                                     replaces (reference file:line)
 ``sfno_b200::spectral_contract``       ``_contract_dhconv`` / ``_contract_diagonal`` ``contractions.py:147-169``
 ``sfno_b200::instance_norm``           ``nn.InstanceNorm2d`` ``sfnonet.py:641-647`` + ``time_scale_shift`` ``:280-287``
 ``sfno_b200::conv1x1``                 ``nn.Conv2d(.., 1)`` ``sfnonet.py:239,614-617,739-742``, ``layers.py:73-75``
+``sfno_b200::conv1x1_ex``              the same + ``nn.Dropout`` (``layers.py:76-80``) on a selectable engine (fp32 / tf32 / bf16)
+``sfno_b200::spectral_conv``           ``SpectralConvS2.forward`` ``s2convolutions.py:158-193`` as one fused call (bf16 / tf32 / fp32)
 ``sfno_b200::net_forward``             ``SphericalFourierNeuralOperatorNet.forward`` ``sfnonet.py:797-841``
 ``sfno_b200::cold_update``             ``x_s + (x_interpolated_s_next - x_interpolated_s)`` ``src/diffusion/dyffusion.py:519``
 =====================================  ==================================================================================
@@ -20,7 +22,7 @@ op                                     replaces (reference file:line)
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 
@@ -154,6 +156,64 @@ def conv1x1(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
 
 @conv1x1.register_fake
 def _(x, weight, bias, residual, act):
+    return x.new_empty(x.shape[0], weight.shape[0], *x.shape[2:], dtype=torch.float32)
+
+
+# ---- fused spectral convolution (SpectralConvS2.forward) ----------------------------------------------------------------
+@torch.library.custom_op("sfno_b200::spectral_conv", mutates_args=())
+def spectral_conv(plan_fwd: int, plan_inv: int, weight: int, x: torch.Tensor, cout: int, nlat_out: int, nlon_out: int,
+                  want_residual: bool) -> List[torch.Tensor]:
+    """x fp32 [B, Cin, H, W] -> [y [B, Cout, H', W'], residual [B, Cin, H', W'] (empty unless want_residual)] in ONE library
+    call (SHT -> contraction -> inverse SHT + bias) on the engine of the plans' precision; ``weight`` is a
+    ``sfno_spectral_weight`` handle holding the packed filter weight and bias."""
+    xf = require_cuda_f32(x, "x")
+    B, cin = int(xf.shape[0]), int(xf.shape[1])
+    y = torch.empty(B, cout, nlat_out, nlon_out, dtype=torch.float32, device=xf.device)
+    res = torch.empty((B, cin, nlat_out, nlon_out) if want_residual else (0,), dtype=torch.float32, device=xf.device)
+    if B == 0:
+        return [y, res]
+    L = _lib.lib()
+    with torch.cuda.device(xf.device):
+        ws = workspace(xf.device, L.sfno_spectral_conv_workspace_bytes(_handle(plan_fwd), _handle(plan_inv), _handle(weight), B), "spectral_conv")
+        _lib.check(L.sfno_spectral_conv(_handle(plan_fwd), _handle(plan_inv), _handle(weight), xf.data_ptr(), y.data_ptr(),
+                                        res.data_ptr() if want_residual else None, B, ws.data_ptr(), ws.numel(), stream_ptr(xf.device)),
+                   "sfno_spectral_conv")
+    return [y, res]
+
+
+@spectral_conv.register_fake
+def _(plan_fwd, plan_inv, weight, x, cout, nlat_out, nlon_out, want_residual):
+    y = x.new_empty(x.shape[0], cout, nlat_out, nlon_out, dtype=torch.float32)
+    res = x.new_empty((x.shape[0], x.shape[1], nlat_out, nlon_out) if want_residual else (0,), dtype=torch.float32)
+    return [y, res]
+
+
+# ---- 1x1 convolution with the full fused epilogue and a selectable engine -----------------------------------------------------
+@torch.library.custom_op("sfno_b200::conv1x1_ex", mutates_args=())
+def conv1x1_ex(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor], act: int,
+               dropout_p: float, seed: int, offset: int, precision: int) -> torch.Tensor:
+    """``conv1x1`` + dropout (Philox stream (seed, offset); p = 0: off) on the engine selected by ``precision``
+    (``_lib.SFNO_PREC``: fp32 CUDA cores | bf16 / tf32 tensor cores); fp32 tensors in and out."""
+    xf = require_cuda_f32(x, "x")
+    w = require_cuda_f32(weight, "weight").reshape(weight.shape[0], -1)
+    B, Ci, Co = int(xf.shape[0]), int(xf.shape[1]), int(w.shape[0])
+    hw = int(xf.numel() // max(B * Ci, 1))
+    y = torch.empty(B, Co, *xf.shape[2:], dtype=torch.float32, device=xf.device)
+    if y.numel() == 0:
+        return y
+    b = None if bias is None else require_cuda_f32(bias, "bias")
+    r = None if residual is None else require_cuda_f32(residual, "residual")
+    L = _lib.lib()
+    with torch.cuda.device(xf.device):
+        ws = workspace(xf.device, L.sfno_conv1x1_ex_workspace_bytes(B, Ci, Co, hw, int(precision)), "conv1x1")
+        _lib.check(L.sfno_conv1x1_ex(xf.data_ptr(), w.data_ptr(), _ptr(b), _ptr(r), y.data_ptr(), B, Ci, Co, hw, int(act), float(dropout_p),
+                                     int(seed), int(offset), int(precision), ws.data_ptr(), ws.numel(), stream_ptr(xf.device)),
+                   "sfno_conv1x1_ex")
+    return y
+
+
+@conv1x1_ex.register_fake
+def _(x, weight, bias, residual, act, dropout_p, seed, offset, precision):
     return x.new_empty(x.shape[0], weight.shape[0], *x.shape[2:], dtype=torch.float32)
 
 

@@ -80,20 +80,56 @@ class SpectralConvS2(nn.Module):
         self.weight = nn.Parameter(scale * torch.randn(*shape, 2))
         if bias:
             self.bias = nn.Parameter(scale * torch.zeros(1, out_channels, 1, 1))
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self._packed: dict = {}    # device -> (sfno_spectral_weight handle, (data_ptr, version) of weight / bias at packing time)
+
+    def __del__(self):
+        try:
+            for h, _ in self._packed.values():
+                _lib.lib().sfno_spectral_weight_destroy(h)
+        except Exception:
+            pass
+
+    def invalidate_parameters(self):
+        """Re-pack the weight at the next call (after writes through ``.data``, e.g. the reference's EMA swap)."""
+        for dev, (h, _) in list(self._packed.items()):
+            self._packed[dev] = (h, None)
+
+    def _weight_handle(self, device):
+        precision = self.forward_transform.precision
+        if self.inverse_transform.precision != precision:
+            raise ValueError("forward and inverse transform must share one precision")
+        bias = getattr(self, "bias", None)
+        key = tuple((p.data_ptr(), p._version) for p in (self.weight, bias) if p is not None)
+        entry = self._packed.get(str(device))
+        if entry is None:
+            h = ctypes.c_void_p()
+            with torch.cuda.device(device):
+                _lib.check(_lib.lib().sfno_spectral_weight_create(ctypes.byref(h), _lib.SFNO_OP[self.operator_type], self.in_channels,
+                                                                  self.out_channels, self.modes_lat, self.modes_lon,
+                                                                  _lib.SFNO_PREC[precision]), "sfno_spectral_weight_create")
+            entry = (h, None)
+        if entry[1] != key:
+            w = require_cuda_f32(self.weight.detach(), "weight")
+            b = None if bias is None else require_cuda_f32(bias.detach().reshape(-1), "bias")
+            with torch.cuda.device(device):
+                _lib.check(_lib.lib().sfno_spectral_weight_set(entry[0], w.data_ptr(), None if b is None else b.data_ptr(),
+                                                               stream_ptr(device)), "sfno_spectral_weight_set")
+            entry = (entry[0], key)
+        self._packed[str(device)] = entry
+        return entry[0]
 
     def forward(self, x):
-        """Stand-alone execution through the op-level C ABI: returns ``(y, residual)`` like the reference."""
+        """Stand-alone execution as ONE fused library call (``sfno_spectral_conv``: SHT -> contraction -> inverse SHT +
+        bias, on the tensor cores when the transforms were built with precision "bf16" / "tf32"); returns
+        ``(y, residual)`` like the reference (``s2convolutions.py:158-193``)."""
         dtype = x.dtype
-        residual = x
         xf = require_cuda_f32(x, "x")
-        X = self.forward_transform(xf)
-        if self.scale_residual:
-            residual = self.inverse_transform(X).to(dtype)
-        Y = torch.ops.sfno_b200.spectral_contract(_lib.SFNO_OP[self.operator_type], torch.view_as_real(X.contiguous()),
-                                                  self.weight.detach())
-        y = self.inverse_transform(torch.view_as_complex(Y))
-        if hasattr(self, "bias"):
-            y = y + self.bias
+        fwd, inv = self.forward_transform, self.inverse_transform
+        y, res = torch.ops.sfno_b200.spectral_conv(fwd._plan(xf.device).value, inv._plan(xf.device).value,
+                                                   self._weight_handle(xf.device).value, xf, self.out_channels, inv.nlat, inv.nlon,
+                                                   bool(self.scale_residual))
+        residual = res.to(dtype) if self.scale_residual else x
         return y.type(dtype), residual
 
 

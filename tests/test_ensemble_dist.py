@@ -31,7 +31,9 @@ class TorchOps:
         spread = (members[None] - members[:, None]).abs().sum((0, 1)) / (E * (E - 1))
         return skill - 0.5 * spread
 
-    def stats(self, members, truth):
+    def stats(self, members, truth, rows=None):
+        if rows is not None:
+            members = members[rows.long()]
         return members.mean(0), members.var(dim=0), (self.crps(members, truth) if truth is not None else None)
 
 

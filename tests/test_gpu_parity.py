@@ -590,3 +590,77 @@ def test_step_glue_matches_reference_classes(dev, case):
     std = torch.tensor([fx["stds"][n] for n in c["out"]]).view(1, -1, 1, 1)
     assert torch.equal(g2.cpu(), fx["gen"])
     assert torch.allclose(den2.cpu(), fx["gen"] * std + mean, rtol=1e-6, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sub-module boundary (SURVEY 8b "must export"): fused spectral convolution and precision-selectable conv1x1
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("operator_type", ["dhconv", "diagonal"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 1.5e-3), ("bf16", 8e-3)])
+@pytest.mark.parametrize("grids", [("equiangular", "legendre-gauss"), ("legendre-gauss", "legendre-gauss")])
+def test_spectral_conv_module_matches_reference_forward(dev, operator_type, precision, tol, grids):
+    """The reference-shaped SpectralConvS2.forward(x) -> (y, residual) (s2convolutions.py:158-193) through the fused
+    sfno_spectral_conv entry point in every precision, against the CPU restatement (oracle transforms + contraction):
+    the sub-module drop-in of INTEGRATION.md section 2b IS the B200-native path."""
+    from spherical_dyffusion_b200.sfnonet import SpectralConvS2
+
+    nlat, nlon, C, B = 36, 72, 32, 3
+    lmax, mmax = nlat, nlon // 2 + 1
+    g = torch.Generator().manual_seed(11)
+    fwd = sb.RealSHT(nlat, nlon, lmax=lmax, mmax=mmax, grid=grids[0], precision=precision)
+    inv = sb.InverseRealSHT(nlat, nlon, lmax=lmax, mmax=mmax, grid=grids[1], precision=precision)
+    conv = SpectralConvS2(fwd, inv, C, C, operator_type=operator_type, bias=True).to(dev)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * 0.1)
+        conv.bias.copy_(torch.randn(conv.bias.shape, generator=g))
+    x = torch.randn(B, C, nlat, nlon, generator=g)
+    o_fwd = oh.RealSHT(nlat, nlon, lmax=lmax, mmax=mmax, grid=grids[0]).float()
+    o_inv = oh.InverseRealSHT(nlat, nlon, lmax=lmax, mmax=mmax, grid=grids[1]).float()
+    X = o_fwd(x)
+    w = conv.weight.detach().cpu()
+    Y = dhconv_contract(X, w) if operator_type == "dhconv" else diagonal_contract(X, w)
+    y_ref = o_inv(Y) + conv.bias.detach().cpu()
+    with torch.inference_mode():
+        y, residual = conv(x.to(dev))
+    e = rel_l2(y, y_ref)
+    print(f"SpectralConvS2[{operator_type}, {precision}, {grids[0]}->{grids[1]}]: y rel-L2 {e:.3e}")
+    assert y.shape == y_ref.shape and e < tol
+    if grids[0] != grids[1]:     # scale_residual: residual = inverse(forward(x)) (s2convolutions.py:166-169)
+        assert conv.scale_residual and rel_l2(residual, o_inv(X)) < tol
+    else:
+        assert residual.data_ptr() == x.to(dev).data_ptr() or torch.equal(residual.cpu(), x)
+    # in-place weight update -> re-packed
+    with torch.no_grad():
+        conv.weight.mul_(2.0)
+    with torch.inference_mode():
+        y2, _ = conv(x.to(dev))
+    assert rel_l2(y2 - conv.bias, 2.0 * (y_ref - conv.bias.detach().cpu())) < 2 * tol
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 8e-4), ("bf16", 6e-3)])
+def test_conv1x1_ex_precisions_and_dropout(dev, precision, tol):
+    """Precision-selectable 1x1 convolution with the fused epilogue (bias -> GELU -> dropout -> + residual) against torch;
+    the dropout mask is a function of the Philox key only, identical on every engine."""
+    g = torch.Generator().manual_seed(5)
+    B, Ci, Co, H, W = 2, 64, 96, 24, 48
+    x = torch.randn(B, Ci, H, W, generator=g)
+    w = torch.randn(Co, Ci, 1, 1, generator=g) * 0.1
+    b = torch.randn(Co, generator=g)
+    r = torch.randn(B, Co, H, W, generator=g)
+    prec = _lib.SFNO_PREC[precision]
+    ref = torch.nn.functional.gelu(torch.nn.functional.conv2d(x, w, b)) + r
+    y = torch.ops.sfno_b200.conv1x1_ex(x.to(dev), w.to(dev), b.to(dev), r.to(dev), 1, 0.0, 0, 0, prec)
+    e = rel_l2(y, ref)
+    print(f"conv1x1_ex[{precision}]: rel-L2 {e:.3e}")
+    assert e < tol
+    p = 0.25
+    yd = torch.ops.sfno_b200.conv1x1_ex(x.to(dev), w.to(dev), b.to(dev), None, 1, p, 7, 3, prec)
+    y0 = torch.ops.sfno_b200.conv1x1_ex(x.to(dev), w.to(dev), b.to(dev), None, 1, 0.0, 0, 0, prec)
+    kept = yd != 0
+    frac = kept.float().mean().item()
+    assert abs(frac - (1 - p)) < 0.01, frac
+    assert rel_l2(yd[kept], y0[kept] / (1 - p)) < 1e-5                  # kept elements are scaled by 1 / keep
+    mask_fp32 = torch.ops.sfno_b200.conv1x1_ex(x.to(dev), w.to(dev), b.to(dev), None, 1, p, 7, 3, _lib.SFNO_PREC["fp32"]) != 0
+    assert (kept != mask_fp32).float().mean().item() < 1e-3             # same mask on every engine (ties of exact zeros aside)
+    yd2 = torch.ops.sfno_b200.conv1x1_ex(x.to(dev), w.to(dev), b.to(dev), None, 1, p, 7, 4, prec)
+    assert ((yd2 != 0) != kept).float().mean().item() > 0.2            # another offset, another mask

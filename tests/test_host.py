@@ -167,7 +167,8 @@ def test_custom_op_layer_is_registered_with_fake_implementations():
 
     import spherical_dyffusion_b200  # noqa: F401
 
-    for name in ("sht_forward", "sht_inverse", "spectral_contract", "instance_norm", "conv1x1", "net_forward", "cold_update"):
+    for name in ("sht_forward", "sht_inverse", "spectral_contract", "instance_norm", "conv1x1", "conv1x1_ex", "spectral_conv",
+                 "net_forward", "cold_update"):
         assert hasattr(torch.ops.sfno_b200, name), name
     with FakeTensorMode():
         x = torch.empty(2, 3, 12, 24)
@@ -178,6 +179,9 @@ def test_custom_op_layer_is_registered_with_fake_implementations():
         assert torch.ops.sfno_b200.conv1x1(x, torch.empty(7, 3, 1, 1), None, None, 1).shape == (2, 7, 12, 24)
         assert torch.ops.sfno_b200.net_forward(0, [x, x[:, :1]], None, 5, False, None).shape == (2, 5, 12, 24)
         assert torch.ops.sfno_b200.cold_update(x, x, x).shape == x.shape
+        assert torch.ops.sfno_b200.conv1x1_ex(x, torch.empty(7, 3, 1, 1), None, None, 1, 0.1, 0, 0, 1).shape == (2, 7, 12, 24)
+        y, res = torch.ops.sfno_b200.spectral_conv(0, 0, 0, x, 5, 12, 24, True)
+        assert y.shape == (2, 5, 12, 24) and res.shape == (2, 3, 12, 24)
 
 
 def test_custom_ops_refuse_cpu_tensors():
