@@ -596,7 +596,7 @@ def test_step_glue_matches_reference_classes(dev, case):
 # sub-module boundary (SURVEY 8b "must export"): fused spectral convolution and precision-selectable conv1x1
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("operator_type", ["dhconv", "diagonal"])
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 1.5e-3), ("bf16", 8e-3)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 6e-4), ("bf16", 4.2e-3)])   # 1.5 x measured (4.0e-4 / 2.76e-3)
 @pytest.mark.parametrize("grids", [("equiangular", "legendre-gauss"), ("legendre-gauss", "legendre-gauss")])
 def test_spectral_conv_module_matches_reference_forward(dev, operator_type, precision, tol, grids):
     """The reference-shaped SpectralConvS2.forward(x) -> (y, residual) (s2convolutions.py:158-193) through the fused
@@ -637,7 +637,7 @@ def test_spectral_conv_module_matches_reference_forward(dev, operator_type, prec
     assert rel_l2(y2 - conv.bias, 2.0 * (y_ref - conv.bias.detach().cpu())) < 2 * tol
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 8e-4), ("bf16", 6e-3)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 2e-4), ("bf16", 2.4e-3)])   # 1.5 x measured (1.22e-4 / 1.6e-3)
 def test_conv1x1_ex_precisions_and_dropout(dev, precision, tol):
     """Precision-selectable 1x1 convolution with the fused epilogue (bias -> GELU -> dropout -> + residual) against torch;
     the dropout mask is a function of the Philox key only, identical on every engine."""
