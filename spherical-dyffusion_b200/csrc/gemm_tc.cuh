@@ -87,6 +87,8 @@ struct TcSched {
   int a_glo, b_glo;  // > 0: the operand's group index splits into {g % glo, g / glo} (4-D tensor map)
   int a_rep, b_rep;  // > 1: shared operand replicated along dims[2]: this CTA reads copy blockIdx.x % rep
   int out_box32, res_box32;   // the output / residual tensor map has 32-row boxes (one TMA instruction per warp and pass)
+  // stationary-A kernels: all K blocks of the CTA's A tile stay resident in shared memory, the ring holds B only
+  int stat_kb, stat_stages;   // K blocks of the resident A tile (= k_blocks), B stages of the ring
   // role-wait profile (tc_debug bit7) or nullptr: cycles summed over CTAs {producer waits for a free stage, MMA waits
   // for operands, MMA waits for a free accumulator, epilogue warp 0 waits for the accumulator, epilogue warp 0 waits
   // for the residual block, CTA lifetime, epilogue warp 0 busy, CTAs}
@@ -124,6 +126,7 @@ template <class Op>
 struct TcTraits {
   static constexpr bool kAvailable = false;
   static constexpr bool kDualM = false;
+  static constexpr bool kStationaryA = false;
   static bool eligible(const Op&) { return false; }
 };
 
@@ -319,7 +322,12 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&v)[8]) {
   }
 }
 
-template <class Op, int BN, bool kDual>
+// kStatA: "stationary A".  Every CTA owns ONE M tile for the whole launch and keeps all K blocks of its A tile (the
+// operand shared by the groups: DFT basis, convolution weights) resident in shared memory; the ring streams only B.
+// The L2 -> shared-memory operand traffic of a tile drops from A + B to B (forward DFT: 245 -> 147 KB per tile,
+// fc1: 160 -> 96 KB): these kernels were bound by operand delivery (profiles/r02_g_tc_dbg_sweep.txt).  A is reloaded
+// only when the group changes and A is per group (per-sample folded weights: 8 times per launch).
+template <class Op, int BN, bool kDual, bool kStatA = false>
 __global__ void __launch_bounds__(tc_threads(BN), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
@@ -327,13 +335,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   using S = TcSmem<BN, Op::kColContig, kDual, Op::kStagingBufs>;
   using E = TcElem<typename Op::InT>;
   constexpr int kBK = E::kBK;              // K block in elements (one 128-byte swizzle span)
-  constexpr int kStages = S::kStages;
+  static_assert(!(kStatA && kDual), "stationary A and dual-M tiles are not combined");
+  const int kStages = kStatA ? sc.stat_stages : S::kStages;   // (a constant for the streaming kernels)
   constexpr uint32_t kTmemCols = 512;  // two accumulator stages of up to 256 fp32 columns, or (dual-M) one stage of two
   constexpr int kBMT = kDual ? 2 * TC_BM : TC_BM;   // rows per tile
   constexpr int kAccStages = kDual ? 1 : 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
-  const uint32_t staging_base = smem_base + kStages * S::kStageBytes;  // 1024-byte aligned: TMA boxes of 8 staged rows
+  // streaming: ring of {A, B} stages.  stationary A: [resident A: stat_kb x 16 KB][ring of B stages]
+  const uint32_t ring_base = smem_base + (kStatA ? (uint32_t)sc.stat_kb * S::kAHalfBytes : 0u);
+  const uint32_t kRingStage = kStatA ? (uint32_t)S::kBBytes : (uint32_t)S::kStageBytes;
+  const uint32_t staging_base = ring_base + (uint32_t)kStages * kRingStage;  // 1024-byte aligned: TMA boxes of staged rows
   const uint32_t bar_base = staging_base + S::kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -341,8 +353,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   auto res_bar = [&](int w) { return bar_base + 8u * (2 * kStages + 6 + w); };  // one per epilogue warp (TMA residual loads)
-  auto a_smem = [&](int s, int h = 0) { return smem_base + s * S::kStageBytes + h * S::kAHalfBytes; };
-  auto b_smem = [&](int s) { return smem_base + s * S::kStageBytes + S::kABytes; };
+  const uint32_t afull_bar = bar_base + 8u * (2 * kStages + 6 + tc_epi_warps(BN)), afree_bar = afull_bar + 8u;   // stationary A
+  auto a_smem = [&](int s, int h = 0) { return kStatA ? smem_base + (uint32_t)s * S::kAHalfBytes   // s = K block of the resident tile
+                                                      : ring_base + (uint32_t)s * kRingStage + (uint32_t)h * S::kAHalfBytes; };
+  auto b_smem = [&](int s) { return ring_base + (uint32_t)s * kRingStage + (kStatA ? 0u : (uint32_t)S::kABytes); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool timed = sc.prof != nullptr;   // role-wait / phase timers only when somebody reads them
@@ -359,6 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       ptx::mbar_init(tempty_bar(a), tc_epi_warps(BN));
     }
     for (int w = 0; w < tc_epi_warps(BN); ++w) ptx::mbar_init(res_bar(w), 1);
+    if (kStatA) { ptx::mbar_init(afull_bar, 1); ptx::mbar_init(afree_bar, 1); }
     ptx::fence_barrier_init();
   }
   if (warp == TC_WARP_MMA) ptx::tmem_alloc(tmem_slot, kTmemCols);
@@ -382,8 +397,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   TileIter it;
   if (Op::kGFastest) it.init(blockIdx.x, gridDim.x, sc.groups, Op::kNFastest ? sc.n_tiles : sc.m_tiles);
   else it.init(blockIdx.x, gridDim.x, Op::kNFastest ? sc.n_tiles : sc.m_tiles, Op::kNFastest ? sc.m_tiles : sc.n_tiles);
+  // stationary A: the CTA's M tile is fixed; it walks a CONTIGUOUS chunk of the (group, N tile) pairs q = g * n_tiles + nt
+  // (group-major), so that a per-group A tile is reloaded at most once or twice per CTA.  The m_tiles CTAs of one chunk
+  // run side by side and share its B tiles in L2.  gridDim.x is a multiple of m_tiles.
+  const int sq_mt = kStatA ? (int)(blockIdx.x % (unsigned)sc.m_tiles) : 0;
+  const int sq_all = kStatA ? sc.groups * sc.n_tiles : 0, sq_lanes = kStatA ? (int)(gridDim.x / (unsigned)sc.m_tiles) : 1;
+  const int sq_chunk = (sq_all + sq_lanes - 1) / sq_lanes;
+  const int sq_step = 1;
+  int sq = kStatA ? (int)(blockIdx.x / (unsigned)sc.m_tiles) * sq_chunk : 0;
+  const int sq_total = kStatA ? (sq + sq_chunk < sq_all ? sq + sq_chunk : sq_all) : 0;
+  auto walk_valid = [&](int tile) { return kStatA ? sq < sq_total : tile < sc.num_tiles; };
+  auto walk_next = [&]() { if (kStatA) sq += sq_step; else it.next(); };
   auto decode = [&](int& g, int& mt, int& nt) {
-    if (Op::kGFastest) {
+    if (kStatA) {
+      g = sq / sc.n_tiles; nt = sq - g * sc.n_tiles; mt = sq_mt;
+    } else if (Op::kGFastest) {
       g = it.a;
       if (Op::kNFastest) { nt = it.b; mt = it.c; } else { mt = it.b; nt = it.c; }
     } else {
@@ -401,13 +429,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == TC_WARP_TMA) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, stat_g = -1;
+      uint32_t phase = 0, afree_phase = 0;
       long long w_empty = 0;
       const int rep_a = sc.a_rep > 1 ? (int)(blockIdx.x % (unsigned)sc.a_rep) : 0;
       const int rep_b = sc.b_rep > 1 ? (int)(blockIdx.x % (unsigned)sc.b_rep) : 0;
       const long long t_cta = timed ? clock64() : 0;
-      for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, it.next()) {
+      for (int tile = blockIdx.x; walk_valid(tile); tile += gridDim.x, walk_next()) {
         int g, mt, nt;
         decode(g, mt, nt);
         if (tile_skipped(g, mt, nt)) continue;
@@ -420,11 +448,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // that share an operand (basis, table, weights) read different K slices of it, which spreads the broadcast
         // over more L2 slices.  fp32 accumulation order differs per CTA but is fixed by the static schedule.
         const int kbeg = op.k_begin(g) / kBK, nkb = sc.k_blocks - kbeg;
-        const int rot = (Op::kRanged || (sc.dbg & 512)) ? 0 : (int)(blockIdx.x % (unsigned)nkb);   // (spectral ops: measured neutral / slower)
+        const int rot = (kStatA || Op::kRanged || (sc.dbg & 512)) ? 0 : (int)(blockIdx.x % (unsigned)nkb);   // (spectral ops: measured neutral / slower)
+        if constexpr (kStatA) {
+          // (re)load the resident A tile: first tile of the CTA, and whenever a per-group A meets a new group
+          if (stat_g == -1 || (sc.a_batched && g != stat_g)) {
+            if (stat_g != -1) { w_empty += ptx::mbar_wait<true>(afree_bar, afree_phase, timed); afree_phase ^= 1u; }   // MMAs on the old tile retired
+            stat_g = g;
+            if (!(sc.dbg & 1)) {
+              ptx::mbar_expect_tx(afull_bar, (uint32_t)sc.stat_kb * S::kAHalfBytes);
+              for (int kb = 0; kb < sc.stat_kb; ++kb) {
+                if (Op::A_KCONTIG) {
+                  ptx::tma_load_4d(a_smem(kb), &tma_a, afull_bar, kb * kBK, m0, ga, ga_hi);
+                } else {
+#pragma unroll
+                  for (int h = 0; h < TC_BM / E::kAtom; ++h)
+                    ptx::tma_load_4d(a_smem(kb) + h * (kBK * 128), &tma_a, afull_bar, m0 + E::kAtom * h, kb * kBK, ga, ga_hi);
+                }
+              }
+            } else {
+              ptx::mbar_arrive(afull_bar);
+            }
+          }
+        }
         for (int ik = 0; ik < nkb; ++ik) {
           const int kb = kbeg + (ik + rot < nkb ? ik + rot : ik + rot - nkb);
           w_empty += ptx::mbar_wait<true>(empty_bar(stage), phase ^ 1u, timed);
-          const bool load_a = !(sc.dbg & 1), load_b = !(sc.dbg & 2);
+          const bool load_a = !kStatA && !(sc.dbg & 1), load_b = !(sc.dbg & 2);
           ptx::mbar_expect_tx(full_bar(stage), (load_a ? halves * S::kAHalfBytes : 0) + (load_b ? S::kBBytes : 0));
           const int k0 = kb * kBK;
           // MN-major operands arrive as atoms of E::kAtom elements (128 bytes) x kBK k-rows
@@ -469,10 +518,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       constexpr uint32_t b_lbo = Op::B_KCONTIG ? 16u : (uint32_t)(kBK * 128), b_kstep = Op::B_KCONTIG ? 32u : kMnStep;
       constexpr uint32_t a_sbo = (!Op::A_KCONTIG && kMn32) ? 512u : 1024u, a_layout = (!Op::A_KCONTIG && kMn32) ? 1u : 2u;
       constexpr uint32_t b_sbo = (!Op::B_KCONTIG && kMn32) ? 512u : 1024u, b_layout = (!Op::B_KCONTIG && kMn32) ? 1u : 2u;
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      int stage = 0, acc = 0, stat_g = -1;
+      uint32_t phase = 0, acc_phase = 0, afull_phase = 0;
       long long w_full = 0, w_tempty = 0;
-      for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, it.next()) {
+      for (int tile = blockIdx.x; walk_valid(tile); tile += gridDim.x, walk_next()) {
         int g, mt, nt;
         decode(g, mt, nt);
         if (tile_skipped(g, mt, nt)) continue;
@@ -482,7 +531,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(kDual ? 0 : acc * BN);
         const int nkb = sc.k_blocks - kb0;
-        const int rot = (Op::kRanged || (sc.dbg & 512)) ? 0 : (int)(blockIdx.x % (unsigned)nkb);   // same walk as the producer
+        const int rot = (kStatA || Op::kRanged || (sc.dbg & 512)) ? 0 : (int)(blockIdx.x % (unsigned)nkb);   // same walk as the producer
+        if constexpr (kStatA) {
+          if (stat_g == -1 || (sc.a_batched && g != stat_g)) {   // a new resident A tile is on its way
+            stat_g = g;
+            w_full += ptx::mbar_wait<true>(afull_bar, afull_phase, timed);
+            afull_phase ^= 1u;
+            ptx::tc_fence_after();
+          }
+        }
         for (int ik = 0; ik < nkb; ++ik) {
           const int kb = kb0 + (ik + rot < nkb ? ik + rot : ik + rot - nkb);
           w_full += ptx::mbar_wait<true>(full_bar(stage), phase, timed);
@@ -491,7 +548,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           for (int k = 0; k < nk; ++k) {
             const uint64_t bd = make_smem_desc(b_smem(stage) + k * b_kstep, b_lbo, b_sbo, b_layout);
             for (int hf = 0; hf < halves; ++hf) {
-              const uint64_t ad = make_smem_desc(a_smem(stage, hf) + k * a_kstep, a_lbo, a_sbo, a_layout);
+              const uint64_t ad = make_smem_desc(a_smem(kStatA ? kb : stage, hf) + k * a_kstep, a_lbo, a_sbo, a_layout);
               if (!(sc.dbg & 16)) ptx::mma_elem<typename Op::InT>(d_tmem + (uint32_t)(hf * BN), ad, bd, idesc, (ik != 0 || k != 0) ? 1u : 0u);
             }
           }
@@ -500,6 +557,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         ptx::mma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+        if constexpr (kStatA) {
+          // the next tile of this CTA belongs to another group and A is per group: tell the producer when the MMAs that
+          // read the resident tile have retired
+          if (sc.a_batched && sq + sq_step < sq_total && (sq + sq_step) / sc.n_tiles != g) ptx::mma_commit(afree_bar);
+        }
       }
       if (sc.prof) {
         atomicAdd(sc.prof + 1, (unsigned long long)w_full);
@@ -517,7 +579,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t acc_phase = 0, res_phase = 0, sbuf = 0;
     long long w_tfull = 0, w_res = 0, c_pro = 0, c_loop = 0, c_tail = 0;
     const long long t_epi = timed ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, it.next()) {
+    for (int tile = blockIdx.x; walk_valid(tile); tile += gridDim.x, walk_next()) {
       int g, mt, nt;
       decode(g, mt, nt);
       if (tile_skipped(g, mt, nt)) continue;
@@ -846,8 +908,24 @@ inline bool tma_operand_ok(const TmaOperand& o) {
   return true;
 }
 
-template <class Op, bool kDual>
-int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what) {
+// shared memory of a stationary-A launch: resident A (k_blocks x 16 KB) + B ring + staging + barriers + alignment slack
+constexpr int kTcMaxSmem = 226 * 1024;
+template <class Op, int BN>
+inline int tc_stat_smem_bytes(int k_blocks, int stages) {
+  using S = TcSmem<BN, Op::kColContig, false, Op::kStagingBufs>;
+  return k_blocks * S::kAHalfBytes + stages * S::kBBytes + S::kStagingBytes + S::kBarrierBytes + 1024;
+}
+// B stages that fit next to a resident A tile of k_blocks K blocks (0: stationary A does not fit / is not worth it)
+template <class Op, int BN>
+inline int tc_stat_stages(int k_blocks) {
+  using S = TcSmem<BN, Op::kColContig, false, Op::kStagingBufs>;
+  const int left = kTcMaxSmem - 1024 - S::kBarrierBytes - S::kStagingBytes - k_blocks * S::kAHalfBytes;
+  const int st = left / S::kBBytes;
+  return st >= 3 ? (st > 6 ? 6 : st) : 0;
+}
+
+template <class Op, bool kDual, bool kStatA = false>
+int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what, int stat_stages = 0) {
   using Tr = TcTraits<Op>;
   constexpr int BN = Tr::BN;
   static_assert(!kDual || 2 * BN <= 512, "dual-M needs both accumulators in TMEM");
@@ -895,17 +973,21 @@ int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what) {
   sc.res_box32 = Tr::has_residual(op) && tma_io_rows(io_res) == 32;
   sc.dbg = g_tc_debug.load(std::memory_order_relaxed);
   sc.prof = (sc.dbg & 128) ? tc_prof_buffer() : nullptr;
-  static bool attr_set = false;
-  auto kern = gemm_tc_kernel<Op, BN, kDual>;
-  if (!attr_set) {
-    SFNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
+  sc.stat_kb = kStatA ? sc.k_blocks : 0;
+  sc.stat_stages = kStatA ? stat_stages : 0;
+  const int smem_bytes = kStatA ? tc_stat_smem_bytes<Op, BN>(sc.k_blocks, stat_stages) : S::kTotal;
+  static std::atomic<int> attr_bytes{0};   // per-process high-water mark of the opt-in (the attribute is per function)
+  auto kern = gemm_tc_kernel<Op, BN, kDual, kStatA>;
+  if (attr_bytes.load(std::memory_order_acquire) < smem_bytes) {
+    SFNO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatA ? kTcMaxSmem : smem_bytes));
+    attr_bytes.store(kStatA ? kTcMaxSmem : smem_bytes, std::memory_order_release);
   }
-  const int grid = std::min(sc.num_tiles, tc_num_sms());
+  int grid = std::min(sc.num_tiles, tc_num_sms());
+  if (kStatA) grid = (tc_num_sms() / sc.m_tiles) * sc.m_tiles;   // every CTA owns one M tile: a multiple of m_tiles
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)tc_threads(BN));
-  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap this kernel's set-up with its predecessor's tail
@@ -920,6 +1002,14 @@ int launch_gemm_tc_impl(const Op& op, cudaStream_t stream, const char* what) {
 // less L2->SMEM operand traffic per output element; tc_debug bit8 forces the single-tile kernel (A/B comparison)
 template <class Op>
 int launch_gemm_tc(const Op& op, cudaStream_t stream, const char* what) {
+  if constexpr (TcTraits<Op>::kStationaryA) {
+    // stationary A when the whole K extent of an A tile fits next to a >= 3-stage B ring and the SMs split evenly over
+    // the M tiles; tc_debug bit 12 forces the streaming kernel (A/B comparison)
+    const int kb = ceil_div(op.K, TcElem<typename Op::InT>::kBK), m_tiles = ceil_div(op.M, TC_BM);
+    const int st = tc_stat_stages<Op, TcTraits<Op>::BN>(kb);
+    if (st > 0 && m_tiles <= tc_num_sms() / 8 && TcTraits<Op>::use_stationary(op) && !(g_tc_debug.load(std::memory_order_relaxed) & 4096))
+      return launch_gemm_tc_impl<Op, false, true>(op, stream, what, st);
+  }
   if constexpr (TcTraits<Op>::kDualM) {
     if (TcTraits<Op>::use_dual(op) && !(g_tc_debug.load(std::memory_order_relaxed) & 256))
       return launch_gemm_tc_impl<Op, true>(op, stream, what);

@@ -12,6 +12,8 @@ struct TcTraitsBase {
   static constexpr bool kAvailable = true;
   static constexpr bool kDualM = false;
   static bool use_dual(const Op&) { return true; }
+  static constexpr bool kStationaryA = false;        // keep the CTA's A tile (shared basis / weights) resident in shared memory
+  static bool use_stationary(const Op&) { return true; }
   static bool extra_ok(const Op&) { return true; }  // vector-store alignment rules of the epilogue, if any
   static void io(const Op&, TmaIo&, TmaIo&) {}       // TMA views of the output / residual tensors
   static bool has_residual(const Op&) { return false; }
@@ -34,6 +36,10 @@ struct TcEligible {
 template <class T>
 struct TcTraits<OpDft<T>> : TcTraitsBase<OpDft<T>>, TcEligible<TcTraits<OpDft<T>>, OpDft<T>> {
   static constexpr int BN = 192;
+  // (stationary A -- each CTA keeps its 128 basis rows resident and streams planes -- was measured: 1.74 vs 1.67 ms per
+  //  forward for the streaming kernel, profiles/r02_i_stationary_ab.txt; the kernel is bound by the latency of the plane
+  //  loads with 3-4 stages in flight, not by the bytes of the basis, so it stays off here)
+  static constexpr bool kStationaryA = false;
   static constexpr uint64_t es = sizeof(T);
   static void operands(const OpDft<T>& op, TmaOperand& a, TmaOperand& b) {
     a.base = op.A; a.dims[0] = op.nlon; a.dims[1] = op.M;                 // basis rows (m,ri), K-contiguous, shared
@@ -153,6 +159,12 @@ template <class T, class TOut, int ACT, int DROP>
 struct TcTraits<OpConv<T, TOut, ACT, DROP>> : TcTraitsBase<OpConv<T, TOut, ACT, DROP>>,
                                                 TcEligible<TcTraits<OpConv<T, TOut, ACT, DROP>>, OpConv<T, TOut, ACT, DROP>> {
   static constexpr int BN = 192;
+  // Stationary A: the CTA keeps its 128 output channels x all input channels of the weights resident and streams pixel
+  // tiles.  Used for SHARED weights that fit next to a >= 3-stage ring (encoder, decoder: decoder0 0.179 -> 0.148 ms,
+  // decoder1 0.082 -> 0.071 ms); with per-sample folded weights (inner skip, fc1) it measured slower than the streaming
+  // kernel (fc1 2.03 vs 1.78 ms per forward, profiles/r02_i_stationary_ab.txt), fc2 (K = 512) does not fit.
+  static constexpr bool kStationaryA = true;
+  static bool use_stationary(const OpConv<T, TOut, ACT, DROP>& op) { return op.w_bstride == 0; }
   static constexpr uint64_t ei = sizeof(T);
   static void operands(const OpConv<T, TOut, ACT, DROP>& op, TmaOperand& a, TmaOperand& b) {
     const bool wb = op.w_bstride != 0;
