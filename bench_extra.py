@@ -29,7 +29,8 @@ def _model(config, dev, precision, seed=0, min_max_time=(0.0, 5.0)):
     """Random-init module of a spherical_dyffusion_b200.configs entry on `dev` (eval mode)."""
     from spherical_dyffusion_b200 import configs
 
-    return configs.build(config, precision=precision, seed=seed, min_max_time=min_max_time, check_time_range=False).to(dev).eval()
+    return configs.build(config, precision=precision, seed=seed, min_max_time=min_max_time, check_time_range=False,
+                         param_check="version").to(dev).eval()
 
 
 def _timeit(fn, steps, warmup):

@@ -68,6 +68,9 @@ int launch_conv(const ConvArgs<T, TOut>& a, cudaStream_t stream, const char* wha
     if (a.drop_p == 0.0f) {
       if (a.act == SFNO_ACT_GELU) return launch_gemm_tc(OpConv<T, TOut, SFNO_ACT_GELU, 0>(a), stream, what);
       if (a.act == SFNO_ACT_NONE) return launch_gemm_tc(OpConv<T, TOut, SFNO_ACT_NONE, 0>(a), stream, what);
+    } else if constexpr (sizeof(T) == sizeof(TOut)) {   // the MLP with inference dropout and precomputed keep masks
+      if (a.drop_mask && a.act == SFNO_ACT_GELU) return launch_gemm_tc(OpConv<T, TOut, SFNO_ACT_GELU, 2>(a), stream, what);
+      if (a.drop_mask && a.act == SFNO_ACT_NONE) return launch_gemm_tc(OpConv<T, TOut, SFNO_ACT_NONE, 2>(a), stream, what);
     }
     return launch_gemm_tc(gen, stream, what);
   }

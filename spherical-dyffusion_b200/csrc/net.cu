@@ -31,7 +31,7 @@ struct BlockParams {
 
 struct WsLayout {
   size_t xin, buf0, xcat, t1, res, hid, fg, X, Y;
-  size_t mean, rstd, a0, d0, a1, d1, tsin, th, trepr, ts, skip_wb, skip_bb, fc1_wb, fc1_bb, dscale, stat_part;
+  size_t mean, rstd, a0, d0, a1, d1, tsin, th, trepr, ts, skip_wb, skip_bb, fc1_wb, fc1_bb, dscale, stat_part, mask1, mask2;
   size_t total;
 };
 
@@ -100,6 +100,10 @@ static WsLayout ws_layout(const sfno_net* n, int B) {
   w.fc1_wb = take((size_t)B * std::max(n->hid, 1) * n->C * e);
   w.fc1_bb = take((size_t)B * std::max(n->hid, 1) * sizeof(float));
   w.dscale = take((size_t)B * sizeof(float));
+  // keep masks of the two MLP dropout sites (one bit per element), only for nets with dropout
+  const bool has_drop = n->cfg.dropout_mlp > 0.0f;
+  w.mask1 = take(has_drop ? (size_t)B * std::max(n->hid, 1) * plane / 8 + 16 : 0);
+  w.mask2 = take(has_drop ? (size_t)B * n->C * plane / 8 + 16 : 0);
   {  // per-slice partial sums of the fused InstanceNorm statistics (tensor-core epilogues)
     const size_t conv_slices = (size_t)conv_stat_slices(n->P);
     const size_t idft_slices = (size_t)idft_stat_slices(n->cfg.nlon);
@@ -202,7 +206,7 @@ static ConvArgs<T, TOut> make_conv(int B, int P, int cin, int cout, const T* in,
   op.A = w; op.Bm = in; op.a_sk = 1; op.b_sk = P;
   op.in_bstride = in_bs; op.w_bstride = w_bs; op.ldw = ldw;
   op.bias = bias; op.bias_bstride = bias_bs; op.act = act;
-  op.drop_p = 0.0f; op.seed = 0; op.offset = 0; op.rng_dev = nullptr; op.branch_scale = nullptr;
+  op.drop_p = 0.0f; op.seed = 0; op.offset = 0; op.rng_dev = nullptr; op.drop_mask = nullptr; op.branch_scale = nullptr;
   op.res = nullptr; op.res_bstride = 0; op.res_a = nullptr; op.res_d = nullptr; op.pos = nullptr;
   op.out = out; op.out_bstride = out_bs; op.stat_part = nullptr;
   op.round_out = 1;   // activations stay inside the net (only the decoder output leaves it, see forward_impl)
@@ -423,10 +427,27 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
     SFNO_TRY(post_launch("fold_fc1"));
     auto f1 = make_conv<T, T>(B, P, C, hid, t1, CP, fc1_wb, (int64_t)hid * C, C, fc1_bb, hid, cfg.activation, hd, (int64_t)hid * P);
     f1.drop_p = pdrop; f1.seed = seed; f1.offset = offset + (uint64_t)i * 4 + 0; f1.rng_dev = rng_dev;
+    // dropout masks by a dedicated kernel at full occupancy (tensor-core path; P % 8 == 0 there): inline, the Philox
+    // rounds doubled the time of fc1 (3.66 vs 1.64 ms per interpolator forward, profiles/r01_o_interp.json)
+    const bool masks = pdrop > 0.0f && conv_uses_tc(f1) && (P % 8) == 0;
+    if (masks) {
+      uint8_t* m1 = (uint8_t*)(ws + w.mask1);
+      const int64_t n8 = (int64_t)B * hid * P / 8;
+      dropout_mask_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n8 / 8 + 1, 256), 148 * 8), 256, 0, st>>>(m1, n8, pdrop, seed, f1.offset, rng_dev);
+      SFNO_TRY(post_launch("dropout_mask"));
+      f1.drop_mask = m1;
+    }
     SFNO_TRY(launch_conv(f1, st, "mlp_fc1"));
     auto f2 = make_conv<T, T>(B, P, hid, C, hd, (int64_t)hid * P, (const T*)bp.fc2_wT, 0, hid, bp.fc2_b, 0, SFNO_ACT_NONE, nxt, nxt_bs);
     f2.drop_p = pdrop; f2.seed = seed; f2.offset = offset + (uint64_t)i * 4 + 1; f2.rng_dev = rng_dev;
     f2.branch_scale = use_dp ? dscale : nullptr;
+    if (masks) {
+      uint8_t* m2 = (uint8_t*)(ws + w.mask2);
+      const int64_t n8 = (int64_t)B * C * P / 8;
+      dropout_mask_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n8 / 8 + 1, 256), 148 * 8), 256, 0, st>>>(m2, n8, pdrop, seed, f2.offset, rng_dev);
+      SFNO_TRY(post_launch("dropout_mask"));
+      f2.drop_mask = m2;
+    }
     if (scale_residual) { f2.res = res; f2.res_bstride = CP; }
     else { f2.res = cur; f2.res_bstride = cur_bs; f2.res_a = a0; f2.res_d = d0; }
     x_stats_fused = false;

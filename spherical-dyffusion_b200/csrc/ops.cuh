@@ -428,6 +428,10 @@ struct ConvArgs {
   // graph-safe Philox state: when set, the stream key is {rng_dev[0], rng_dev[1] + offset} read on the device, so a
   // captured CUDA graph draws fresh masks on every replay (the forward advances rng_dev[1] after its last kernel)
   const uint64_t* rng_dev;
+  // optional precomputed keep mask, one bit per output element in the order ((g * M + m) * N + n), bit j of byte i =
+  // element 8 i + j: exactly the bits dropout_keep_mask8 would produce inline.  A dedicated kernel generates them at
+  // full occupancy (dropout_mask_kernel); inline, Philox costs as many issue slots as the rest of the epilogue.
+  const uint8_t* drop_mask;
   const float* branch_scale;              // [batch] DropPath factor (0 or 1/keep) or nullptr
   const T* res; int64_t res_bstride;      // residual [b][cout][hw] or nullptr
   const float* res_a; const float* res_d; // [batch*cout] affine on the residual or nullptr
@@ -437,7 +441,10 @@ struct ConvArgs {
   // optional fused InstanceNorm statistics of the OUTPUT: stat_part[(slice*2 + {0,1}) * (G*M) + g*M + m]
   float* stat_part;
 };
-// ACT / DROP < 0: decided at run time (CUDA-core engine and rarely used combinations)
+// ACT / DROP < 0: decided at run time (CUDA-core engine and rarely used combinations); DROP = 0: dropout off; DROP = 2:
+// dropout on with the keep bits read from drop_mask -- both at compile time (the tensor-core instantiations of the MLP
+// with inference dropout keep the packed GELU, carry no Philox code and lose the per-element run-time tests: the
+// run-time variant cost 3.4 vs 1.65 ms per forward in fc1)
 template <class T, class TOut, int ACT = -1, int DROP = -1>
 struct OpConv : ConvArgs<T, TOut>, FullRanges, NoSplitBox {
   static constexpr bool kSimtRowsOnFastLanes = true;
@@ -494,14 +501,17 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges, NoSplitBox {
     if (dropping()) {   // the 1/keep factor of the dropout rides on the DropPath scale
       r.rng_base = ((uint64_t)g * this->M + m) * (uint64_t)this->N;
       r.scale *= dropout_keep_scale(dropout_threshold16(this->drop_p));
-      r.seed = this->rng_dev ? this->rng_dev[0] : this->seed;
-      r.offset = this->offset + (this->rng_dev ? this->rng_dev[1] : 0ull);
+      if constexpr (DROP != 2) {   // inline Philox key (the mask variant never evaluates it)
+        r.seed = this->rng_dev ? this->rng_dev[0] : this->seed;
+        r.offset = this->offset + (this->rng_dev ? this->rng_dev[1] : 0ull);
+      }
     }
     return r;
   }
   __device__ Row row(int g, int m) const { return row_f<-1>(g, m); }
   __device__ bool dropping() const {
     if constexpr (DROP == 0) return false;
+    else if constexpr (DROP == 2) return true;
     else return this->drop_p > 0.0f;
   }
   __device__ void store(const Row& r, int, int, int n, float acc) const {
@@ -514,7 +524,12 @@ struct OpConv : ConvArgs<T, TOut>, FullRanges, NoSplitBox {
   template <int F>
   __device__ void compute8(Row& r, int n, const float (&acc)[8], const float (&res)[8], float (&o)[8]) const {
     uint32_t keep = 0xffu;
-    if (dropping()) keep = dropout_keep_mask8(r.seed, r.offset, r.rng_base + n, dropout_threshold16(this->drop_p));
+    if constexpr (DROP == 2) {
+      keep = (uint32_t)__ldg(this->drop_mask + ((r.rng_base + (uint64_t)n) >> 3));
+    } else if (dropping()) {
+      keep = this->drop_mask ? (uint32_t)__ldg(this->drop_mask + ((r.rng_base + (uint64_t)n) >> 3))
+                             : dropout_keep_mask8(r.seed, r.offset, r.rng_base + n, dropout_threshold16(this->drop_p));
+    }
     const f2 b2 = f2_splat(r.bias), sc2 = f2_splat(r.scale), ra2 = f2_splat(r.ra), rd2 = f2_splat(r.rd);
     float t[8];
     if (feat_on<F, F_POS>(r.pos != nullptr)) load_vec8(r.pos + n, t);

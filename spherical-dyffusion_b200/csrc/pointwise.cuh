@@ -282,6 +282,23 @@ static __global__ void round_tf32_kernel(float* __restrict__ p, int64_t n) {
 constexpr unsigned SFNO_RNG_OFFSETS_PER_FORWARD = 4096;
 static __global__ void rng_advance_kernel(uint64_t* state, uint64_t by) { state[1] += by; }
 
+// Keep masks of one dropout site, one bit per element (bit j of byte i = element 8 i + j), identical to what
+// dropout_keep_mask8 yields inline for the same Philox key: one Philox4x32-7 block per byte.  n8 = elements / 8.
+static __global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n8, float p, uint64_t seed, uint64_t offset,
+                                           const uint64_t* __restrict__ rng_dev) {
+  if (rng_dev) { seed = rng_dev[0]; offset += rng_dev[1]; }
+  const uint32_t thr = dropout_threshold16(p);
+  const int64_t n64 = n8 >> 3;   // eight bytes per thread and store
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n64; i += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long w = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w |= (unsigned long long)dropout_keep_mask8(seed, offset, (uint64_t)(i * 8 + j) << 3, thr) << (8 * j);
+    reinterpret_cast<unsigned long long*>(mask)[i] = w;
+  }
+  for (int64_t i = (n64 << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x)
+    mask[i] = (uint8_t)dropout_keep_mask8(seed, offset, (uint64_t)i << 3, thr);
+}
+
 // position-weighted checksum of the bit patterns of `count` fp32 tensors, out[t] pre-zeroed (grid.y = tensor).
 // 16-byte loads, four in flight per thread: the kernel streams ~0.85 GB of parameters of the ACE net per call.
 static __global__ void __launch_bounds__(512) param_fingerprint_kernel(const float* const* __restrict__ ptrs, const int64_t* __restrict__ numel,

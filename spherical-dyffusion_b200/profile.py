@@ -67,6 +67,35 @@ def algorithmic_work(model, batch: int):
     return w
 
 
+def live_fraction(model) -> float:
+    """Share of the (l, m) spectral grid the triangular kernels touch: degree l is live for wavenumber m iff
+    l >= live_l0(m) = min(m & ~63, (lmax - 1) & ~63) (csrc/ops.cuh).  1.0 for the diagonal operator (dense transforms)."""
+    if model.operator_type != "dhconv":
+        return 1.0
+    L, M = model.modes_lat, model.modes_lon
+    last = ((L - 1) & ~63) if L > 0 else 0
+    live = sum(L - min(m & ~63, last) for m in range(M))
+    return live / float(L * M)
+
+
+def executed_work(model, batch: int):
+    """name -> (flops, bytes) the triangular kernels actually execute / move (only the live part of the spectral tensors
+    and Legendre tables); other kernels are dense and not listed."""
+    e = 2 if model.precision == "bf16" else 4
+    B, C = batch, model.embed_dim
+    H, W = model.img_shape
+    Lm, Mm = model.modes_lat, model.modes_lon
+    f = live_fraction(model)
+    S = B * C * Lm * Mm * 2 * e
+    Fb = B * C * H * Mm * 2 * e
+    tab = Mm * Lm * H * e
+    return {
+        "legendre_fwd": (f * 4.0 * B * C * Mm * Lm * H, Fb + f * (S + tab)),
+        "legendre_inv": (f * 4.0 * B * C * Mm * Lm * H, Fb + f * (S + tab)),
+        "dhconv": (f * 8.0 * B * C * C * Lm * Mm, 2 * f * S + 4 * C * C * Lm * e),
+    }
+
+
 def _ncu_traffic(kernel_name):
     """DRAM bytes per launch of `kernel_name` from the committed ncu capture (profiles/ncu_traffic.json), else None."""
     import json
@@ -110,6 +139,7 @@ def roofline_from_profile(recs, pk, model=None, batch=None):
             out["traffic_source"] = "profiles/ncu_traffic.json (ncu --set full, dram read + write bytes of one launch)" if out["traffic"] else None
         # every GEMM-shaped kernel against its own bound (all of them sit below the ridge at ACE size -> HBM)
         table = {}
+        executed = executed_work(model, batch)
         for name, (flops, nbytes) in algorithmic_work(model, batch).items():
             if name in recs and recs[name]["launches"] > 0 and nbytes > 0:
                 sec = recs[name]["ms_total"] / recs[name]["launches"] * 1e-3
@@ -117,7 +147,13 @@ def roofline_from_profile(recs, pk, model=None, batch=None):
                                "frac_hbm": round(nbytes / sec / 1e9 / pk["hbm_gbs"], 3),
                                "TFLOPs": round(flops / sec / 1e12, 1),
                                "frac_tensor": round(flops / sec / 1e12 / pk["bf16_tflops_sustained"], 3)}
+                if name in executed:   # triangular kernels: what they execute / move, next to the dense accounting above
+                    xf, xb = executed[name]
+                    table[name].update({"GBps_executed": round(xb / sec / 1e9, 1), "frac_hbm_executed": round(xb / sec / 1e9 / pk["hbm_gbs"], 3),
+                                        "TFLOPs_executed": round(xf / sec / 1e12, 1),
+                                        "frac_tensor_executed": round(xf / sec / 1e12 / pk["bf16_tflops_sustained"], 3)})
         out["per_kernel_roofline"] = table
+        out["live_fraction_of_spectral_grid"] = round(live_fraction(model), 4)
         # BASELINE.json's "SHT tensor-pipe % of peak": the transform pair (longitude DFT + Legendre, both directions) and
         # the spectral contraction as one aggregate -- dense algorithmic flops of all their launches / their summed time
         work = algorithmic_work(model, batch)
@@ -126,11 +162,15 @@ def roofline_from_profile(recs, pk, model=None, batch=None):
             live = [n for n in names if n in recs and recs[n]["ms_total"] > 0]
             if len(live) == len(names):
                 flops = sum(work[n][0] * recs[n]["launches"] for n in live)
+                xflops = sum(executed.get(n, work[n])[0] * recs[n]["launches"] for n in live)
                 sec = sum(recs[n]["ms_total"] for n in live) * 1e-3
                 out.setdefault("tensor_pipe", {})[key] = {
-                    "TFLOPs_dense": round(flops / sec / 1e12, 1), "ms_per_forward": round(sec * 1e3, 4),
+                    "TFLOPs_dense": round(flops / sec / 1e12, 1), "TFLOPs_executed": round(xflops / sec / 1e12, 1),
+                    "ms_per_forward": round(sec * 1e3, 4),
                     "frac_of_bf16_sustained": round(flops / sec / 1e12 / pk["bf16_tflops_sustained"], 3),
+                    "frac_of_bf16_sustained_executed": round(xflops / sec / 1e12 / pk["bf16_tflops_sustained"], 3),
                     "frac_of_bf16_burst": round(flops / sec / 1e12 / pk["bf16_tflops"], 3)}
-        out["per_kernel_roofline_note"] = ("DENSE algorithmic bytes / flops per launch (SURVEY 8d); the Legendre and dhconv "
-                                           "kernels execute only the l >= m half, so their fractions are upper bounds on the traffic actually moved")
+        out["per_kernel_roofline_note"] = ("frac_hbm / frac_tensor use the DENSE algorithmic bytes / flops per launch (SURVEY 8d); the Legendre "
+                                           "and dhconv kernels execute only the live part of the spectral grid (live_fraction_of_spectral_grid): "
+                                           "their *_executed entries count what is actually computed / moved")
     return out

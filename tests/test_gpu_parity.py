@@ -664,3 +664,73 @@ def test_conv1x1_ex_precisions_and_dropout(dev, precision, tol):
     assert (kept != mask_fp32).float().mean().item() < 1e-3             # same mask on every engine (ties of exact zeros aside)
     yd2 = torch.ops.sfno_b200.conv1x1_ex(x.to(dev), w.to(dev), b.to(dev), None, 1, p, 7, 4, prec)
     assert ((yd2 != 0) != kept).float().mean().item() > 0.2            # another offset, another mask
+
+
+def test_spectral_conv_180x360_triangular_bf16_vs_oracle(dev):
+    """The triangular tensor-core kernels (Legendre stores only live degrees, dhconv visits only live wavenumbers, inverse
+    Legendre contracts only over live degrees) at the ACE grid against the CPU oracle -- not against the other engine."""
+    from spherical_dyffusion_b200.sfnonet import SpectralConvS2
+
+    nlat, nlon, C, B = 180, 360, 64, 2
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(B, C, nlat, nlon, generator=g)
+    X = oh.RealSHT(nlat, nlon, lmax=180, mmax=181, grid="equiangular").float()(x)
+    o_inv = oh.InverseRealSHT(nlat, nlon, lmax=180, mmax=181, grid="legendre-gauss").float()
+    for precision, tol in (("bf16", 4.2e-3), ("tf32", 6e-4)):
+        fwd = sb.RealSHT(nlat, nlon, lmax=180, mmax=181, grid="equiangular", precision=precision)
+        inv = sb.InverseRealSHT(nlat, nlon, lmax=180, mmax=181, grid="legendre-gauss", precision=precision)
+        conv = SpectralConvS2(fwd, inv, C, C, operator_type="dhconv", bias=True).to(dev)
+        with torch.no_grad():
+            conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * 0.1)
+            conv.bias.copy_(torch.randn(conv.bias.shape, generator=g))
+        y_ref = o_inv(dhconv_contract(X, conv.weight.detach().cpu())) + conv.bias.detach().cpu()
+        with torch.inference_mode():
+            y, residual = conv(x.to(dev))
+        e, er = rel_l2(y, y_ref), rel_l2(residual, o_inv(X))
+        print(f"SpectralConvS2 180x360 dhconv {precision}: y rel-L2 {e:.3e}, residual {er:.3e}")
+        assert e < tol and er < 1.7 * tol
+
+
+def test_mlp_dropout_with_injected_masks(dev):
+    """layers.py:73-80 with inference dropout: fc1 -> GELU -> Dropout(p) -> fc2 -> Dropout(p).  The masks the library
+    draws are read back from its outputs (an element is dropped iff it is exactly zero) and INJECTED into a torch
+    restatement: positions, scaling by 1 / (1 - p) and the order activation -> dropout must then agree to fp32 accuracy."""
+    g = torch.Generator().manual_seed(9)
+    B, C, hid, H, W, p = 2, 32, 64, 16, 32, 0.1
+    x = torch.randn(B, C, H, W, generator=g)
+    w1, b1 = torch.randn(hid, C, 1, 1, generator=g) * 0.2, torch.randn(hid, generator=g) * 0.1
+    w2, b2 = torch.randn(C, hid, 1, 1, generator=g) * 0.2, torch.randn(C, generator=g) * 0.1
+    fp32 = _lib.SFNO_PREC["fp32"]
+    h = torch.ops.sfno_b200.conv1x1_ex(x.to(dev), w1.to(dev), b1.to(dev), None, 1, p, 5, 0, fp32)
+    y = torch.ops.sfno_b200.conv1x1_ex(h, w2.to(dev), b2.to(dev), None, 0, p, 5, 1, fp32)
+    m1, m2 = (h != 0).float().cpu(), (y != 0).float().cpu()
+    assert abs(m1.mean().item() - (1 - p)) < 0.01 and abs(m2.mean().item() - (1 - p)) < 0.02
+    F = torch.nn.functional
+    h_ref = F.gelu(F.conv2d(x, w1, b1)) * m1 / (1 - p)
+    y_ref = F.conv2d(h_ref, w2, b2) * m2 / (1 - p)
+    assert rel_l2(h, h_ref) < 1e-5 and rel_l2(y, y_ref) < 1e-5
+
+
+def test_net_dropout_masks_identical_on_both_engines(dev):
+    """Inside the net the tensor-core MLP reads its keep bits from masks generated by dropout_mask_kernel; the CUDA-core
+    engine evaluates the same Philox blocks inline.  Same key -> same masks: the two bf16 runs differ by rounding noise
+    only, while another key changes the output by an order of magnitude more."""
+    cfg = SFNOConfig(num_input_channels=6, num_output_channels=6, num_conditional_channels=0, spatial_shape=(32, 64),
+                     embed_dim=64, num_layers=3, dropout_mlp=0.2, drop_path_rate=0.0, with_time_emb=False)
+    sd = perturb_affine_and_biases(random_state_dict(cfg, seed=4, spectral_gain=16.0))
+    m = module_from_cfg(cfg, sd, dev, "bf16")
+    x = torch.randn(4, 6, 32, 64, generator=torch.Generator().manual_seed(2)).to(dev)
+    with torch.inference_mode(), m.inference_dropout_scope(condition=True):
+        m.seed_dropout(3)
+        y_tc = m(x).clone()
+        m.seed_dropout(4)
+        y_other = m(x).clone()
+        _lib.set_option("force_simt", 1)
+        try:
+            m.seed_dropout(3)
+            y_simt = m(x).clone()
+        finally:
+            _lib.set_option("force_simt", 0)
+    same, other = rel_l2(y_tc, y_simt), rel_l2(y_tc, y_other)
+    print(f"dropout masks: tensor-core (mask kernel) vs CUDA-core (inline Philox), same key {same:.3e}; other key {other:.3e}")
+    assert same < 2e-2 and other > 5 * same

@@ -242,7 +242,7 @@ def test_roofline_arithmetic_from_a_per_launch_profile():
     from spherical_dyffusion_b200.profile import algorithmic_work, roofline_from_profile
 
     model = SimpleNamespace(precision="bf16", embed_dim=256, in_chans=36, out_chans=34, img_shape=(180, 360), modes_lat=180,
-                            modes_lon=181, mlp_ratio=2.0, big_skip=True)
+                            modes_lon=181, mlp_ratio=2.0, big_skip=True, operator_type="dhconv")
     pk = dict(bf16_tflops=1654.5, hbm_gbs=6554.6, bf16_tflops_sustained=1377.3, source="measured")
     ms = {"host_before_first_launch": (0.32, 1), "dft_inv": (2.0, 10), "dft_fwd": (1.7, 10), "legendre_fwd": (0.95, 10),
           "legendre_inv": (1.0, 10), "dhconv": (1.0, 8), "mlp_fc1": (1.8, 8), "convert_input": (0.03, 1)}
@@ -259,3 +259,8 @@ def test_roofline_arithmetic_from_a_per_launch_profile():
     dense = sum(algorithmic_work(model, 8)[k][0] * 10 for k in ("dft_fwd", "legendre_fwd", "legendre_inv", "dft_inv"))
     assert abs(sht["TFLOPs_dense"] - dense / 5.65e-3 / 1e12) < 0.06
     assert out["tensor_pipe"]["sht_and_spectral_conv"]["ms_per_forward"] == 6.65
+    # the triangular kernels execute the live part of the (l, m) grid only: 21 700 of 32 580 entries at lmax 180 / mmax 181
+    assert abs(out["live_fraction_of_spectral_grid"] - 21700 / 32580) < 1e-4
+    leg = out["per_kernel_roofline"]["legendre_fwd"]
+    assert abs(leg["TFLOPs_executed"] / leg["TFLOPs"] - 21700 / 32580) < 2e-3 and leg["frac_hbm_executed"] < leg["frac_hbm"]
+    assert sht["TFLOPs_executed"] < sht["TFLOPs_dense"] and "TFLOPs_executed" not in out["per_kernel_roofline"]["dft_fwd"]
