@@ -218,7 +218,7 @@ using namespace sfno;
 
 extern "C" {
 
-int sfno_b200_abi_version(void) { return 1; }
+int sfno_b200_abi_version(void) { return 2; }   // 2: round-2 entry points (rng state, tf32, spectral_conv, ensemble moments, step glue)
 
 const char* sfno_b200_status_string(int status) {
   switch (status) {

@@ -706,9 +706,10 @@ def test_mlp_dropout_with_injected_masks(dev):
     m1, m2 = (h != 0).float().cpu(), (y != 0).float().cpu()
     assert abs(m1.mean().item() - (1 - p)) < 0.01 and abs(m2.mean().item() - (1 - p)) < 0.02
     F = torch.nn.functional
-    h_ref = F.gelu(F.conv2d(x, w1, b1)) * m1 / (1 - p)
-    y_ref = F.conv2d(h_ref, w2, b2) * m2 / (1 - p)
-    assert rel_l2(h, h_ref) < 1e-5 and rel_l2(y, y_ref) < 1e-5
+    keep = 1.0 - round(p * 65536) / 65536.0     # the library decides on 16 random bits per element: p is a multiple of 2^-16
+    h_ref = F.gelu(F.conv2d(x, w1, b1)) * m1 / keep
+    y_ref = F.conv2d(h_ref, w2, b2) * m2 / keep
+    assert rel_l2(h, h_ref) < 2e-6 and rel_l2(y, y_ref) < 4e-6
 
 
 def test_net_dropout_masks_identical_on_both_engines(dev):

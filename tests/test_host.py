@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(cdll, name), f"{name} declared in include/sfno_b200.h but not exported"
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     L = sb.lib()
-    assert L.sfno_b200_abi_version() == 1
+    assert L.sfno_b200_abi_version() == 2
     assert L.sfno_b200_status_string(-3) == b"workspace too small"
 
 
