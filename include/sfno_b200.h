@@ -277,6 +277,35 @@ int sfno_prescribe_denormalize(float* gen_norm_dev, const float* target_norm_dev
                                int interpolate, const float* mean_dev, const float* std_dev, float* gen_denorm_dev,
                                int channels, int batch, int64_t hw, void* stream);
 
+/* ---- backward pass of the op-level entry points -------------------------------------------
+ * Autograd formulas of the custom ops: everything a training step of the reference's modules needs when their transforms,
+ * contraction, 1x1 convolutions and norms run through this library.
+ * Adjoint transforms: RealSHT / InverseRealSHT are real-linear maps between [fields][nlat][nlon] and the (re, im) pairs of
+ * [fields][lmax][mmax]; the gradient of a real loss w.r.t. their input is the transposed map applied to the gradient
+ * w.r.t. their output.  They run on the plan's engine (fp32 / tf32 / bf16) as the opposite transform's GEMM ops on
+ * transposed tables (built on first use; workspace as sfno_sht_workspace_bytes). */
+int sfno_sht_forward_adjoint(sfno_sht_plan* plan, const float* grad_coeffs_dev, float* grad_x_dev, int64_t fields,
+                             void* workspace_dev, size_t workspace_bytes, void* stream);
+int sfno_sht_inverse_adjoint(sfno_sht_plan* plan, const float* grad_x_dev, float* grad_coeffs_dev, int64_t fields,
+                             void* workspace_dev, size_t workspace_bytes, void* stream);
+/* _contract_dhconv / _contract_diagonal (contractions.py:147-169): grad_x = sum_o grad_out conj(w), grad_w = sum_{b(,m)}
+ * conj(x) grad_out (complex64, interleaved, reference layouts as sfno_spectral_contract); either output may be NULL. */
+int sfno_spectral_contract_backward(int operator_type, const float* x_dev, const float* weight_dev, const float* grad_out_dev,
+                                    float* grad_x_dev, float* grad_w_dev, int batch, int cin, int cout, int lmax, int mmax,
+                                    void* stream);
+/* nn.Conv2d(cin, cout, 1): grad_w[cout][cin] = sum_{b,p} grad_y[b][o][p] x[b][c][p] (split-K partial GEMMs + reduction),
+ * grad_b[cout] = sum_{b,p} grad_y (grad_b_dev may be NULL).  grad_x is sfno_conv1x1 of grad_y with the transposed weight. */
+size_t sfno_conv1x1_weight_grad_workspace_bytes(int batch, int cin, int cout, int64_t hw);
+int sfno_conv1x1_weight_grad(const float* x_dev, const float* grad_y_dev, float* grad_w_dev, float* grad_b_dev, int batch,
+                             int cin, int cout, int64_t hw, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* nn.InstanceNorm2d (+ the per-(b,c) affine y = xhat * A + D that sfno_instance_norm fuses: A = gamma (1 + scale),
+ * D = beta (1 + scale) + shift): grad_x [batch][C][hw], and per plane grad_a = sum grad_out xhat, grad_d = sum grad_out
+ * ([batch][C]; the chain rule to gamma / beta / scale / shift is host-side arithmetic on these small arrays).
+ * affine_a_dev [batch][C] or NULL (= 1). */
+int sfno_instance_norm_backward(const float* x_dev, const float* grad_out_dev, const float* affine_a_dev, float* grad_x_dev,
+                                float* grad_a_dev, float* grad_d_dev, int batch, int channels, int64_t hw, float eps,
+                                void* stream);
+
 /* ---- parameter fingerprints ---------------------------------------------------------------------------
  * out_dev[i] = position-weighted 64-bit checksum of the bit patterns of tensor i (ptrs_dev[i], numel_dev[i] fp32
  * elements), one launch for all tensors.  The host wrapper compares it with the value recorded at the last

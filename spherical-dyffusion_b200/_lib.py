@@ -91,6 +91,14 @@ _SIGNATURES = {
     "sfno_normalize_pack": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfno_prescribe_denormalize": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
                                            c_void_p, c_int, c_int, c_int64, c_void_p]),
+    "sfno_sht_forward_adjoint": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "sfno_sht_inverse_adjoint": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "sfno_spectral_contract_backward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                                c_void_p]),
+    "sfno_conv1x1_weight_grad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int64]),
+    "sfno_conv1x1_weight_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_size_t, c_void_p]),
+    "sfno_instance_norm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float,
+                                            c_void_p]),
     "sfno_cold_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 

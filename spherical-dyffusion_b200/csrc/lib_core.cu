@@ -111,9 +111,46 @@ int sht_tables_upload(int nlat, int nlon, int lmax, int mmax, int grid, int prec
   return st;
 }
 
+template <class T>
+static int upload_adjoint(const ShtTables& h, ShtDeviceTables& d) {
+  // analysis table transposed to [m][k][l] (the layout of the synthesis table pt)
+  std::vector<double> wt((size_t)d.mmax * d.nlat * d.lmax), e, et;
+  for (int m = 0; m < d.mmax; ++m)
+    for (int l = 0; l < d.lmax; ++l)
+      for (int k = 0; k < d.nlat; ++k)
+        wt[((size_t)m * d.nlat + k) * d.lmax + l] = h.weights[((size_t)m * d.lmax + l) * d.nlat + k];
+  SFNO_TRY(upload_padded<T>(wt, (int64_t)d.mmax * d.nlat, d.lmax, d.Lq, &d.wq_t, &d.bytes));
+  // synthesis table in the analysis layout [m][l][k]
+  SFNO_TRY(upload_padded<T>(h.pct, (int64_t)d.mmax * d.lmax, d.nlat, d.Kp, &d.pct_a, &d.bytes));
+  // forward basis [2mmax][nlon] -> [nlon][2mmax]
+  build_dft_forward(d.nlon, d.mmax, e);
+  et.assign((size_t)d.nlon * 2 * d.mmax, 0.0);
+  for (int r = 0; r < 2 * d.mmax; ++r)
+    for (int j = 0; j < d.nlon; ++j) et[(size_t)j * 2 * d.mmax + r] = e[(size_t)r * d.nlon + j];
+  SFNO_TRY(upload_padded<T>(et, d.nlon, 2 * d.mmax, d.Kq2, &d.efwd_t, &d.bytes, d.basis_reps));
+  // inverse basis [nlon][2mmax] -> [2mmax][nlon]
+  build_dft_inverse(d.nlon, d.mmax, e);
+  et.assign((size_t)2 * d.mmax * d.nlon, 0.0);
+  for (int j = 0; j < d.nlon; ++j)
+    for (int r = 0; r < 2 * d.mmax; ++r) et[(size_t)r * d.nlon + j] = e[(size_t)j * 2 * d.mmax + r];
+  SFNO_TRY(upload_padded<T>(et, 2 * d.mmax, d.nlon, d.Wp, &d.einv_t, &d.bytes, d.basis_reps));
+  return SFNO_OK;
+}
+
+int sht_tables_enable_adjoint(ShtDeviceTables& d) {
+  if (d.wq_t) return SFNO_OK;
+  ShtTables h;
+  if (!build_sht_tables(d.nlat, d.nlon, d.lmax, d.mmax, d.grid, h)) return fail(SFNO_ERR_INVALID_ARGUMENT, "invalid SHT geometry");
+  g_upload_tf32 = d.precision == SFNO_PREC_TF32;
+  const int st = d.precision == SFNO_PREC_BF16 ? upload_adjoint<bf16>(h, d) : upload_adjoint<float>(h, d);
+  g_upload_tf32 = false;
+  return st;
+}
+
 void sht_tables_free(ShtDeviceTables& t) {
   cudaFree(t.wq); cudaFree(t.pt); cudaFree(t.efwd); cudaFree(t.einv);
-  t.wq = t.pt = t.efwd = t.einv = nullptr;
+  cudaFree(t.wq_t); cudaFree(t.efwd_t); cudaFree(t.pct_a); cudaFree(t.einv_t);
+  t.wq = t.pt = t.efwd = t.einv = t.wq_t = t.efwd_t = t.pct_a = t.einv_t = nullptr;
 }
 
 // ---- stand-alone SHT through the same ops the network uses (B = 1, C = fields) -----------------------
@@ -131,8 +168,11 @@ static ShtWs sht_ws_layout(const ShtDeviceTables& t, int64_t fields) {
   return w;
 }
 
+// analysis-shaped pair (longitude GEMM with `basis` as the A operand, then per-wavenumber GEMM with `table` as the A
+// operand): the forward transform with (efwd, wq), the ADJOINT of the inverse transform with (einv^T, pct)
 template <class T>
-static int sht_forward_impl(const ShtDeviceTables& t, const float* x, float* coeffs, int64_t fields, char* ws, cudaStream_t st) {
+static int sht_forward_impl(const ShtDeviceTables& t, const void* basis, const void* table, const float* x, float* coeffs, int64_t fields,
+                            char* ws, cudaStream_t st) {
   const ShtWs L = sht_ws_layout(t, fields);
   T* xt = (T*)(ws + L.x_off);
   T* F = (T*)(ws + L.f_off);
@@ -148,7 +188,7 @@ static int sht_forward_impl(const ShtDeviceTables& t, const float* x, float* coe
   }
   OpDft<T> dft{};
   dft.G = C; dft.M = 2 * t.mmax; dft.N = t.nlat; dft.K = t.nlon;
-  dft.A = (const T*)t.efwd; dft.Bm = xin; dft.a_sk = 1; dft.b_sk = 1;
+  dft.A = (const T*)basis; dft.Bm = xin; dft.a_sk = 1; dft.b_sk = 1;
   dft.f = F; dft.aff_a = nullptr; dft.aff_d = nullptr;
   dft.B = 1; dft.C = C; dft.nlat = t.nlat; dft.nlon = t.nlon; dft.Kp = t.Kp; dft.Wp = t.Wp; dft.x_bstride = 0;
   dft.a_reps = t.basis_reps;
@@ -156,7 +196,7 @@ static int sht_forward_impl(const ShtDeviceTables& t, const float* x, float* coe
   SFNO_TRY(launch_gemm(dft, st, "dft_fwd"));
   OpLeg<T> leg{};
   leg.G = t.mmax; leg.M = t.lmax; leg.N = 2 * C; leg.K = t.nlat;
-  leg.A = (const T*)t.wq; leg.Bm = F; leg.a_sk = 1; leg.b_sk = 1;
+  leg.A = (const T*)table; leg.Bm = F; leg.a_sk = 1; leg.b_sk = 1;
   leg.x = X; leg.Kp = t.Kp; leg.lmax = t.lmax; leg.mmax = t.mmax; leg.triangular = 0;
   SFNO_TRY(launch_gemm(leg, st, "legendre_fwd"));
   const int64_t total = fields * t.lmax * t.mmax * 2;
@@ -164,8 +204,10 @@ static int sht_forward_impl(const ShtDeviceTables& t, const float* x, float* coe
   return post_launch("internal_to_coeffs");
 }
 
+// synthesis-shaped pair: the inverse transform with (pt, einv), the ADJOINT of the forward transform with (wq^T, efwd^T)
 template <class T>
-static int sht_inverse_impl(const ShtDeviceTables& t, const float* coeffs, float* x, int64_t fields, char* ws, cudaStream_t st) {
+static int sht_inverse_impl(const ShtDeviceTables& t, const void* table, const void* basis, const float* coeffs, float* x, int64_t fields,
+                            char* ws, cudaStream_t st) {
   const ShtWs L = sht_ws_layout(t, fields);
   T* xt = (T*)(ws + L.x_off);
   T* Gb = (T*)(ws + L.f_off);
@@ -176,14 +218,14 @@ static int sht_inverse_impl(const ShtDeviceTables& t, const float* coeffs, float
   SFNO_TRY(post_launch("coeffs_to_internal"));
   OpIleg<T> il{};
   il.G = t.mmax; il.M = 2 * C; il.N = t.nlat; il.K = t.lmax;
-  il.A = X; il.Bm = (const T*)t.pt; il.b_sk = 1;
+  il.A = X; il.Bm = (const T*)table; il.b_sk = 1;
   il.a_goff = il.M; il.a_sk = (int64_t)t.mmax * il.M;  // X layout [l][m][rows]
   il.g_out = Gb; il.B = 1; il.C = C; il.Kp = t.Kp; il.Lq = t.Lq; il.nlat = t.nlat; il.triangular = 0;
   il.round_out = 1;    // G feeds the inverse-DFT MMA
   SFNO_TRY(launch_gemm(il, st, "legendre_inv"));
   IdftArgs<T, float> id{};
   id.G = 1; id.M = C * t.Kp; id.N = t.nlon; id.K = 2 * t.mmax;
-  id.A = Gb; id.Bm = (const T*)t.einv; id.a_sk = id.M; id.b_sk = 1;
+  id.A = Gb; id.Bm = (const T*)basis; id.a_sk = id.M; id.b_sk = 1;
   id.out = x; id.out_bstride = 0; id.bias = nullptr; id.add = nullptr; id.add_bstride = 0; id.act = SFNO_ACT_NONE;
   id.C = C; id.nlat = t.nlat; id.nlon = t.nlon; id.Kp = t.Kp; id.Kq2 = t.Kq2; id.b_reps = t.basis_reps; id.stat_part = nullptr;
   (void)xt;
@@ -312,8 +354,9 @@ int sfno_sht_forward(const sfno_sht_plan* plan, const float* x_dev, float* coeff
   if (workspace_bytes < sht_ws_layout(plan->t, fields).total) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   Tf32Scope tf32(plan->t.precision == SFNO_PREC_TF32);
-  return plan->t.precision == SFNO_PREC_BF16 ? sht_forward_impl<bf16>(plan->t, x_dev, coeffs_dev, fields, (char*)workspace_dev, st)
-                                             : sht_forward_impl<float>(plan->t, x_dev, coeffs_dev, fields, (char*)workspace_dev, st);
+  const ShtDeviceTables& t = plan->t;
+  return t.precision == SFNO_PREC_BF16 ? sht_forward_impl<bf16>(t, t.efwd, t.wq, x_dev, coeffs_dev, fields, (char*)workspace_dev, st)
+                                       : sht_forward_impl<float>(t, t.efwd, t.wq, x_dev, coeffs_dev, fields, (char*)workspace_dev, st);
 }
 
 int sfno_sht_inverse(const sfno_sht_plan* plan, const float* coeffs_dev, float* x_dev, int64_t fields,
@@ -323,8 +366,38 @@ int sfno_sht_inverse(const sfno_sht_plan* plan, const float* coeffs_dev, float* 
   if (workspace_bytes < sht_ws_layout(plan->t, fields).total) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   Tf32Scope tf32(plan->t.precision == SFNO_PREC_TF32);
-  return plan->t.precision == SFNO_PREC_BF16 ? sht_inverse_impl<bf16>(plan->t, coeffs_dev, x_dev, fields, (char*)workspace_dev, st)
-                                             : sht_inverse_impl<float>(plan->t, coeffs_dev, x_dev, fields, (char*)workspace_dev, st);
+  const ShtDeviceTables& t = plan->t;
+  return t.precision == SFNO_PREC_BF16 ? sht_inverse_impl<bf16>(t, t.pt, t.einv, coeffs_dev, x_dev, fields, (char*)workspace_dev, st)
+                                       : sht_inverse_impl<float>(t, t.pt, t.einv, coeffs_dev, x_dev, fields, (char*)workspace_dev, st);
+}
+
+// ---- adjoint transforms (backward pass of the two custom ops) -------------------------------------------
+// Both transforms are real-linear maps between [fields][nlat][nlon] and the (re, im) pairs of [fields][lmax][mmax]; their
+// adjoints are the transposed maps, which have the SHAPE of the opposite transform with transposed tables.
+int sfno_sht_forward_adjoint(sfno_sht_plan* plan, const float* grad_coeffs_dev, float* grad_x_dev, int64_t fields, void* workspace_dev,
+                             size_t workspace_bytes, void* stream) {
+  SFNO_CHECK_ARG(plan && grad_coeffs_dev && grad_x_dev && workspace_dev, "NULL argument");
+  SFNO_CHECK_ARG(fields > 0 && fields < (1 << 24), "bad field count %lld", (long long)fields);
+  if (workspace_bytes < sht_ws_layout(plan->t, fields).total) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
+  SFNO_TRY(sht_tables_enable_adjoint(plan->t));
+  cudaStream_t st = (cudaStream_t)stream;
+  Tf32Scope tf32(plan->t.precision == SFNO_PREC_TF32);
+  const ShtDeviceTables& t = plan->t;
+  return t.precision == SFNO_PREC_BF16 ? sht_inverse_impl<bf16>(t, t.wq_t, t.efwd_t, grad_coeffs_dev, grad_x_dev, fields, (char*)workspace_dev, st)
+                                       : sht_inverse_impl<float>(t, t.wq_t, t.efwd_t, grad_coeffs_dev, grad_x_dev, fields, (char*)workspace_dev, st);
+}
+
+int sfno_sht_inverse_adjoint(sfno_sht_plan* plan, const float* grad_x_dev, float* grad_coeffs_dev, int64_t fields, void* workspace_dev,
+                             size_t workspace_bytes, void* stream) {
+  SFNO_CHECK_ARG(plan && grad_coeffs_dev && grad_x_dev && workspace_dev, "NULL argument");
+  SFNO_CHECK_ARG(fields > 0 && fields < (1 << 24), "bad field count %lld", (long long)fields);
+  if (workspace_bytes < sht_ws_layout(plan->t, fields).total) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
+  SFNO_TRY(sht_tables_enable_adjoint(plan->t));
+  cudaStream_t st = (cudaStream_t)stream;
+  Tf32Scope tf32(plan->t.precision == SFNO_PREC_TF32);
+  const ShtDeviceTables& t = plan->t;
+  return t.precision == SFNO_PREC_BF16 ? sht_forward_impl<bf16>(t, t.einv_t, t.pct_a, grad_x_dev, grad_coeffs_dev, fields, (char*)workspace_dev, st)
+                                       : sht_forward_impl<float>(t, t.einv_t, t.pct_a, grad_x_dev, grad_coeffs_dev, fields, (char*)workspace_dev, st);
 }
 
 int sfno_spectral_contract(int operator_type, const float* x_dev, const float* weight_dev, float* out_dev, int batch,

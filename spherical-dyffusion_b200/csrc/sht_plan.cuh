@@ -18,10 +18,18 @@ struct ShtDeviceTables {
   int basis_reps = 16;   // replicas of the two DFT bases (L2 broadcast spreading)
   void* efwd = nullptr;  // [basis_reps][2*mmax][Wp]  forward DFT basis, A operand of OpDft
   void* einv = nullptr;  // [basis_reps][nlon][Kq2]   inverse DFT basis, B operand of OpIdft
+  // transposed tables of the ADJOINT transforms (backward pass, built on demand by sht_tables_enable_adjoint):
+  //   adjoint of the analysis  = synthesis-shaped ops with (wq^T, efwd^T);  adjoint of the synthesis = analysis-shaped ops
+  //   with (einv^T, pct in [m][l][k] layout)
+  void* wq_t = nullptr;    // [mmax][nlat][Lq]            analysis table transposed   (B operand of OpIleg)
+  void* efwd_t = nullptr;  // [basis_reps][nlon][Kq2]     forward DFT basis transposed (B operand of OpIdft)
+  void* pct_a = nullptr;   // [mmax][lmax][Kp]            synthesis table in analysis layout (A operand of OpLeg)
+  void* einv_t = nullptr;  // [basis_reps][2*mmax][Wp]    inverse DFT basis transposed (A operand of OpDft)
   size_t bytes = 0;
 };
 
 int sht_tables_upload(int nlat, int nlon, int lmax, int mmax, int grid, int precision, ShtDeviceTables& out);
+int sht_tables_enable_adjoint(ShtDeviceTables& t);
 void sht_tables_free(ShtDeviceTables& t);
 
 }  // namespace sfno
