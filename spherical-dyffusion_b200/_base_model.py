@@ -73,7 +73,18 @@ class BaseModel(nn.Module):
         self.log_text = logging.getLogger(name or type(self).__name__)
         if not verbose:
             self.log_text.setLevel(logging.WARN)
-        self.criterion = None      # no loss on the inference path
+        # src/losses/losses.py:66-79 (the two criteria the released configurations use; "preds" key as _base_model.py:80-103)
+        self.criterion = None
+        if loss_function is not None:
+            name = (loss_function if isinstance(loss_function, str) else loss_function.get("_target_", "").split(".")[-1])
+            name = name.lower().strip().replace("-", "_")
+            if name in ("l1", "mae", "mean_absolute_error"):
+                self.criterion = nn.ModuleDict({"preds": nn.L1Loss()})
+            elif name in ("l2", "mse", "mean_squared_error"):
+                self.criterion = nn.ModuleDict({"preds": nn.MSELoss()})
+            else:
+                raise ValueError(f"Unknown loss function {name}")
+        self.loss_function_weights = loss_function_weights if loss_function_weights is not None else {}
         self.ema_scope = None      # may be set by the experiment module (_base_experiment.py:386-401)
         self._channel_dim = 1      # NCHW
 
@@ -115,8 +126,27 @@ class BaseModel(nn.Module):
             raise RuntimeError(f"inputs.shape: {inputs.shape}, condition.shape: {extra.shape}") from e
 
     # ---- entry points the experiment / diffusion wrappers call -------------------------------------------------------------
-    def get_loss(self, *args, **kwargs):
-        raise NotImplementedError("training (get_loss / backward) is out of scope of the B200 inference path (SURVEY 8f-4)")
+    def get_loss(self, inputs, targets, raw_targets=None, condition=None, metadata: Any = None, predictions_mask=None,
+                 return_predictions: bool = False, predictions_post_process=None, targets_pre_process=None, **kwargs):
+        """``_base_model.py:194-263`` (tensor predictions): forward, optional post-processing / masking, criterion.  The
+        forward runs through the differentiable custom ops when gradients are enabled, so ``loss["loss"].backward()``
+        backpropagates through the library's adjoint kernels."""
+        if self.criterion is None:
+            raise ValueError("the model was built without a loss_function")
+
+        def mask_data(data):
+            return data[..., predictions_mask] if predictions_mask is not None else data
+
+        predictions = self(inputs, condition=condition, **kwargs) if torch.is_tensor(inputs) else self(**inputs, condition=condition, **kwargs)
+        if predictions_post_process is not None:
+            predictions = predictions_post_process(predictions)
+        preds_m, targets_m = mask_data(predictions), mask_data(targets)
+        assert preds_m.shape == targets_m.shape, \
+            f"Be careful: Predictions shape {preds_m.shape} != targets shape {targets_m.shape}. Missing singleton dimensions after batch dim. can be fatal."
+        loss_dict = dict(loss=self.criterion["preds"](preds_m, targets_m))
+        if return_predictions:
+            return loss_dict, predictions
+        return loss_dict
 
     def predict_forward(self, *inputs: Tensor, metadata: Any = None, **kwargs):
         """``_base_model.py:265-270``: plain call; ``metadata`` is accepted and unused, as in the reference."""

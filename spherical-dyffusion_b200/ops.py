@@ -17,6 +17,7 @@ op                                     replaces (reference file:line)
 ``sfno_b200::spectral_conv``           ``SpectralConvS2.forward`` ``s2convolutions.py:158-193`` as one fused call (bf16 / tf32 / fp32)
 ``sfno_b200::net_forward``             ``SphericalFourierNeuralOperatorNet.forward`` ``sfnonet.py:797-841``
 ``sfno_b200::cold_update``             ``x_s + (x_interpolated_s_next - x_interpolated_s)`` ``src/diffusion/dyffusion.py:519``
+``sfno_b200::*_adjoint / *_backward``  autograd formulas of the ops above (registered with ``torch.library.register_autograd``)
 =====================================  ==================================================================================
 """
 from __future__ import annotations
@@ -267,3 +268,209 @@ def cold_update(x_s: torch.Tensor, x_next: torch.Tensor, x_cur: torch.Tensor) ->
 @cold_update.register_fake
 def _(x_s, x_next, x_cur):
     return torch.empty_like(x_s, dtype=torch.float32)
+
+
+# =========================================================================================================================
+# Backward pass: autograd formulas of the custom ops.  Every formula is itself a custom op over the C ABI --
+# the adjoint transforms run the opposite transform's GEMM ops on transposed tables (on the plan's engine), the weight
+# gradient of the 1x1 convolution is a split-K GEMM, the contraction and norm gradients are dedicated kernels.
+# =========================================================================================================================
+@torch.library.custom_op("sfno_b200::sht_forward_adjoint", mutates_args=())
+def sht_forward_adjoint(plan: int, grad_coeffs: torch.Tensor, nlat: int, nlon: int) -> torch.Tensor:
+    """Transposed RealSHT: gradient w.r.t. x [..., nlat, nlon] from the gradient w.r.t. the (re, im) pairs [..., lmax, mmax, 2]."""
+    g = require_cuda_f32(grad_coeffs, "grad_coeffs")
+    lead = g.shape[:-3]
+    fields = int(torch.Size(lead).numel()) if len(lead) else 1
+    out = torch.empty(*lead, nlat, nlon, dtype=torch.float32, device=g.device)
+    if fields == 0:
+        return out
+    L = _lib.lib()
+    with torch.cuda.device(g.device):
+        ws = workspace(g.device, L.sfno_sht_workspace_bytes(_handle(plan), fields), "sht")
+        _lib.check(L.sfno_sht_forward_adjoint(_handle(plan), g.data_ptr(), out.data_ptr(), fields, ws.data_ptr(), ws.numel(),
+                                              stream_ptr(g.device)), "sfno_sht_forward_adjoint")
+    return out
+
+
+@sht_forward_adjoint.register_fake
+def _(plan, grad_coeffs, nlat, nlon):
+    return grad_coeffs.new_empty(*grad_coeffs.shape[:-3], nlat, nlon, dtype=torch.float32)
+
+
+@torch.library.custom_op("sfno_b200::sht_inverse_adjoint", mutates_args=())
+def sht_inverse_adjoint(plan: int, grad_x: torch.Tensor, lmax: int, mmax: int) -> torch.Tensor:
+    """Transposed InverseRealSHT: gradient w.r.t. the coefficient pairs [..., lmax, mmax, 2] from the gradient w.r.t. x."""
+    g = require_cuda_f32(grad_x, "grad_x")
+    lead = g.shape[:-2]
+    fields = int(torch.Size(lead).numel()) if len(lead) else 1
+    out = torch.empty(*lead, lmax, mmax, 2, dtype=torch.float32, device=g.device)
+    if fields == 0:
+        return out
+    L = _lib.lib()
+    with torch.cuda.device(g.device):
+        ws = workspace(g.device, L.sfno_sht_workspace_bytes(_handle(plan), fields), "sht")
+        _lib.check(L.sfno_sht_inverse_adjoint(_handle(plan), g.data_ptr(), out.data_ptr(), fields, ws.data_ptr(), ws.numel(),
+                                              stream_ptr(g.device)), "sfno_sht_inverse_adjoint")
+    return out
+
+
+@sht_inverse_adjoint.register_fake
+def _(plan, grad_x, lmax, mmax):
+    return grad_x.new_empty(*grad_x.shape[:-2], lmax, mmax, 2, dtype=torch.float32)
+
+
+@torch.library.custom_op("sfno_b200::spectral_contract_backward", mutates_args=())
+def spectral_contract_backward(operator_type: int, x: torch.Tensor, weight: torch.Tensor, grad_out: torch.Tensor) -> List[torch.Tensor]:
+    """[grad_x, grad_weight] of ``spectral_contract`` (complex as (re, im) pairs): sum_o g conj(w), sum_{b(,m)} conj(x) g."""
+    xf, w, g = require_cuda_f32(x, "x"), require_cuda_f32(weight, "weight"), require_cuda_f32(grad_out, "grad_out")
+    B, Ci, Lm, Mm = (int(v) for v in xf.shape[:4])
+    Co = int(w.shape[1])
+    gx, gw = torch.empty_like(xf), torch.empty_like(w)
+    if xf.numel() and g.numel():
+        with torch.cuda.device(xf.device):
+            _lib.check(_lib.lib().sfno_spectral_contract_backward(int(operator_type), xf.data_ptr(), w.data_ptr(), g.data_ptr(), gx.data_ptr(),
+                                                                  gw.data_ptr(), B, Ci, Co, Lm, Mm, stream_ptr(xf.device)),
+                       "sfno_spectral_contract_backward")
+    return [gx, gw]
+
+
+@spectral_contract_backward.register_fake
+def _(operator_type, x, weight, grad_out):
+    return [torch.empty_like(x, dtype=torch.float32), torch.empty_like(weight, dtype=torch.float32)]
+
+
+@torch.library.custom_op("sfno_b200::conv1x1_weight_grad", mutates_args=())
+def conv1x1_weight_grad(x: torch.Tensor, grad_y: torch.Tensor) -> List[torch.Tensor]:
+    """[grad_weight [Cout, Cin], grad_bias [Cout]] of a 1x1 convolution from x [B, Cin, H, W] and grad_y [B, Cout, H, W]."""
+    xf, g = require_cuda_f32(x, "x"), require_cuda_f32(grad_y, "grad_y")
+    B, Ci, Co = int(xf.shape[0]), int(xf.shape[1]), int(g.shape[1])
+    hw = int(xf.numel() // max(B * Ci, 1))
+    gw = torch.zeros(Co, Ci, dtype=torch.float32, device=xf.device)
+    gb = torch.zeros(Co, dtype=torch.float32, device=xf.device)
+    if xf.numel() and g.numel():
+        L = _lib.lib()
+        with torch.cuda.device(xf.device):
+            ws = workspace(xf.device, L.sfno_conv1x1_weight_grad_workspace_bytes(B, Ci, Co, hw), "wgrad")
+            _lib.check(L.sfno_conv1x1_weight_grad(xf.data_ptr(), g.data_ptr(), gw.data_ptr(), gb.data_ptr(), B, Ci, Co, hw, ws.data_ptr(),
+                                                  ws.numel(), stream_ptr(xf.device)), "sfno_conv1x1_weight_grad")
+    return [gw, gb]
+
+
+@conv1x1_weight_grad.register_fake
+def _(x, grad_y):
+    return [x.new_empty(grad_y.shape[1], x.shape[1], dtype=torch.float32), x.new_empty(grad_y.shape[1], dtype=torch.float32)]
+
+
+@torch.library.custom_op("sfno_b200::instance_norm_backward", mutates_args=())
+def instance_norm_backward(x: torch.Tensor, grad_out: torch.Tensor, affine_a: Optional[torch.Tensor], eps: float) -> List[torch.Tensor]:
+    """[grad_x, grad_a [B, C] = sum grad_out xhat, grad_d [B, C] = sum grad_out] for y = xhat * affine_a + d per (b, c) plane."""
+    xf, g = require_cuda_f32(x, "x"), require_cuda_f32(grad_out, "grad_out")
+    B, C = int(xf.shape[0]), int(xf.shape[1])
+    hw = int(xf.numel() // max(B * C, 1))
+    gx = torch.empty_like(xf)
+    da = torch.zeros(B, C, dtype=torch.float32, device=xf.device)
+    dd = torch.zeros(B, C, dtype=torch.float32, device=xf.device)
+    a = None if affine_a is None else require_cuda_f32(affine_a, "affine_a")
+    if xf.numel():
+        with torch.cuda.device(xf.device):
+            _lib.check(_lib.lib().sfno_instance_norm_backward(xf.data_ptr(), g.data_ptr(), _ptr(a), gx.data_ptr(), da.data_ptr(), dd.data_ptr(),
+                                                              B, C, hw, float(eps), stream_ptr(xf.device)), "sfno_instance_norm_backward")
+    return [gx, da, dd]
+
+
+@instance_norm_backward.register_fake
+def _(x, grad_out, affine_a, eps):
+    return [torch.empty_like(x, dtype=torch.float32), x.new_empty(x.shape[0], x.shape[1], dtype=torch.float32),
+            x.new_empty(x.shape[0], x.shape[1], dtype=torch.float32)]
+
+
+# ---- autograd registrations -------------------------------------------------------------------------------------------------
+def _sht_forward_setup(ctx, inputs, output):
+    plan, x, _, _ = inputs
+    ctx.plan, ctx.grid = int(plan), (int(x.shape[-2]), int(x.shape[-1]))
+
+
+def _sht_forward_backward(ctx, grad):
+    return None, torch.ops.sfno_b200.sht_forward_adjoint(ctx.plan, grad.contiguous(), ctx.grid[0], ctx.grid[1]), None, None
+
+
+def _sht_inverse_setup(ctx, inputs, output):
+    plan, coeffs, _, _ = inputs
+    ctx.plan, ctx.modes = int(plan), (int(coeffs.shape[-3]), int(coeffs.shape[-2]))
+
+
+def _sht_inverse_backward(ctx, grad):
+    return None, torch.ops.sfno_b200.sht_inverse_adjoint(ctx.plan, grad.contiguous(), ctx.modes[0], ctx.modes[1]), None, None
+
+
+def _contract_setup(ctx, inputs, output):
+    op, x, w = inputs
+    ctx.op = int(op)
+    ctx.save_for_backward(x, w)
+
+
+def _contract_backward(ctx, grad):
+    x, w = ctx.saved_tensors
+    gx, gw = torch.ops.sfno_b200.spectral_contract_backward(ctx.op, x, w, grad.contiguous())
+    return None, gx.reshape(x.shape), gw.reshape(w.shape)
+
+
+def _conv_setup(ctx, inputs, output):
+    x, weight, bias, residual, act = inputs
+    ctx.act, ctx.has_bias, ctx.has_res, ctx.wshape = int(act), bias is not None, residual is not None, tuple(weight.shape)
+    ctx.save_for_backward(x, weight)
+
+
+def _conv_backward(ctx, grad):
+    if ctx.act != 0:
+        raise NotImplementedError("conv1x1 with a fused activation has no backward: use act=0 and apply the activation outside "
+                                  "(the trainable forward of SphericalFourierNeuralOperatorNet does)")
+    x, weight = ctx.saved_tensors
+    g = grad.contiguous()
+    w2 = weight.reshape(weight.shape[0], -1)
+    gx = torch.ops.sfno_b200.conv1x1(g, w2.t().contiguous(), None, None, 0).reshape(x.shape) if ctx.needs_input_grad[0] else None
+    gw = gb = None
+    if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        gw, gb = torch.ops.sfno_b200.conv1x1_weight_grad(x, g)
+        gw = gw.reshape(ctx.wshape)
+    return gx, gw, (gb if ctx.has_bias else None), (grad if ctx.has_res else None), None
+
+
+def _norm_setup(ctx, inputs, output):
+    x, gamma, beta, scale, shift, eps = inputs
+    ctx.eps = float(eps)
+    ctx.flags = (gamma is not None, beta is not None, scale is not None, shift is not None)
+    ctx.save_for_backward(x, gamma, beta, scale, shift)
+
+
+def _norm_backward(ctx, grad):
+    x, gamma, beta, scale, shift = ctx.saved_tensors
+    B, C = x.shape[0], x.shape[1]
+    one_plus = (1.0 + scale) if scale is not None else None                       # [B, C]
+    a = None
+    if gamma is not None or one_plus is not None:
+        a = torch.ones(B, C, dtype=torch.float32, device=x.device)
+        if gamma is not None:
+            a = a * gamma.reshape(1, C)
+        if one_plus is not None:
+            a = a * one_plus
+    gx, da, dd = torch.ops.sfno_b200.instance_norm_backward(x, grad.contiguous(), a, ctx.eps)
+    # y = xhat * gamma (1 + scale) + beta (1 + scale) + shift: chain rule on the [B, C] sums
+    s1 = one_plus if one_plus is not None else 1.0
+    g_gamma = (da * s1).sum(0).reshape(gamma.shape) if gamma is not None else None
+    g_beta = (dd * s1).sum(0).reshape(beta.shape) if beta is not None else None
+    g_scale = None
+    if scale is not None:
+        g_scale = da * (gamma.reshape(1, C) if gamma is not None else 1.0)
+        if beta is not None:
+            g_scale = g_scale + dd * beta.reshape(1, C)
+        g_scale = g_scale.reshape(scale.shape)
+    g_shift = dd.reshape(shift.shape) if shift is not None else None
+    return gx.reshape(x.shape), g_gamma, g_beta, g_scale, g_shift, None
+
+
+torch.library.register_autograd("sfno_b200::sht_forward", _sht_forward_backward, setup_context=_sht_forward_setup)
+torch.library.register_autograd("sfno_b200::sht_inverse", _sht_inverse_backward, setup_context=_sht_inverse_setup)
+torch.library.register_autograd("sfno_b200::spectral_contract", _contract_backward, setup_context=_contract_setup)
+torch.library.register_autograd("sfno_b200::conv1x1", _conv_backward, setup_context=_conv_setup)
+torch.library.register_autograd("sfno_b200::instance_norm", _norm_backward, setup_context=_norm_setup)

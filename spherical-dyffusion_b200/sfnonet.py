@@ -564,10 +564,97 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
                                f"[B,{self.in_chans},{self.img_shape[0]},{self.img_shape[1]}], got {[tuple(t.shape) for t in parts]}")
         return parts
 
+    # ---- trainable forward -----------------------------------------------------------------------------------
+    @staticmethod
+    def _linear(x, weight, bias):
+        """nn.Linear on [B, in] through the 1x1-convolution op (pixels = batch), so that the backward is the library's."""
+        B = x.shape[0]
+        y = torch.ops.sfno_b200.conv1x1(x.t().reshape(1, x.shape[1], B, 1), weight, bias, None, 0)
+        return y.reshape(weight.shape[0], B).t()
+
+    def _forward_trainable(self, parts, time):
+        """The forward of ``sfnonet.py:797-841`` composed from the differentiable custom ops (``ops.py``): transforms,
+        contraction, 1x1 convolutions and InstanceNorm run -- forward and backward -- in the library (the transforms on the
+        engine of ``precision``, the convolutions on the fp32 CUDA-core engine); activations, adds, concatenations, dropout
+        and the sinusoidal embedding are elementwise torch glue.  Used whenever a gradient is required; the fused
+        whole-network executor (``sfno_net_forward``) is the inference path."""
+        F = torch.nn.functional
+        ops = torch.ops.sfno_b200
+        act = {"gelu": F.gelu, "relu": F.relu, "silu": F.silu}[self.activation_name]
+        x = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+        residual_big = x
+        x = ops.conv1x1(x, self.encoder[0].weight, self.encoder[0].bias, None, 0)
+        x = ops.conv1x1(act(x), self.encoder[2].weight, None, None, 0)
+        if isinstance(getattr(self, "pos_embed", None), nn.Parameter):
+            x = x + self.pos_embed
+        t_repr = None
+        if self.with_time_emb:
+            t = time * self.time_scaler + self.time_shift if self.time_rescale else time      # sfnonet.py:783-784
+            half = self.embed_dim // 2
+            freq = torch.exp(torch.arange(half, device=t.device, dtype=torch.float32) * (-math.log(10000) / (half - 1)))
+            e = t[:, None] * freq[None, :]
+            e = torch.cat((e.sin(), e.cos()), dim=-1)                                             # misc.py:21-33
+            t_repr = self._linear(F.gelu(self._linear(e, self.time_emb_mlp[1].weight, self.time_emb_mlp[1].bias)),
+                                  self.time_emb_mlp[3].weight, self.time_emb_mlp[3].bias)
+        eps = 1e-6
+        has_norm = self.normalization_layer == "instance_norm"
+        for blk in self.blocks:
+            scale = shift = None
+            if blk.time_mlp is not None:
+                ss = self._linear(F.silu(t_repr), blk.time_mlp[1].weight, blk.time_mlp[1].bias)   # sfnonet.py:280-287
+                scale, shift = ss.chunk(2, dim=1)
+            before = blk.time_scale_shift_before_filter
+
+            def norm(v, layer, with_time):
+                g, b = (layer.weight, layer.bias) if has_norm else (None, None)
+                sc, sh = (scale.contiguous(), shift.contiguous()) if (with_time and scale is not None) else (None, None)
+                if has_norm:
+                    return ops.instance_norm(v, g, b, sc, sh, eps)
+                return v * (sc[:, :, None, None] + 1) + sh[:, :, None, None] if sc is not None else v
+
+            x_norm = norm(x, blk.norm0, before)
+            filt = blk.filter.filter
+            fwd, inv = filt.forward_transform, filt.inverse_transform
+            X = ops.sht_forward(fwd._plan(x.device).value, x_norm, fwd.lmax, fwd.mmax)
+            residual = ops.sht_inverse(inv._plan(x.device).value, X, inv.nlat, inv.nlon) if filt.scale_residual else x_norm
+            Y = ops.spectral_contract(_lib.SFNO_OP[filt.operator_type], X, filt.weight)
+            y = ops.sht_inverse(inv._plan(x.device).value, Y, inv.nlat, inv.nlon) + filt.bias
+            y = act(y + ops.conv1x1(residual, blk.inner_skip.weight, blk.inner_skip.bias, None, 0))
+            y = norm(y, blk.norm1, not before)
+            fc = [m for m in blk.mlp.fwd if isinstance(m, nn.Conv2d)]
+            drops = [m for m in blk.mlp.fwd if isinstance(m, nn.Dropout)]
+            y = act(ops.conv1x1(y, fc[0].weight, fc[0].bias, None, 0))
+            if drops:
+                y = drops[0](y)
+            y = ops.conv1x1(y, fc[1].weight, fc[1].bias, None, 0)
+            if drops:
+                y = drops[0](y)
+            if isinstance(blk.drop_path, DropPath) and blk.drop_path.training and blk.drop_path.drop_prob:
+                keep = 1.0 - blk.drop_path.drop_prob                                               # drop_path.py:5-22
+                mask = torch.floor(keep + torch.rand(y.shape[0], 1, 1, 1, device=y.device, dtype=y.dtype))
+                y = y / keep * mask
+            x = y + residual
+        if self.big_skip:
+            x = torch.cat((x, residual_big), dim=1)
+        x = act(ops.conv1x1(x, self.decoder[0].weight, self.decoder[0].bias, None, 0))
+        x = ops.conv1x1(x, self.decoder[2].weight, None, None, 0)
+        return x, t_repr
+
     def forward(self, inputs, time=None, condition=None, static_condition=None, return_time_emb: bool = False, **kwargs):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("the B200 path is inference-only; call under torch.no_grad()/inference_mode() and .eval()")
         parts = self._input_parts(inputs, condition, static_condition)
+        needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in parts) or any(p.requires_grad for p in self.parameters()))
+        if needs_grad:
+            parts = [require_cuda_f32(t, "inputs") if not t.requires_grad else t.float() for t in parts]
+            if self.with_time_emb:
+                assert self.min_time is not None and self.max_time is not None, \
+                    "min_time and max_time must be set before using time embedding"
+                if time is None:
+                    raise ValueError("time is None but with_time_emb is True")
+                if not torch.is_tensor(time):
+                    time = torch.full((parts[0].shape[0],), float(time), dtype=torch.float32, device=parts[0].device)
+                time = time.to(device=parts[0].device, dtype=torch.float32).reshape(-1)
+            out, t_repr = self._forward_trainable(parts, time)
+            return (out, t_repr) if return_time_emb else out
         in_dtype = inputs.dtype
         parts = [require_cuda_f32(t, "inputs") for t in parts]
         x = parts[0]

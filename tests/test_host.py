@@ -126,7 +126,7 @@ def test_module_error_behaviour_mirrors_reference():
     with pytest.raises(NotImplementedError):
         sb.SphericalFourierNeuralOperatorNet(num_input_channels=1, num_output_channels=1, spatial_shape_in=(8, 16),
                                              spatial_shape_out=(8, 16), normalization_layer="layer_norm", scale_factor=1)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):      # built without a loss_function: no criterion
         m.get_loss(x, x)
 
 
