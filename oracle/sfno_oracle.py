@@ -97,6 +97,7 @@ def random_state_dict(cfg: SFNOConfig, seed: int = 0, spectral_gain: float = 1.0
     C, Cin, Cout = cfg.embed_dim, cfg.in_chans, cfg.num_output_channels
     H, W = cfg.spatial_shape
     L = int((H // cfg.scale_factor) * cfg.hard_thresholding_fraction)
+    M = int((W // cfg.scale_factor // 2 + 1) * cfg.hard_thresholding_fraction)
     hid = int(C * cfg.mlp_ratio)
     tdim = C * cfg.time_dim_mult
     sd: Dict[str, torch.Tensor] = {}
@@ -118,7 +119,8 @@ def random_state_dict(cfg: SFNOConfig, seed: int = 0, spectral_gain: float = 1.0
         if cfg.with_time_emb:
             sd[p + "time_mlp.1.weight"] = _trunc_normal((2 * C, tdim), 0.02, g)
             sd[p + "time_mlp.1.bias"] = torch.zeros(2 * C)
-        sd[p + "filter.filter.weight"] = spectral_gain / (C * C) * torch.randn(C, C, L, 2, generator=g)
+        wshape = (C, C, L, 2) if cfg.operator_type == "dhconv" else (C, C, L, M, 2)   # s2convolutions.py:139-147
+        sd[p + "filter.filter.weight"] = spectral_gain / (C * C) * torch.randn(*wshape, generator=g)
         sd[p + "filter.filter.bias"] = torch.zeros(1, C, 1, 1)
         sd[p + "inner_skip.weight"] = _trunc_normal((C, C, 1, 1), 0.02, g)
         sd[p + "inner_skip.bias"] = torch.zeros(C)

@@ -165,8 +165,8 @@ def test_instance_norm_gradients(dev, affine, with_time):
 NET_CASES = {
     "dhconv_time_12x24": SFNOConfig(spatial_shape=(12, 24), num_input_channels=3, num_output_channels=2, num_conditional_channels=2,
                                     embed_dim=16, num_layers=3, operator_type="dhconv", with_time_emb=True, min_time=0.0, max_time=6.0),
-    "diagonal_scale2_16x32": SFNOConfig(spatial_shape=(16, 32), num_input_channels=4, num_output_channels=4, embed_dim=12, num_layers=2,
-                                        operator_type="diagonal", scale_factor=2, data_grid="legendre-gauss", with_time_emb=False),
+    "diagonal_lg_16x32": SFNOConfig(spatial_shape=(16, 32), num_input_channels=4, num_output_channels=4, embed_dim=12, num_layers=2,
+                                        operator_type="diagonal", data_grid="legendre-gauss", with_time_emb=False),
     "dhconv_nonorm_18x36": SFNOConfig(spatial_shape=(18, 36), num_input_channels=2, num_output_channels=3, embed_dim=8, num_layers=2,
                                       operator_type="dhconv", normalization_layer="none", big_skip=False, pos_embed=False,
                                       with_time_emb=False),
@@ -176,21 +176,31 @@ NET_CASES = {
 }
 
 
-def _oracle_grads(cfg, sd, x, target, time, condition, loss):
-    o = SFNOOracle(cfg, sd)
+def _oracle_grads(cfg, sd, x, target, time, condition, loss, dtype=torch.float32):
+    o = SFNOOracle(cfg, sd, dtype=dtype)
     o.sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in o.sd.items()}
-    xr = _leaf(x)
+    xr = _leaf(x.to(dtype))
     out = o._forward(xr, time=time, condition=condition)
-    l = (out - target).abs().mean() if loss == "l1" else (out - target).square().mean()
+    l = (out - target.to(dtype)).abs().mean() if loss == "l1" else (out - target.to(dtype)).square().mean()
     l.backward()
-    return float(l), xr.grad, {k: v.grad for k, v in o.sd.items() if torch.is_tensor(v) and v.requires_grad}, out.detach()
+    return float(l.detach()), xr.grad, {k: v.grad for k, v in o.sd.items() if torch.is_tensor(v) and v.requires_grad}, out.detach()
 
 
 @pytest.mark.parametrize("case", sorted(NET_CASES))
-@pytest.mark.parametrize("precision,tol", [("fp32", GRAD_TOL), ("tf32", 4e-3), ("bf16", 4e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", GRAD_TOL), ("tf32", 1.8e-3), ("bf16", 1.35e-2)])
 def test_net_loss_gradients_match_oracle_autograd(dev, case, precision, tol):
+    """d loss / d (every parameter, input) of ``get_loss`` vs autograd through the oracle evaluated in fp64.
+
+    fp32 engine: EVERY parameter's gradient is within 1e-4 of the fp64 gradient, relative to its own norm -- or, where the
+    gradient cancels to (nearly) zero in exact arithmetic (a bias in front of an InstanceNorm: mlp.fwd.2.bias of every block
+    but the last has a true gradient of 1e-20), no further from it than 4x the error of fp32 CPU autograd through the same
+    algorithm.  Tensor-core engines (transforms in tf32 / bf16, everything else fp32): the whole gradient vector is within
+    the mode's forward bound (tests/test_gpu_parity.py); the worst single parameter is printed, not bounded -- small
+    gradients that are differences of large path contributions inherit the absolute error of the large ones."""
     cfg = NET_CASES[case]
     sd = perturb_affine_and_biases(random_state_dict(cfg, seed=3, spectral_gain=4.0), seed=4)
+    if cfg.normalization_layer == "none":
+        sd = {k: v for k, v in sd.items() if ".norm0." not in k and ".norm1." not in k}
     g = torch.Generator().manual_seed(11)
     B = 3
     H, W = cfg.spatial_shape
@@ -199,7 +209,8 @@ def test_net_loss_gradients_match_oracle_autograd(dev, case, precision, tol):
     target = torch.randn(B, cfg.num_output_channels, H, W, generator=g)
     time = torch.tensor([1.0, 2.0, 5.0]) if cfg.with_time_emb else None
     loss = "l1" if "time" in case else "mse"
-    l_ref, gx_ref, gp_ref, out_ref = _oracle_grads(cfg, sd, x, target, time, cond, loss)
+    l_ref, gx_ref, gp_ref, out_ref = _oracle_grads(cfg, sd, x, target, time, cond, loss, torch.float64)
+    _, gx_32, gp_32, _ = _oracle_grads(cfg, sd, x, target, time, cond, loss, torch.float32)
 
     m = sb.SphericalFourierNeuralOperatorNet(
         num_input_channels=cfg.num_input_channels, num_output_channels=cfg.num_output_channels,
@@ -215,27 +226,32 @@ def test_net_loss_gradients_match_oracle_autograd(dev, case, precision, tol):
     if time is not None:
         kwargs["time"] = time.to(dev)
     loss_dict, preds = m.get_loss(xd, target.to(dev), condition=None if cond is None else cond.to(dev), return_predictions=True, **kwargs)
-    assert rel_l2(preds.detach(), out_ref) < (GRAD_TOL if precision == "fp32" else tol)
+    assert rel_l2(preds.detach(), out_ref) < tol
     loss_dict["loss"].backward()
     assert abs(float(loss_dict["loss"]) - l_ref) <= (1e-5 if precision == "fp32" else tol) * abs(l_ref)
-    worst = ("input", rel_l2(xd.grad, gx_ref))
-    missing = []
+    e_in = rel_l2(xd.grad, gx_ref)
+    worst = ("input", e_in)
+    num = den = 0.0
     for name, p in m.named_parameters():
-        if p.grad is None:
-            missing.append(name)
-            continue
-        ref = gp_ref[name]
+        assert p.grad is not None, f"{name} has no gradient"
         assert p.grad.shape == p.shape
-        e = rel_l2(p.grad, ref.reshape(p.shape)) if float(ref.abs().max()) > 0 else float(p.grad.abs().max())
-        if e > worst[1]:
-            worst = (name, e)
-    print(f"{case} {precision}: loss {float(loss_dict['loss']):.6f} (oracle {l_ref:.6f}); worst gradient {worst[0]} rel-L2 {worst[1]:.3e}")
-    assert not missing, f"parameters without a gradient: {missing}"
-    assert worst[1] < tol, worst
+        ref = gp_ref[name].reshape(p.shape)
+        err = float((p.grad.cpu().double() - ref).norm())
+        err32 = float((gp_32[name].reshape(p.shape).double() - ref).norm())
+        n = float(ref.norm())
+        num, den = num + err * err, den + n * n
+        if precision == "fp32":
+            assert err <= tol * n + 4.0 * err32, (name, err, n, err32)
+        if n > 0 and err / n > worst[1] and n > 1e-12:
+            worst = (name, err / n)
+    e_all = math.sqrt(num / den)
+    print(f"{case} {precision}: loss {float(loss_dict['loss']):.6f} (oracle {l_ref:.6f}); gradient rel-L2: input {e_in:.3e}, "
+          f"all parameters {e_all:.3e}, worst single parameter {worst[0]} {worst[1]:.3e}")
+    assert e_in < tol and e_all < tol
 
 
 def test_training_step_reduces_loss_and_inference_path_sees_new_weights(dev):
-    """A few SGD steps through the library's backward lower the loss, and the fused inference executor
+    """A few optimizer steps through the library's backward lower the loss, and the fused inference executor
     (``sfno_net_forward``) picks the updated parameters up (version-counter check of ``sync_parameters``)."""
     cfg = NET_CASES["dhconv_time_12x24"]
     sd = random_state_dict(cfg, seed=5, spectral_gain=4.0)
@@ -250,17 +266,17 @@ def test_training_step_reduces_loss_and_inference_path_sees_new_weights(dev):
     g = torch.Generator().manual_seed(1)
     x = torch.randn(4, cfg.num_input_channels, 12, 24, generator=g).to(dev)
     cond = torch.randn(4, cfg.num_conditional_channels, 12, 24, generator=g).to(dev)
-    target = (0.1 * torch.randn(4, cfg.num_output_channels, 12, 24, generator=g)).to(dev)
+    target = 0.5 * x[:, :cfg.num_output_channels] - 0.25 * cond      # learnable through the big skip
     time = torch.tensor([1.0, 2.0, 3.0, 4.0], device=dev)
-    opt = torch.optim.SGD(m.parameters(), lr=0.05)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2)
     losses = []
-    for _ in range(8):
+    for _ in range(30):
         opt.zero_grad()
         l = m.get_loss(x, target, condition=cond, time=time)["loss"]
         l.backward()
         opt.step()
         losses.append(float(l))
-    assert losses[-1] < 0.9 * losses[0], losses
+    assert losses[-1] < 0.5 * losses[0], losses
     m.eval()
     with torch.no_grad():
         fused = m(x, time=time, condition=cond)
