@@ -353,7 +353,7 @@ def run_rollout(args, dev, world, rank):
     rank advancing its members as one batch through DYffusion sampling windows (6 forecaster + 10 interpolator forwards
     per window, interpolator dropout live, one captured CUDA graph per window), with the per-step ensemble statistics of
     src/evaluation/metrics.py:166-246 (mean, spread, RMSE, spread-skill ratio, fair CRPS) INSIDE the timed region:
-    NCCL all-gather of the members + one fused statistics kernel per 6-hour step.  The reference loops over the members
+    NCCL all-to-all of grid-point slices of the members + one fused statistics kernel on the slice per 6-hour step.  The reference loops over the members
     sequentially at batch 1 (src/ace_inference/inference/loop.py:199-208)."""
     import torch.distributed as dist
 
@@ -401,12 +401,12 @@ def run_rollout(args, dev, world, rank):
     local = max_local_members(members, world)
     out = {
         "workload": f"{members}-member ensemble rollout, {windows} windows = {steps} x 6-h steps, member-major over {world} GPU(s), "
-                    f"interpolator dropout on, per-step mean/spread/rmse/ssr/fair-CRPS (all-gather + fused kernel) inside the timed region",
+                    f"interpolator dropout on, per-step mean/spread/rmse/ssr/fair-CRPS (all-to-all of grid-point slices + fused kernel on the slice + all-gather of the result maps) inside the timed region",
         "members": members, "windows": windows, "steps": steps, "max_local_members": local,
         "ideal_speedup_vs_1gpu": members / local, "ms_total": ms, "ensemble_steps_per_s": steps_per_s,
         "ensemble_sypd": steps_per_s * 86400.0 / STEPS_PER_YEAR, "member_steps_per_s_aggregate": steps_per_s * members,
         "statistics_ms_total": ms_stats, "statistics_share": ms_stats / ms,
-        "statistics_bytes_gathered_per_step": int(members * 34 * 180 * 360 * 4) if world > 1 else 0,
+        "statistics_bytes_received_per_rank_per_step": int(members * 34 * 180 * 360 * 4 // world) if world > 1 else 0,
         "window_graph": bool(not args.no_graph), "forwards_per_window": dy.forwards_per_window(),
         "last_crps_mean": float(hist["crps"][-1].mean()), "last_spread_mean": float(hist["spread"][-1].mean()),
     }

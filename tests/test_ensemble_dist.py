@@ -1,4 +1,4 @@
-"""Multi-rank host logic on CPU: member sharding and the statistics collectives (world_size 2, gloo).
+"""Multi-rank host logic on CPU: member sharding and the statistics collectives (world_size 2 and 3, gloo).
 The local arithmetic is replaced by a torch stand-in (the product's CudaEnsembleOps needs a GPU); what is under
 test is the sharding, padding, all-reduce / all-gather plumbing and the metric definitions of metrics.py."""
 import os
@@ -73,6 +73,16 @@ def _worker(rank, world, port, E, results):
         out = stats.step(local, truth=truth, weights=weights)
         ref = _reference_metrics(members, truth, weights)
         ok = all(torch.allclose(out[k], ref[k], rtol=1e-4, atol=1e-5) for k in ref)
+        # a field whose point count (3 * 5 * 7 = 105) does not divide into equal 16-byte-aligned slices: 56 + 49
+        m2 = torch.randn(E, 3, 5, 7, generator=g) - 0.5
+        t2 = torch.randn(3, 5, 7, generator=g)
+        ref2 = _reference_metrics(m2, t2, torch.ones(5, 7))
+        o2 = stats.step(m2[stats.local_ids], truth=t2, weights=None)
+        ok = ok and all(torch.allclose(o2[k], ref2[k], rtol=1e-4, atol=1e-5) for k in ref2)
+        buf, rows, lo, hi = stats.exchange_slices(local)
+        ns = buf.shape[1]
+        ok = ok and (lo, hi) == (rank * ns, min((rank + 1) * ns, 216))
+        ok = ok and torch.equal(buf[rows.long()].sort(dim=0).values[:, : hi - lo], members.reshape(E, -1)[:, lo:hi].sort(dim=0).values)
         # without a truth field: no gather, two all-reduces (sums -> pivot, shifted moments); a large offset must not hurt
         big = local + 1.0e5
         nt = stats.step(big, weights=weights)
@@ -85,15 +95,15 @@ def _worker(rank, world, port, E, results):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("E", [5, 8])
-def test_statistics_two_ranks_gloo(E):
+@pytest.mark.parametrize("E,world", [(5, 2), (8, 2), (7, 3)])
+def test_statistics_multi_rank_gloo(E, world):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(2, port, E, results), nprocs=2, join=True)
-    assert dict(results) == {0: True, 1: True}
+    mp.spawn(_worker, args=(world, port, E, results), nprocs=world, join=True)
+    assert dict(results) == {r: True for r in range(world)}
 
 
 def test_statistics_single_process_matches_metrics():
