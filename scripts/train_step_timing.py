@@ -35,6 +35,23 @@ for precision, B in (("bf16", 4), ("tf32", 4), ("fp32", 2)):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
+    # per-launch profile of one step (library launches; torch glue between two launches is booked on the later one)
+    import ctypes
+    from spherical_dyffusion_b200 import _lib
+    from spherical_dyffusion_b200._util import stream_ptr
+    L = _lib.lib()
+    _lib.check(L.sfno_b200_profile_begin(stream_ptr(dev)), "profile_begin")
+    step()
+    names = ctypes.create_string_buffer(1 << 18)
+    cap = 16384
+    arr = (ctypes.c_float * cap)()
+    nrec = _lib.check(L.sfno_b200_profile_end(names, len(names), arr, cap), "profile_end")
+    acc = {}
+    for nm, t in zip(names.value.decode().split("\n"), list(arr)[:nrec]):
+        a = acc.setdefault(nm, [0.0, 0])
+        a[0] += t
+        a[1] += 1
+    prof = {k: [round(v[0], 2), v[1]] for k, v in sorted(acc.items(), key=lambda kv: -kv[1][0])[:16]}
     m.eval()
     with torch.no_grad():
         for _ in range(2):
@@ -46,7 +63,7 @@ for precision, B in (("bf16", 4), ("tf32", 4), ("fp32", 2)):
         torch.cuda.synchronize()
     print(json.dumps({"precision": precision, "batch": B, "train_step_ms": round(ms, 2), "samples_per_s": round(B / ms * 1e3, 1),
                       "fused_inference_forward_ms": round(e0.elapsed_time(e1) / n, 2),
-                      "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2)}))
+                      "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2), "profile_ms_launches": prof}))
     del m
     torch.cuda.empty_cache()
     torch.cuda.reset_peak_memory_stats()
