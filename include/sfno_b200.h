@@ -133,6 +133,18 @@ size_t sfno_spectral_conv_workspace_bytes(const sfno_sht_plan* fwd, const sfno_s
 int sfno_spectral_conv(const sfno_sht_plan* fwd, const sfno_sht_plan* inv, const sfno_spectral_weight* weight,
                        const float* x_dev, float* y_dev, float* residual_dev, int batch, void* workspace_dev,
                        size_t workspace_bytes, void* stream);
+/* Backward of sfno_spectral_conv (what autograd derives for s2convolutions.py:158-193): from the cotangents grad_y_dev
+ * [batch][cout][nlat'][nlon'] and grad_residual_dev (NULL or [batch][cin][nlat'][nlon'], the scale_residual output) it
+ * writes grad_x_dev [batch][cin][nlat][nlon] (NULL: skipped), grad_weight_dev (layout of filter.weight; NULL: skipped;
+ * needs x_dev) and grad_bias_dev [cout] (NULL: skipped).  weight_dev is filter.weight itself (fp32, reference layout).
+ * The transposed transforms and the conjugate-transposed contraction run on the ops of the plans' precision; the weight
+ * gradient is an fp32 per-degree GEMM over the (wavenumber, sample) rows. */
+size_t sfno_spectral_conv_backward_workspace_bytes(const sfno_sht_plan* fwd, const sfno_sht_plan* inv,
+                                                   const sfno_spectral_weight* weight, int batch);
+int sfno_spectral_conv_backward(sfno_sht_plan* fwd, sfno_sht_plan* inv, const sfno_spectral_weight* weight,
+                                const float* weight_dev, const float* x_dev, const float* grad_y_dev,
+                                const float* grad_residual_dev, float* grad_x_dev, float* grad_weight_dev,
+                                float* grad_bias_dev, int batch, void* workspace_dev, size_t workspace_bytes, void* stream);
 /* nn.Conv2d(cin, cout, 1) with the fused epilogue of the hot path -- + bias -> activation -> dropout(p; Philox stream
  * (seed, offset); layers.py:76-80, live at inference: dyffusion.py:226-235) + residual -- and a selectable engine:
  * SFNO_PREC_BF16 / SFNO_PREC_TF32 stage the operands in the workspace and run the tensor-core op, SFNO_PREC_F32 is

@@ -2,6 +2,7 @@
 // adjoint transforms (lib_core.cu: sfno_sht_forward_adjoint / sfno_sht_inverse_adjoint, which reuse the forward GEMM ops on
 // transposed tables) they let the reference's modules -- or this package's trainable forward -- backpropagate through
 // native kernels.  fp32 CUDA-core arithmetic; these are functional, not yet tuned, kernels.
+#include "backward.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 
@@ -140,6 +141,11 @@ __global__ void __launch_bounds__(512) instance_norm_backward_kernel(const float
   if (threadIdx.x == 0) { dA[bc] = (float)SGX; dD[bc] = (float)SG; }
 }
 
+int launch_bias_grad(const float* gy, int B, int C, int64_t hw, float* gb, cudaStream_t st) {
+  bias_grad_kernel<<<C, 256, 0, st>>>(gy, B, C, hw, gb);
+  return post_launch("bias_grad");
+}
+
 static int pick_splits(int64_t hw) {   // a divisor of hw, <= 32, chunks of >= 512 pixels
   int best = 1;
   for (int s = 2; s <= 32; ++s)
@@ -173,8 +179,7 @@ int sfno_conv1x1_weight_grad(const float* x_dev, const float* grad_y_dev, float*
   reduce_groups_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n, 256), 1024), 256, 0, st>>>(op.part, op.G, n, grad_w_dev);
   SFNO_TRY(post_launch("reduce_groups"));
   if (grad_b_dev) {
-    bias_grad_kernel<<<cout, 256, 0, st>>>(grad_y_dev, batch, cout, hw, grad_b_dev);
-    SFNO_TRY(post_launch("bias_grad"));
+    SFNO_TRY(launch_bias_grad(grad_y_dev, batch, cout, hw, grad_b_dev, st));
   }
   return SFNO_OK;
 }

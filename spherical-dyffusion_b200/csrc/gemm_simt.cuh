@@ -10,6 +10,12 @@ namespace sfno {
 
 constexpr int SIMT_BM = 128, SIMT_BN = 128, SIMT_BK = 16, SIMT_THREADS = 256;
 
+// per-group end of the contraction range: ops that define k_end(g) contract over [k_begin(g), k_end(g)), the others to op.K
+template <class Op>
+__device__ __forceinline__ auto simt_k_end(const Op& op, int g, int) -> decltype(op.k_end(g)) { return op.k_end(g); }
+template <class Op>
+__device__ __forceinline__ int simt_k_end(const Op& op, int, long) { return op.K; }
+
 template <class Op>
 __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(const Op op) {
   __shared__ float As[SIMT_BK][SIMT_BM + 4];
@@ -17,7 +23,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(const Op op) {
   const int g = blockIdx.z;
   const int m0 = blockIdx.x * SIMT_BM, n0 = blockIdx.y * SIMT_BN;
   const int t = threadIdx.x;
-  const int M = op.M, K = op.K;
+  const int M = op.M, K = simt_k_end(op, g, 0);
   const int N = op.n_end(g), n_lo = op.n_begin(g);   // per-group column range actually produced
   const int m_hi = op.m_end(g), m_lo = op.m_begin(g);  // per-group row range actually produced
   if (n0 >= N || n0 + SIMT_BN <= n_lo || m0 >= m_hi || m0 + SIMT_BM <= m_lo) return;  // block-uniform

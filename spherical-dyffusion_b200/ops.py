@@ -23,7 +23,7 @@ op                                     replaces (reference file:line)
 from __future__ import annotations
 
 import ctypes
-from typing import List, Optional, Sequence
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -384,7 +384,97 @@ def _(x, grad_out, affine_a, eps):
             x.new_empty(x.shape[0], x.shape[1], dtype=torch.float32)]
 
 
+@torch.library.custom_op("sfno_b200::spectral_conv_diff", mutates_args=())
+def spectral_conv_diff(plan_fwd: int, plan_inv: int, handle: int, weight: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor,
+                       nlat_out: int, nlon_out: int, want_residual: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``spectral_conv`` with the filter weight / bias as tensor inputs so that autograd reaches them (``handle`` must hold
+    their packed form: ``SpectralConvS2._weight_handle``); the backward is ``spectral_conv_backward``."""
+    y, res = spectral_conv(plan_fwd, plan_inv, handle, x, int(weight.shape[1]), nlat_out, nlon_out, want_residual)
+    return y, res
+
+
+@spectral_conv_diff.register_fake
+def _(plan_fwd, plan_inv, handle, weight, bias, x, nlat_out, nlon_out, want_residual):
+    y = x.new_empty(x.shape[0], weight.shape[1], nlat_out, nlon_out, dtype=torch.float32)
+    res = x.new_empty((x.shape[0], x.shape[1], nlat_out, nlon_out) if want_residual else (0,), dtype=torch.float32)
+    return y, res
+
+
+@torch.library.custom_op("sfno_b200::spectral_conv_backward", mutates_args=())
+def spectral_conv_backward(plan_fwd: int, plan_inv: int, handle: int, weight: torch.Tensor, x: torch.Tensor, grad_y: torch.Tensor,
+                           grad_residual: Optional[torch.Tensor], need_x: bool, need_weight: bool, need_bias: bool) -> List[torch.Tensor]:
+    """[grad_x, grad_weight, grad_bias] of the fused spectral convolution (each empty when not needed): transposed transforms and
+    the conjugate-transposed contraction on the plans' engine, the weight gradient as an fp32 per-degree GEMM."""
+    xf, w, gy = require_cuda_f32(x, "x"), require_cuda_f32(weight, "weight"), require_cuda_f32(grad_y, "grad_y")
+    gr = None if grad_residual is None else require_cuda_f32(grad_residual, "grad_residual")
+    B = int(xf.shape[0])
+    dev = xf.device
+    gx = torch.empty_like(xf) if need_x else torch.empty(0, dtype=torch.float32, device=dev)
+    gw = torch.empty_like(w) if need_weight else torch.empty(0, dtype=torch.float32, device=dev)
+    gb = torch.empty(int(w.shape[1]), dtype=torch.float32, device=dev) if need_bias else torch.empty(0, dtype=torch.float32, device=dev)
+    if B == 0:
+        return [gx, gw.zero_(), gb.zero_()]
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws = workspace(dev, L.sfno_spectral_conv_backward_workspace_bytes(_handle(plan_fwd), _handle(plan_inv), _handle(handle), B),
+                       "spectral_conv_bwd")
+        _lib.check(L.sfno_spectral_conv_backward(_handle(plan_fwd), _handle(plan_inv), _handle(handle), w.data_ptr(), xf.data_ptr(),
+                                                 gy.data_ptr(), _ptr(gr), gx.data_ptr() if need_x else None,
+                                                 gw.data_ptr() if need_weight else None, gb.data_ptr() if need_bias else None, B,
+                                                 ws.data_ptr(), ws.numel(), stream_ptr(dev)), "sfno_spectral_conv_backward")
+    return [gx, gw, gb]
+
+
+@spectral_conv_backward.register_fake
+def _(plan_fwd, plan_inv, handle, weight, x, grad_y, grad_residual, need_x, need_weight, need_bias):
+    e = lambda: x.new_empty(0, dtype=torch.float32)
+    return [torch.empty_like(x, dtype=torch.float32) if need_x else e(), torch.empty_like(weight, dtype=torch.float32) if need_weight else e(),
+            x.new_empty(weight.shape[1], dtype=torch.float32) if need_bias else e()]
+
+
 # ---- autograd registrations -------------------------------------------------------------------------------------------------
+def _spec_setup(ctx, inputs, output):
+    plan_fwd, plan_inv, handle, weight, bias, x, _, _, want_residual = inputs
+    ctx.args = (int(plan_fwd), int(plan_inv), int(handle), bool(want_residual), None if bias is None else tuple(bias.shape))
+    ctx.save_for_backward(weight, x)
+
+
+def _spec_backward(ctx, grad_y, grad_res):
+    weight, x = ctx.saved_tensors
+    plan_fwd, plan_inv, handle, want_residual, bias_shape = ctx.args
+    need_x, need_w = ctx.needs_input_grad[5], ctx.needs_input_grad[3]
+    need_b = bias_shape is not None and ctx.needs_input_grad[4]
+    gres = grad_res.contiguous() if (want_residual and grad_res is not None and grad_res.numel()) else None
+    gx, gw, gb = torch.ops.sfno_b200.spectral_conv_backward(plan_fwd, plan_inv, handle, weight, x, grad_y.contiguous(), gres, need_x, need_w,
+                                                            need_b)
+    return (None, None, None, gw if need_w else None, gb.reshape(bias_shape) if need_b else None, gx if need_x else None, None, None, None)
+
+
+def _conv_ex_setup(ctx, inputs, output):
+    x, weight, bias, residual, act, dropout_p, _, _, precision = inputs
+    ctx.cfg = (int(act), float(dropout_p), int(precision), bias is not None, residual is not None, tuple(weight.shape))
+    ctx.save_for_backward(x, weight)
+
+
+def _conv_ex_backward(ctx, grad):
+    act, p, precision, has_bias, has_res, wshape = ctx.cfg
+    if act != 0 or p != 0.0:
+        raise NotImplementedError("conv1x1_ex with a fused activation / dropout has no backward: use act=0, dropout_p=0 and apply them "
+                                  "outside (the trainable forward of SphericalFourierNeuralOperatorNet does)")
+    x, weight = ctx.saved_tensors
+    g = grad.contiguous()
+    w2 = weight.reshape(weight.shape[0], -1)
+    gx = None
+    if ctx.needs_input_grad[0]:
+        gx = torch.ops.sfno_b200.conv1x1_ex(g, w2.t().contiguous(), None, None, 0, 0.0, 0, 0, precision).reshape(x.shape)
+    gw = gb = None
+    if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+        gw, gb = torch.ops.sfno_b200.conv1x1_weight_grad(x, g)
+        gw = gw.reshape(wshape)
+    return gx, gw, (gb if has_bias else None), (grad if has_res else None), None, None, None, None, None
+
+
+
 def _sht_forward_setup(ctx, inputs, output):
     plan, x, _, _ = inputs
     ctx.plan, ctx.grid = int(plan), (int(x.shape[-2]), int(x.shape[-1]))
@@ -474,3 +564,5 @@ torch.library.register_autograd("sfno_b200::sht_inverse", _sht_inverse_backward,
 torch.library.register_autograd("sfno_b200::spectral_contract", _contract_backward, setup_context=_contract_setup)
 torch.library.register_autograd("sfno_b200::conv1x1", _conv_backward, setup_context=_conv_setup)
 torch.library.register_autograd("sfno_b200::instance_norm", _norm_backward, setup_context=_norm_setup)
+torch.library.register_autograd("sfno_b200::spectral_conv_diff", _spec_backward, setup_context=_spec_setup)
+torch.library.register_autograd("sfno_b200::conv1x1_ex", _conv_ex_backward, setup_context=_conv_ex_setup)

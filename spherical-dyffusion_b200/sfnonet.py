@@ -122,13 +122,14 @@ class SpectralConvS2(nn.Module):
     def forward(self, x):
         """Stand-alone execution as ONE fused library call (``sfno_spectral_conv``: SHT -> contraction -> inverse SHT +
         bias, on the tensor cores when the transforms were built with precision "bf16" / "tf32"); returns
-        ``(y, residual)`` like the reference (``s2convolutions.py:158-193``)."""
+        ``(y, residual)`` like the reference (``s2convolutions.py:158-193``).  Differentiable: the backward is one library call
+        too (``sfno_spectral_conv_backward``)."""
         dtype = x.dtype
         xf = require_cuda_f32(x, "x")
         fwd, inv = self.forward_transform, self.inverse_transform
-        y, res = torch.ops.sfno_b200.spectral_conv(fwd._plan(xf.device).value, inv._plan(xf.device).value,
-                                                   self._weight_handle(xf.device).value, xf, self.out_channels, inv.nlat, inv.nlon,
-                                                   bool(self.scale_residual))
+        y, res = torch.ops.sfno_b200.spectral_conv_diff(fwd._plan(xf.device).value, inv._plan(xf.device).value,
+                                                        self._weight_handle(xf.device).value, self.weight, getattr(self, "bias", None), xf,
+                                                        inv.nlat, inv.nlon, bool(self.scale_residual))
         residual = res.to(dtype) if self.scale_residual else x
         return y.type(dtype), residual
 
@@ -574,17 +575,21 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
 
     def _forward_trainable(self, parts, time):
         """The forward of ``sfnonet.py:797-841`` composed from the differentiable custom ops (``ops.py``): transforms,
-        contraction, 1x1 convolutions and InstanceNorm run -- forward and backward -- in the library (the transforms on the
-        engine of ``precision``, the convolutions on the fp32 CUDA-core engine); activations, adds, concatenations, dropout
-        and the sinusoidal embedding are elementwise torch glue.  Used whenever a gradient is required; the fused
+        contraction, 1x1 convolutions and InstanceNorm run -- forward and backward -- in the library, on the engine of
+        ``precision`` (tensor cores in bf16 / tf32; weight gradients are fp32 CUDA-core GEMMs); activations, adds,
+        concatenations, dropout and the sinusoidal embedding are elementwise torch glue.  Used whenever a gradient is required; the fused
         whole-network executor (``sfno_net_forward``) is the inference path."""
         F = torch.nn.functional
         ops = torch.ops.sfno_b200
         act = {"gelu": F.gelu, "relu": F.relu, "silu": F.silu}[self.activation_name]
+        prec = _lib.SFNO_PREC[self.precision]
+
+        def conv(v, layer):   # nn.Conv2d(.., 1) on the engine of ``precision`` (tensor cores in bf16 / tf32), forward and backward
+            return ops.conv1x1_ex(v, layer.weight, layer.bias, None, 0, 0.0, 0, 0, prec)
+
         x = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
         residual_big = x
-        x = ops.conv1x1(x, self.encoder[0].weight, self.encoder[0].bias, None, 0)
-        x = ops.conv1x1(act(x), self.encoder[2].weight, None, None, 0)
+        x = conv(act(conv(x, self.encoder[0])), self.encoder[2])
         if isinstance(getattr(self, "pos_embed", None), nn.Parameter):
             x = x + self.pos_embed
         t_repr = None
@@ -615,18 +620,18 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
             x_norm = norm(x, blk.norm0, before)
             filt = blk.filter.filter
             fwd, inv = filt.forward_transform, filt.inverse_transform
-            X = ops.sht_forward(fwd._plan(x.device).value, x_norm, fwd.lmax, fwd.mmax)
-            residual = ops.sht_inverse(inv._plan(x.device).value, X, inv.nlat, inv.nlon) if filt.scale_residual else x_norm
-            Y = ops.spectral_contract(_lib.SFNO_OP[filt.operator_type], X, filt.weight)
-            y = ops.sht_inverse(inv._plan(x.device).value, Y, inv.nlat, inv.nlon) + filt.bias
-            y = act(y + ops.conv1x1(residual, blk.inner_skip.weight, blk.inner_skip.bias, None, 0))
+            # SHT -> contraction -> inverse SHT (+ bias) as ONE differentiable library call (s2convolutions.py:158-193)
+            y, res = ops.spectral_conv_diff(fwd._plan(x.device).value, inv._plan(x.device).value, filt._weight_handle(x.device).value,
+                                            filt.weight, getattr(filt, "bias", None), x_norm, inv.nlat, inv.nlon, bool(filt.scale_residual))
+            residual = res if filt.scale_residual else x_norm
+            y = act(y + conv(residual, blk.inner_skip))
             y = norm(y, blk.norm1, not before)
             fc = [m for m in blk.mlp.fwd if isinstance(m, nn.Conv2d)]
             drops = [m for m in blk.mlp.fwd if isinstance(m, nn.Dropout)]
-            y = act(ops.conv1x1(y, fc[0].weight, fc[0].bias, None, 0))
+            y = act(conv(y, fc[0]))
             if drops:
                 y = drops[0](y)
-            y = ops.conv1x1(y, fc[1].weight, fc[1].bias, None, 0)
+            y = conv(y, fc[1])
             if drops:
                 y = drops[0](y)
             if isinstance(blk.drop_path, DropPath) and blk.drop_path.training and blk.drop_path.drop_prob:
@@ -636,8 +641,7 @@ class SphericalFourierNeuralOperatorNet(BaseModel):
             x = y + residual
         if self.big_skip:
             x = torch.cat((x, residual_big), dim=1)
-        x = act(ops.conv1x1(x, self.decoder[0].weight, self.decoder[0].bias, None, 0))
-        x = ops.conv1x1(x, self.decoder[2].weight, None, None, 0)
+        x = conv(act(conv(x, self.decoder[0])), self.decoder[2])
         return x, t_repr
 
     def forward(self, inputs, time=None, condition=None, static_condition=None, return_time_emb: bool = False, **kwargs):

@@ -12,7 +12,7 @@ __path__.append(_PKG_DIR)
 from ._lib import LIB_PATH, SfnoLibraryError, lib, load_library  # noqa: E402,F401
 from . import ops  # noqa: E402,F401  (torch.ops.sfno_b200.* custom-op layer)
 from .harmonics import InverseRealSHT, RealSHT  # noqa: E402,F401
-from .sfnonet import SphericalFourierNeuralOperatorNet  # noqa: E402,F401
+from .sfnonet import SpectralConvS2, SphericalFourierNeuralOperatorNet  # noqa: E402,F401
 
-__all__ = ["SphericalFourierNeuralOperatorNet", "RealSHT", "InverseRealSHT", "ops", "lib", "load_library", "LIB_PATH",
+__all__ = ["SphericalFourierNeuralOperatorNet", "SpectralConvS2", "RealSHT", "InverseRealSHT", "ops", "lib", "load_library", "LIB_PATH",
            "SfnoLibraryError"]

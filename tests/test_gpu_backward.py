@@ -104,6 +104,54 @@ def test_spectral_contract_gradients(dev, op, B, Ci, Co, L, M):
     assert rel_l2(xd.grad, xr.grad) < 2e-6 and rel_l2(wd.grad, wr.grad) < 2e-6
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", GRAD_TOL), ("tf32", 2e-3), ("bf16", 1.2e-2)])
+@pytest.mark.parametrize("op,cin,cout", [("dhconv", 6, 4), ("dhconv", 64, 64), ("diagonal", 5, 5)])
+@pytest.mark.parametrize("grid_in,grid_out,nlat,nlon", [("equiangular", "equiangular", 16, 32), ("equiangular", "legendre-gauss", 24, 48),
+                                                         ("legendre-gauss", "legendre-gauss", 90, 180)])
+def test_fused_spectral_conv_gradients(dev, precision, tol, op, cin, cout, grid_in, grid_out, nlat, nlon):
+    """``SpectralConvS2.forward`` (one library call forward, one backward) against autograd through the oracle's transforms
+    and contraction (s2convolutions.py:158-193), with and without the resampled residual (``scale_residual``)."""
+    lmax, mmax = nlat, nlon // 2 + 1
+    B = 3
+    g = torch.Generator().manual_seed(nlat + cin)
+    x = torch.randn(B, cin, nlat, nlon, generator=g)
+    w = torch.randn(*((cin, cout, lmax, 2) if op == "dhconv" else (cin, cout, lmax, mmax, 2)), generator=g) / math.sqrt(cin)
+    b = torch.randn(1, cout, 1, 1, generator=g)
+    cy, cr = torch.randn(B, cout, nlat, nlon, generator=g), torch.randn(B, cin, nlat, nlon, generator=g)
+    scale_residual = grid_in != grid_out
+    o_sht = oh.RealSHT(nlat, nlon, lmax=lmax, mmax=mmax, grid=grid_in).double()
+    o_isht = oh.InverseRealSHT(nlat, nlon, lmax=lmax, mmax=mmax, grid=grid_out).double()
+    xr, wr, br = _leaf(x.double()), _leaf(w.double()), _leaf(b.double())
+    X = o_sht(xr)
+    Y = (dhconv_contract if op == "dhconv" else diagonal_contract)(X, wr)
+    y_ref = o_isht(Y) + br
+    loss = (y_ref * cy.double()).sum()
+    if scale_residual:
+        loss = loss + (o_isht(X) * cr.double()).sum()
+    loss.backward()
+
+    sht = sb.RealSHT(nlat, nlon, lmax=lmax, mmax=mmax, grid=grid_in, precision=precision)
+    isht = sb.InverseRealSHT(nlat, nlon, lmax=lmax, mmax=mmax, grid=grid_out, precision=precision)
+    conv = sb.SpectralConvS2(sht, isht, cin, cout, operator_type=op, bias=True).to(dev)
+    with torch.no_grad():
+        conv.weight.copy_(w)
+        conv.bias.copy_(b)
+    assert bool(conv.scale_residual) == scale_residual
+    xd = _leaf(x, dev)
+    y, res = conv(xd)
+    assert rel_l2(y.detach(), y_ref.detach()) < tol
+    loss_d = (y * cy.to(dev)).sum()
+    if scale_residual:
+        loss_d = loss_d + (res * cr.to(dev)).sum()
+    else:
+        assert res is xd
+    loss_d.backward()
+    errs = {"x": rel_l2(xd.grad, xr.grad), "weight": rel_l2(conv.weight.grad, wr.grad), "bias": rel_l2(conv.bias.grad, br.grad)}
+    print(f"fused spectral conv gradients {precision} {op} {cin}->{cout} {grid_in}->{grid_out} {nlat}x{nlon}: " +
+          ", ".join(f"{k} {v:.3e}" for k, v in errs.items()))
+    assert max(errs.values()) < tol, errs
+
+
 @pytest.mark.parametrize("B,cin,cout,H,W,bias,res", [(2, 5, 16, 12, 24, True, False), (3, 36, 40, 18, 36, False, True),
                                                       (2, 130, 34, 180, 360, True, True), (8, 64, 128, 90, 180, True, False)])
 def test_conv1x1_gradients(dev, B, cin, cout, H, W, bias, res):
@@ -126,6 +174,27 @@ def test_conv1x1_gradients(dev, B, cin, cout, H, W, bias, res):
             assert a.grad.shape == a.shape
             e = rel_l2(a.grad, ref.grad)
             assert e < 5e-6, (name, e)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 5e-6), ("tf32", 1.5e-3), ("bf16", 8e-3)])
+def test_conv1x1_ex_gradients_on_each_engine(dev, precision, tol):
+    g = torch.Generator().manual_seed(8)
+    B, cin, cout, H, W = 2, 64, 96, 30, 64
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 1, 1, generator=g) / math.sqrt(cin)
+    b = torch.randn(cout, generator=g)
+    cot = torch.randn(B, cout, H, W, generator=g)
+    xr, wr, br = _leaf(x.double()), _leaf(w.double()), _leaf(b.double())
+    (torch.nn.functional.conv2d(xr, wr, br) * cot.double()).sum().backward()
+    xd, wd, bd = _leaf(x, dev), _leaf(w, dev), _leaf(b, dev)
+    y = torch.ops.sfno_b200.conv1x1_ex(xd, wd, bd, None, 0, 0.0, 0, 0, _lib.SFNO_PREC[precision])
+    (y * cot.to(dev)).sum().backward()
+    errs = {"x": rel_l2(xd.grad, xr.grad), "weight": rel_l2(wd.grad, wr.grad), "bias": rel_l2(bd.grad, br.grad)}
+    print(f"conv1x1_ex gradients {precision}: " + ", ".join(f"{k} {v:.3e}" for k, v in errs.items()))
+    assert max(errs.values()) < tol, errs
+    y2 = torch.ops.sfno_b200.conv1x1_ex(xd, wd, bd, None, _lib.SFNO_ACT["gelu"], 0.0, 0, 0, _lib.SFNO_PREC[precision])
+    with pytest.raises(NotImplementedError):
+        y2.sum().backward()
 
 
 def test_conv1x1_with_fused_activation_refuses_backward(dev):

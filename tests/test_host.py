@@ -168,7 +168,8 @@ def test_custom_op_layer_is_registered_with_fake_implementations():
     import spherical_dyffusion_b200  # noqa: F401
 
     for name in ("sht_forward", "sht_inverse", "spectral_contract", "instance_norm", "conv1x1", "conv1x1_ex", "spectral_conv",
-                 "net_forward", "cold_update"):
+                 "net_forward", "cold_update", "sht_forward_adjoint", "sht_inverse_adjoint", "spectral_contract_backward",
+                 "conv1x1_weight_grad", "instance_norm_backward", "spectral_conv_diff", "spectral_conv_backward"):
         assert hasattr(torch.ops.sfno_b200, name), name
     with FakeTensorMode():
         x = torch.empty(2, 3, 12, 24)
@@ -182,6 +183,20 @@ def test_custom_op_layer_is_registered_with_fake_implementations():
         assert torch.ops.sfno_b200.conv1x1_ex(x, torch.empty(7, 3, 1, 1), None, None, 1, 0.1, 0, 0, 1).shape == (2, 7, 12, 24)
         y, res = torch.ops.sfno_b200.spectral_conv(0, 0, 0, x, 5, 12, 24, True)
         assert y.shape == (2, 5, 12, 24) and res.shape == (2, 3, 12, 24)
+        # backward ops
+        w = torch.empty(3, 5, 12, 2)
+        y, res = torch.ops.sfno_b200.spectral_conv_diff(0, 0, 0, w, None, x, 12, 24, False)
+        assert y.shape == (2, 5, 12, 24) and res.numel() == 0
+        gx, gw, gb = torch.ops.sfno_b200.spectral_conv_backward(0, 0, 0, w, x, y, None, True, True, False)
+        assert gx.shape == x.shape and gw.shape == w.shape and gb.numel() == 0
+        assert torch.ops.sfno_b200.sht_forward_adjoint(0, torch.empty(2, 3, 12, 13, 2), 12, 24).shape == (2, 3, 12, 24)
+        assert torch.ops.sfno_b200.sht_inverse_adjoint(0, x, 12, 13).shape == (2, 3, 12, 13, 2)
+        gx, gw = torch.ops.sfno_b200.spectral_contract_backward(0, torch.empty(2, 3, 12, 13, 2), w, torch.empty(2, 5, 12, 13, 2))
+        assert gx.shape == (2, 3, 12, 13, 2) and gw.shape == w.shape
+        gw, gb = torch.ops.sfno_b200.conv1x1_weight_grad(x, torch.empty(2, 7, 12, 24))
+        assert gw.shape == (7, 3) and gb.shape == (7,)
+        gx, da, dd = torch.ops.sfno_b200.instance_norm_backward(x, x, None, 1e-6)
+        assert gx.shape == x.shape and da.shape == (2, 3) and dd.shape == (2, 3)
 
 
 def test_custom_ops_refuse_cpu_tensors():
