@@ -317,6 +317,14 @@ int sfno_conv1x1_weight_grad(const float* x_dev, const float* grad_y_dev, float*
 int sfno_instance_norm_backward(const float* x_dev, const float* grad_out_dev, const float* affine_a_dev, float* grad_x_dev,
                                 float* grad_a_dev, float* grad_d_dev, int batch, int channels, int64_t hw, float eps,
                                 void* stream);
+/* Backward of sfno_conv1x1_ex (activation NONE, no dropout) on the engine of `precision`: grad_x_dev [batch][cin][hw]
+ * (NULL: skipped; needs weight_dev [cout][cin]) = the forward op with the transposed weight; grad_w_dev [cout][cin]
+ * (NULL: skipped; needs x_dev) = split-K GEMM over the pixels -- tensor cores with fp32 partial sums in bf16 / tf32
+ * -- and grad_b_dev [cout] (NULL: skipped). */
+size_t sfno_conv1x1_backward_workspace_bytes(int batch, int cin, int cout, int64_t hw, int precision);
+int sfno_conv1x1_backward(const float* x_dev, const float* grad_y_dev, const float* weight_dev, float* grad_x_dev,
+                          float* grad_w_dev, float* grad_b_dev, int batch, int cin, int cout, int64_t hw, int precision,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- parameter fingerprints ---------------------------------------------------------------------------
  * out_dev[i] = position-weighted 64-bit checksum of the bit patterns of tensor i (ptrs_dev[i], numel_dev[i] fp32

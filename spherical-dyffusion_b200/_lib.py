@@ -84,6 +84,9 @@ _SIGNATURES = {
     "sfno_spectral_weight_destroy": (c_int, [c_void_p]),
     "sfno_spectral_conv_workspace_bytes": (c_size_t, [c_void_p, c_void_p, c_void_p, c_int]),
     "sfno_spectral_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "sfno_conv1x1_backward_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int64, c_int]),
+    "sfno_conv1x1_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int,
+                                      c_void_p, c_size_t, c_void_p]),
     "sfno_spectral_conv_backward_workspace_bytes": (c_size_t, [c_void_p, c_void_p, c_void_p, c_int]),
     "sfno_spectral_conv_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_int, c_void_p, c_size_t, c_void_p]),

@@ -4,7 +4,9 @@
 // native kernels.  fp32 CUDA-core arithmetic; these are functional, not yet tuned, kernels.
 #include "backward.cuh"
 #include "common.cuh"
-#include "gemm_simt.cuh"
+#include "engine.cuh"
+#include "ops.cuh"
+#include "pointwise.cuh"
 
 namespace sfno {
 
@@ -28,6 +30,64 @@ struct OpWgrad {
   __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = acc; }
 };
 
+// The same split-K weight gradient for the tensor-core engine: operands in T (bf16 / TF32-exact fp32), K-contiguous,
+// partial sums in fp32.  The K chunk of a group is a TMA dimension of the operand views ({pixel in chunk, row, chunk,
+// sample}, group g -> {g % splits, g / splits}), so every group contracts over [0, K) like any other batched GEMM.
+template <class T>
+struct OpWgradTc : NoFeatures {
+  static constexpr bool kGFastest = false;
+  static constexpr bool kSimtRowsOnFastLanes = false;
+  static constexpr bool kRanged = true;
+  static constexpr bool A_KCONTIG = true, B_KCONTIG = true, kColContig = true, kNFastest = false;
+  using OutT = float;
+  using InT = T;
+  __device__ bool out_tf32() const { return false; }
+  __device__ int m_begin(int) const { return 0; }
+  __device__ int m_end(int) const { return M; }
+  __device__ int n_begin(int) const { return 0; }
+  __device__ int n_end(int) const { return N; }
+  __device__ int k_begin(int) const { return 0; }
+  int G, M, N, K;              // G = batch * splits, M = cout, N = cin, K = pixels per chunk
+  const T* A; const T* Bm; int64_t a_sk, b_sk;   // A = gy [b][cout][hw], Bm = x [b][cin][hw]
+  int splits; int64_t hw;
+  float* part;                 // [G][M][N]
+  __device__ int64_t a_off(int g, int m) const { const int b = g / splits, s = g - b * splits; return ((int64_t)b * M + m) * hw + (int64_t)s * K; }
+  __device__ int64_t b_off(int g, int n) const { const int b = g / splits, s = g - b * splits; return ((int64_t)b * N + n) * hw + (int64_t)s * K; }
+  __device__ int n_store() const { return N; }
+  __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const { c[0] = col0; c[1] = row0; c[2] = g; c[3] = 0; c[4] = 0; }
+  struct Row { float* out; const float* res; bool valid; __device__ float stat_s() const { return 0.0f; } __device__ float stat_q() const { return 0.0f; } };
+  __device__ Row row(int g, int m) const { return Row{part + ((int64_t)g * M + m) * N, nullptr, true}; }
+  template <int F> __device__ Row row_f(int g, int m) const { return row(g, m); }
+  __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = acc; }
+  template <int F>
+  __device__ void compute8(Row&, int, const float (&acc)[8], const float (&)[8], float (&o)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = acc[i];
+  }
+};
+
+template <class T>
+struct TcTraits<OpWgradTc<T>> : TcTraitsBase<OpWgradTc<T>>, TcEligible<TcTraits<OpWgradTc<T>>, OpWgradTc<T>> {
+  static constexpr int BN = 256;
+  static constexpr uint64_t es = sizeof(T);
+  static void operands(const OpWgradTc<T>& op, TmaOperand& a, TmaOperand& b) {
+    const uint64_t batches = (uint64_t)(op.G / op.splits);
+    a.base = op.A; a.dims[0] = op.K; a.dims[1] = op.M; a.dims[2] = op.splits; a.dims[3] = batches;
+    a.strides[0] = (uint64_t)op.hw * es; a.strides[1] = (uint64_t)op.K * es; a.strides[2] = (uint64_t)op.M * op.hw * es;
+    a.batched = true; a.group_lo = op.splits;
+    b.base = op.Bm; b.dims[0] = op.K; b.dims[1] = op.N; b.dims[2] = op.splits; b.dims[3] = batches;
+    b.strides[0] = (uint64_t)op.hw * es; b.strides[1] = (uint64_t)op.K * es; b.strides[2] = (uint64_t)op.N * op.hw * es;
+    b.batched = true; b.group_lo = op.splits;
+  }
+  static bool extra_ok(const OpWgradTc<T>& op) { return aligned16(op.part) && op.N % 8 == 0; }
+  static void io(const OpWgradTc<T>& op, TmaIo& o, TmaIo&) {
+    o.base = op.part; o.es = 4; o.ok = true;
+    o.dims[0] = op.N; o.dims[1] = op.M; o.dims[2] = op.G;
+    o.strides[0] = (uint64_t)op.N * 4; o.strides[1] = (uint64_t)op.M * op.N * 4;
+    o.box_rows[0] = 32;
+  }
+};
+
 __global__ void reduce_groups_kernel(const float* __restrict__ part, int G, int64_t n, float* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.0f;
@@ -36,14 +96,25 @@ __global__ void reduce_groups_kernel(const float* __restrict__ part, int G, int6
   }
 }
 
-// gb[o] = sum_{b,p} gy[b][o][p]; one block per output channel
-__global__ void bias_grad_kernel(const float* __restrict__ gy, int B, int C, int64_t hw, float* __restrict__ gb) {
+// gb[o] = sum_{b,p} gy[b][o][p]; one block of 1024 threads per output channel, 16-byte loads where the planes allow
+__global__ void __launch_bounds__(1024) bias_grad_kernel(const float* __restrict__ gy, int B, int C, int64_t hw, float* __restrict__ gb) {
   __shared__ float sh[32];
   const int o = blockIdx.x;
   float s = 0.0f;
+  const bool vec = (hw & 3) == 0 && (reinterpret_cast<uintptr_t>(gy) & 15) == 0;
   for (int b = 0; b < B; ++b) {
     const float* p = gy + ((int64_t)b * C + o) * hw;
-    for (int64_t i = threadIdx.x; i < hw; i += blockDim.x) s += p[i];
+    if (vec) {
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+      float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+      for (int64_t i = threadIdx.x; i < (hw >> 2); i += blockDim.x) {
+        const float4 v = p4[i];
+        s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+      }
+      s += (s0 + s1) + (s2 + s3);
+    } else {
+      for (int64_t i = threadIdx.x; i < hw; i += blockDim.x) s += p[i];
+    }
   }
   for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
@@ -142,7 +213,7 @@ __global__ void __launch_bounds__(512) instance_norm_backward_kernel(const float
 }
 
 int launch_bias_grad(const float* gy, int B, int C, int64_t hw, float* gb, cudaStream_t st) {
-  bias_grad_kernel<<<C, 256, 0, st>>>(gy, B, C, hw, gb);
+  bias_grad_kernel<<<C, 1024, 0, st>>>(gy, B, C, hw, gb);
   return post_launch("bias_grad");
 }
 
@@ -153,11 +224,128 @@ static int pick_splits(int64_t hw) {   // a divisor of hw, <= 32, chunks of >= 5
   return best;
 }
 
+// K chunks for the tensor-core weight gradient: a divisor of hw whose chunk keeps the TMA strides 16-byte aligned, with
+// enough (sample, chunk, tile) units to fill the machine
+static int pick_splits_tc(int64_t hw, int batch, int cin, int cout) {
+  const int tiles = ceil_div(cout, 128) * ceil_div(cin, 256);
+  int best = 1;
+  for (int s = 1; s <= 64; ++s) {
+    if (hw % s != 0 || (hw / s) % 8 != 0 || hw / s < 512) continue;
+    best = s;
+    if ((int64_t)batch * s * tiles >= 2 * 148) break;
+  }
+  return best;
+}
+
+// [rows][cols] fp32 -> transposed [cols][ld] T, zero padded (weights of the data-gradient convolution)
+template <class T>
+static __global__ void pack_transposed_kernel(const float* __restrict__ src, int rows, int cols, int ld, T* __restrict__ dst, int round_tf32) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)cols * ld) return;
+  const int c = (int)(i / ld), r = (int)(i - (int64_t)c * ld);
+  float v = r < rows ? src[(int64_t)r * cols + c] : 0.0f;
+  if (round_tf32) v = tf32_rna(v);
+  dst[i] = from_f32<T>(v);
+}
+
+struct ConvBwdWs { size_t gyt, xt, wt, part, total; };
+static ConvBwdWs conv_bwd_ws_layout(int B, int cin, int cout, int64_t hw, int precision) {
+  const size_t e = precision == SFNO_PREC_BF16 ? 2 : 4;
+  const bool stage = precision != SFNO_PREC_F32;
+  ConvBwdWs w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  w.gyt = take(stage ? (size_t)B * cout * hw * e : 0);
+  w.xt = take(stage ? (size_t)B * cin * hw * e : 0);
+  w.wt = take((size_t)cin * round_up(cout, 8) * e);
+  const int splits = std::max(pick_splits(hw), pick_splits_tc(hw, B, cin, cout));
+  w.part = take((size_t)B * splits * cin * cout * sizeof(float));
+  w.total = off + 1024;
+  return w;
+}
+
+template <class T>
+static int conv1x1_backward_impl(const float* x, const float* gy, const float* wgt, float* gx, float* gw, float* gb, int B, int cin, int cout,
+                                 int64_t hw, bool tf32, int precision, char* ws, cudaStream_t st) {
+  const ConvBwdWs L = conv_bwd_ws_layout(B, cin, cout, hw, precision);
+  const bool stage = precision != SFNO_PREC_F32;
+  Tf32Scope scope(tf32);
+  const T* gyt = (const T*)gy;
+  const T* xt = (const T*)x;
+  if (stage) {
+    ConcatParts parts{};
+    parts.src[0] = gy; parts.channels[0] = cout; parts.nparts = 1;
+    concat_convert_kernel<T><<<dim3(256, B), 256, 0, st>>>(parts, hw, (T*)(ws + L.gyt), (int64_t)cout * hw, tf32 ? 1 : 0);
+    SFNO_TRY(post_launch("convert_grad"));
+    gyt = (const T*)(ws + L.gyt);
+  }
+  if (gx) {   // gx[b][c][p] = sum_o w[o][c] gy[b][o][p]: the forward op with the transposed weight
+    const int ldw = round_up(cout, 8);
+    T* wt = (T*)(ws + L.wt);
+    pack_transposed_kernel<T><<<(unsigned)ceil_div64((int64_t)cin * ldw, 256), 256, 0, st>>>(wgt, cout, cin, ldw, wt, tf32 ? 1 : 0);
+    SFNO_TRY(post_launch("pack_transposed"));
+    ConvArgs<T, float> op{};
+    op.G = B; op.M = cin; op.N = (int)hw; op.K = cout;
+    op.A = wt; op.Bm = gyt; op.a_sk = 1; op.b_sk = hw;
+    op.in_bstride = (int64_t)cout * hw; op.w_bstride = 0; op.ldw = ldw;
+    op.bias = nullptr; op.bias_bstride = 0; op.act = SFNO_ACT_NONE;
+    op.drop_p = 0.0f; op.seed = 0; op.offset = 0; op.rng_dev = nullptr; op.drop_mask = nullptr; op.branch_scale = nullptr;
+    op.res = nullptr; op.res_bstride = 0; op.res_a = nullptr; op.res_d = nullptr; op.pos = nullptr;
+    op.out = gx; op.out_bstride = (int64_t)cin * hw; op.stat_part = nullptr; op.round_out = 0;
+    SFNO_TRY(launch_conv(op, st, "conv1x1_data_grad"));
+  }
+  if (gw) {
+    if (stage) {
+      ConcatParts parts{};
+      parts.src[0] = x; parts.channels[0] = cin; parts.nparts = 1;
+      concat_convert_kernel<T><<<dim3(256, B), 256, 0, st>>>(parts, hw, (T*)(ws + L.xt), (int64_t)cin * hw, tf32 ? 1 : 0);
+      SFNO_TRY(post_launch("convert_input"));
+      xt = (const T*)(ws + L.xt);
+    }
+    OpWgradTc<T> op{};
+    op.splits = stage ? pick_splits_tc(hw, B, cin, cout) : pick_splits(hw);
+    op.hw = hw;
+    op.G = B * op.splits; op.M = cout; op.N = cin; op.K = (int)(hw / op.splits);
+    op.A = gyt; op.Bm = xt; op.a_sk = 1; op.b_sk = 1; op.part = (float*)(ws + L.part);
+    SFNO_TRY(launch_gemm(op, st, "conv1x1_weight_grad"));
+    const int64_t n = (int64_t)cout * cin;
+    reduce_groups_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n, 256), 1024), 256, 0, st>>>(op.part, op.G, n, gw);
+    SFNO_TRY(post_launch("reduce_groups"));
+  }
+  if (gb) SFNO_TRY(launch_bias_grad(gy, B, cout, hw, gb, st));
+  return SFNO_OK;
+}
+
 }  // namespace sfno
 
 using namespace sfno;
 
 extern "C" {
+
+// Backward of sfno_conv1x1_ex without activation / dropout, on the engine of `precision`: data gradient = the forward op
+// with the transposed weight, weight gradient = split-K GEMM over the pixels (tensor cores in bf16 / tf32, fp32 partials).
+size_t sfno_conv1x1_backward_workspace_bytes(int batch, int cin, int cout, int64_t hw, int precision) {
+  if (batch <= 0 || cin <= 0 || cout <= 0 || hw <= 0) return 0;
+  return conv_bwd_ws_layout(batch, cin, cout, hw, precision).total;
+}
+
+int sfno_conv1x1_backward(const float* x_dev, const float* grad_y_dev, const float* weight_dev, float* grad_x_dev, float* grad_w_dev,
+                          float* grad_b_dev, int batch, int cin, int cout, int64_t hw, int precision, void* workspace_dev,
+                          size_t workspace_bytes, void* stream) {
+  SFNO_CHECK_ARG(grad_y_dev && workspace_dev, "NULL argument");
+  SFNO_CHECK_ARG(!grad_x_dev || weight_dev, "the data gradient needs the weight");
+  SFNO_CHECK_ARG(!grad_w_dev || x_dev, "the weight gradient needs x");
+  SFNO_CHECK_ARG(batch > 0 && cin > 0 && cout > 0 && hw > 0 && hw < (1ll << 31), "bad sizes");
+  SFNO_CHECK_ARG(precision == SFNO_PREC_F32 || precision == SFNO_PREC_BF16 || precision == SFNO_PREC_TF32, "bad precision %d", precision);
+  SFNO_CHECK_ARG(((uintptr_t)workspace_dev & 1023) == 0, "workspace must be 1024-byte aligned");
+  if (workspace_bytes < sfno_conv1x1_backward_workspace_bytes(batch, cin, cout, hw, precision)) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == SFNO_PREC_BF16)
+    return conv1x1_backward_impl<bf16>(x_dev, grad_y_dev, weight_dev, grad_x_dev, grad_w_dev, grad_b_dev, batch, cin, cout, hw, false, precision,
+                                       (char*)workspace_dev, st);
+  return conv1x1_backward_impl<float>(x_dev, grad_y_dev, weight_dev, grad_x_dev, grad_w_dev, grad_b_dev, batch, cin, cout, hw,
+                                      precision == SFNO_PREC_TF32, precision, (char*)workspace_dev, st);
+}
 
 size_t sfno_conv1x1_weight_grad_workspace_bytes(int batch, int cin, int cout, int64_t hw) {
   if (batch <= 0 || cin <= 0 || cout <= 0 || hw <= 0) return 0;

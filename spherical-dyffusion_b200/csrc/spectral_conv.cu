@@ -128,10 +128,19 @@ static int spectral_conv_impl(const ShtDeviceTables& f, const ShtDeviceTables& i
 //   gW = conj(SHT(x)) . GY summed over (m, b)   (per-degree GEMM over the (m, b) rows), gbias = sum gy
 // -- the same tensor-core ops as the forward for everything but the weight gradient (fp32 CUDA-core GEMM).
 
-// gWp[l][(ri',o)][(ri,c)] = sum_{(m,b)} GY[l][(m,b)][(ri',o)] * X[l][(m,b)][(ri,c)]
+// gWp[l][(ri',o)][(ri,c)] = sum_{(m,b)} GY[l][(m,b)][(ri',o)] * X[l][(m,b)][(ri,c)]: per degree, both operands with the
+// GEMM row / column index contiguous (MN-major) and the contraction over the (m, b) rows.  Tensor cores in bf16 / tf32
+// (fp32 result), CUDA cores in fp32.  The tensor-core engine contracts over ALL rows: the caller zero-fills the rows the
+// triangular transforms do not write; the CUDA-core engine stops at the live rows (k_end).
 template <class T>
-struct OpDhconvWgrad {
-  static constexpr bool A_KCONTIG = false, B_KCONTIG = false, kSimtRowsOnFastLanes = false;
+struct OpDhconvWgrad : NoFeatures {
+  static constexpr bool kGFastest = false;
+  static constexpr bool kSimtRowsOnFastLanes = false;
+  static constexpr bool kRanged = true;
+  static constexpr bool A_KCONTIG = false, B_KCONTIG = false, kColContig = true, kNFastest = false;
+  using OutT = float;
+  using InT = T;
+  __device__ bool out_tf32() const { return false; }
   int G, M, N, K;              // G = lmax, M = 2*cout, N = 2*cin, K = mmax*B rows
   const T* A; const T* Bm; int64_t a_sk, b_sk;
   int B, lmax, triangular;
@@ -149,9 +158,36 @@ struct OpDhconvWgrad {
   }
   __device__ int64_t a_off(int g, int m) const { return (int64_t)g * K * M + m; }
   __device__ int64_t b_off(int g, int n) const { return (int64_t)g * K * N + n; }
-  struct Row { float* out; };
-  __device__ Row row(int g, int m) const { return Row{out + ((int64_t)g * M + m) * N}; }
+  __device__ int n_store() const { return N; }
+  __device__ void io_coords(int g, int row0, int col0, int (&c)[5]) const { c[0] = col0; c[1] = row0; c[2] = g; c[3] = 0; c[4] = 0; }
+  struct Row { float* out; const float* res; bool valid; __device__ float stat_s() const { return 0.0f; } __device__ float stat_q() const { return 0.0f; } };
+  __device__ Row row(int g, int m) const { return Row{out + ((int64_t)g * M + m) * N, nullptr, true}; }
+  template <int F> __device__ Row row_f(int g, int m) const { return row(g, m); }
   __device__ void store(const Row& r, int, int, int n, float acc) const { r.out[n] = acc; }
+  template <int F>
+  __device__ void compute8(Row&, int, const float (&acc)[8], const float (&)[8], float (&o)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = acc[i];
+  }
+};
+
+template <class T>
+struct TcTraits<OpDhconvWgrad<T>> : TcTraitsBase<OpDhconvWgrad<T>>, TcEligible<TcTraits<OpDhconvWgrad<T>>, OpDhconvWgrad<T>> {
+  static constexpr int BN = 256;
+  static constexpr uint64_t es = sizeof(T);
+  static void operands(const OpDhconvWgrad<T>& op, TmaOperand& a, TmaOperand& b) {
+    a.base = op.A; a.dims[0] = op.M; a.dims[1] = op.K; a.dims[2] = op.G;   // M-contiguous: {(ri',o), (m,b), l}
+    a.strides[0] = (uint64_t)op.M * es; a.strides[1] = (uint64_t)op.K * op.M * es; a.batched = true;
+    b.base = op.Bm; b.dims[0] = op.N; b.dims[1] = op.K; b.dims[2] = op.G;  // N-contiguous: {(ri,c), (m,b), l}
+    b.strides[0] = (uint64_t)op.N * es; b.strides[1] = (uint64_t)op.K * op.N * es; b.batched = true;
+  }
+  static bool extra_ok(const OpDhconvWgrad<T>& op) { return aligned16(op.out) && op.N % 8 == 0 && op.M % 8 == 0; }
+  static void io(const OpDhconvWgrad<T>& op, TmaIo& o, TmaIo&) {
+    o.base = op.out; o.es = 4; o.ok = true;
+    o.dims[0] = op.N; o.dims[1] = op.M; o.dims[2] = op.G;
+    o.strides[0] = (uint64_t)op.N * 4; o.strides[1] = (uint64_t)op.M * op.N * 4;
+    o.box_rows[0] = 32;
+  }
 };
 
 // packed real form of the conjugate-transposed dhconv weight: rows (ri, c), cols (ri', o) = Wp^T
@@ -173,18 +209,27 @@ static __global__ void pack_dhconv_weight_adjoint_kernel(const float* __restrict
   }
 }
 
-// gw[c][o][l] = (gWp[(0,o)][(0,c)] + gWp[(1,o)][(1,c)],  gWp[(1,o)][(0,c)] - gWp[(0,o)][(1,c)])
-static __global__ void unpack_dhconv_wgrad_kernel(const float* __restrict__ gwp, int cin, int cout, int L, float2* __restrict__ gw) {
-  const int64_t total = (int64_t)cin * cout * L;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int l = (int)(i % L);
-    const int64_t r = i / L;
-    const int o = (int)(r % cout), c = (int)(r / cout);
-    const float* p = gwp + (int64_t)l * 4 * cin * cout;
-    const int64_t N = 2 * cin;
-    const float a = p[(int64_t)o * N + c], d = p[(int64_t)(cout + o) * N + cin + c];
-    const float b1 = p[(int64_t)(cout + o) * N + c], b0 = p[(int64_t)o * N + cin + c];
-    gw[i] = make_float2(a + d, b1 - b0);
+// gw[c][o][l] = (gWp[l][(0,o)][(0,c)] + gWp[l][(1,o)][(1,c)],  gWp[l][(1,o)][(0,c)] - gWp[l][(0,o)][(1,c)])
+// One block per (32 input channels, 32 degrees, output channel): reads run along c, writes along l, through a shared tile.
+static __global__ void __launch_bounds__(256) unpack_dhconv_wgrad_kernel(const float* __restrict__ gwp, int cin, int cout, int L,
+                                                                         float2* __restrict__ gw) {
+  __shared__ float2 tile[32][33];
+  const int c0 = blockIdx.x * 32, l0 = blockIdx.y * 32, o = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int64_t N = 2 * cin;
+  for (int j = ty; j < 32; j += 8) {
+    const int l = l0 + j, c = c0 + tx;
+    if (l < L && c < cin) {
+      const float* p = gwp + (int64_t)l * 4 * cin * cout;
+      const float a = p[(int64_t)o * N + c], d = p[(int64_t)(cout + o) * N + cin + c];
+      const float b1 = p[(int64_t)(cout + o) * N + c], b0 = p[(int64_t)o * N + cin + c];
+      tile[j][tx] = make_float2(a + d, b1 - b0);
+    }
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, l = l0 + tx;
+    if (c < cin && l < L) gw[((int64_t)c * cout + o) * L + l] = tile[tx][j];
   }
 }
 
@@ -292,6 +337,10 @@ static int spectral_conv_backward_impl(const ShtDeviceTables& f, const ShtDevice
   const int tri = dh;
   const int64_t plane_f = (int64_t)f.nlat * f.nlon, plane_i = (int64_t)i.nlat * i.nlon;
   const T* src;
+  if (dh && gw) {   // the weight-gradient GEMM of the tensor-core engine contracts over every (m, b) row
+    SFNO_CUDA(cudaMemsetAsync(GY, 0, (size_t)f.lmax * f.mmax * B * 2 * w->cout * sizeof(T), st));
+    SFNO_CUDA(cudaMemsetAsync(X, 0, (size_t)f.lmax * f.mmax * B * 2 * w->cin * sizeof(T), st));
+  }
   // GY = iSHT^T gy
   SFNO_TRY(stage_field<T>(gy, B, w->cout, plane_i, tf32, xt, &src, st));
   SFNO_TRY(spec_forward<T>(i, i.einv_t, i.pct_a, B, w->cout, src, FG, GY, tri, st));
@@ -330,10 +379,9 @@ static int spectral_conv_backward_impl(const ShtDeviceTables& f, const ShtDevice
       op.G = f.lmax; op.M = 2 * w->cout; op.N = 2 * w->cin; op.K = f.mmax * B;
       op.A = GY; op.Bm = X; op.a_sk = 2 * w->cout; op.b_sk = 2 * w->cin;
       op.B = B; op.lmax = f.lmax; op.triangular = 1; op.out = gwp;
-      SFNO_TRY(launch_gemm_simt(op, st, "dhconv_weight_grad"));
-      const int64_t total = (int64_t)w->cin * w->cout * f.lmax;
-      unpack_dhconv_wgrad_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 16), 256, 0, st>>>(gwp, w->cin, w->cout, f.lmax,
-                                                                                                                 (float2*)gw);
+      SFNO_TRY(launch_gemm(op, st, "dhconv_weight_grad"));
+      unpack_dhconv_wgrad_kernel<<<dim3(ceil_div(w->cin, 32), ceil_div(f.lmax, 32), w->cout), 256, 0, st>>>(gwp, w->cin, w->cout, f.lmax,
+                                                                                                          (float2*)gw);
       SFNO_TRY(post_launch("unpack_dhconv_wgrad"));
     } else {
       const int64_t total = (int64_t)w->cin * w->cout * f.lmax * f.mmax;

@@ -384,6 +384,40 @@ def _(x, grad_out, affine_a, eps):
             x.new_empty(x.shape[0], x.shape[1], dtype=torch.float32)]
 
 
+@torch.library.custom_op("sfno_b200::conv1x1_backward", mutates_args=())
+def conv1x1_backward(x: torch.Tensor, grad_y: torch.Tensor, weight: torch.Tensor, need_x: bool, need_weight: bool, need_bias: bool,
+                     precision: int) -> List[torch.Tensor]:
+    """[grad_x, grad_weight [Cout, Cin], grad_bias [Cout]] (each empty when not needed) of a 1x1 convolution on the engine of
+    ``precision``: one staging of grad_y serves the data gradient (forward op, transposed weight) and the weight gradient
+    (split-K GEMM over the pixels, tensor cores with fp32 partial sums in bf16 / tf32)."""
+    xf, g = require_cuda_f32(x, "x"), require_cuda_f32(grad_y, "grad_y")
+    w = require_cuda_f32(weight, "weight").reshape(weight.shape[0], -1)
+    B, Ci, Co = int(xf.shape[0]), int(xf.shape[1]), int(g.shape[1])
+    hw = int(xf.numel() // max(B * Ci, 1))
+    dev = xf.device
+    e = lambda: torch.empty(0, dtype=torch.float32, device=dev)
+    gx = torch.empty_like(xf) if need_x else e()
+    gw = torch.empty(Co, Ci, dtype=torch.float32, device=dev) if need_weight else e()
+    gb = torch.empty(Co, dtype=torch.float32, device=dev) if need_bias else e()
+    if xf.numel() == 0 or g.numel() == 0:
+        return [gx.zero_(), gw.zero_(), gb.zero_()]
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws = workspace(dev, L.sfno_conv1x1_backward_workspace_bytes(B, Ci, Co, hw, int(precision)), "conv1x1_bwd")
+        _lib.check(L.sfno_conv1x1_backward(xf.data_ptr(), g.data_ptr(), w.data_ptr(), gx.data_ptr() if need_x else None,
+                                           gw.data_ptr() if need_weight else None, gb.data_ptr() if need_bias else None, B, Ci, Co, hw,
+                                           int(precision), ws.data_ptr(), ws.numel(), stream_ptr(dev)), "sfno_conv1x1_backward")
+    return [gx, gw, gb]
+
+
+@conv1x1_backward.register_fake
+def _(x, grad_y, weight, need_x, need_weight, need_bias, precision):
+    e = lambda: x.new_empty(0, dtype=torch.float32)
+    return [torch.empty_like(x, dtype=torch.float32) if need_x else e(),
+            x.new_empty(grad_y.shape[1], x.shape[1], dtype=torch.float32) if need_weight else e(),
+            x.new_empty(grad_y.shape[1], dtype=torch.float32) if need_bias else e()]
+
+
 @torch.library.custom_op("sfno_b200::spectral_conv_diff", mutates_args=())
 def spectral_conv_diff(plan_fwd: int, plan_inv: int, handle: int, weight: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor,
                        nlat_out: int, nlon_out: int, want_residual: bool) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -462,15 +496,11 @@ def _conv_ex_backward(ctx, grad):
         raise NotImplementedError("conv1x1_ex with a fused activation / dropout has no backward: use act=0, dropout_p=0 and apply them "
                                   "outside (the trainable forward of SphericalFourierNeuralOperatorNet does)")
     x, weight = ctx.saved_tensors
-    g = grad.contiguous()
-    w2 = weight.reshape(weight.shape[0], -1)
-    gx = None
-    if ctx.needs_input_grad[0]:
-        gx = torch.ops.sfno_b200.conv1x1_ex(g, w2.t().contiguous(), None, None, 0, 0.0, 0, 0, precision).reshape(x.shape)
-    gw = gb = None
-    if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
-        gw, gb = torch.ops.sfno_b200.conv1x1_weight_grad(x, g)
-        gw = gw.reshape(wshape)
+    need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
+    gx, gw, gb = torch.ops.sfno_b200.conv1x1_backward(x, grad.contiguous(), weight, need_x, need_w, need_b, precision)
+    gx = gx if need_x else None
+    gw = gw.reshape(wshape) if need_w else None
+    gb = gb if need_b else None
     return gx, gw, (gb if has_bias else None), (grad if has_res else None), None, None, None, None, None
 
 

@@ -169,7 +169,7 @@ def test_custom_op_layer_is_registered_with_fake_implementations():
 
     for name in ("sht_forward", "sht_inverse", "spectral_contract", "instance_norm", "conv1x1", "conv1x1_ex", "spectral_conv",
                  "net_forward", "cold_update", "sht_forward_adjoint", "sht_inverse_adjoint", "spectral_contract_backward",
-                 "conv1x1_weight_grad", "instance_norm_backward", "spectral_conv_diff", "spectral_conv_backward"):
+                 "conv1x1_weight_grad", "conv1x1_backward", "instance_norm_backward", "spectral_conv_diff", "spectral_conv_backward"):
         assert hasattr(torch.ops.sfno_b200, name), name
     with FakeTensorMode():
         x = torch.empty(2, 3, 12, 24)
