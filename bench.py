@@ -393,9 +393,13 @@ def run_rollout(args, dev, world, rank):
         dist.barrier()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1), ro.stats_ms()], device=dev, dtype=torch.float64)
+    t_min = t.clone()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_stats = float(t[0]), float(t[1])
+        dist.all_reduce(t_min, op=dist.ReduceOp.MIN)
+    # the statistics step of a rank with fewer members starts early and then waits inside the collective for the rank with
+    # the most members: the MAX over ranks is exchange + kernel + that wait, the MIN is what the critical-path rank pays
+    ms, ms_stats, ms_stats_min = float(t[0]), float(t[1]), float(t_min[1])
     steps = windows * h
     steps_per_s = steps / (ms * 1e-3)
     local = max_local_members(members, world)
@@ -406,6 +410,7 @@ def run_rollout(args, dev, world, rank):
         "ideal_speedup_vs_1gpu": members / local, "ms_total": ms, "ensemble_steps_per_s": steps_per_s,
         "ensemble_sypd": steps_per_s * 86400.0 / STEPS_PER_YEAR, "member_steps_per_s_aggregate": steps_per_s * members,
         "statistics_ms_total": ms_stats, "statistics_share": ms_stats / ms,
+        "statistics_ms_critical_rank": ms_stats_min, "statistics_share_critical_rank": ms_stats_min / ms,
         "statistics_bytes_received_per_rank_per_step": int(members * 34 * 180 * 360 * 4 // world) if world > 1 else 0,
         "window_graph": bool(not args.no_graph), "forwards_per_window": dy.forwards_per_window(),
         "last_crps_mean": float(hist["crps"][-1].mean()), "last_spread_mean": float(hist["spread"][-1].mean()),
