@@ -52,6 +52,14 @@ struct sfno_net {
   void* dec0_w = nullptr; float* dec0_b = nullptr; void* dec1_w = nullptr;
   std::string names;
   std::vector<void*> allocations;
+  // Option "mask_overlap" (default off): generate the dropout masks of block i on a forked stream while the spectral kernels
+  // of block i run, the main stream joining before fc1.  Measured SLOWER than the in-line mask launches (interpolator forward
+  // 15.17 vs 14.1-14.7 ms, window 230 vs 225 ms, profiles/r02_q_mask_overlap_ab.json): the mask blocks that fit next to a
+  // persistent GEMM CTA run at a fraction of their full-occupancy speed and take issue slots from its epilogue warps.
+  // Stream / events are created with the net (not inside a capture).
+  int mask_overlap = 0;
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> ev_start, ev_mask;
   int stop_after_block = -2;  // -2: run everything; -1: stop after encoder(+pos); i: stop after block i
   // bookkeeping of the last forward for debug taps
   size_t last_x_off = 0; int64_t last_x_bstride = 0; int last_batch = 0;
@@ -334,6 +342,11 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
   if (n->stop_after_block == -1) return SFNO_OK;
 
   const int64_t ts_bs = (int64_t)nl * 2 * C;
+  // forked mask generation: only for the tensor-core path with masks, never under the per-launch profile (its events
+  // live on the main stream) or with a debug tap (an early return would leave the fork unjoined)
+  const bool overlap_masks = n->mask_overlap && n->side != nullptr && dropout && cfg.dropout_mlp > 0.0f && tc_allowed<T>() && (P % 8) == 0 &&
+                             n->stop_after_block == -2 && !g_profile_on.load(std::memory_order_relaxed);
+  auto mask_grid = [](int64_t n8) { return (unsigned)std::min<int64_t>(ceil_div64(n8 / 8 + 1, 128), 148 * 4); };
   for (int i = 0; i < nl; ++i) {
     const BlockParams& bp = n->blocks[i];
     const ShtDeviceTables& fwd = (i == 0) ? n->data_grid : n->lg_grid;
@@ -342,6 +355,18 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
     T* nxt; int64_t nxt_bs;
     buf_of(nl - 1 - i, &nxt, &nxt_bs);
     const float* ts_i = cfg.with_time_emb ? ts + (int64_t)i * 2 * C : nullptr;
+
+    if (overlap_masks) {   // fork: this block's two keep masks are generated next to its spectral kernels
+      SFNO_CUDA(cudaEventRecord(n->ev_start[i], st));
+      SFNO_CUDA(cudaStreamWaitEvent(n->side, n->ev_start[i], 0));
+      const float pd = cfg.dropout_mlp;
+      const int64_t n8a = (int64_t)B * hid * P / 8, n8b = (int64_t)B * C * P / 8;
+      dropout_mask_kernel<<<mask_grid(n8a), 128, 0, n->side>>>((uint8_t*)(ws + w.mask1), n8a, pd, seed, offset + (uint64_t)i * 4 + 0, rng_dev);
+      SFNO_TRY(post_launch("dropout_mask"));
+      dropout_mask_kernel<<<mask_grid(n8b), 128, 0, n->side>>>((uint8_t*)(ws + w.mask2), n8b, pd, seed, offset + (uint64_t)i * 4 + 1, rng_dev);
+      SFNO_TRY(post_launch("dropout_mask"));
+      SFNO_CUDA(cudaEventRecord(n->ev_mask[i], n->side));
+    }
 
     // norm0 (+ time scale/shift before the filter) as a per-(b,c) affine  (sfnonet.py:290-299)
     const bool time_before = cfg.with_time_emb && cfg.time_scale_shift_before_filter;
@@ -430,11 +455,14 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
     // dropout masks by a dedicated kernel at full occupancy (tensor-core path; P % 8 == 0 there): inline, the Philox
     // rounds doubled the time of fc1 (3.66 vs 1.64 ms per interpolator forward, profiles/r01_o_interp.json)
     const bool masks = pdrop > 0.0f && conv_uses_tc(f1) && (P % 8) == 0;
+    if (overlap_masks) SFNO_CUDA(cudaStreamWaitEvent(st, n->ev_mask[i], 0));   // join (also when this block ends up without masks)
     if (masks) {
       uint8_t* m1 = (uint8_t*)(ws + w.mask1);
-      const int64_t n8 = (int64_t)B * hid * P / 8;
-      dropout_mask_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n8 / 8 + 1, 256), 148 * 8), 256, 0, st>>>(m1, n8, pdrop, seed, f1.offset, rng_dev);
-      SFNO_TRY(post_launch("dropout_mask"));
+      if (!overlap_masks) {
+        const int64_t n8 = (int64_t)B * hid * P / 8;
+        dropout_mask_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n8 / 8 + 1, 256), 148 * 8), 256, 0, st>>>(m1, n8, pdrop, seed, f1.offset, rng_dev);
+        SFNO_TRY(post_launch("dropout_mask"));
+      }
       f1.drop_mask = m1;
     }
     SFNO_TRY(launch_conv(f1, st, "mlp_fc1"));
@@ -443,9 +471,11 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
     f2.branch_scale = use_dp ? dscale : nullptr;
     if (masks) {
       uint8_t* m2 = (uint8_t*)(ws + w.mask2);
-      const int64_t n8 = (int64_t)B * C * P / 8;
-      dropout_mask_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n8 / 8 + 1, 256), 148 * 8), 256, 0, st>>>(m2, n8, pdrop, seed, f2.offset, rng_dev);
-      SFNO_TRY(post_launch("dropout_mask"));
+      if (!overlap_masks) {
+        const int64_t n8 = (int64_t)B * C * P / 8;
+        dropout_mask_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n8 / 8 + 1, 256), 148 * 8), 256, 0, st>>>(m2, n8, pdrop, seed, f2.offset, rng_dev);
+        SFNO_TRY(post_launch("dropout_mask"));
+      }
       f2.drop_mask = m2;
     }
     if (scale_residual) { f2.res = res; f2.res_bstride = CP; }
@@ -503,6 +533,15 @@ int sfno_net_create(const sfno_net_config* c, sfno_net** out) {
 
   auto* n = new sfno_net();
   n->cfg = *c;
+  if (c->dropout_mlp > 0.0f) {
+    bool ok = cudaStreamCreateWithFlags(&n->side, cudaStreamNonBlocking) == cudaSuccess;
+    n->ev_start.assign(c->num_layers, nullptr);
+    n->ev_mask.assign(c->num_layers, nullptr);
+    for (int i = 0; ok && i < c->num_layers; ++i)
+      ok = cudaEventCreateWithFlags(&n->ev_start[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&n->ev_mask[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); if (n->side) cudaStreamDestroy(n->side); n->side = nullptr; }
+  }
   n->P = c->nlat * c->nlon; n->C = c->embed_dim; n->Cin = c->in_chans; n->Cin_p = round_up(c->in_chans, 8);
   n->Cout = c->out_chans; n->Ccat = c->embed_dim + (c->big_skip ? c->in_chans : 0); n->Ccat_p = round_up(n->Ccat, 8);
   n->hid = c->mlp_hidden; n->tdim = c->with_time_emb ? c->time_dim : 0; n->L = c->lmax; n->M = c->mmax; n->nl = c->num_layers;
@@ -563,6 +602,9 @@ int sfno_net_create(const sfno_net_config* c, sfno_net** out) {
 
 int sfno_net_destroy(sfno_net* n) {
   if (!n) return SFNO_OK;
+  for (cudaEvent_t e : n->ev_start) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : n->ev_mask) if (e) cudaEventDestroy(e);
+  if (n->side) cudaStreamDestroy(n->side);
   for (void* p : n->allocations) cudaFree(p);
   sht_tables_free(n->data_grid);
   sht_tables_free(n->lg_grid);
@@ -584,6 +626,7 @@ int sfno_net_set_param(sfno_net* n, const char* name, const float* value_dev, in
 int sfno_net_set_option(sfno_net* n, const char* key, int64_t value) {
   SFNO_CHECK_ARG(n && key, "NULL argument");
   if (strcmp(key, "stop_after_block") == 0) { n->stop_after_block = (int)value; return SFNO_OK; }
+  if (strcmp(key, "mask_overlap") == 0) { n->mask_overlap = value != 0 && n->side != nullptr; return SFNO_OK; }
   return fail(SFNO_ERR_INVALID_ARGUMENT, "unknown option %s", key);
 }
 
