@@ -142,7 +142,7 @@ class BaseModel(nn.Module):
             predictions = predictions_post_process(predictions)
         preds_m, targets_m = mask_data(predictions), mask_data(targets)
         assert preds_m.shape == targets_m.shape, \
-            f"Be careful: Predictions shape {preds_m.shape} != targets shape {targets_m.shape}. Missing singleton dimensions after batch dim. can be fatal."
+            f"predictions {tuple(preds_m.shape)} and targets {tuple(targets_m.shape)} differ in shape (a missing singleton dimension would broadcast silently)"
         loss_dict = dict(loss=self.criterion["preds"](preds_m, targets_m))
         if return_predictions:
             return loss_dict, predictions
