@@ -143,9 +143,10 @@ class BaseModel(nn.Module):
         preds_m, targets_m = mask_data(predictions), mask_data(targets)
         assert preds_m.shape == targets_m.shape, \
             f"predictions {tuple(preds_m.shape)} and targets {tuple(targets_m.shape)} differ in shape (a missing singleton dimension would broadcast silently)"
+        assert len(self.loss_function_weights) == 0, "Loss function weights are not supported for this case"
         loss_dict = dict(loss=self.criterion["preds"](preds_m, targets_m))
         if return_predictions:
-            return loss_dict, predictions
+            return loss_dict, preds_m      # the reference returns the (post-processed) predictions AFTER the mask (:235-236)
         return loss_dict
 
     def predict_forward(self, *inputs: Tensor, metadata: Any = None, **kwargs):
