@@ -56,7 +56,7 @@ bool idft_uses_tc(const IdftArgs<T, TOut>& a) {
   return tc_allowed<T>() && TcTraits<Gen>::eligible(Gen(a));
 }
 // statistics partials per row: one per 64-column slice of every N tile
-constexpr int kConvBN = 192, kIdftBN = 192;
+constexpr int kConvBN = SFNO_TC_CONV_BN, kIdftBN = 192;
 inline int conv_stat_slices(int64_t hw) { return (int)ceil_div64(hw, kConvBN) * (kConvBN / TC_SLICE_COLS); }
 inline int idft_stat_slices(int nlon) { return ceil_div(nlon, kIdftBN) * (kIdftBN / TC_SLICE_COLS); }
 

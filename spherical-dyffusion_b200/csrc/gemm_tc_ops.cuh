@@ -155,10 +155,16 @@ struct TcTraits<OpIdft<T, TOut, ACT>> : TcTraitsBase<OpIdft<T, TOut, ACT>>,
   }
 };
 
+// engine experiment: N tile of the 1x1 convolutions (192 -> 12 epilogue warps at <= 127 registers, 4 operand stages;
+// 256 -> 16 epilogue warps at <= 112 registers, 3 stages)
+#ifndef SFNO_TC_CONV_BN
+#define SFNO_TC_CONV_BN 192
+#endif
+
 template <class T, class TOut, int ACT, int DROP>
 struct TcTraits<OpConv<T, TOut, ACT, DROP>> : TcTraitsBase<OpConv<T, TOut, ACT, DROP>>,
                                                 TcEligible<TcTraits<OpConv<T, TOut, ACT, DROP>>, OpConv<T, TOut, ACT, DROP>> {
-  static constexpr int BN = 192;
+  static constexpr int BN = SFNO_TC_CONV_BN;
   // Stationary A: the CTA keeps its 128 output channels x all input channels of the weights resident and streams pixel
   // tiles.  Used for SHARED weights that fit next to a >= 3-stage ring (encoder, decoder: decoder0 0.179 -> 0.148 ms,
   // decoder1 0.082 -> 0.071 ms); with per-sample folded weights (inner skip, fc1) it measured slower than the streaming
