@@ -1,6 +1,6 @@
 """Per-parameter gradient errors of the differentiable forward vs an fp64 oracle (and the fp32 CPU oracle's own error)."""
 import sys
-sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")  # run from the repository root: python tests/diag_grads.py fp32
 import torch
 from oracle.sfno_oracle import SFNOOracle, perturb_affine_and_biases, random_state_dict, rel_l2
 import spherical_dyffusion_b200 as sb
