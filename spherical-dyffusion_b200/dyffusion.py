@@ -342,11 +342,10 @@ class DYffusion:
     # ---- run a program ------------------------------------------------------------------------------------------------
     @staticmethod
     def _cold(x: Tensor, nxt: Tensor, cur: Tensor) -> Tensor:
-        """x + (nxt - cur).  CUDA tensors: one fused kernel of the library.  CPU tensors only occur in the host-logic
-        tests, where the CPU oracle stands in for the networks."""
-        if x.is_cuda:
-            return torch.ops.sfno_b200.cold_update(x, nxt, cur)
-        return x + (nxt - cur)
+        """x + (nxt - cur) as one fused kernel of the library (``sfno_cold_update``).  There is no CPU path: the custom op
+        raises for CPU tensors (the host-logic tests, where CPU stand-ins replace the networks, substitute this method
+        in ``tests/conftest.py``)."""
+        return torch.ops.sfno_b200.cold_update(x, nxt, cur)
 
     def _execute(self, prog: WindowProgram, ic: Tensor, kwargs: Dict) -> Tuple[Tensor, Dict[str, Tensor]]:
         slot: Dict[str, Tensor] = {"x": ic}

@@ -45,3 +45,24 @@ def pytest_sessionstart(session):
     if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
         subprocess.run(["make", "-C", os.path.join(ROOT, "spherical-dyffusion_b200", "csrc"), "-j", str(min(8, os.cpu_count() or 2))],
                        check=False, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
+@pytest.fixture(autouse=True, scope="session")
+def _host_logic_cold_update():
+    """The product's cold-sampling update is a CUDA kernel with no CPU path.  The host-logic tests drive the window program
+    with CPU stand-ins for the networks (the oracle), so for CPU tensors -- and only for those -- the three-operand update is
+    evaluated with torch here, in the tests.  CUDA tensors still take the product's kernel."""
+    import torch
+
+    from spherical_dyffusion_b200.dyffusion import DYffusion
+
+    product = DYffusion._cold
+
+    def cold(x, nxt, cur):
+        if x.is_cuda:
+            return product(x, nxt, cur)
+        return x + (nxt - cur)
+
+    DYffusion._cold = staticmethod(cold)
+    yield
+    DYffusion._cold = staticmethod(product)
