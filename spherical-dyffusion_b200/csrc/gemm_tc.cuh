@@ -26,6 +26,9 @@
 
 namespace sfno {
 
+#ifndef SFNO_TC_WAIT_HINT_NS
+#define SFNO_TC_WAIT_HINT_NS 0    // > 0: the single-thread roles wait with mbarrier.try_wait's suspend-time hint instead of nanosleep polling
+#endif
 #ifndef SFNO_TC_BACKOFF_NS
 #define SFNO_TC_BACKOFF_NS 64   // sleep of the single-thread roles (TMA producer, MMA issuer) between barrier polls
 #endif
@@ -153,12 +156,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// the same with a suspend-time hint (ns): the hardware may park the thread for up to that long and wakes it when the phase
+// completes -- a blocked single-thread role then issues no polling instructions on its scheduler
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 // Blocking wait with a watchdog: a pipeline bug traps (-> CUDA error) after ~2 s instead of hanging the GPU.
 template <bool kBackoff = false>
 __device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity, bool timed = false) {
   if (!timed) {
     if (mbar_try_wait(bar, parity)) return 0;
     const long long t0 = clock64();
+#if SFNO_TC_WAIT_HINT_NS > 0
+    if (kBackoff) {   // single-thread roles: parked by the hardware between polls
+      while (!mbar_try_wait_hint(bar, parity, SFNO_TC_WAIT_HINT_NS)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+      return 0;
+    }
+#endif
     while (!mbar_try_wait(bar, parity)) {
       if (kBackoff) __nanosleep(SFNO_TC_BACKOFF_NS);  // single-thread roles with slack: do not compete with the epilogue warps for issue slots
       if (clock64() - t0 > 4000000000LL) __trap();
