@@ -735,3 +735,34 @@ def test_net_dropout_masks_identical_on_both_engines(dev):
     same, other = rel_l2(y_tc, y_simt), rel_l2(y_tc, y_other)
     print(f"dropout masks: tensor-core (mask kernel) vs CUDA-core (inline Philox), same key {same:.3e}; other key {other:.3e}")
     assert same < 2e-2 and other > 5 * same
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ragged shapes: odd batches, channel counts that break the 32-row store boxes, grids whose tiles have tails
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("tf32", TF32_BOUND), ("bf16", BF16_BOUND)])
+@pytest.mark.parametrize("B,embed,nlat,nlon,grid", [
+    (1, 32, 24, 48, "equiangular"),
+    (3, 32, 24, 48, "legendre-gauss"),
+    (5, 24, 24, 48, "equiangular"),        # embed % 32 != 0: eight-row boxes in the inverse Legendre transform
+    (7, 40, 33, 64, "equiangular"),        # odd nlat, 33 degrees, rows of a tile straddle samples
+    (2, 16, 45, 96, "legendre-gauss"),     # nlon / 2 + 1 = 49 wavenumbers
+])
+def test_net_ragged_shapes_match_oracle(dev, precision, tol, B, embed, nlat, nlon, grid):
+    cfg = SFNOConfig(spatial_shape=(nlat, nlon), num_input_channels=5, num_output_channels=3, num_conditional_channels=2, embed_dim=embed,
+                     num_layers=2, operator_type="dhconv", with_time_emb=True, data_grid=grid, min_time=0.0, max_time=5.0)
+    sd = perturb_affine_and_biases(random_state_dict(cfg, seed=B, spectral_gain=float(embed * embed) / 4.0), seed=B + 1)
+    g = torch.Generator().manual_seed(100 + B)
+    x = torch.randn(B, 5, nlat, nlon, generator=g)
+    c = torch.randn(B, 2, nlat, nlon, generator=g)
+    t = torch.rand(B, generator=g) * 5.0
+    ref = SFNOOracle(cfg, sd)(x, time=t, condition=c)
+    m = module_from_cfg(cfg, sd, dev, precision=precision)
+    with torch.inference_mode():
+        y = m(x.to(dev), time=t.to(dev), condition=c.to(dev))
+        y1 = m(x[-1:].to(dev), time=t[-1:].to(dev), condition=c[-1:].to(dev))     # the last sample alone
+    e = rel_l2(y, ref)
+    print(f"ragged {precision} B={B} embed={embed} {nlat}x{nlon} {grid}: rel-L2 {e:.3e}; last sample alone vs in batch {rel_l2(y1, y[-1:]):.3e}")
+    assert torch.isfinite(y).all()
+    assert e < tol
+    assert rel_l2(y1, y[-1:]) < (1e-5 if precision == "fp32" else 1.4 * tol)
