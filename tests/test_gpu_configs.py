@@ -185,3 +185,35 @@ def test_ace_sampling_window_vs_oracle(dev):
         assert max(errs.values()) < bound, (precision, errs)
         del fore, ipol
         torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_more_than_2_31_elements_per_tensor_720x1440_embed512_batch3(dev, precision):
+    """Config 5 width at batch 3: the hidden tensor of the MLP has 3 x 1024 x 720 x 1440 = 3.2e9 elements, past 32-bit
+    indexing.  Sample 2 computed alone must agree with row 2 of the batch to the precision of the mode (rows are independent
+    samples; the two launches walk the K blocks of a tile in different orders, so the agreement is not bit-exact): an index
+    that wrapped would corrupt the later samples at O(1)."""
+    cfg = _scaled_cfg(512)
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(3, 34, 720, 1440, generator=g, device=dev)
+    c = torch.randn(3, 2, 720, 1440, generator=g, device=dev)
+    t = torch.tensor([4.0, 1.0, 2.5], device=dev)
+    with torch.device(dev):
+        torch.manual_seed(7)
+        m = sb.SphericalFourierNeuralOperatorNet(
+            num_input_channels=34, num_output_channels=34, num_output_channels_raw=34, num_conditional_channels=2,
+            spatial_shape_in=(720, 1440), spatial_shape_out=(720, 1440), precision=precision, param_check="version",
+            **cfg.model_kwargs())
+        for blk in m.blocks:
+            blk.filter.filter.weight.data.mul_(512.0)
+    m.set_min_max_time(0, 5)
+    m = m.eval()
+    with torch.inference_mode():
+        y = m(x, time=t, condition=c).clone()
+        y2 = m(x[2:3].contiguous(), time=t[2:3], condition=c[2:3].contiguous()).clone()
+    e = rel_l2(y[2:3], y2)
+    print(f"720x1440 embed 512 batch 3 ({precision}): sample 2 alone vs in batch rel-L2 {e:.3e}")
+    assert torch.isfinite(y).all()
+    assert e < {"bf16": 1.35e-2, "tf32": 1.8e-3}[precision]      # measured 5.6e-3 / 7.6e-4
+    del m
+    torch.cuda.empty_cache()
