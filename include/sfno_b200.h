@@ -57,7 +57,9 @@ int64_t sfno_b200_launch_count(void);
  * bits 0-4 is set): 1 skip A-operand loads, 2 skip B-operand loads, 4 skip global stores, 16 skip the MMAs;
  * correct-result switches: 128 = accumulate the role-wait counters read by sfno_b200_tc_counters, 256 = single 128-row
  * tiles where an op would use dual-M tiles, 512 = every CTA walks the K blocks from block 0 (no per-CTA rotation),
- * 1024 = plain stream order (no programmatic dependent launch). */
+ * 1024 = plain stream order (no programmatic dependent launch).
+ * "nvtx" = 1 (or SFNO_NVTX=1 in the environment): the network forward, its blocks and the op-level entry points push
+ * named NVTX ranges for tracing tools; off by default. */
 int sfno_b200_set_option(const char* key, int64_t value);
 
 /* Measurement hook: cycles summed over the CTAs of all tensor-core launches since the last call (tc_debug bit 7):

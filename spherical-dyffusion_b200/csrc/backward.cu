@@ -340,6 +340,7 @@ int sfno_conv1x1_backward(const float* x_dev, const float* grad_y_dev, const flo
   SFNO_CHECK_ARG(((uintptr_t)workspace_dev & 1023) == 0, "workspace must be 1024-byte aligned");
   if (workspace_bytes < sfno_conv1x1_backward_workspace_bytes(batch, cin, cout, hw, precision)) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  NvtxRange range("sfno_conv1x1_backward");
   if (precision == SFNO_PREC_BF16)
     return conv1x1_backward_impl<bf16>(x_dev, grad_y_dev, weight_dev, grad_x_dev, grad_w_dev, grad_b_dev, batch, cin, cout, hw, false, precision,
                                        (char*)workspace_dev, st);

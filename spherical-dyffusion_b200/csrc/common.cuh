@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -51,6 +53,17 @@ inline int post_launch(const char* what) {
   }
   return SFNO_OK;
 }
+
+// ---- optional NVTX ranges (sfno_b200_set_option("nvtx", 1) or SFNO_NVTX=1 in the environment): forward, blocks, op-level
+// entry points show up as named ranges on the timeline of a tracing tool; off by default (no cost beyond one atomic load)
+extern std::atomic<int> g_nvtx_on;
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* name) : on(g_nvtx_on.load(std::memory_order_relaxed) != 0) { if (on) nvtxRangePushA(name); }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // ---- small math ---------------------------------------------------------------------------------------
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

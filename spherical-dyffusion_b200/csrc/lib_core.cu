@@ -13,6 +13,7 @@ namespace sfno {
 
 std::atomic<int64_t> g_launch_count{0};
 std::atomic<int> g_profile_on{0};
+std::atomic<int> g_nvtx_on{[] { const char* e = getenv("SFNO_NVTX"); return (e && e[0] && e[0] != '0') ? 1 : 0; }()};
 
 // Per-launch timing: one CUDA event after every launch on the profiled stream; durations are differences of
 // consecutive events (the path is a single in-order stream, so launches execute back to back).

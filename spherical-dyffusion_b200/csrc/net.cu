@@ -348,6 +348,9 @@ static int forward_impl(sfno_net* n, const ConcatParts& parts, const float* time
                              n->stop_after_block == -2 && !g_profile_on.load(std::memory_order_relaxed);
   auto mask_grid = [](int64_t n8) { return (unsigned)std::min<int64_t>(ceil_div64(n8 / 8 + 1, 128), 148 * 4); };
   for (int i = 0; i < nl; ++i) {
+    char range_name[32];
+    snprintf(range_name, sizeof(range_name), "sfno block %d", i);
+    NvtxRange block_range(range_name);
     const BlockParams& bp = n->blocks[i];
     const ShtDeviceTables& fwd = (i == 0) ? n->data_grid : n->lg_grid;
     const ShtDeviceTables& inv = (i == nl - 1) ? n->data_grid : n->lg_grid;
@@ -514,6 +517,7 @@ int sfno_b200_set_option(const char* key, int64_t value) {
   if (!key) return fail(SFNO_ERR_INVALID_ARGUMENT, "key is NULL");
   if (strcmp(key, "force_simt") == 0) { g_force_simt.store((int)value); return SFNO_OK; }
   if (strcmp(key, "tc_debug") == 0) { g_tc_debug.store((int)value); return SFNO_OK; }
+  if (strcmp(key, "nvtx") == 0) { g_nvtx_on.store(value != 0); return SFNO_OK; }
   return fail(SFNO_ERR_INVALID_ARGUMENT, "unknown option %s", key);
 }
 
@@ -649,6 +653,7 @@ static int forward_dispatch(sfno_net* n, const ConcatParts& parts, const float* 
   if (csum != n->Cin) return fail(SFNO_ERR_SHAPE_MISMATCH, "input parts have %d channels in total, the net expects %d", csum, n->Cin);
   if (workspace_bytes < ws_layout(n, batch).total) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small: %zu < %zu", workspace_bytes, ws_layout(n, batch).total);
   cudaStream_t st = (cudaStream_t)stream;
+  NvtxRange range("sfno_net_forward");
   return n->cfg.precision == SFNO_PREC_BF16
              ? forward_impl<bf16>(n, parts, time_dev, y_dev, batch, dropout_enabled, seed, offset, rng_dev, (char*)workspace_dev, st)
              : forward_impl<float>(n, parts, time_dev, y_dev, batch, dropout_enabled, seed, offset, rng_dev, (char*)workspace_dev, st);

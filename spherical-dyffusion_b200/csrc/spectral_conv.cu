@@ -505,6 +505,7 @@ int sfno_spectral_conv(const sfno_sht_plan* fwd, const sfno_sht_plan* inv, const
   SFNO_CHECK_ARG(((uintptr_t)workspace_dev & 1023) == 0, "workspace must be 1024-byte aligned");
   if (workspace_bytes < spec_ws_layout(f, i, batch, w->cin, w->cout).total) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  NvtxRange range("sfno_spectral_conv");
   return f.precision == SFNO_PREC_BF16 ? spectral_conv_impl<bf16>(f, i, w, x_dev, y_dev, residual_dev, batch, (char*)workspace_dev, st)
                                        : spectral_conv_impl<float>(f, i, w, x_dev, y_dev, residual_dev, batch, (char*)workspace_dev, st);
 }
@@ -531,6 +532,7 @@ int sfno_spectral_conv_backward(sfno_sht_plan* fwd, sfno_sht_plan* inv, const sf
   SFNO_CHECK_ARG(((uintptr_t)workspace_dev & 1023) == 0, "workspace must be 1024-byte aligned");
   if (workspace_bytes < sfno_spectral_conv_backward_workspace_bytes(fwd, inv, w, batch)) return fail(SFNO_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  NvtxRange range("sfno_spectral_conv_backward");
   return f.precision == SFNO_PREC_BF16
              ? spectral_conv_backward_impl<bf16>(f, i, w, weight_dev, x_dev, grad_y_dev, grad_residual_dev, grad_x_dev, grad_weight_dev,
                                                  grad_bias_dev, batch, (char*)workspace_dev, st)

@@ -279,3 +279,13 @@ def test_roofline_arithmetic_from_a_per_launch_profile():
     leg = out["per_kernel_roofline"]["legendre_fwd"]
     assert abs(leg["TFLOPs_executed"] / leg["TFLOPs"] - 21700 / 32580) < 2e-3 and leg["frac_hbm_executed"] < leg["frac_hbm"]
     assert sht["TFLOPs_executed"] < sht["TFLOPs_dense"] and "TFLOPs_executed" not in out["per_kernel_roofline"]["dft_fwd"]
+
+
+def test_library_options():
+    """Library-wide switches exist and reject unknown keys (the NVTX ranges need no device)."""
+    from spherical_dyffusion_b200 import _lib
+
+    _lib.set_option("nvtx", 1)
+    _lib.set_option("nvtx", 0)
+    with pytest.raises(Exception):
+        _lib.set_option("no_such_option", 1)
