@@ -437,7 +437,7 @@ int sfno_instance_norm(const float* x_dev, float* y_dev, const float* gamma_dev,
     time_affine_compose_kernel<<<ceil_div(BC, 256), 256, 0, st>>>(a, d, scale_dev, shift_dev, BC);
     SFNO_TRY(post_launch("time_affine_compose"));
   }
-  affine_apply_kernel<<<dim3((unsigned)std::min<int64_t>(ceil_div64(hw, 256), 1024), BC), 256, 0, st>>>(x_dev, y_dev, a, d, hw);
+  affine_apply_kernel<<<dim3((unsigned)std::min<int64_t>(ceil_div64(hw, 256 * 16), 16), BC), 256, 0, st>>>(x_dev, y_dev, a, d, hw);
   return post_launch("affine_apply");
 }
 

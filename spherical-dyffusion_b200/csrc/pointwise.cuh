@@ -388,6 +388,14 @@ static __global__ void concat_convert_kernel(ConcatParts parts, int64_t hw, T* _
         u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
         d4[i] = u;
       }
+    } else if (sizeof(T) == 4 && per % 4 == 0 && ((((uintptr_t)s) | ((uintptr_t)d)) & 15) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(s);
+      float4* d4 = reinterpret_cast<float4*>(d);
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (per >> 2); i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = s4[i];
+        if (round_tf32) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }
+        d4[i] = v;
+      }
     } else {
       for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x)
         d[i] = from_f32<T>(round_tf32 ? tf32_rna(s[i]) : s[i]);
@@ -429,8 +437,20 @@ static __global__ void affine_apply_kernel(const float* __restrict__ x, float* _
                                     const float* __restrict__ d, int64_t hw) {
   const int bc = blockIdx.y;
   const float aa = a[bc], dd = d[bc];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x)
-    y[(int64_t)bc * hw + i] = fmaf(aa, x[(int64_t)bc * hw + i], dd);
+  const float* xp = x + (int64_t)bc * hw;
+  float* yp = y + (int64_t)bc * hw;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if ((hw & 3) == 0 && ((reinterpret_cast<uintptr_t>(xp) | reinterpret_cast<uintptr_t>(yp)) & 15) == 0) {   // 16-byte path
+    const float4* x4 = reinterpret_cast<const float4*>(xp);
+    float4* y4 = reinterpret_cast<float4*>(yp);
+    for (int64_t i = tid; i < (hw >> 2); i += nth) {
+      float4 v = x4[i];
+      v.x = fmaf(aa, v.x, dd); v.y = fmaf(aa, v.y, dd); v.z = fmaf(aa, v.z, dd); v.w = fmaf(aa, v.w, dd);
+      y4[i] = v;
+    }
+  } else {
+    for (int64_t i = tid; i < hw; i += nth) yp[i] = fmaf(aa, xp[i], dd);
+  }
 }
 
 // reference coefficient layout <-> internal spectral layout (B = 1, C = fields):
