@@ -187,13 +187,14 @@ def test_ace_sampling_window_vs_oracle(dev):
         torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("precision", ["bf16"])   # (tf32 shares the indexing; measured once: 7.6e-4, profiles/r02_y_pytest_big.log)
 def test_more_than_2_31_elements_per_tensor_720x1440_embed512_batch3(dev, precision):
     """Config 5 width at batch 3: the hidden tensor of the MLP has 3 x 1024 x 720 x 1440 = 3.2e9 elements, past 32-bit
     indexing.  Sample 2 computed alone must agree with row 2 of the batch to the precision of the mode (rows are independent
     samples; the two launches walk the K blocks of a tile in different orders, so the agreement is not bit-exact): an index
-    that wrapped would corrupt the later samples at O(1)."""
-    cfg = _scaled_cfg(512)
+    that wrapped would corrupt the later samples at O(1).  One block keeps the set-up (1.5 GB of spectral weights per block,
+    the 720 x 1440 tables) short."""
+    cfg = _scaled_cfg(512, layers=1)
     g = torch.Generator(device=dev).manual_seed(5)
     x = torch.randn(3, 34, 720, 1440, generator=g, device=dev)
     c = torch.randn(3, 2, 720, 1440, generator=g, device=dev)
