@@ -215,6 +215,6 @@ def test_more_than_2_31_elements_per_tensor_720x1440_embed512_batch3(dev, precis
     e = rel_l2(y[2:3], y2)
     print(f"720x1440 embed 512 batch 3 ({precision}): sample 2 alone vs in batch rel-L2 {e:.3e}")
     assert torch.isfinite(y).all()
-    assert e < {"bf16": 1.35e-2, "tf32": 1.8e-3}[precision]      # measured 5.6e-3 / 7.6e-4
+    assert e < {"bf16": 1.35e-2, "tf32": 1.8e-3}[precision]      # measured 2.0e-3 (one block; two blocks: 5.6e-3 / 7.6e-4)
     del m
     torch.cuda.empty_cache()
