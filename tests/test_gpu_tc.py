@@ -89,8 +89,38 @@ TF32_CASES = [
 ]
 
 
+_BATCH = None
+
+
+def _batch_results():
+    """All cases of this file in ONE child process (one CUDA context instead of ~110): results keyed by (op code, dims,
+    tc_debug).  A case that kills the child leaves the later keys missing; those cases are then re-run one by one."""
+    global _BATCH
+    if _BATCH is None:
+        cases = [[OPS[c[0]], c[1] + [0] * (6 - len(c[1])), 0] for c in CASES]
+        cases += [[OPS[c[0]] + 100, c[1] + [0] * (6 - len(c[1])), 0] for c in TF32_CASES]
+        cases += [[OPS[c[0]], c[1] + [0] * (6 - len(c[1])), c[2]] for c in VARIANTS]
+        env = dict(os.environ)
+        env.pop("SFNO_TC_DEBUG", None)
+        _BATCH = {}
+        try:
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tc_selftest_cli.py"), "--batch"], input=json.dumps(cases),
+                               capture_output=True, text=True, timeout=900, env=env)
+            for line in p.stdout.splitlines():
+                if line.startswith("{"):
+                    r = json.loads(line)
+                    _BATCH[(r["op"], tuple(r["dims"]), r["tc_debug"])] = r
+        except Exception:
+            pass
+    return _BATCH
+
+
 def _run_case(op, dims, tc_debug=0, tf32=False):
-    cmd = [sys.executable, os.path.join(ROOT, "tests", "tc_selftest_cli.py"), str(OPS[op] + (100 if tf32 else 0))] + [str(d) for d in dims]
+    code = OPS[op] + (100 if tf32 else 0)
+    hit = _batch_results().get((code, tuple(dims + [0] * (6 - len(dims))), tc_debug))
+    if hit is not None:
+        return hit
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "tc_selftest_cli.py"), str(code)] + [str(d) for d in dims]
     env = dict(os.environ)
     env.pop("SFNO_TC_DEBUG", None)
     if tc_debug:
