@@ -289,3 +289,43 @@ def test_library_options():
     _lib.set_option("nvtx", 0)
     with pytest.raises(Exception):
         _lib.set_option("no_such_option", 1)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(operator_type="dhconv", with_time_emb=True, data_grid="equiangular"),                       # scale_residual in first / last block
+    dict(operator_type="diagonal", with_time_emb=False, data_grid="legendre-gauss"),
+    dict(operator_type="dhconv", with_time_emb=True, time_scale_shift_before_filter=False, normalization_layer="none", big_skip=False,
+         pos_embed=False, dropout_mlp=0.1, drop_path_rate=0.1),
+])
+def test_trainable_forward_and_backward_wiring_with_fake_tensors(monkeypatch, kw):
+    """Host logic of the backward pass without a GPU: the differentiable forward and every registered autograd formula run on
+    fake tensors (the ops' fake implementations stand in for the library), so shapes, argument order and the set of
+    parameters that receive a gradient are checked on the CPU.  Plans / weight handles are dummies; numbers are not computed."""
+    import ctypes
+
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    from spherical_dyffusion_b200 import harmonics, sfnonet
+
+    monkeypatch.setattr(harmonics._ShtBase, "_plan", lambda self, dev: ctypes.c_void_p(1))
+    monkeypatch.setattr(sfnonet.SpectralConvS2, "_weight_handle", lambda self, dev: ctypes.c_void_p(2))
+    monkeypatch.setattr(sfnonet, "require_cuda_f32", lambda t, name: t.float())
+    m = sb.SphericalFourierNeuralOperatorNet(num_input_channels=3, num_output_channels=2, num_output_channels_raw=2,
+                                             num_conditional_channels=2, spatial_shape_in=(12, 24), spatial_shape_out=(12, 24),
+                                             embed_dim=16, num_layers=3, precision="bf16", loss_function="mse", scale_factor=1, **kw)
+    if kw.get("with_time_emb"):
+        m.set_min_max_time(0, 5)
+    m.train()
+    with FakeTensorMode(allow_non_fake_inputs=True):
+        fake = {n: torch.nn.Parameter(torch.empty(p.shape)) for n, p in m.named_parameters()}
+        x = torch.empty(4, 3, 12, 24, requires_grad=True)
+        c, y = torch.empty(4, 2, 12, 24), torch.empty(4, 2, 12, 24)
+        kwargs = dict(condition=c)
+        if kw.get("with_time_emb"):
+            kwargs["time"] = torch.empty(4)
+        out = torch.func.functional_call(m, fake, args=(x,), kwargs=kwargs)
+        assert out.shape == y.shape
+        (out - y).square().mean().backward()
+        assert x.grad.shape == x.shape
+        missing = [n for n, p in fake.items() if p.grad is None or p.grad.shape != p.shape]
+        assert not missing, missing
