@@ -694,7 +694,7 @@ int sfno_param_fingerprint(const float* const* ptrs_dev, const int64_t* numel_de
   SFNO_CHECK_ARG(ptrs_dev && numel_dev && out_dev && count > 0, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   SFNO_CUDA(cudaMemsetAsync(out_dev, 0, (size_t)count * sizeof(uint64_t), st));
-  param_fingerprint_kernel<<<dim3(64, (unsigned)count), 512, 0, st>>>(ptrs_dev, numel_dev, (unsigned long long*)out_dev);
+  param_fingerprint_kernel<<<dim3((unsigned)count, 64), 512, 0, st>>>(ptrs_dev, numel_dev, (unsigned long long*)out_dev);
   return post_launch("param_fingerprint");
 }
 

@@ -299,17 +299,20 @@ static __global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n
     mask[i] = (uint8_t)dropout_keep_mask8(seed, offset, (uint64_t)i << 3, thr);
 }
 
-// position-weighted checksum of the bit patterns of `count` fp32 tensors, out[t] pre-zeroed (grid.y = tensor).
+// position-weighted checksum of the bit patterns of `count` fp32 tensors, out[t] pre-zeroed.  grid = (tensor, chunk): the
+// tensor index is the FAST block index, so the blocks of all large tensors become resident together (with the tensor as
+// the slow index the eight 94 MB spectral weights of an ACE net were streamed one after the other by 64 blocks each).
 // 16-byte loads, four in flight per thread: the kernel streams ~0.85 GB of parameters of the ACE net per call.
 static __global__ void __launch_bounds__(512) param_fingerprint_kernel(const float* const* __restrict__ ptrs, const int64_t* __restrict__ numel,
                                                                        unsigned long long* __restrict__ out) {
-  const int t = blockIdx.y;
+  const int t = blockIdx.x;
   const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(ptrs[t]);
   const int64_t n = numel[t];
   const unsigned long long kMul = 0x9E3779B97F4A7C15ull;
   unsigned long long acc = 0;
   auto mix = [&](uint32_t v, int64_t i) { acc += (unsigned long long)v * ((kMul * (unsigned long long)(i + 1)) | 1ull); };
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.y * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.y * blockDim.x;
+  if ((int64_t)blockIdx.y * blockDim.x >= n) return;   // block-uniform: this block lies past the end of a small tensor
   int64_t done = 0;
   if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
     const uint4* __restrict__ p4 = reinterpret_cast<const uint4*>(p);
@@ -330,7 +333,14 @@ static __global__ void __launch_bounds__(512) param_fingerprint_kernel(const flo
   }
   for (int64_t i = done + tid; i < n; i += nth) mix(p[i], i);
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0 && acc != 0) atomicAdd(out + t, acc);
+  __shared__ unsigned long long warp_sum[16];   // one atomic per block, not per warp (integer sums: order does not matter)
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += warp_sum[w];
+    if (s != 0) atomicAdd(out + t, s);
+  }
 }
 
 // ---- conversions -----------------------------------------------------------------------------------------
